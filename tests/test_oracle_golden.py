@@ -1,0 +1,356 @@
+"""Pins the CPU oracle against every known-answer test the reference holds for the hot path
+(SURVEY.md section 4 / 8(c)).  Each test names the reference test it restates."""
+import numpy as np
+import pytest
+
+import oracle as O
+
+A = O.algebraic
+VISION = "3q1rk1/2R1bppp/pP2p3/N2b4/1r6/4BP2/1P1Q2PP/R5K1 b - -"  # life.rs:1141
+
+
+def bits(x):
+    return int(np.float32(x).view(np.uint32))
+
+
+# ---------------------------------------------------------------- space.rs tests
+def test_locale_packing_and_pinpoints():
+    # space.rs:365-386
+    assert O.locale(0, 0) == 0 and O.locale(7, 7) == 0x77
+    assert A("a1") == O.locale(0, 0) and A("c4") == O.locale(3, 2)
+    # space.rs:379-386: Locale::new(2, 3) (the test's "c4" variable, really d3) pinpoints 524288
+    for r in range(8):
+        for f in range(8):
+            assert O.to_algebraic(O.locale(r, f)) == "abcdefgh"[f] + str(r + 1)  # space.rs:342-363
+    w = O.empty_world()
+    w["plane"][0] = 1
+    assert O.preserve(w).startswith("8/8/8/8/8/8/8/P7")  # a1 -> bit 0
+    w["plane"][0] = 524288
+    assert O.preserve(w).startswith("8/8/8/8/8/3P4/")  # Locale::new(2, 3) -> 524288
+
+
+def test_generated_tables():
+    # furniture/tablemaker.py:41-62, 91-109; test_landmark.rs:1-17
+    L = O.lib()
+    pony = (O.C.c_uint64 * 64).in_dll(L, "LO_PONY_MOVEMENT_TABLE")
+    fig = (O.C.c_uint64 * 64).in_dll(L, "LO_FIGUREHEAD_MOVEMENT_TABLE")
+    assert pony[0] == 0x20400 and fig[0] == 0x302
+    assert sum(bin(x).count("1") for x in pony) == 336
+    assert sum(bin(x).count("1") for x in fig) == 420
+    assert L.lo_center_of_the_world() == 0x00003C3C3C3C0000
+    assert L.lo_forward_contour(1) == 0xFF00 and L.lo_forward_contour(2) == 0xFF0000
+    assert L.lo_forward_contour(6) == 0xFF << 48 and L.lo_forward_contour(5) == 0xFF << 40
+    for f in range(8):
+        m = L.lo_sideways_contour(f)
+        assert m == 0x0101010101010101 << f and bin(m).count("1") == 8
+
+
+# ---------------------------------------------------------------- life.rs tests
+def test_basic_leering_test():
+    # life.rs:1262-1266
+    assert O.is_being_leered_at_by(O.new_world(), O.locale(2, 5), O.ORANGE)
+
+
+def test_concerning_castling_legality():
+    # life.rs:1268-1274
+    assert O.new_world()["service_eligibility"] == 0b1111
+
+
+def test_concerning_castling_restrictions():
+    # life.rs:1276-1307
+    ws = O.reconstruct("rnbqkbnr/pppppppp/8/8/8/5N2/PPPPBPPP/RNBQK2R w KQkq -")
+    c = O.apply(ws, O.ORANGE, O.FIGUREHEAD, O.locale(0, 4), O.locale(0, 5))
+    assert not c["tree"]["service_eligibility"] & 0b10
+    c = O.apply(ws, O.ORANGE, O.COP, O.locale(0, 7), O.locale(0, 6))
+    assert not c["tree"]["service_eligibility"] & 0b10
+
+
+@pytest.mark.parametrize(
+    "fen,count",
+    [
+        ("8/8/4k3/8/8/8/8/4K2R w K -", 1),
+        ("8/8/4k3/8/8/8/8/R3K2R w KQ -", 2),
+        ("8/8/4k3/8/8/8/8/R3KN1R w Q -", 1),
+        ("8/8/4k3/8/8/4b3/8/R3KN1R w Q -", 0),  # can't move into endangerment
+        ("8/8/4k3/8/b7/8/8/R3KN1R w Q - 0 1", 0),  # nor through it
+    ],
+)
+def test_concerning_castling_availability(fen, count):
+    # life.rs:1309-1337
+    ws = O.reconstruct(fen)
+    assert len(O.piece_lookahead("service", ws, O.ORANGE, False)) == count
+
+
+def test_concerning_castling_actually_working():
+    # life.rs:1339-1348
+    ws = O.reconstruct("8/8/4k3/8/8/8/8/4K2R w K -")
+    prems = O.piece_lookahead("service", ws, O.ORANGE, False)
+    assert len(prems) == 1
+    assert not prems[0]["tree"]["service_eligibility"] & 0b10
+    assert O.preserve(prems[0]["tree"]) == "8/8/4k3/8/8/8/8/5RK1 b - -"
+
+
+def test_concerning_castling_out_of_check():
+    # life.rs:1350-1358
+    ws = O.reconstruct("8/8/4k3/8/4r3/8/8/4K2R w K -")
+    assert len(O.piece_lookahead("service", ws, O.ORANGE, False)) == 0
+
+
+def test_concerning_servant_ascension():
+    # life.rs:1360-1387
+    w = O.empty_world()
+    w["plane"][0] |= np.uint64(1) << np.uint64(8 * 6 + 0)  # a7
+    prems = O.piece_lookahead("servant", w, O.ORANGE, True)
+    assert all(p["whither"] == A("a8") for p in prems)
+    assert [p["ascension"] & 7 for p in prems] == [O.PONY, O.SCHOLAR, O.COP, O.PRINCESS]
+    assert all(p["ascension"] >> 3 == O.ORANGE for p in prems)
+
+
+def test_orange_servant_lookahead_from_original_position():
+    # life.rs:1407-1416
+    assert len(O.piece_lookahead("servant", O.new_world(), O.ORANGE, False)) == 16
+
+
+def test_orange_pony_lookahead_from_original_position():
+    # life.rs:1418-1432 -- pins generation order
+    prems = O.piece_lookahead("pony", O.new_world(), O.ORANGE, False)
+    assert len(prems) == 4
+
+    def locales(plane):
+        return [(i // 8, i % 8) for i in range(64) if (int(plane) >> i) & 1]
+
+    got = [locales(p["tree"]["plane"][O.PONY]) for p in prems]
+    assert got == [[(0, 6), (2, 0)], [(0, 6), (2, 2)], [(0, 1), (2, 5)], [(0, 1), (2, 7)]]
+
+
+def test_concerning_scholar_lookahead():
+    # life.rs:1434-1456
+    w = O.empty_world()
+    w["plane"][O.SCHOLAR] |= np.uint64(1) << np.uint64(4)  # e1
+    w["plane"][O.PRINCESS] |= np.uint64(1) << np.uint64(8 * 2 + 2)  # c3
+    w["plane"][6 + O.PRINCESS] |= np.uint64(1) << np.uint64(8 * 2 + 6)  # g3
+    prems = O.piece_lookahead("scholar", w, O.ORANGE, False)
+    got = [O.to_algebraic(p["whither"]) for p in prems]
+    assert got == ["d2", "f2", "g3"]
+    assert prems[2]["hospitalization"] == O.agent(O.BLUE, O.PRINCESS)
+
+
+def test_concerning_taking_turns():
+    # life.rs:1468-1477
+    s1 = O.new_world()
+    s2 = O.lookahead(s1)[0]["tree"]
+    s3 = O.lookahead(s2)[0]["tree"]
+    assert (s1["initiative"], s2["initiative"], s3["initiative"]) == (O.ORANGE, O.BLUE, O.ORANGE)
+
+
+def test_concerning_peaceful_patch_application():
+    # life.rs:1479-1496 (the reference's "e2"/"e4" here are Locale::new(4,1)/(4,3), i.e. b5/d5)
+    c = O.apply(O.new_world(), O.ORANGE, O.SERVANT, O.locale(4, 1), O.locale(4, 3))
+    plane = int(c["tree"]["plane"][0])
+    assert plane >> (8 * 4 + 3) & 1 and not plane >> (8 * 4 + 1) & 1
+
+
+def test_concerning_stunning_in_natural_setting():
+    # life.rs:1498-1551
+    s = O.new_world()
+    c1 = O.apply(s, O.ORANGE, O.SERVANT, A("e2"), A("e4"))
+    assert c1["hospitalization"] == O.NONE
+    c2 = O.apply(c1["tree"], O.BLUE, O.SERVANT, A("d7"), A("d5"))
+    assert c2["hospitalization"] == O.NONE
+    prems = O.piece_lookahead("servant", c2["tree"], O.ORANGE, False)
+    stunnings = [p for p in prems if p["hospitalization"] != O.NONE]
+    assert len(stunnings) == 1
+    assert stunnings[0]["hospitalization"] == O.agent(O.BLUE, O.SERVANT)
+    assert stunnings[0]["whither"] == A("d5")
+    c3 = O.apply(c2["tree"], O.ORANGE, O.SERVANT, A("e4"), A("d5"))
+    assert c3["hospitalization"] == O.agent(O.BLUE, O.SERVANT)
+    assert int(c3["tree"]["plane"][0]) >> (8 * 4 + 3) & 1
+
+
+def death_of_a_fool():
+    # life.rs:1553-1584
+    w = O.new_world()
+    for team, frm, to in [(O.ORANGE, "f2", "f3"), (O.BLUE, "e7", "e5"), (O.ORANGE, "g2", "g4")]:
+        c = O.apply(w, team, O.SERVANT, A(frm), A(to))
+        assert not O.in_critical_endangerment(c["tree"], team)  # careful_apply
+        w = c["tree"]
+    return O.apply(w, O.BLUE, O.PRINCESS, A("d8"), A("h4"))["tree"]
+
+
+def test_concerning_critical_endangerment():
+    # life.rs:1586-1594
+    eden = O.new_world()
+    assert not O.in_critical_endangerment(eden, O.ORANGE)
+    assert not O.in_critical_endangerment(eden, O.BLUE)
+    v_day = death_of_a_fool()
+    assert O.in_critical_endangerment(v_day, O.ORANGE)
+    assert not O.in_critical_endangerment(v_day, O.BLUE)
+
+
+def test_concerning_fools_assasination():
+    # life.rs:1596-1602
+    assert len(O.lookahead(death_of_a_fool())) == 0
+
+
+def test_concerning_preservation_and_reconstruction_of_historical_worlds():
+    # life.rs:1604-1636
+    eden = O.new_world()
+    book_of_eden = "rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq -"
+    assert O.preserve(eden) == book_of_eden
+    assert O.reconstruct(book_of_eden).tobytes() == eden.tobytes()
+    patchset = [(O.ORANGE, O.SERVANT, "e2", "e4"), (O.BLUE, O.SERVANT, "c7", "c5"), (O.ORANGE, O.PONY, "g1", "f3")]
+    books = [
+        "rnbqkbnr/pppppppp/8/8/4P3/8/PPPP1PPP/RNBQKBNR b KQkq e3",
+        "rnbqkbnr/pp1ppppp/8/2p5/4P3/8/PPPP1PPP/RNBQKBNR w KQkq c6",
+        "rnbqkbnr/pp1ppppp/8/2p5/4P3/5N2/PPPP1PPP/RNBQKB1R b KQkq -",
+    ]
+    world = eden
+    for (team, job, frm, to), book in zip(patchset, books):
+        world = O.apply(world, team, job, A(frm), A(to))["tree"]
+        assert O.preserve(world) == book
+        assert O.reconstruct(book).tobytes() == world.tobytes()
+
+
+def test_concerning_passing_by():
+    # life.rs:1644-1657
+    w = O.apply(O.new_world(), O.ORANGE, O.SERVANT, A("e2"), A("e4"))["tree"]
+    assert w["passing_by"] == A("e3")
+    w = O.apply(w, O.BLUE, O.SERVANT, A("c7"), A("c6"))["tree"]
+    assert w["passing_by"] == O.NONE
+
+
+def test_concerning_passing_by_in_action():
+    # life.rs:1659-1682
+    w = O.reconstruct("rnbqkbnr/ppp2ppp/4p3/3pP3/8/8/PPPP1PPP/RNBQKBNR w KQkq d6 0 3")
+    prems = [p for p in O.piece_lookahead("servant", w, O.ORANGE, False) if p["whence"] == A("e5")]
+    assert len(prems) == 1
+    best = prems[0]
+    assert (best["team"], best["job"], best["whence"], best["whither"]) == (O.ORANGE, O.SERVANT, A("e5"), A("d6"))
+    assert best["hospitalization"] == O.agent(O.BLUE, O.SERVANT)
+    assert O.preserve(best["tree"]) == "rnbqkbnr/ppp2ppp/3Pp3/8/8/8/PPPP1PPP/RNBQKBNR b KQkq -"
+
+
+def test_benchmark_apply_patches_are_all_applicable():
+    # life.rs:1216-1260 -- the six apply() kinds the reference benches
+    ws = O.reconstruct("rnbqk2r/p1pp1ppp/1p5n/8/1bPPpP2/6PP/PP1BP3/RN1QKBNR b KQkq f3 0 6")
+    ep = O.apply(ws, O.BLUE, O.SERVANT, A("e4"), A("f3"))
+    assert ep["hospitalization"] == O.agent(O.ORANGE, O.SERVANT)
+    assert O.preserve(ep["tree"]) == "rnbqk2r/p1pp1ppp/1p5n/8/1bPP4/5pPP/PP1BP3/RN1QKBNR w KQkq -"
+    castle = O.apply(ws, O.BLUE, O.FIGUREHEAD, A("e8"), A("g8"))
+    assert O.preserve(castle["tree"]) == "rnbq1rk1/p1pp1ppp/1p5n/8/1bPPpP2/6PP/PP1BP3/RN1QKBNR w KQ -"
+    capture = O.apply(ws, O.BLUE, O.SCHOLAR, A("b4"), A("d2"))
+    assert capture["hospitalization"] == O.agent(O.ORANGE, O.SCHOLAR)
+    lose_east = O.apply(ws, O.BLUE, O.COP, A("h8"), A("h7"))
+    assert O.preserve(lose_east["tree"]).split(" ")[2] == "KQq"
+    lose_all = O.apply(ws, O.BLUE, O.FIGUREHEAD, A("e8"), A("f8"))
+    assert O.preserve(lose_all["tree"]).split(" ")[2] == "KQ"
+
+
+# ---------------------------------------------------------------- mind.rs tests
+def test_concerning_fairness_of_the_initial_position():
+    # mind.rs:654-660: exactly 0.0, not approximately
+    assert float(O.score(O.new_world())) - 0.5 == 0.0
+    assert bits(O.score(O.new_world())) == 0x3F000000
+
+
+def test_concerning_lazy_servants():
+    # mind.rs:789-794
+    doubled = O.reconstruct("k7/pp6/8/8/8/P7/P7/K7 w - -")
+    not_doubled = O.reconstruct("k7/pp6/8/8/8/8/PP6/K7 w - -")
+    assert O.score(doubled) < O.score(not_doubled)
+
+
+def test_concerning_servant_ascension_choices():
+    # mind.rs:662-675
+    ws = O.reconstruct("8/q1P1k/8/8/8/8/6PP/7K w - -")
+    roots, scores = O.kickoff(ws, 3, True)
+    best = int(np.argmax(scores))
+    assert scores[best] > 0.0
+    assert O.preserve(roots[best]["tree"]) == "2N5/q3k3/8/8/8/8/6PP/7K b - -"
+    assert float(scores[best]) == 4.69921875  # SURVEY.md 8(c) probe value, re-derived here
+
+
+def test_experimentally_about_kickoff():
+    # mind.rs:677-734
+    def scenario(flip):
+        world = O.empty_world()
+        me, them = (O.BLUE, O.ORANGE) if flip else (O.ORANGE, O.BLUE)
+        world["plane"][6 * them + O.PONY] |= np.uint64(1) << np.uint64(0)
+        world["plane"][6 * me + O.SCHOLAR] |= np.uint64(1) << np.uint64(8 * 2 + 2)
+        world["plane"][6 * them + O.SERVANT] |= np.uint64(1) << np.uint64(8 * 7 + 1)
+        world["plane"][6 * me + O.PONY] |= np.uint64(1) << np.uint64(8 * 5 + 2)
+        world["plane"][6 * them + O.SERVANT] |= np.uint64(1) << np.uint64(8 * 3 + 6)
+        world["initiative"] = me
+        return world
+
+    for flip in (False, True):
+        roots, scores = O.kickoff(scenario(flip), 2, True)
+        best = int(np.argmax(scores))
+        assert roots[best]["whither"] == O.locale(0, 0)
+        if not flip:
+            assert float(scores[best]) == 4.5  # SURVEY.md 8(c) probe value, re-derived here
+
+
+def test_mate_detection_like_correspondence():
+    # main.rs:458-471: "R6k/6pp/8/8/8/8/8/8 b - -" -> no replies and Blue endangered -> Orange triumphant
+    w = O.reconstruct("R6k/6pp/8/8/8/8/8/8 b - -")
+    assert len(O.lookahead(w)) == 0
+    assert O.in_critical_endangerment(w, O.BLUE)
+
+
+# ---------------------------------------------------------------- survey-probe goldens re-derived
+def test_score_bit_patterns():
+    assert bits(O.score(O.apply(O.new_world(), 0, 0, A("e2"), A("e4"))["tree"])) == 0xBECCCCCD
+    assert bits(O.score(O.reconstruct(VISION))) == 0xBEFFCCCC
+    kiwi = "r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq -"
+    assert bits(O.score(O.reconstruct(kiwi))) == 0x3DCCCCC7
+    assert bits(O.score(O.reconstruct("8/q1P1k/8/8/8/8/6PP/7K w - -"))) == 0xC0600CCD
+    assert bits(O.score(O.reconstruct("k7/pp6/8/8/8/P7/P7/K7 w - -"))) == 0x00000000
+
+
+PERFT = [
+    ("rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq -", [20, 400, 8902, 197281]),
+    ("r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq -", [48, 2038, 97814]),  # b-file quirk
+    ("rnbq1k1r/pp1Pbppp/2p5/8/2B5/8/PPP1NnPP/RNBQK2R w KQ -", [44, 1486, 62416]),  # phantom cop
+    ("r3k2r/Pppp1ppp/1b3nbN/nP6/BBP1P3/q4N2/Pp1P2PP/R2Q1RK1 w kq -", [6, 258, 9221]),
+    ("8/2p5/3p4/KP5r/1R3p1k/8/4P1P1/8 w - -", [14, 191, 2812, 43238]),  # castling-free: equals chess
+    ("r4rk1/1pp1qppp/p1np1n2/2b1p1B1/2B1P1b1/P1NP1N2/1PP1QPPP/R4RK1 w - -", [46, 2079, 89890]),
+]
+
+
+@pytest.mark.parametrize("fen,counts", PERFT)
+def test_perft_counts(fen, counts):
+    w = O.reconstruct(fen)
+    for depth, expected in enumerate(counts, start=1):
+        assert O.perft(w, depth) == expected
+    assert int(O.perft_divide(w, len(counts), threads=4).sum()) == counts[-1]
+
+
+def test_quirks():
+    # SURVEY.md 8(a) deviations 2-4
+    w = O.reconstruct("4k3/8/8/8/8/8/8/4K2n w K -")
+    la = O.lookahead(w)
+    assert len(la) == 5
+    assert "4k3/8/8/8/8/8/8/5RKn b - -" in [O.preserve(c["tree"]) for c in la]  # phantom cop
+    w = O.reconstruct("4k3/8/8/7R/8/8/8/4K2R w K -")
+    c = O.apply(w, O.ORANGE, O.COP, A("h5"), A("g5"))
+    assert O.preserve(c["tree"]).split(" ")[2] == "-"  # any cop leaving file 7 clears east
+    w = O.reconstruct("4k3/8/8/8/8/8/8/7R w K -")
+    assert "4k3/8/8/8/8/8/8/5RK1 b - -" in [O.preserve(c["tree"]) for c in O.reckless_lookahead(w)]  # resurrection
+
+
+def test_opening_negamax_tops():
+    # all-equal tops -0.4 (d1), 0.5 (d2), -0.4 (d3)
+    w = O.new_world()
+    for depth, top in [(1, np.float32(-0.4)), (2, np.float32(0.5)), (3, np.float32(-0.4))]:
+        _, scores = O.kickoff(w, depth, False, threads=4)
+        assert abs(float(scores.max()) - float(top)) < 1e-6
+
+
+def test_playout_is_deterministic_and_legal():
+    a, plies = O.playout(0x1EAF11E, 7)
+    b, _ = O.playout(0x1EAF11E, 7)
+    assert a.tobytes() == b.tobytes() and 16 <= plies <= 60
+    batch = O.playout_batch(0x1EAF11E, 0, 16)
+    assert batch[7].tobytes() == a.tobytes()
+    assert len({x.tobytes() for x in batch}) > 8
