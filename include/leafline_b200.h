@@ -1,0 +1,153 @@
+/*
+ * leafline_b200.h -- C ABI of the B200-native leaf layer (movegen + static scoring) for Leafline.
+ *
+ * The reference (zackmdavis/Leafline) has no FFI layer: its boundary for this path is the Rust
+ * method surface of `WorldState` / `Patch` / `Commit` (src/life.rs) and `mind::score` /
+ * `kickoff` (src/mind.rs).  Each entry point below names the reference item it replaces; the
+ * Rust-side `extern "C"` shim a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C types only; the caller owns every host buffer, the library owns device memory,
+ *    streams and scratch between ll_init() and ll_shutdown(); no pointer is retained after return.
+ *  - every call returns LL_OK (0) or a negative LL_ERR_*; ll_last_error() gives a thread-local
+ *    message.  Nothing unwinds or aborts across this boundary (the reference panics instead:
+ *    src/sorceries.rs:2-4).
+ *  - there is NO CPU fallback: without a CUDA device ll_init() fails with LL_ERR_NO_DEVICE.
+ *  - an ll_ctx is NOT thread-safe; use one ll_ctx per host thread (the reference calls the leaf
+ *    layer from one thread per root move, src/mind.rs:405).
+ *  - positions must be "well-formed" (domain W: no two planes overlap; at most one
+ *    figurehead per team; a set service-eligibility bit implies that team's figurehead, if any,
+ *    stands on its home e-square; passing_by is None or an empty square directly behind an enemy
+ *    servant on its double-step rank).  Every state reachable from a well-formed state by the
+ *    reference's own move generator is well-formed.  Other inputs are rejected with
+ *    LL_ERR_DOMAIN rather than answered differently from the reference.
+ */
+#ifndef LEAFLINE_B200_H
+#define LEAFLINE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LL_OK 0
+#define LL_ERR_INVALID_ARG (-1)
+#define LL_ERR_CUDA (-2)
+#define LL_ERR_CAPACITY (-3) /* an output buffer is too small; nothing is written past its capacity */
+#define LL_ERR_DOMAIN (-4)   /* a position is outside the well-formed domain W */
+#define LL_ERR_NO_DEVICE (-5)
+#define LL_ERR_OOM (-6)
+
+/* src/identity.rs:8-11, 36-43 */
+enum { LL_ORANGE = 0, LL_BLUE = 1 };
+enum { LL_SERVANT = 0, LL_PONY = 1, LL_SCHOLAR = 2, LL_COP = 3, LL_PRINCESS = 4, LL_FIGUREHEAD = 5 };
+#define LL_NONE 0xFF
+#define LL_AGENT(team, job) ((uint8_t)(((team) << 3) | (job)))
+
+/* replaces `WorldState` (src/life.rs:157-176).  plane[6*team + job] follows the reference's field
+ * order (orange servants .. orange figurehead, blue servants .. blue figurehead); bit 8*rank+file,
+ * a1 = bit 0 (src/space.rs:65-71).  service_eligibility bits as src/life.rs:178-181.
+ * passing_by: 0xFF = None, else rank<<4|file exactly as src/space.rs:34 packs a Locale. */
+typedef struct ll_world_t {
+    uint64_t plane[12];
+    uint8_t initiative;
+    uint8_t service_eligibility;
+    uint8_t passing_by;
+    uint8_t pad[5];
+} ll_world_t; /* 104 bytes */
+
+/* replaces `Patch` (src/life.rs:15-20) + `Commit` (src/life.rs:77-83).  whence / whither are
+ * Locales (rank<<4|file); hospitalization / ascension are 0xFF = None, else LL_AGENT(team, job). */
+typedef struct ll_commit_t {
+    uint8_t team, job, whence, whither;
+    uint8_t hospitalization, ascension;
+    uint8_t pad[2];
+    ll_world_t tree;
+} ll_commit_t; /* 112 bytes */
+
+typedef struct ll_ctx ll_ctx;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+int ll_init(int device, ll_ctx **ctx); /* one context per (host thread, CUDA device) */
+int ll_shutdown(ll_ctx *ctx);
+const char *ll_last_error(void);
+/* launch on the caller's stream (a cudaStream_t / CUstream, e.g. torch.cuda.current_stream().cuda_stream);
+ * NULL restores the context's own stream. */
+int ll_set_stream(ll_ctx *ctx, void *cuda_stream);
+int ll_synchronize(ll_ctx *ctx);
+int ll_device_sm_count(ll_ctx *ctx);
+
+/* ---- batched leaf layer, HOST buffers (the drop-in calls) ---------------------------------- */
+
+/* replaces `mind::score(WorldState) -> f32` (src/mind.rs:50-143), n positions at once. */
+int ll_score_batch(ll_ctx *ctx, const ll_world_t *worlds, size_t n, float *scores);
+
+/* replaces `WorldState::lookahead()` (src/life.rs:1078) when nihilistically == 0 and
+ * `WorldState::reckless_lookahead()` (src/life.rs:1082) otherwise.  For world i its commits are
+ * commits[offsets[i] .. offsets[i+1]) in the reference's order (SURVEY.md 8(a) "canonical move
+ * order").  offsets has n+1 entries; commits may be NULL to obtain only the counts. */
+int ll_lookahead_batch(ll_ctx *ctx, const ll_world_t *worlds, size_t n, int nihilistically, uint32_t *offsets,
+                       ll_commit_t *commits, size_t commits_cap);
+
+/* replaces `WorldState::in_critical_endangerment(team)` (src/life.rs:678-690) for team[i] on world i. */
+int ll_in_critical_endangerment_batch(ll_ctx *ctx, const ll_world_t *worlds, const uint8_t *teams, size_t n,
+                                      uint8_t *endangered);
+
+/* perft = number of leaves of the legal-move tree (recursive `lookahead()`);
+ * depth 0 -> 1.  per_root (nullable, root_cap entries) receives the leaf count below each root
+ * move in canonical order and *n_roots their number ("divide").  With shard_world > 1 only the
+ * work units u (2-ply prefixes, canonical order) with u % shard_world == shard_rank are counted:
+ * summing the results of all ranks (a u64 allreduce) gives the full answer. */
+int ll_perft(ll_ctx *ctx, const ll_world_t *root, int depth, int shard_rank, int shard_world, uint64_t *leaves,
+             uint64_t *per_root, uint32_t root_cap, uint32_t *n_roots);
+
+/* replaces the leaf / horizon rule of `α_β_negamax_search` (src/mind.rs:279-287, quiet = None) for
+ * n frontier nodes: values[i] = exact negamax value of frontier[i] for its side to move over
+ * `plies` plies of reckless_lookahead() children with orientation * score leaves. */
+int ll_horizon_batch(ll_ctx *ctx, const ll_world_t *frontier, size_t n, int plies, float *values);
+
+/* replaces `kickoff` (src/mind.rs:375-448) without TT / history / threads: roots = lookahead()
+ * (or reckless_lookahead() if nihilistically), scores[i] = -value(child_i, depth-1), canonical
+ * (unsorted) order.  With shard_world > 1 only roots i % shard_world == shard_rank are searched;
+ * the others get -INFINITY (gather with a max). */
+int ll_kickoff(ll_ctx *ctx, const ll_world_t *root, int depth, int nihilistically, int shard_rank, int shard_world,
+               ll_commit_t *roots, float *scores, uint32_t root_cap, uint32_t *n_roots, uint64_t *leaves_scored);
+
+/* ---- device-resident positions (structure-of-arrays u64 planes in HBM) ---------------------- */
+
+/* 12 planes of `stride` u64 each (plane j of position i at planes[j*stride + i]; stride is a
+ * multiple of 2 so every plane is 16-byte aligned) + one u32 of meta per position
+ * (bit 0 initiative, bits 1-4 service_eligibility, bits 8-15 passing_by).  All DEVICE pointers. */
+typedef struct ll_soa_t {
+    uint64_t *planes;
+    uint32_t *meta;
+    size_t stride;
+    size_t n;
+} ll_soa_t;
+
+int ll_soa_alloc(ll_ctx *ctx, size_t n, ll_soa_t *soa);
+int ll_soa_free(ll_ctx *ctx, ll_soa_t *soa);
+int ll_soa_upload(ll_ctx *ctx, const ll_world_t *worlds, size_t n, ll_soa_t *dst);          /* H2D + repack */
+int ll_soa_download(ll_ctx *ctx, const ll_soa_t *src, size_t first, size_t n, ll_world_t *worlds);
+/* scores[i] for the positions already resident in HBM; d_scores is a DEVICE pointer. Asynchronous. */
+int ll_score_soa(ll_ctx *ctx, const ll_soa_t *soa, float *d_scores);
+/* horizon values for resident positions; d_values is a DEVICE pointer. */
+int ll_horizon_soa(ll_ctx *ctx, const ll_soa_t *soa, int plies, float *d_values, uint64_t *leaves_scored);
+/* seeded random-playout positions first_index .. first_index+n-1 of the set defined in DESIGN.md
+ * (SURVEY.md 8(d) config 3), generated on the device. */
+int ll_playout_soa(ll_ctx *ctx, uint64_t seed, uint64_t first_index, size_t n, ll_soa_t *dst);
+
+/* ---- per-kernel device timing (CUDA events on the launching stream) ------------------------- */
+int ll_timing_enable(ll_ctx *ctx, int on);
+int ll_timing_reset(ll_ctx *ctx);
+/* accumulated milliseconds and launch count of the named kernel since the last reset */
+int ll_timing_query(ll_ctx *ctx, const char *kernel, double *ms, uint64_t *launches);
+/* total number of this library's kernel launches since ll_init (for bench.py's gpu_launches) */
+uint64_t ll_launch_count(ll_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,225 @@
+"""leafline_b200 -- B200-native leaf layer (legal move generation + static scoring) for Leafline.
+
+Host-side mirror of the reference's interface for this path, over the C ABI in
+include/leafline_b200.h (hand-written sm_100a CUDA, leafline_b200/csrc/):
+
+    reference (Rust)                                  here
+    ------------------------------------------------  ------------------------------------------
+    WorldState::new()              life.rs:184-221    new_world()
+    WorldState::reconstruct(s)     life.rs:428-507    reconstruct(s)
+    world.preserve()               life.rs:293-360    preserve(world)
+    world.lookahead()              life.rs:1078       Engine.lookahead(worlds)
+    world.reckless_lookahead()     life.rs:1082       Engine.reckless_lookahead(worlds)
+    world.in_critical_endangerment life.rs:678        Engine.in_critical_endangerment(worlds, teams)
+    mind::score(world)             mind.rs:50         Engine.score(worlds)
+    α_β_negamax_search leaf rule   mind.rs:279-287    Engine.horizon(worlds, plies)
+    mind::kickoff(world, depth..)  mind.rs:441        Engine.kickoff(world, depth, nihilistically)
+
+Positions are numpy records of WORLD_DTYPE (= ll_world_t, 104 bytes), commits of COMMIT_DTYPE
+(= ll_commit_t).  Everything is batch-first.  There is no CPU path: constructing an Engine
+without the built library or without a CUDA device raises.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from ._abi import COMMIT_DTYPE, WORLD_DTYPE, LeaflineError, Soa  # noqa: F401
+from .runes import preserve, reconstruct  # noqa: F401
+
+ORANGE, BLUE = 0, 1
+SERVANT, PONY, SCHOLAR, COP, PRINCESS, FIGUREHEAD = range(6)
+NONE = 0xFF
+PLAYOUT_SEED = 0x1EAF11E
+
+
+def locale(rank, file):
+    """space.rs:34 packing of a Locale."""
+    return (rank << 4) | file
+
+
+def algebraic(name):
+    """space.rs:53-63."""
+    return locale(ord(name[1]) - 49, ord(name[0]) - 97)
+
+
+def to_algebraic(loc):
+    """space.rs:49-51."""
+    return "abcdefgh"[loc & 15] + str((loc >> 4) + 1)
+
+
+def agent(team, job):
+    return (team << 3) | job
+
+
+def new_world():
+    """WorldState::new() (life.rs:184-221)."""
+    return reconstruct("rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq -")
+
+
+def _worlds(worlds):
+    a = np.ascontiguousarray(worlds, dtype=WORLD_DTYPE)
+    return a.reshape(-1)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """One ll_ctx: a CUDA device, a stream and the HBM scratch of the leaf layer.  Not thread-safe."""
+
+    def __init__(self, device=0):
+        self._lib = _abi.load()
+        self._ctx = C.c_void_p()
+        _abi.check(self._lib.ll_init(device, C.byref(self._ctx)))
+        self.device = device
+
+    def close(self):
+        if self._ctx:
+            self._lib.ll_shutdown(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- plumbing
+    def set_stream(self, cuda_stream):
+        _abi.check(self._lib.ll_set_stream(self._ctx, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        _abi.check(self._lib.ll_synchronize(self._ctx))
+
+    @property
+    def sm_count(self):
+        return self._lib.ll_device_sm_count(self._ctx)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.ll_launch_count(self._ctx))
+
+    def timing(self, on=True):
+        _abi.check(self._lib.ll_timing_enable(self._ctx, int(on)))
+
+    def timing_reset(self):
+        _abi.check(self._lib.ll_timing_reset(self._ctx))
+
+    def timing_query(self, kernel):
+        ms, launches = C.c_double(0), C.c_uint64(0)
+        _abi.check(self._lib.ll_timing_query(self._ctx, kernel.encode(), C.byref(ms), C.byref(launches)))
+        return ms.value, launches.value
+
+    # ---- the leaf layer on host buffers
+    def score(self, worlds):
+        """mind::score for every world (mind.rs:50-143) -> float32[n]."""
+        w = _worlds(worlds)
+        out = np.empty(len(w), dtype=np.float32)
+        _abi.check(self._lib.ll_score_batch(self._ctx, _ptr(w), len(w), _ptr(out)))
+        return out
+
+    def lookahead_counts(self, worlds, nihilistically=False):
+        w = _worlds(worlds)
+        offsets = np.zeros(len(w) + 1, dtype=np.uint32)
+        _abi.check(self._lib.ll_lookahead_batch(self._ctx, _ptr(w), len(w), int(nihilistically), _ptr(offsets), None, 0))
+        return np.diff(offsets.astype(np.int64))
+
+    def lookahead(self, worlds, nihilistically=False):
+        """lookahead() / reckless_lookahead() of every world -> (offsets[n+1], commits) in reference order."""
+        w = _worlds(worlds)
+        offsets = np.zeros(len(w) + 1, dtype=np.uint32)
+        _abi.check(self._lib.ll_lookahead_batch(self._ctx, _ptr(w), len(w), int(nihilistically), _ptr(offsets), None, 0))
+        total = int(offsets[-1])
+        commits = np.zeros(total, dtype=COMMIT_DTYPE)
+        if total:
+            _abi.check(
+                self._lib.ll_lookahead_batch(self._ctx, _ptr(w), len(w), int(nihilistically), _ptr(offsets), _ptr(commits), total)
+            )
+        return offsets, commits
+
+    def reckless_lookahead(self, worlds):
+        return self.lookahead(worlds, nihilistically=True)
+
+    def in_critical_endangerment(self, worlds, teams):
+        w = _worlds(worlds)
+        t = np.ascontiguousarray(np.broadcast_to(np.asarray(teams, dtype=np.uint8), (len(w),)))
+        out = np.zeros(len(w), dtype=np.uint8)
+        _abi.check(self._lib.ll_in_critical_endangerment_batch(self._ctx, _ptr(w), _ptr(t), len(w), _ptr(out)))
+        return out.astype(bool)
+
+    def perft(self, world, depth, shard=(0, 1)):
+        """Leaf count of the legal-move tree -> (leaves, per_root[n_roots]) for this shard."""
+        w = _worlds(world)
+        leaves, n_roots = C.c_uint64(0), C.c_uint32(0)
+        per_root = np.zeros(1024, dtype=np.uint64)
+        _abi.check(
+            self._lib.ll_perft(self._ctx, _ptr(w), depth, shard[0], shard[1], C.byref(leaves), _ptr(per_root), 1024, C.byref(n_roots))
+        )
+        return int(leaves.value), per_root[: n_roots.value].copy()
+
+    def horizon(self, worlds, plies):
+        """Exact negamax value of each frontier node over `plies` reckless plies (mind.rs:279-287)."""
+        w = _worlds(worlds)
+        out = np.empty(len(w), dtype=np.float32)
+        _abi.check(self._lib.ll_horizon_batch(self._ctx, _ptr(w), len(w), plies, _ptr(out)))
+        return out
+
+    def kickoff(self, world, depth, nihilistically=False, shard=(0, 1)):
+        """mind::kickoff without TT/history: (root commits, root scores, leaves scored), canonical order."""
+        w = _worlds(world)
+        roots = np.zeros(1024, dtype=COMMIT_DTYPE)
+        scores = np.zeros(1024, dtype=np.float32)
+        n_roots, scored = C.c_uint32(0), C.c_uint64(0)
+        _abi.check(
+            self._lib.ll_kickoff(
+                self._ctx, _ptr(w), depth, int(nihilistically), shard[0], shard[1], _ptr(roots), _ptr(scores), 1024,
+                C.byref(n_roots), C.byref(scored),
+            )
+        )
+        return roots[: n_roots.value].copy(), scores[: n_roots.value].copy(), int(scored.value)
+
+    # ---- positions resident in HBM (SoA planes)
+    def soa_alloc(self, n):
+        soa = Soa()
+        _abi.check(self._lib.ll_soa_alloc(self._ctx, n, C.byref(soa)))
+        return soa
+
+    def soa_free(self, soa):
+        _abi.check(self._lib.ll_soa_free(self._ctx, C.byref(soa)))
+
+    def soa_upload(self, worlds, soa=None):
+        w = _worlds(worlds)
+        if soa is None:
+            soa = self.soa_alloc(len(w))
+        _abi.check(self._lib.ll_soa_upload(self._ctx, _ptr(w), len(w), C.byref(soa)))
+        return soa
+
+    def soa_download(self, soa, first=0, n=None):
+        n = soa.n - first if n is None else n
+        out = np.zeros(n, dtype=WORLD_DTYPE)
+        _abi.check(self._lib.ll_soa_download(self._ctx, C.byref(soa), first, n, _ptr(out)))
+        return out
+
+    def score_soa(self, soa, d_scores_ptr):
+        """Asynchronous: scores of resident positions into the DEVICE buffer at d_scores_ptr."""
+        _abi.check(self._lib.ll_score_soa(self._ctx, C.byref(soa), C.c_void_p(d_scores_ptr)))
+
+    def horizon_soa(self, soa, plies, d_values_ptr):
+        scored = C.c_uint64(0)
+        _abi.check(self._lib.ll_horizon_soa(self._ctx, C.byref(soa), plies, C.c_void_p(d_values_ptr), C.byref(scored)))
+        return int(scored.value)
+
+    def playout_soa(self, n, seed=PLAYOUT_SEED, first_index=0, soa=None):
+        """Seeded random-playout positions generated on the device (DESIGN.md "playout set")."""
+        if soa is None:
+            soa = self.soa_alloc(n)
+        _abi.check(self._lib.ll_playout_soa(self._ctx, seed, first_index, n, C.byref(soa)))
+        return soa

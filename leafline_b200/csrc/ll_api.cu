@@ -1,0 +1,760 @@
+// ll_api.cu -- the C ABI (include/leafline_b200.h) over the CUDA kernels.  No torch types, no CPU
+// fallback: every entry point runs on the device or fails with an LL_ERR_* code.
+#include "../../include/leafline_b200.h"
+#include "ll_kernels.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace ll;
+
+static thread_local char g_error[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof g_error, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t e_ = (expr);                                                                            \
+        if (e_ != cudaSuccess)                                                                              \
+            return fail(e_ == cudaErrorMemoryAllocation ? LL_ERR_OOM : LL_ERR_CUDA, "%s: %s (%s:%d)", #expr, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                        \
+    } while (0)
+#define LL_TRY(expr)              \
+    do {                          \
+        int rc_ = (expr);         \
+        if (rc_ != LL_OK) return rc_; \
+    } while (0)
+
+namespace {
+
+struct DevBuf { // grow-only device allocation
+    void *ptr = nullptr;
+    size_t cap = 0;
+};
+
+struct Frontier { // one BFS level resident in HBM
+    DevBuf planes, meta, root, counts, block_sums, block_base, cmeta, values;
+    size_t cap = 0; // positions
+    size_t n = 0;
+    Soa soa() const { return Soa{(u64 *)planes.ptr, (u32 *)meta.ptr, cap}; }
+};
+
+struct TimedLaunch {
+    std::string name;
+    cudaEvent_t start, stop;
+};
+
+} // namespace
+
+struct ll_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::vector<Frontier> levels;
+    Frontier ext; // scratch (counts / scan / values) used when level 0 aliases caller-owned planes
+    DevBuf aos_in, aos_out, scalars, scores, teams, flags;
+    void *pinned = nullptr; // small host staging
+    size_t pinned_cap = 0;
+    bool timing = false;
+    std::vector<TimedLaunch> timed;
+    uint64_t launches = 0;
+};
+
+namespace {
+
+int ensure(ll_ctx *ctx, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return LL_OK;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (b.ptr) CUDA_TRY(cudaFree(b.ptr));
+    b.ptr = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&b.ptr, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        e = cudaMalloc(&b.ptr, want);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(LL_ERR_OOM, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return LL_OK;
+}
+
+size_t nblocks(size_t n, size_t per = BLOCK) { return (n + per - 1) / per; }
+
+// make level `l` able to hold `n` positions (contents are NOT preserved when it grows)
+int reserve_level(ll_ctx *ctx, size_t l, size_t n, bool with_cmeta, bool with_values) {
+    if (ctx->levels.size() <= l) ctx->levels.resize(l + 1);
+    Frontier &f = ctx->levels[l];
+    if (n > f.cap) {
+        size_t cap = ((n + n / 8 + 63) / 64) * 64; // even stride, 16-byte aligned planes
+        LL_TRY(ensure(ctx, f.planes, cap * 12 * sizeof(u64)));
+        LL_TRY(ensure(ctx, f.meta, cap * sizeof(u32)));
+        LL_TRY(ensure(ctx, f.root, cap * sizeof(u32)));
+        LL_TRY(ensure(ctx, f.counts, cap * sizeof(u32)));
+        LL_TRY(ensure(ctx, f.block_sums, (nblocks(cap) + 1) * sizeof(u32)));
+        LL_TRY(ensure(ctx, f.block_base, (nblocks(cap) + 1) * sizeof(u64)));
+        f.cap = cap;
+    }
+    if (with_cmeta) LL_TRY(ensure(ctx, f.cmeta, f.cap * sizeof(u32)));
+    if (with_values) LL_TRY(ensure(ctx, f.values, f.cap * sizeof(float)));
+    return LL_OK;
+}
+
+struct Timed { // RAII-less helper: brackets one launch with events when timing is on
+    ll_ctx *ctx;
+    int idx = -1;
+    Timed(ll_ctx *c, const char *name) : ctx(c) {
+        ctx->launches++;
+        if (!ctx->timing) return;
+        TimedLaunch t;
+        t.name = name;
+        if (cudaEventCreate(&t.start) != cudaSuccess || cudaEventCreate(&t.stop) != cudaSuccess) return;
+        cudaEventRecord(t.start, ctx->stream);
+        ctx->timed.push_back(t);
+        idx = (int)ctx->timed.size() - 1;
+    }
+    ~Timed() {
+        if (idx >= 0) cudaEventRecord(ctx->timed[idx].stop, ctx->stream);
+    }
+};
+
+int check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(LL_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    return LL_OK;
+}
+
+int pinned(ll_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->pinned_cap) return LL_OK;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr;
+    ctx->pinned_cap = 0;
+    CUDA_TRY(cudaMallocHost(&ctx->pinned, bytes + 4096));
+    ctx->pinned_cap = bytes + 4096;
+    return LL_OK;
+}
+
+// scalars buffer layout (u64 slots): 0 = first bad index, 1 = scan total, 2 = leaf total, 3 = leaves scored,
+// 8.. = per-root counts
+constexpr size_t SC_BAD = 0, SC_TOTAL = 1, SC_LEAVES = 2, SC_SCORED = 3, SC_PER_ROOT = 8, SC_SLOTS = 8 + 1024;
+
+int upload_worlds(ll_ctx *ctx, const ll_world_t *worlds, size_t n, size_t level) {
+    LL_TRY(reserve_level(ctx, level, n, false, false));
+    LL_TRY(ensure(ctx, ctx->aos_in, n * sizeof(ll_world_t)));
+    CUDA_TRY(cudaMemcpyAsync(ctx->aos_in.ptr, worlds, n * sizeof(ll_world_t), cudaMemcpyHostToDevice, ctx->stream));
+    Frontier &f = ctx->levels[level];
+    f.n = n;
+    if (n) {
+        Timed t(ctx, "aos_to_soa");
+        k_aos_to_soa<<<(unsigned)nblocks(n), BLOCK, 0, ctx->stream>>>((const u64 *)ctx->aos_in.ptr, n, f.soa(), 0);
+    }
+    return check_launch("k_aos_to_soa");
+}
+
+int validate_level(ll_ctx *ctx, const Soa &soa, size_t n) {
+    if (!n) return LL_OK;
+    u64 *sc = (u64 *)ctx->scalars.ptr;
+    CUDA_TRY(cudaMemsetAsync(sc + SC_BAD, 0xFF, sizeof(u64), ctx->stream));
+    {
+        Timed t(ctx, "validate");
+        k_validate<<<(unsigned)nblocks(n), BLOCK, 0, ctx->stream>>>(soa, n, (unsigned long long *)(sc + SC_BAD));
+    }
+    LL_TRY(check_launch("k_validate"));
+    u64 bad = 0;
+    CUDA_TRY(cudaMemcpyAsync(&bad, sc + SC_BAD, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (bad != ~0ull)
+        return fail(LL_ERR_DOMAIN, "position %llu is not well-formed (see include/leafline_b200.h, domain W)",
+                    (unsigned long long)bad);
+    return LL_OK;
+}
+
+// count the commits of every node of level l (counts + block bases stay on the device); returns the total
+int count_level(ll_ctx *ctx, size_t l, bool nihil, u64 *total_out) {
+    Frontier &f = ctx->levels[l];
+    *total_out = 0;
+    if (!f.n) return LL_OK;
+    const size_t nb = nblocks(f.n);
+    u64 *sc = (u64 *)ctx->scalars.ptr;
+    {
+        Timed t(ctx, nihil ? "count_reckless" : "count_legal");
+        if (nihil) k_count<true><<<(unsigned)nb, BLOCK, 0, ctx->stream>>>(f.soa(), f.n, (u32 *)f.counts.ptr, (u32 *)f.block_sums.ptr);
+        else k_count<false><<<(unsigned)nb, BLOCK, 0, ctx->stream>>>(f.soa(), f.n, (u32 *)f.counts.ptr, (u32 *)f.block_sums.ptr);
+    }
+    LL_TRY(check_launch("k_count"));
+    {
+        Timed t(ctx, "scan_block_sums");
+        k_scan_block_sums<<<1, 1024, 0, ctx->stream>>>((u32 *)f.block_sums.ptr, (u64 *)f.block_base.ptr, nb, sc + SC_TOTAL);
+    }
+    LL_TRY(check_launch("k_scan_block_sums"));
+    CUDA_TRY(cudaMemcpyAsync(total_out, sc + SC_TOTAL, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return LL_OK;
+}
+
+// expand level l into level l+1 (count_level(l) must have run).  root_mode: 0 none, 1 inherit, 2 own index
+int emit_level(ll_ctx *ctx, size_t l, bool nihil, u64 total, bool with_cmeta, int root_mode) {
+    LL_TRY(reserve_level(ctx, l + 1, (size_t)total, with_cmeta, false));
+    Frontier &f = ctx->levels[l];
+    Frontier &g = ctx->levels[l + 1];
+    g.n = (size_t)total;
+    if (!f.n || !total) return LL_OK;
+    u32 *cmeta = with_cmeta ? (u32 *)g.cmeta.ptr : nullptr;
+    const u32 *root_in = root_mode == 1 ? (const u32 *)f.root.ptr : nullptr;
+    u32 *root_out = root_mode ? (u32 *)g.root.ptr : nullptr;
+    {
+        Timed t(ctx, nihil ? "emit_reckless" : "emit_legal");
+        if (nihil)
+            k_emit<true><<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(f.soa(), f.n, (const u32 *)f.counts.ptr, (const u64 *)f.block_base.ptr,
+                                                                           g.soa(), cmeta, root_in, root_out, root_mode == 2);
+        else
+            k_emit<false><<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(f.soa(), f.n, (const u32 *)f.counts.ptr, (const u64 *)f.block_base.ptr,
+                                                                            g.soa(), cmeta, root_in, root_out, root_mode == 2);
+    }
+    return check_launch("k_emit");
+}
+
+int check_ctx(ll_ctx *ctx) {
+    if (!ctx) return fail(LL_ERR_INVALID_ARG, "null context");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return LL_OK;
+}
+
+// horizon values of level `l` nodes (n of them) into levels[l].values; uses levels l+1.. as scratch
+int horizon_levels(ll_ctx *ctx, size_t l, int plies, uint64_t *scored_total) {
+    Frontier &f0 = ctx->levels[l];
+    LL_TRY(reserve_level(ctx, l, f0.n, false, true));
+    u64 *sc = (u64 *)ctx->scalars.ptr;
+    if (!f0.n) return LL_OK;
+    if (plies <= 0) {
+        Timed t(ctx, "leaf_values");
+        k_leaf_values<<<(unsigned)nblocks(f0.n), BLOCK, 0, ctx->stream>>>(f0.soa(), f0.n, (float *)f0.values.ptr);
+        if (scored_total) *scored_total += f0.n;
+        return check_launch("k_leaf_values");
+    }
+    // expand plies-1 levels of reckless children
+    size_t bottom = l;
+    for (int p = 0; p < plies - 1; p++) {
+        u64 total = 0;
+        LL_TRY(count_level(ctx, bottom, true, &total));
+        LL_TRY(emit_level(ctx, bottom, true, total, false, 0));
+        bottom++;
+    }
+    Frontier &fb = ctx->levels[bottom];
+    LL_TRY(reserve_level(ctx, bottom, fb.n, false, true));
+    CUDA_TRY(cudaMemsetAsync(sc + SC_SCORED, 0, sizeof(u64), ctx->stream));
+    if (fb.n) {
+        Timed t(ctx, "horizon_last_ply");
+        k_horizon_last_ply<<<(unsigned)nblocks(fb.n), BLOCK, 0, ctx->stream>>>(fb.soa(), fb.n, (float *)fb.values.ptr, sc + SC_SCORED);
+    }
+    LL_TRY(check_launch("k_horizon_last_ply"));
+    for (size_t lev = bottom; lev > l; lev--) {
+        Frontier &par = ctx->levels[lev - 1];
+        Frontier &chi = ctx->levels[lev];
+        LL_TRY(reserve_level(ctx, lev - 1, par.n, false, true));
+        Timed t(ctx, "backup");
+        k_backup<<<(unsigned)nblocks(par.n), BLOCK, 0, ctx->stream>>>(par.soa(), par.n, (const u32 *)par.counts.ptr, (const u64 *)par.block_base.ptr,
+                                                                     (const float *)chi.values.ptr, (float *)par.values.ptr);
+        LL_TRY(check_launch("k_backup"));
+    }
+    if (scored_total) {
+        u64 s = 0;
+        CUDA_TRY(cudaMemcpyAsync(&s, sc + SC_SCORED, sizeof s, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        *scored_total += s;
+    }
+    return LL_OK;
+}
+
+} // namespace
+
+// ================================================================================================ ABI
+
+extern "C" const char *ll_last_error(void) { return g_error; }
+
+extern "C" int ll_init(int device, ll_ctx **out) {
+    if (!out) return fail(LL_ERR_INVALID_ARG, "null out pointer");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(LL_ERR_NO_DEVICE, "no CUDA device available (%s); leafline_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= count) return fail(LL_ERR_INVALID_ARG, "device %d out of range (0..%d)", device, count - 1);
+    CUDA_TRY(cudaSetDevice(device));
+    ll_ctx *ctx = new ll_ctx();
+    ctx->device = device;
+    ctx->levels.reserve(64); // references to levels stay valid while deeper levels are added
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    // generated tables, furniture/tablemaker.py:41-62
+    u64 pony[64], fig[64];
+    static const int pony_opt[8][2] = {{1, 2}, {-1, 2}, {1, -2}, {-1, -2}, {2, 1}, {-2, 1}, {2, -1}, {-2, -1}};
+    for (int r = 0; r < 8; r++)
+        for (int f = 0; f < 8; f++) {
+            u64 a = 0, b = 0;
+            for (int k = 0; k < 8; k++) {
+                int rr = r + pony_opt[k][0], ff = f + pony_opt[k][1];
+                if (rr >= 0 && rr < 8 && ff >= 0 && ff < 8) a |= 1ull << (8 * rr + ff);
+            }
+            for (int i = -1; i <= 1; i++)
+                for (int j = -1; j <= 1; j++) {
+                    if (!i && !j) continue;
+                    int rr = r + i, ff = f + j;
+                    if (rr >= 0 && rr < 8 && ff >= 0 && ff < 8) b |= 1ull << (8 * rr + ff);
+                }
+            pony[8 * r + f] = a;
+            fig[8 * r + f] = b;
+        }
+    CUDA_TRY(cudaMemcpyToSymbol(d_pony_table, pony, sizeof pony));
+    CUDA_TRY(cudaMemcpyToSymbol(d_figurehead_table, fig, sizeof fig));
+    int rc = ensure(ctx, ctx->scalars, SC_SLOTS * sizeof(u64));
+    if (rc != LL_OK) {
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return LL_OK;
+}
+
+extern "C" int ll_shutdown(ll_ctx *ctx) {
+    if (!ctx) return LL_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    auto drop = [](DevBuf &b) {
+        if (b.ptr) cudaFree(b.ptr);
+        b.ptr = nullptr;
+        b.cap = 0;
+    };
+    drop(ctx->ext.counts); drop(ctx->ext.block_sums); drop(ctx->ext.block_base); drop(ctx->ext.values);
+    for (Frontier &f : ctx->levels) {
+        drop(f.planes); drop(f.meta); drop(f.root); drop(f.counts); drop(f.block_sums); drop(f.block_base); drop(f.cmeta); drop(f.values);
+    }
+    drop(ctx->aos_in); drop(ctx->aos_out); drop(ctx->scalars); drop(ctx->scores); drop(ctx->teams); drop(ctx->flags);
+    for (TimedLaunch &t : ctx->timed) {
+        cudaEventDestroy(t.start);
+        cudaEventDestroy(t.stop);
+    }
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return LL_OK;
+}
+
+extern "C" int ll_set_stream(ll_ctx *ctx, void *cuda_stream) {
+    LL_TRY(check_ctx(ctx));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return LL_OK;
+}
+
+extern "C" int ll_synchronize(ll_ctx *ctx) {
+    LL_TRY(check_ctx(ctx));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return LL_OK;
+}
+
+extern "C" int ll_device_sm_count(ll_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+
+extern "C" int ll_timing_enable(ll_ctx *ctx, int on) {
+    LL_TRY(check_ctx(ctx));
+    ctx->timing = on != 0;
+    return LL_OK;
+}
+extern "C" int ll_timing_reset(ll_ctx *ctx) {
+    LL_TRY(check_ctx(ctx));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (TimedLaunch &t : ctx->timed) {
+        cudaEventDestroy(t.start);
+        cudaEventDestroy(t.stop);
+    }
+    ctx->timed.clear();
+    return LL_OK;
+}
+extern "C" int ll_timing_query(ll_ctx *ctx, const char *kernel, double *ms, uint64_t *launches) {
+    LL_TRY(check_ctx(ctx));
+    if (!kernel) return fail(LL_ERR_INVALID_ARG, "null kernel name");
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    double total = 0;
+    uint64_t count = 0;
+    for (TimedLaunch &t : ctx->timed)
+        if (t.name == kernel) {
+            float e = 0;
+            CUDA_TRY(cudaEventElapsedTime(&e, t.start, t.stop));
+            total += e;
+            count++;
+        }
+    if (ms) *ms = total;
+    if (launches) *launches = count;
+    return LL_OK;
+}
+extern "C" uint64_t ll_launch_count(ll_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- scoring -----------------------------------------------------------------------------------------
+
+static int launch_score(ll_ctx *ctx, const Soa &soa, size_t n, float *d_out) {
+    if (!n) return LL_OK;
+    Timed t(ctx, "score");
+    k_score<<<(unsigned)nblocks((n + 1) / 2, 256), 256, 0, ctx->stream>>>(soa, n, d_out);
+    return check_launch("k_score");
+}
+
+extern "C" int ll_score_batch(ll_ctx *ctx, const ll_world_t *worlds, size_t n, float *scores) {
+    LL_TRY(check_ctx(ctx));
+    if (n && (!worlds || !scores)) return fail(LL_ERR_INVALID_ARG, "null buffer");
+    if (!n) return LL_OK;
+    LL_TRY(upload_worlds(ctx, worlds, n, 0));
+    LL_TRY(ensure(ctx, ctx->scores, (n + 1) * sizeof(float)));
+    LL_TRY(launch_score(ctx, ctx->levels[0].soa(), n, (float *)ctx->scores.ptr));
+    CUDA_TRY(cudaMemcpyAsync(scores, ctx->scores.ptr, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return LL_OK;
+}
+
+extern "C" int ll_score_soa(ll_ctx *ctx, const ll_soa_t *soa, float *d_scores) {
+    LL_TRY(check_ctx(ctx));
+    if (!soa || !d_scores) return fail(LL_ERR_INVALID_ARG, "null argument");
+    if (soa->stride & 1) return fail(LL_ERR_INVALID_ARG, "stride must be even");
+    return launch_score(ctx, Soa{(u64 *)soa->planes, soa->meta, soa->stride}, soa->n, d_scores);
+}
+
+// ---- movegen -----------------------------------------------------------------------------------------
+
+extern "C" int ll_lookahead_batch(ll_ctx *ctx, const ll_world_t *worlds, size_t n, int nihilistically, uint32_t *offsets,
+                                  ll_commit_t *commits, size_t commits_cap) {
+    LL_TRY(check_ctx(ctx));
+    if (!offsets || (n && !worlds)) return fail(LL_ERR_INVALID_ARG, "null buffer");
+    offsets[0] = 0;
+    if (!n) return LL_OK;
+    LL_TRY(upload_worlds(ctx, worlds, n, 0));
+    LL_TRY(validate_level(ctx, ctx->levels[0].soa(), n));
+    u64 total = 0;
+    LL_TRY(count_level(ctx, 0, nihilistically != 0, &total));
+    if (total > 0xFFFFFFFFull) return fail(LL_ERR_CAPACITY, "more than 2^32 commits in one batch");
+    Frontier &f = ctx->levels[0];
+    LL_TRY(ensure(ctx, ctx->flags, (n + 1) * sizeof(u32)));
+    {
+        Timed t(ctx, "offsets");
+        k_offsets<<<(unsigned)nblocks(n), BLOCK, 0, ctx->stream>>>((const u32 *)f.counts.ptr, (const u64 *)f.block_base.ptr, n, (u32 *)ctx->flags.ptr);
+    }
+    LL_TRY(check_launch("k_offsets"));
+    CUDA_TRY(cudaMemcpyAsync(offsets, ctx->flags.ptr, (n + 1) * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!commits) {
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return LL_OK;
+    }
+    if (total > commits_cap) {
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return fail(LL_ERR_CAPACITY, "%llu commits do not fit the capacity of %zu", (unsigned long long)total, commits_cap);
+    }
+    LL_TRY(emit_level(ctx, 0, nihilistically != 0, total, true, 0));
+    if (total) {
+        Frontier &g = ctx->levels[1];
+        LL_TRY(ensure(ctx, ctx->aos_out, (size_t)total * sizeof(ll_commit_t)));
+        {
+            Timed t(ctx, "commits_to_aos");
+            k_commits_to_aos<<<(unsigned)nblocks((size_t)total), BLOCK, 0, ctx->stream>>>(g.soa(), (const u32 *)g.cmeta.ptr, (size_t)total, (u64 *)ctx->aos_out.ptr);
+        }
+        LL_TRY(check_launch("k_commits_to_aos"));
+        CUDA_TRY(cudaMemcpyAsync(commits, ctx->aos_out.ptr, (size_t)total * sizeof(ll_commit_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return LL_OK;
+}
+
+extern "C" int ll_in_critical_endangerment_batch(ll_ctx *ctx, const ll_world_t *worlds, const uint8_t *teams, size_t n, uint8_t *endangered) {
+    LL_TRY(check_ctx(ctx));
+    if (n && (!worlds || !teams || !endangered)) return fail(LL_ERR_INVALID_ARG, "null buffer");
+    if (!n) return LL_OK;
+    for (size_t i = 0; i < n; i++)
+        if (teams[i] > 1) return fail(LL_ERR_INVALID_ARG, "teams[%zu] is not a team", i);
+    LL_TRY(upload_worlds(ctx, worlds, n, 0));
+    LL_TRY(validate_level(ctx, ctx->levels[0].soa(), n));
+    LL_TRY(ensure(ctx, ctx->teams, 2 * n));
+    unsigned char *d_teams = (unsigned char *)ctx->teams.ptr, *d_out = d_teams + n;
+    CUDA_TRY(cudaMemcpyAsync(d_teams, teams, n, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        Timed t(ctx, "endangered");
+        k_endangered<<<(unsigned)nblocks(n), BLOCK, 0, ctx->stream>>>(ctx->levels[0].soa(), n, d_teams, d_out);
+    }
+    LL_TRY(check_launch("k_endangered"));
+    CUDA_TRY(cudaMemcpyAsync(endangered, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return LL_OK;
+}
+
+// ---- perft -------------------------------------------------------------------------------------------
+
+extern "C" int ll_perft(ll_ctx *ctx, const ll_world_t *root, int depth, int shard_rank, int shard_world, uint64_t *leaves,
+                        uint64_t *per_root, uint32_t root_cap, uint32_t *n_roots) {
+    LL_TRY(check_ctx(ctx));
+    if (!root || !leaves) return fail(LL_ERR_INVALID_ARG, "null argument");
+    if (depth < 0 || depth > 32) return fail(LL_ERR_INVALID_ARG, "depth %d out of range", depth);
+    if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) return fail(LL_ERR_INVALID_ARG, "bad shard %d/%d", shard_rank, shard_world);
+    *leaves = 0;
+    if (n_roots) *n_roots = 0;
+    LL_TRY(upload_worlds(ctx, root, 1, 0));
+    LL_TRY(validate_level(ctx, ctx->levels[0].soa(), 1));
+    if (depth == 0) {
+        *leaves = shard_rank == 0 ? 1 : 0;
+        return LL_OK;
+    }
+    u64 *sc = (u64 *)ctx->scalars.ptr;
+    CUDA_TRY(cudaMemsetAsync(sc + SC_LEAVES, 0, sizeof(u64), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(sc + SC_PER_ROOT, 0, 1024 * sizeof(u64), ctx->stream));
+    const int shard_ply = depth - 1 < 2 ? depth - 1 : 2; // units = frontier nodes at this ply
+    u64 root_count = 0;
+    size_t l = 0;
+    bool sharded = shard_world == 1;
+    for (int ply = 0;; ply++) {
+        if (!sharded && ply == shard_ply) { // keep this rank's units
+            Frontier &f = ctx->levels[l];
+            const size_t kept = f.n > (size_t)shard_rank ? (f.n - shard_rank + shard_world - 1) / shard_world : 0;
+            LL_TRY(reserve_level(ctx, l + 1, kept, false, false));
+            Frontier &g = ctx->levels[l + 1];
+            if (kept) {
+                Timed t(ctx, "shard_filter");
+                k_shard_filter<<<(unsigned)nblocks(kept), BLOCK, 0, ctx->stream>>>(ctx->levels[l].soa(), (const u32 *)ctx->levels[l].root.ptr, ctx->levels[l].n,
+                                                                                  g.soa(), (u32 *)g.root.ptr, shard_rank, shard_world);
+                LL_TRY(check_launch("k_shard_filter"));
+            }
+            g.n = kept;
+            l++;
+            sharded = true;
+        }
+        Frontier &f = ctx->levels[l];
+        if (ply == depth - 1) { // frontier reached: bulk-count the leaves
+            if (f.n) {
+                Timed t(ctx, "count_leaves");
+                k_count_leaves<<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(f.soa(), f.n, ply == 0 ? nullptr : (const u32 *)f.root.ptr,
+                                                                                 ply == 0 ? nullptr : sc + SC_PER_ROOT, sc + SC_LEAVES);
+                LL_TRY(check_launch("k_count_leaves"));
+            }
+            break;
+        }
+        u64 total = 0;
+        LL_TRY(count_level(ctx, l, false, &total));
+        if (ply == 0) {
+            root_count = total;
+            if (root_count > 1024) return fail(LL_ERR_CAPACITY, "more than 1024 root moves");
+        }
+        LL_TRY(emit_level(ctx, l, false, total, false, ply == 0 ? 2 : 1));
+        l++;
+        if (!total) break;
+    }
+    u64 host[1 + 1024];
+    CUDA_TRY(cudaMemcpyAsync(&host[0], sc + SC_LEAVES, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(&host[1], sc + SC_PER_ROOT, 1024 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *leaves = host[0];
+    if (depth == 1) { // the root's own move count: every root move is one leaf
+        root_count = host[0];
+        if (shard_world > 1 && shard_rank != 0) root_count = 0;
+    }
+    if (n_roots) *n_roots = (uint32_t)root_count;
+    if (per_root) {
+        if (root_count > root_cap) return fail(LL_ERR_CAPACITY, "%llu root moves do not fit root_cap %u", (unsigned long long)root_count, root_cap);
+        for (u64 i = 0; i < root_count; i++) per_root[i] = depth == 1 ? 1 : host[1 + i];
+    }
+    return LL_OK;
+}
+
+// ---- horizon / kickoff -------------------------------------------------------------------------------
+
+extern "C" int ll_horizon_batch(ll_ctx *ctx, const ll_world_t *frontier, size_t n, int plies, float *values) {
+    LL_TRY(check_ctx(ctx));
+    if (n && (!frontier || !values)) return fail(LL_ERR_INVALID_ARG, "null buffer");
+    if (plies < 0 || plies > 8) return fail(LL_ERR_INVALID_ARG, "plies %d out of range", plies);
+    if (!n) return LL_OK;
+    LL_TRY(upload_worlds(ctx, frontier, n, 0));
+    LL_TRY(validate_level(ctx, ctx->levels[0].soa(), n));
+    LL_TRY(horizon_levels(ctx, 0, plies, nullptr));
+    CUDA_TRY(cudaMemcpyAsync(values, ctx->levels[0].values.ptr, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return LL_OK;
+}
+
+extern "C" int ll_horizon_soa(ll_ctx *ctx, const ll_soa_t *soa, int plies, float *d_values, uint64_t *leaves_scored) {
+    LL_TRY(check_ctx(ctx));
+    if (!soa || !d_values) return fail(LL_ERR_INVALID_ARG, "null argument");
+    if (plies < 0 || plies > 8) return fail(LL_ERR_INVALID_ARG, "plies %d out of range", plies);
+    if (leaves_scored) *leaves_scored = 0;
+    if (!soa->n) return LL_OK;
+    // level 0 aliases the caller's planes for the duration of the call; its scratch arrays persist in ctx->ext
+    if (ctx->levels.empty()) ctx->levels.resize(1);
+    Frontier &ext = ctx->ext;
+    LL_TRY(ensure(ctx, ext.counts, soa->stride * sizeof(u32)));
+    LL_TRY(ensure(ctx, ext.block_sums, (nblocks(soa->stride) + 1) * sizeof(u32)));
+    LL_TRY(ensure(ctx, ext.block_base, (nblocks(soa->stride) + 1) * sizeof(u64)));
+    LL_TRY(ensure(ctx, ext.values, soa->stride * sizeof(float)));
+    const Frontier saved = ctx->levels[0];
+    Frontier view = ext;
+    view.planes.ptr = soa->planes;
+    view.planes.cap = soa->stride * 12 * sizeof(u64);
+    view.meta.ptr = soa->meta;
+    view.meta.cap = soa->stride * sizeof(u32);
+    view.cap = soa->stride;
+    view.n = soa->n;
+    ctx->levels[0] = view;
+    int rc = horizon_levels(ctx, 0, plies, leaves_scored);
+    if (rc == LL_OK && cudaMemcpyAsync(d_values, ctx->levels[0].values.ptr, soa->n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess)
+        rc = fail(LL_ERR_CUDA, "copy of horizon values failed");
+    if (rc == LL_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(LL_ERR_CUDA, "synchronize failed");
+    ctx->levels[0] = saved;
+    return rc;
+}
+
+extern "C" int ll_kickoff(ll_ctx *ctx, const ll_world_t *root, int depth, int nihilistically, int shard_rank, int shard_world,
+                          ll_commit_t *roots, float *scores, uint32_t root_cap, uint32_t *n_roots, uint64_t *leaves_scored) {
+    LL_TRY(check_ctx(ctx));
+    if (!root || !scores || !n_roots) return fail(LL_ERR_INVALID_ARG, "null argument");
+    if (depth < 1 || depth > 9) return fail(LL_ERR_INVALID_ARG, "depth %d out of range (1..9)", depth);
+    if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) return fail(LL_ERR_INVALID_ARG, "bad shard %d/%d", shard_rank, shard_world);
+    *n_roots = 0;
+    if (leaves_scored) *leaves_scored = 0;
+    LL_TRY(upload_worlds(ctx, root, 1, 0));
+    LL_TRY(validate_level(ctx, ctx->levels[0].soa(), 1));
+    u64 total = 0;
+    LL_TRY(count_level(ctx, 0, nihilistically != 0, &total)); // mind.rs:388-392
+    if (total > root_cap) return fail(LL_ERR_CAPACITY, "%llu root moves do not fit root_cap %u", (unsigned long long)total, root_cap);
+    *n_roots = (uint32_t)total;
+    if (!total) return LL_OK;
+    LL_TRY(emit_level(ctx, 0, nihilistically != 0, total, true, 2));
+    Frontier &g = ctx->levels[1];
+    if (roots) {
+        LL_TRY(ensure(ctx, ctx->aos_out, (size_t)total * sizeof(ll_commit_t)));
+        {
+            Timed t(ctx, "commits_to_aos");
+            k_commits_to_aos<<<(unsigned)nblocks((size_t)total), BLOCK, 0, ctx->stream>>>(g.soa(), (const u32 *)g.cmeta.ptr, (size_t)total, (u64 *)ctx->aos_out.ptr);
+        }
+        LL_TRY(check_launch("k_commits_to_aos"));
+        CUDA_TRY(cudaMemcpyAsync(roots, ctx->aos_out.ptr, (size_t)total * sizeof(ll_commit_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    size_t search_level = 1;
+    size_t kept = (size_t)total;
+    if (shard_world > 1) { // this rank's root subtrees
+        kept = total > (u64)shard_rank ? (size_t)((total - shard_rank + shard_world - 1) / shard_world) : 0;
+        LL_TRY(reserve_level(ctx, 2, kept, false, false));
+        Frontier &h = ctx->levels[2];
+        if (kept) {
+            Timed t(ctx, "shard_filter");
+            k_shard_filter<<<(unsigned)nblocks(kept), BLOCK, 0, ctx->stream>>>(ctx->levels[1].soa(), (const u32 *)ctx->levels[1].root.ptr, ctx->levels[1].n,
+                                                                              h.soa(), (u32 *)h.root.ptr, shard_rank, shard_world);
+            LL_TRY(check_launch("k_shard_filter"));
+        }
+        h.n = kept;
+        search_level = 2;
+    }
+    uint64_t scored = 0;
+    LL_TRY(horizon_levels(ctx, search_level, depth - 1, &scored)); // mind.rs:406-411: full window per root
+    if (leaves_scored) *leaves_scored = scored;
+    std::vector<float> vals(kept);
+    if (kept) CUDA_TRY(cudaMemcpyAsync(vals.data(), ctx->levels[search_level].values.ptr, kept * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (u64 i = 0; i < total; i++) scores[i] = -INFINITY;
+    for (size_t o = 0; o < kept; o++) scores[(size_t)shard_rank + o * (size_t)shard_world] = -vals[o]; // mind.rs:425
+    return LL_OK;
+}
+
+// ---- device-resident positions -----------------------------------------------------------------------
+
+extern "C" int ll_soa_alloc(ll_ctx *ctx, size_t n, ll_soa_t *soa) {
+    LL_TRY(check_ctx(ctx));
+    if (!soa) return fail(LL_ERR_INVALID_ARG, "null soa");
+    memset(soa, 0, sizeof *soa);
+    const size_t stride = ((n + 63) / 64) * 64;
+    if (!stride) return LL_OK;
+    cudaError_t e = cudaMalloc((void **)&soa->planes, stride * 12 * sizeof(u64));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(LL_ERR_OOM, "cudaMalloc of %zu positions failed: %s", n, cudaGetErrorString(e));
+    }
+    e = cudaMalloc((void **)&soa->meta, stride * sizeof(u32));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(soa->planes);
+        soa->planes = nullptr;
+        return fail(LL_ERR_OOM, "cudaMalloc of %zu positions failed: %s", n, cudaGetErrorString(e));
+    }
+    CUDA_TRY(cudaMemsetAsync(soa->planes, 0, stride * 12 * sizeof(u64), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(soa->meta, 0, stride * sizeof(u32), ctx->stream));
+    soa->stride = stride;
+    soa->n = n;
+    return LL_OK;
+}
+
+extern "C" int ll_soa_free(ll_ctx *ctx, ll_soa_t *soa) {
+    LL_TRY(check_ctx(ctx));
+    if (!soa) return LL_OK;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (soa->planes) cudaFree(soa->planes);
+    if (soa->meta) cudaFree(soa->meta);
+    memset(soa, 0, sizeof *soa);
+    return LL_OK;
+}
+
+extern "C" int ll_soa_upload(ll_ctx *ctx, const ll_world_t *worlds, size_t n, ll_soa_t *dst) {
+    LL_TRY(check_ctx(ctx));
+    if (!dst || (n && !worlds)) return fail(LL_ERR_INVALID_ARG, "null argument");
+    if (n > dst->stride) return fail(LL_ERR_CAPACITY, "%zu positions do not fit stride %zu", n, dst->stride);
+    dst->n = n;
+    if (!n) return LL_OK;
+    LL_TRY(ensure(ctx, ctx->aos_in, n * sizeof(ll_world_t)));
+    CUDA_TRY(cudaMemcpyAsync(ctx->aos_in.ptr, worlds, n * sizeof(ll_world_t), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        Timed t(ctx, "aos_to_soa");
+        k_aos_to_soa<<<(unsigned)nblocks(n), BLOCK, 0, ctx->stream>>>((const u64 *)ctx->aos_in.ptr, n, Soa{(u64 *)dst->planes, dst->meta, dst->stride}, 0);
+    }
+    LL_TRY(check_launch("k_aos_to_soa"));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return LL_OK;
+}
+
+extern "C" int ll_soa_download(ll_ctx *ctx, const ll_soa_t *src, size_t first, size_t n, ll_world_t *worlds) {
+    LL_TRY(check_ctx(ctx));
+    if (!src || (n && !worlds)) return fail(LL_ERR_INVALID_ARG, "null argument");
+    if (first + n > src->n) return fail(LL_ERR_INVALID_ARG, "range %zu+%zu exceeds %zu positions", first, n, src->n);
+    if (!n) return LL_OK;
+    LL_TRY(ensure(ctx, ctx->aos_out, n * sizeof(ll_world_t)));
+    {
+        Timed t(ctx, "soa_to_aos");
+        k_soa_to_aos<<<(unsigned)nblocks(n), BLOCK, 0, ctx->stream>>>(Soa{(u64 *)src->planes, src->meta, src->stride}, first, n, (u64 *)ctx->aos_out.ptr);
+    }
+    LL_TRY(check_launch("k_soa_to_aos"));
+    CUDA_TRY(cudaMemcpyAsync(worlds, ctx->aos_out.ptr, n * sizeof(ll_world_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return LL_OK;
+}
+
+extern "C" int ll_playout_soa(ll_ctx *ctx, uint64_t seed, uint64_t first_index, size_t n, ll_soa_t *dst) {
+    LL_TRY(check_ctx(ctx));
+    if (!dst) return fail(LL_ERR_INVALID_ARG, "null soa");
+    if (n > dst->stride) return fail(LL_ERR_CAPACITY, "%zu positions do not fit stride %zu", n, dst->stride);
+    dst->n = n;
+    if (!n) return LL_OK;
+    {
+        Timed t(ctx, "playout");
+        k_playout<<<(unsigned)nblocks(n), BLOCK, 0, ctx->stream>>>(seed, first_index, n, Soa{(u64 *)dst->planes, dst->meta, dst->stride});
+    }
+    return check_launch("k_playout");
+}

@@ -1,0 +1,360 @@
+// ll_kernels.cuh -- the CUDA kernels of the leaf layer (sm_100a).  See DESIGN.md for the roofline
+// that bounds each one.  Host-side launch wrappers live in ll_api.cu.
+#pragma once
+#include "ll_device.cuh"
+
+namespace ll {
+
+constexpr int BLOCK = 128;
+
+// ---- sinks for the canonical generator -----------------------------------------------------------
+struct CountSink {
+    u32 n = 0;
+    __device__ __forceinline__ void operator()(const Pos &, u32) { n++; }
+};
+struct EmitSink { // writes children (and optionally their commit metadata / root ids) at out[idx++]
+    Soa out;
+    u32 *cmeta;
+    u32 *root_out;
+    size_t idx;
+    u32 root;
+    bool root_is_index;
+    __device__ __forceinline__ void operator()(const Pos &c, u32 m) {
+        soa_store(out, idx, c);
+        if (cmeta) cmeta[idx] = m;
+        if (root_out) root_out[idx] = root_is_index ? (u32)idx : root;
+        idx++;
+    }
+};
+struct SelectSink { // keeps the k-th commit
+    u32 n = 0, k;
+    Pos chosen;
+    __device__ __forceinline__ void operator()(const Pos &c, u32) {
+        if (n == k) chosen = c;
+        n++;
+    }
+};
+struct LeafMaxSink { // mind.rs:279-287 one ply above the horizon: max over children of -(orientation * score)
+    float best = -INFINITY;
+    u32 n = 0;
+    __device__ __forceinline__ void operator()(const Pos &c, u32) {
+        const float s = score(c);
+        const float child_value = meta_stm(c.meta) ? -s : s; // orientation(initiative) * score, mind.rs:283
+        best = fmaxf(best, -child_value);
+        n++;
+    }
+};
+
+// ---- block-level helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ u32 warp_inclusive_scan(u32 v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+// exclusive scan of one u32 per thread over a BLOCK-thread block; *total gets the block sum
+__device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32 *total) {
+    __shared__ u32 warp_sums[BLOCK / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 inc = warp_inclusive_scan(v);
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    u32 base = 0, sum = 0;
+#pragma unroll
+    for (int w = 0; w < BLOCK / 32; w++) {
+        if (w < warp) base += warp_sums[w];
+        sum += warp_sums[w];
+    }
+    __syncthreads();
+    *total = sum;
+    return base + inc - v;
+}
+
+// ---- layout kernels: ll_world_t (array of 104-byte structs) <-> SoA planes -------------------------
+// The 104-byte struct is 13 u64 words; word 12 holds initiative | eligibility<<8 | passing_by<<16.
+__global__ void __launch_bounds__(BLOCK) k_aos_to_soa(const u64 *__restrict__ aos, size_t n, Soa out, size_t out_first) {
+    __shared__ u64 tile[BLOCK * 13];
+    const size_t base = (size_t)blockIdx.x * BLOCK;
+    const size_t in_block = min((size_t)BLOCK, n - base);
+    for (size_t w = threadIdx.x; w < in_block * 13; w += BLOCK) tile[w] = aos[base * 13 + w]; // coalesced
+    __syncthreads();
+    if (threadIdx.x < in_block) {
+        const u64 *s = tile + threadIdx.x * 13; // stride 13 words: conflict-free (13 is odd)
+        const size_t i = out_first + base + threadIdx.x;
+#pragma unroll
+        for (int j = 0; j < 12; j++) out.pl[(size_t)j * out.stride + i] = s[j];
+        const u64 m = s[12];
+        out.meta[i] = make_meta((u32)(m & 1u), (u32)((m >> 8) & 0xFu), (u32)((m >> 16) & 0xFFu));
+    }
+}
+__device__ __forceinline__ u64 meta_to_word(u32 meta) {
+    return (u64)meta_stm(meta) | ((u64)meta_elig(meta) << 8) | ((u64)meta_pb(meta) << 16);
+}
+__global__ void __launch_bounds__(BLOCK) k_soa_to_aos(Soa in, size_t first, size_t n, u64 *__restrict__ aos) {
+    __shared__ u64 tile[BLOCK * 13];
+    const size_t base = (size_t)blockIdx.x * BLOCK;
+    const size_t in_block = min((size_t)BLOCK, n - base);
+    if (threadIdx.x < in_block) {
+        u64 *s = tile + threadIdx.x * 13;
+        const size_t i = first + base + threadIdx.x;
+#pragma unroll
+        for (int j = 0; j < 12; j++) s[j] = in.pl[(size_t)j * in.stride + i];
+        s[12] = meta_to_word(in.meta[i]);
+    }
+    __syncthreads();
+    for (size_t w = threadIdx.x; w < in_block * 13; w += BLOCK) aos[base * 13 + w] = tile[w];
+}
+// children SoA + packed commit metadata -> ll_commit_t (14 u64 words: header word + the 13-word tree)
+__global__ void __launch_bounds__(BLOCK) k_commits_to_aos(Soa in, const u32 *__restrict__ cmeta, size_t n, u64 *__restrict__ aos) {
+    __shared__ u64 tile[BLOCK * 15]; // 15: odd stride, conflict-free
+    const size_t base = (size_t)blockIdx.x * BLOCK;
+    const size_t in_block = min((size_t)BLOCK, n - base);
+    if (threadIdx.x < in_block) {
+        u64 *s = tile + threadIdx.x * 15;
+        const size_t i = base + threadIdx.x;
+        const u32 m = cmeta[i];
+        const u32 team = m & 1u, job = (m >> 1) & 7u, from = (m >> 4) & 63u, to = (m >> 10) & 63u;
+        const u32 hosp = (m >> 16) & 0xFu, asc = (m >> 20) & 0xFu;
+        const u64 hosp_byte = hosp == JOB_NONE ? 0xFFull : (u64)(((team ^ 1u) << 3) | hosp);
+        const u64 asc_byte = asc == JOB_NONE ? 0xFFull : (u64)((team << 3) | asc);
+        s[0] = (u64)team | ((u64)job << 8) | ((u64)sq_to_loc((int)from) << 16) | ((u64)sq_to_loc((int)to) << 24) |
+               (hosp_byte << 32) | (asc_byte << 40);
+#pragma unroll
+        for (int j = 0; j < 12; j++) s[1 + j] = in.pl[(size_t)j * in.stride + i];
+        s[13] = meta_to_word(in.meta[i]);
+    }
+    __syncthreads();
+    for (size_t w = threadIdx.x; w < in_block * 14; w += BLOCK) aos[base * 14 + w] = tile[(w / 14) * 15 + (w % 14)];
+}
+
+// ---- validation -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK) k_validate(Soa in, size_t n, unsigned long long *first_bad) {
+    const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    if (!well_formed(soa_load(in, i))) atomicMin(first_bad, (unsigned long long)i);
+}
+
+// ---- static scoring: HBM-bound streaming kernel, 2 positions per thread, 128-bit loads ---------------
+__global__ void __launch_bounds__(256) k_score(Soa in, size_t n, float *__restrict__ out) {
+    const size_t pair = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const size_t i = pair * 2;
+    if (i >= n) return;
+    Pos a, b;
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+        const ulonglong2 v = __ldcs(reinterpret_cast<const ulonglong2 *>(in.pl + (size_t)j * in.stride + i));
+        a.pl[j] = v.x;
+        b.pl[j] = v.y;
+    }
+    const uint2 m = __ldcs(reinterpret_cast<const uint2 *>(in.meta + i));
+    a.meta = m.x;
+    b.meta = m.y;
+    const float sa = score(a), sb = score(b);
+    if (i + 1 < n && ((reinterpret_cast<uintptr_t>(out) & 7u) == 0)) {
+        __stcs(reinterpret_cast<float2 *>(out + i), make_float2(sa, sb));
+    } else {
+        out[i] = sa;
+        if (i + 1 < n) out[i + 1] = sb;
+    }
+}
+
+// ---- movegen: count / offsets / emit -------------------------------------------------------------------
+template <bool NIHIL> __global__ void __launch_bounds__(BLOCK) k_count(Soa in, size_t n, u32 *__restrict__ counts, u32 *__restrict__ block_sums) {
+    const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    CountSink sink;
+    if (i < n) {
+        const Pos p = soa_load(in, i);
+        lookahead<NIHIL>(p, sink);
+        counts[i] = sink.n;
+    }
+    u32 total;
+    block_exclusive_scan(sink.n, &total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// single block: block_sums[0..nb) -> exclusive prefix in place (u64 running total written to *total)
+__global__ void __launch_bounds__(1024) k_scan_block_sums(u32 *block_sums, u64 *block_base, size_t nb, u64 *total) {
+    __shared__ u64 warp_sums[32];
+    __shared__ u64 carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (size_t start = 0; start < nb; start += 1024) {
+        const size_t i = start + threadIdx.x;
+        const u64 v = i < nb ? block_sums[i] : 0;
+        u64 inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            u64 t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) warp_sums[warp] = inc;
+        __syncthreads();
+        u64 base = carry_s;
+        for (int w = 0; w < warp; w++) base += warp_sums[w];
+        if (i < nb) block_base[i] = base + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = base + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry_s;
+}
+
+// offsets[i] = exclusive prefix of counts (offsets[n] = total), as u32 for the host ABI
+__global__ void __launch_bounds__(BLOCK) k_offsets(const u32 *__restrict__ counts, const u64 *__restrict__ block_base, size_t n, u32 *__restrict__ offsets) {
+    const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    const u32 c = i < n ? counts[i] : 0;
+    u32 total;
+    const u32 ex = block_exclusive_scan(c, &total);
+    const u64 base = block_base[blockIdx.x];
+    if (i < n) offsets[i] = (u32)(base + ex);
+    if (i == n - 1) offsets[n] = (u32)(base + ex + c);
+}
+
+template <bool NIHIL>
+__global__ void __launch_bounds__(BLOCK) k_emit(Soa in, size_t n, const u32 *__restrict__ counts, const u64 *__restrict__ block_base, Soa out,
+                                                u32 *__restrict__ cmeta, const u32 *__restrict__ root_in, u32 *__restrict__ root_out, int root_is_index) {
+    const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    const u32 c = i < n ? counts[i] : 0;
+    u32 total;
+    const u32 ex = block_exclusive_scan(c, &total);
+    if (i >= n || c == 0) return;
+    EmitSink sink{out, cmeta, root_out, (size_t)(block_base[blockIdx.x] + ex), root_in ? root_in[i] : 0u, root_is_index != 0};
+    const Pos p = soa_load(in, i);
+    lookahead<NIHIL>(p, sink);
+}
+
+// keep the units u with u % world == rank (frontier sharding by subtree)
+__global__ void __launch_bounds__(BLOCK) k_shard_filter(Soa in, const u32 *__restrict__ root_in, size_t n, Soa out, u32 *__restrict__ root_out, int rank, int world) {
+    const size_t o = (size_t)blockIdx.x * BLOCK + threadIdx.x; // o-th kept unit = unit rank + o*world
+    const size_t i = (size_t)rank + o * (size_t)world;
+    if (i >= n) return;
+    soa_store(out, o, soa_load(in, i));
+    root_out[o] = root_in[i];
+}
+
+// ---- perft tail: count the legal moves of every frontier node, accumulate per root --------------------
+__global__ void __launch_bounds__(BLOCK) k_count_leaves(Soa in, size_t n, const u32 *__restrict__ root_in, u64 *__restrict__ per_root, u64 *__restrict__ total) {
+    const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    CountSink sink;
+    u32 root = 0xFFFFFFFFu;
+    if (i < n) {
+        const Pos p = soa_load(in, i);
+        lookahead<false>(p, sink);
+        root = root_in ? root_in[i] : 0u;
+    }
+    // frontier order keeps a root's nodes contiguous, so a warp sees very few distinct roots
+    const unsigned peers = __match_any_sync(0xffffffffu, root);
+    const u32 sum = __reduce_add_sync(peers, sink.n);
+    if ((threadIdx.x & 31) == __ffs((int)peers) - 1 && root != 0xFFFFFFFFu && sum) {
+        if (per_root) atomicAdd(per_root + root, (u64)sum);
+        atomicAdd(total, (u64)sum);
+    }
+}
+
+// ---- horizon (mind.rs:279-287) -------------------------------------------------------------------------
+// value[i] of frontier node i one ply above the leaves: children generated, scored and reduced in
+// registers -- the leaves never touch HBM.  No pseudo-legal children -> the node is itself a leaf.
+__global__ void __launch_bounds__(BLOCK) k_horizon_last_ply(Soa in, size_t n, float *__restrict__ values, u64 *__restrict__ leaves_scored) {
+    const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    u32 scored = 0;
+    if (i < n) {
+        const Pos p = soa_load(in, i);
+        LeafMaxSink sink;
+        lookahead<true>(p, sink);
+        float v = sink.best;
+        if (sink.n == 0) {
+            const float s = score(p);
+            v = meta_stm(p.meta) ? -s : s;
+        }
+        values[i] = v;
+        scored = sink.n ? sink.n : 1u;
+    }
+    scored = __reduce_add_sync(0xffffffffu, scored);
+    if ((threadIdx.x & 31) == 0 && scored) atomicAdd(leaves_scored, (u64)scored);
+}
+// plies == 0: value = orientation * score
+__global__ void __launch_bounds__(BLOCK) k_leaf_values(Soa in, size_t n, float *__restrict__ values) {
+    const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    const Pos p = soa_load(in, i);
+    const float s = score(p);
+    values[i] = meta_stm(p.meta) ? -s : s;
+}
+// negamax back-up of one level: parent = max over its children of -child; childless parent -> leaf rule
+__global__ void __launch_bounds__(BLOCK) k_backup(Soa parents, size_t n, const u32 *__restrict__ counts, const u64 *__restrict__ block_base,
+                                                  const float *__restrict__ child_values, float *__restrict__ values) {
+    const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    const u32 c = i < n ? counts[i] : 0;
+    u32 total;
+    const u32 ex = block_exclusive_scan(c, &total);
+    if (i >= n) return;
+    float v;
+    if (c == 0) {
+        const Pos p = soa_load(parents, i);
+        const float s = score(p);
+        v = meta_stm(p.meta) ? -s : s;
+    } else {
+        const size_t first = (size_t)(block_base[blockIdx.x] + ex);
+        v = -INFINITY;
+        for (u32 k = 0; k < c; k++) v = fmaxf(v, -child_values[first + k]);
+    }
+    values[i] = v;
+}
+__global__ void __launch_bounds__(BLOCK) k_negate(const float *__restrict__ in, size_t n, float *__restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i < n) out[i] = -in[i];
+}
+
+// ---- life.rs:678-690 for an explicit team ------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK) k_endangered(Soa in, size_t n, const unsigned char *__restrict__ teams, unsigned char *__restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    const Pos p = soa_load(in, i);
+    out[i] = teams[i] == 0 ? in_critical_endangerment<0>(p) : in_critical_endangerment<1>(p);
+}
+
+// ---- seeded random playouts (DESIGN.md "playout set"; restated on the CPU by oracle lo_playout) -------
+__device__ __forceinline__ u64 mix64(u64 z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ Pos opening_position() { // life.rs:184-215
+    Pos p;
+    p.pl[0] = 0xFF00ull; p.pl[1] = 0x42ull; p.pl[2] = 0x24ull; p.pl[3] = 0x81ull; p.pl[4] = 0x08ull; p.pl[5] = 0x10ull;
+    p.pl[6] = 0xFF00ull << 40; p.pl[7] = 0x42ull << 56; p.pl[8] = 0x24ull << 56; p.pl[9] = 0x81ull << 56;
+    p.pl[10] = 0x08ull << 56; p.pl[11] = 0x10ull << 56;
+    p.meta = make_meta(0, 0xF, 0xFF);
+    return p;
+}
+__global__ void __launch_bounds__(BLOCK) k_playout(u64 seed, u64 first_index, size_t n, Soa out) {
+    const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    const u64 h0 = mix64(seed + first_index + i);
+    Pos p = opening_position();
+    for (u64 attempt = 0; attempt < 1024; attempt++) {
+        const u64 h1 = mix64(h0 ^ (attempt * 0xD1B54A32D192ED03ull));
+        p = opening_position();
+        const int plies = 16 + (int)(((mix64(h1) >> 32) * 45ull) >> 32);
+        int k = 0;
+        for (; k < plies; k++) {
+            CountSink counter;
+            lookahead<false>(p, counter);
+            if (counter.n == 0) break;
+            const u64 r = mix64(h1 + (u64)(k + 1) * 0x9E3779B97F4A7C15ull) >> 32;
+            SelectSink select;
+            select.k = (u32)((r * (u64)counter.n) >> 32);
+            lookahead<false>(p, select);
+            p = select.chosen;
+        }
+        if (k == plies) break;
+    }
+    soa_store(out, i, p);
+}
+
+} // namespace ll

@@ -1,0 +1,357 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle.
+Integer / byte / index results must be bit-exact; f32 scores are compared bit-for-bit too (the
+north-star tolerance is 1e-5 relative; the kernel reproduces the reference's rounding sequence)."""
+import numpy as np
+import pytest
+
+import oracle as O
+from positions import (KIWIPETE, NAMED, OPENING, POSITION_3, POSITION_4, POSITION_5, POSITION_6, named_worlds,
+                       reckless_walk_worlds)
+
+pytestmark = pytest.mark.gpu
+
+SCORE_RTOL = 1e-5  # BASELINE.json north_star
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import __graft_entry__ as entry
+
+    entry.build()
+    import leafline_b200 as ll
+
+    e = ll.Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def playouts():
+    return O.playout_batch(0x1EAF11E, 0, 1024)
+
+
+@pytest.fixture(scope="module")
+def reckless_worlds():
+    return reckless_walk_worlds(seed=5, games=30, plies=50)
+
+
+def assert_scores(got, want):
+    assert got.dtype == np.float32
+    np.testing.assert_allclose(got, want, rtol=SCORE_RTOL, atol=0)
+    assert got.tobytes() == want.tobytes(), "scores are within tolerance but not bit-exact"
+
+
+# ---------------------------------------------------------------- score (mind.rs:50-143)
+def test_score_golden_bit_patterns(eng):
+    import leafline_b200 as ll
+
+    cases = {
+        OPENING: 0x3F000000,
+        "rnbqkbnr/pppppppp/8/8/4P3/8/PPPP1PPP/RNBQKBNR b KQkq e3": 0xBECCCCCD,
+        "3q1rk1/2R1bppp/pP2p3/N2b4/1r6/4BP2/1P1Q2PP/R5K1 b - -": 0xBEFFCCCC,
+        KIWIPETE: 0x3DCCCCC7,
+        "8/q1P1k/8/8/8/8/6PP/7K w - -": 0xC0600CCD,
+        "k7/pp6/8/8/8/P7/P7/K7 w - -": 0x00000000,
+    }
+    worlds = np.array([ll.reconstruct(f) for f in cases], dtype=ll.WORLD_DTYPE)
+    got = eng.score(worlds)
+    assert [int(x) for x in got.view(np.uint32)] == list(cases.values())
+
+
+def test_score_matches_oracle_on_all_position_sets(eng, playouts, reckless_worlds):
+    for worlds in (named_worlds(), playouts, reckless_worlds, playouts[:1], playouts[:3]):
+        assert_scores(eng.score(worlds), O.score_batch(worlds))
+
+
+def test_score_empty_batch(eng):
+    assert len(eng.score(np.zeros(0, dtype=O.WORLD_DTYPE))) == 0
+
+
+def test_score_resident_soa_matches_host_path(eng, playouts):
+    import torch
+
+    soa = eng.soa_upload(playouts[:777])
+    out = torch.empty(777, dtype=torch.float32, device="cuda")
+    eng.score_soa(soa, out.data_ptr())
+    eng.synchronize()
+    assert_scores(out.cpu().numpy(), O.score_batch(playouts[:777]))
+    back = eng.soa_download(soa)
+    assert back.tobytes() == playouts[:777].tobytes()
+    eng.soa_free(soa)
+
+
+# ---------------------------------------------------------------- lookahead (life.rs:1052-1084)
+def check_lookahead(eng, worlds, nihilistically):
+    offsets, commits = eng.lookahead(worlds, nihilistically=nihilistically)
+    assert offsets[0] == 0 and len(offsets) == len(worlds) + 1
+    ref = O.reckless_lookahead if nihilistically else O.lookahead
+    for i, w in enumerate(worlds):
+        want = ref(w)
+        got = commits[offsets[i]:offsets[i + 1]]
+        assert len(got) == len(want), (i, O.preserve(w), len(got), len(want))
+        assert got.tobytes() == want.tobytes(), (i, O.preserve(w))
+    counts = eng.lookahead_counts(worlds, nihilistically=nihilistically)
+    assert list(counts) == list(np.diff(offsets.astype(np.int64)))
+
+
+@pytest.mark.parametrize("nihilistically", [False, True])
+def test_lookahead_named_positions(eng, nihilistically):
+    check_lookahead(eng, named_worlds(), nihilistically)
+
+
+@pytest.mark.parametrize("nihilistically", [False, True])
+def test_lookahead_playout_positions(eng, playouts, nihilistically):
+    check_lookahead(eng, playouts[:400], nihilistically)
+
+
+@pytest.mark.parametrize("nihilistically", [False, True])
+def test_lookahead_reckless_walk_positions(eng, reckless_worlds, nihilistically):
+    # no-figurehead boards, phantom cops, resurrected figureheads
+    check_lookahead(eng, reckless_worlds[:500], nihilistically)
+
+
+def test_lookahead_known_answers_of_the_reference(eng):
+    import leafline_b200 as ll
+
+    # life.rs:1407-1432: 20 opening moves, pony order b1a3 b1c3 g1f3 g1h3
+    offsets, commits = eng.lookahead(ll.new_world())
+    assert offsets[1] == 20
+    ponies = [(ll.to_algebraic(c["whence"]), ll.to_algebraic(c["whither"])) for c in commits if c["job"] == ll.PONY]
+    assert ponies == [("b1", "a3"), ("b1", "c3"), ("g1", "f3"), ("g1", "h3")]
+    # life.rs:1360-1387: ascension order Pony, Scholar, Cop, Princess
+    w = np.zeros((), dtype=ll.WORLD_DTYPE)
+    w["plane"][0] = 1 << 48
+    w["passing_by"] = 0xFF
+    _, commits = eng.reckless_lookahead(w)
+    assert [c["ascension"] & 7 for c in commits] == [ll.PONY, ll.SCHOLAR, ll.COP, ll.PRINCESS]
+    # life.rs:1339-1348
+    _, commits = eng.lookahead(ll.reconstruct("8/8/4k3/8/8/8/8/4K2R w K -"))
+    assert "8/8/4k3/8/8/8/8/5RK1 b - -" in [ll.preserve(c["tree"]) for c in commits]
+    # life.rs:1596-1602: fool's mate -> nothing to do
+    fool = ll.reconstruct("rnb1kbnr/pppp1ppp/8/4p3/6Pq/5P2/PPPPP2P/RNBQKBNR w KQkq -")
+    assert eng.lookahead(fool)[0][1] == 0
+    # life.rs:1659-1682: passing by
+    _, commits = eng.lookahead(ll.reconstruct("rnbqkbnr/ppp2ppp/4p3/3pP3/8/8/PPPP1PPP/RNBQKBNR w KQkq d6 0 3"))
+    ep = [c for c in commits if c["whence"] == ll.algebraic("e5")]
+    assert len(ep) == 1 and ll.preserve(ep[0]["tree"]) == "rnbqkbnr/ppp2ppp/3Pp3/8/8/8/PPPP1PPP/RNBQKBNR b KQkq -"
+    assert ep[0]["hospitalization"] == ll.agent(ll.BLUE, ll.SERVANT)
+
+
+def test_lookahead_empty_batch_and_capacity_error(eng):
+    import leafline_b200 as ll
+    from leafline_b200 import _abi
+    import ctypes as C
+
+    offsets, commits = eng.lookahead(np.zeros(0, dtype=O.WORLD_DTYPE))
+    assert list(offsets) == [0] and len(commits) == 0
+    w = np.ascontiguousarray(ll.new_world()).reshape(1)
+    offs = np.zeros(2, dtype=np.uint32)
+    small = np.zeros(5, dtype=ll.COMMIT_DTYPE)
+    rc = eng._lib.ll_lookahead_batch(eng._ctx, w.ctypes.data_as(C.c_void_p), 1, 0, offs.ctypes.data_as(C.c_void_p),
+                                     small.ctypes.data_as(C.c_void_p), 5)
+    assert rc == _abi.ERR_CAPACITY and offs[1] == 20
+    assert not small.tobytes().strip(b"\0"), "nothing may be written past / into a too-small buffer"
+
+
+def test_domain_errors_are_reported_not_guessed(eng):
+    import leafline_b200 as ll
+
+    bad = ll.new_world().copy()
+    bad["plane"][1] |= bad["plane"][0]  # ponies overlap servants
+    with pytest.raises(ll.LeaflineError) as e:
+        eng.lookahead(np.array([ll.new_world(), bad], dtype=ll.WORLD_DTYPE))
+    assert e.value.code == -4 and "position 1" in str(e.value)
+    two_kings = ll.reconstruct("4k3/8/8/8/8/8/8/K3K3 w - -")
+    with pytest.raises(ll.LeaflineError):
+        eng.perft(two_kings, 2)
+
+
+def test_in_critical_endangerment(eng, playouts, reckless_worlds):
+    import leafline_b200 as ll
+
+    v_day = ll.reconstruct("rnb1kbnr/pppp1ppp/8/4p3/6Pq/5P2/PPPPP2P/RNBQKBNR w KQkq -")  # life.rs:1586-1594
+    assert list(eng.in_critical_endangerment([v_day, v_day], [ll.ORANGE, ll.BLUE])) == [True, False]
+    for worlds in (playouts[:300], reckless_worlds[:300]):
+        for team in (0, 1):
+            got = eng.in_critical_endangerment(worlds, team)
+            want = [O.in_critical_endangerment(w, team) for w in worlds]
+            assert list(got) == want
+
+
+# ---------------------------------------------------------------- perft (recursive lookahead() leaf count)
+PERFT = [
+    (OPENING, [20, 400, 8902, 197281, 4865609]),
+    (KIWIPETE, [48, 2038, 97814]),
+    (POSITION_5, [44, 1486, 62416]),
+    (POSITION_4, [6, 258, 9221]),
+    (POSITION_3, [14, 191, 2812, 43238]),
+    (POSITION_6, [46, 2079, 89890]),
+]
+
+
+@pytest.mark.parametrize("fen,counts", PERFT)
+def test_perft_counts(eng, fen, counts):
+    import leafline_b200 as ll
+
+    w = ll.reconstruct(fen)
+    assert eng.perft(w, 0)[0] == 1
+    for depth, expected in enumerate(counts, start=1):
+        leaves, per_root = eng.perft(w, depth)
+        assert leaves == expected
+        assert len(per_root) == counts[0] and int(per_root.sum()) == expected
+
+
+@pytest.mark.parametrize("fen,depth", [(OPENING, 4), (KIWIPETE, 3), (POSITION_5, 3), (POSITION_4, 3)])
+def test_perft_divide_matches_oracle(eng, fen, depth):
+    import leafline_b200 as ll
+
+    _, per_root = eng.perft(ll.reconstruct(fen), depth)
+    assert list(per_root) == list(O.perft_divide(O.reconstruct(fen), depth, threads=8))
+
+
+def test_perft_depth_6_opening_bit_exact(eng):
+    import leafline_b200 as ll
+
+    leaves, per_root = eng.perft(ll.new_world(), 6)
+    assert leaves == 119060324  # BASELINE.json configs[1]
+    assert int(per_root.sum()) == 119060324
+
+
+def test_perft_deeper_trees_are_consistent_across_split_depths(eng):
+    # size-independent property: perft(d) == sum over children of perft(d-1), at sizes the oracle cannot reach
+    import leafline_b200 as ll
+
+    for fen, depth in ((KIWIPETE, 5), (POSITION_4, 5), (POSITION_5, 5)):
+        w = ll.reconstruct(fen)
+        leaves, per_root = eng.perft(w, depth)
+        _, commits = eng.lookahead(w)
+        again = [eng.perft(c["tree"], depth - 1)[0] for c in commits]
+        assert list(per_root) == again and leaves == sum(again)
+
+
+@pytest.mark.parametrize("world_size", [2, 3, 8])
+def test_perft_shards_sum_to_the_whole(eng, world_size):
+    import leafline_b200 as ll
+
+    for fen, depth in ((OPENING, 5), (KIWIPETE, 4), (OPENING, 1), (OPENING, 2)):
+        w = ll.reconstruct(fen)
+        whole, whole_roots = eng.perft(w, depth)
+        parts = [eng.perft(w, depth, shard=(r, world_size)) for r in range(world_size)]
+        assert sum(p[0] for p in parts) == whole
+        n = max(len(p[1]) for p in parts)
+        summed = np.zeros(n, dtype=np.uint64)
+        for p in parts:
+            summed[: len(p[1])] += p[1]
+        assert list(summed) == list(whole_roots)
+
+
+# ---------------------------------------------------------------- horizon / kickoff (mind.rs:279-287, 375-448)
+@pytest.mark.parametrize("plies", [0, 1, 2])
+def test_horizon_matches_exact_negamax(eng, playouts, reckless_worlds, plies):
+    n = {0: 200, 1: 100, 2: 24}[plies]
+    for worlds in (playouts[:n], reckless_worlds[:n], named_worlds()[:n]):
+        got = eng.horizon(worlds, plies)
+        want = np.array([O.negamax(w, plies) for w in worlds], dtype=np.float32)
+        assert np.array_equal(got, want), np.nonzero(got != want)
+
+
+def test_horizon_depth_3_on_a_few(eng, playouts):
+    worlds = playouts[:4]
+    got = eng.horizon(worlds, 3)
+    want = np.array([O.negamax(w, 3) for w in worlds], dtype=np.float32)
+    assert np.array_equal(got, want)
+
+
+def check_kickoff(eng, world, depth, nihilistically):
+    roots, scores, scored = eng.kickoff(world, depth, nihilistically=nihilistically)
+    want_roots, want_scores = O.kickoff(world, depth, nihilistically, threads=8)
+    assert roots.tobytes() == want_roots.tobytes()
+    assert np.array_equal(scores, want_scores)
+    assert scored > 0
+    return roots, scores
+
+
+def test_kickoff_known_answers_of_the_reference(eng):
+    import leafline_b200 as ll
+
+    # mind.rs:662-675: under-promotion to a pony
+    ws = ll.reconstruct("8/q1P1k/8/8/8/8/6PP/7K w - -")
+    roots, scores = check_kickoff(eng, ws, 3, True)
+    best = int(np.argmax(scores))
+    assert scores[best] > 0 and ll.preserve(roots[best]["tree"]) == "2N5/q3k3/8/8/8/8/6PP/7K b - -"
+    assert float(scores[best]) == 4.69921875
+    # mind.rs:677-734: take the pony, both colours
+    for fen in ("1p6/8/2N5/8/6p1/2B5/8/n7 w - -", "1P6/8/2n5/8/6P1/2b5/8/N7 b - -"):
+        roots, scores = check_kickoff(eng, ll.reconstruct(fen), 2, True)
+        assert roots[int(np.argmax(scores))]["whither"] == ll.locale(0, 0)
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3])
+def test_kickoff_opening_matches_oracle(eng, depth):
+    import leafline_b200 as ll
+
+    _, scores = check_kickoff(eng, ll.new_world(), depth, False)
+    top = {1: -0.4, 2: 0.5, 3: -0.4}[depth]
+    assert abs(float(scores.max()) - top) < 1e-6
+
+
+def test_kickoff_depth_4_kiwipete_matches_oracle(eng):
+    import leafline_b200 as ll
+
+    check_kickoff(eng, ll.reconstruct(KIWIPETE), 3, False)
+    check_kickoff(eng, ll.reconstruct(POSITION_5), 3, True)
+
+
+@pytest.mark.parametrize("world_size", [2, 4])
+def test_kickoff_shards_gather_to_the_whole(eng, world_size):
+    import leafline_b200 as ll
+
+    w = ll.reconstruct(KIWIPETE)
+    _, whole, _ = eng.kickoff(w, 3)
+    gathered = np.full(len(whole), -np.inf, dtype=np.float32)
+    for r in range(world_size):
+        _, part, _ = eng.kickoff(w, 3, shard=(r, world_size))
+        gathered = np.maximum(gathered, part)
+    assert np.array_equal(gathered, whole)
+
+
+# ---------------------------------------------------------------- seeded playout set (config 3)
+def test_device_playouts_match_oracle(eng, playouts):
+    soa = eng.playout_soa(1024)
+    eng.synchronize()
+    got = eng.soa_download(soa)
+    assert got.tobytes() == playouts.tobytes()
+    tail = eng.playout_soa(64, first_index=5000)
+    eng.synchronize()
+    assert eng.soa_download(tail).tobytes() == O.playout_batch(0x1EAF11E, 5000, 64).tobytes()
+    eng.soa_free(soa)
+    eng.soa_free(tail)
+
+
+def test_full_size_score_batch_properties(eng):
+    # BASELINE.json configs[2] at full size (2^24 positions): properties the oracle need not be run for
+    import torch
+
+    n = 1 << 24
+    soa = eng.playout_soa(n)
+    out = torch.empty(n, dtype=torch.float32, device="cuda")
+    eng.score_soa(soa, out.data_ptr())
+    eng.synchronize()
+    scores = out.cpu().numpy()
+    assert np.isfinite(scores).all()
+    # prefix against the oracle, bit-exact
+    k = 4096
+    worlds = eng.soa_download(soa, 0, k)
+    assert worlds.tobytes() == O.playout_batch(0x1EAF11E, 0, k).tobytes()
+    assert scores[:k].tobytes() == O.score_batch(worlds).tobytes()
+    # a strided sample across the whole set against the oracle
+    idx = np.arange(0, n, n // 512)
+    for i in idx[:64]:
+        w = eng.soa_download(soa, int(i), 1)
+        assert np.float32(scores[i]) == O.score(w[0])
+    # idempotence: scoring again gives identical bits
+    out2 = torch.empty_like(out)
+    eng.score_soa(soa, out2.data_ptr())
+    eng.synchronize()
+    assert torch.equal(out, out2)
+    eng.soa_free(soa)
