@@ -214,19 +214,22 @@ int emit_level(ll_ctx *ctx, size_t l, bool nihil, u64 total, bool with_cmeta, in
     Frontier &g = ctx->levels[l + 1];
     g.n = (size_t)total;
     if (!f.n || !total) return LL_OK;
-    u32 *cmeta = with_cmeta ? (u32 *)g.cmeta.ptr : nullptr;
-    const u32 *root_in = root_mode == 1 ? (const u32 *)f.root.ptr : nullptr;
-    u32 *root_out = root_mode ? (u32 *)g.root.ptr : nullptr;
+    ExpandArgs a{};
+    a.in = f.soa();
+    a.n = f.n;
+    a.counts = (const u32 *)f.counts.ptr;
+    a.block_base = (const u64 *)f.block_base.ptr;
+    a.root_in = root_mode == 1 ? (const u32 *)f.root.ptr : nullptr;
+    a.out = g.soa();
+    a.cmeta = with_cmeta ? (u32 *)g.cmeta.ptr : nullptr;
+    a.root_out = root_mode ? (u32 *)g.root.ptr : nullptr;
+    a.root_is_index = root_mode == 2;
     {
         Timed t(ctx, nihil ? "emit_reckless" : "emit_legal");
-        if (nihil)
-            k_emit<true><<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(f.soa(), f.n, (const u32 *)f.counts.ptr, (const u64 *)f.block_base.ptr,
-                                                                           g.soa(), cmeta, root_in, root_out, root_mode == 2);
-        else
-            k_emit<false><<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(f.soa(), f.n, (const u32 *)f.counts.ptr, (const u64 *)f.block_base.ptr,
-                                                                            g.soa(), cmeta, root_in, root_out, root_mode == 2);
+        if (nihil) k_expand<true, MODE_EMIT><<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(a);
+        else k_expand<false, MODE_EMIT><<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(a);
     }
-    return check_launch("k_emit");
+    return check_launch("k_expand<EMIT>");
 }
 
 int check_ctx(ll_ctx *ctx) {
@@ -259,10 +262,15 @@ int horizon_levels(ll_ctx *ctx, size_t l, int plies, uint64_t *scored_total) {
     LL_TRY(reserve_level(ctx, bottom, fb.n, false, true));
     CUDA_TRY(cudaMemsetAsync(sc + SC_SCORED, 0, sizeof(u64), ctx->stream));
     if (fb.n) {
+        ExpandArgs a{};
+        a.in = fb.soa();
+        a.n = fb.n;
+        a.values = (float *)fb.values.ptr;
+        a.scored = sc + SC_SCORED;
         Timed t(ctx, "horizon_last_ply");
-        k_horizon_last_ply<<<(unsigned)nblocks(fb.n), BLOCK, 0, ctx->stream>>>(fb.soa(), fb.n, (float *)fb.values.ptr, sc + SC_SCORED);
+        k_expand<true, MODE_HORIZON><<<(unsigned)nblocks(fb.n), BLOCK, 0, ctx->stream>>>(a);
     }
-    LL_TRY(check_launch("k_horizon_last_ply"));
+    LL_TRY(check_launch("k_expand<HORIZON>"));
     for (size_t lev = bottom; lev > l; lev--) {
         Frontier &par = ctx->levels[lev - 1];
         Frontier &chi = ctx->levels[lev];
@@ -522,7 +530,11 @@ extern "C" int ll_perft(ll_ctx *ctx, const ll_world_t *root, int depth, int shar
     u64 *sc = (u64 *)ctx->scalars.ptr;
     CUDA_TRY(cudaMemsetAsync(sc + SC_LEAVES, 0, sizeof(u64), ctx->stream));
     CUDA_TRY(cudaMemsetAsync(sc + SC_PER_ROOT, 0, 1024 * sizeof(u64), ctx->stream));
-    const int shard_ply = depth - 1 < 2 ? depth - 1 : 2; // units = frontier nodes at this ply
+    // The last two plies are fused: the nodes at ply depth-2 are expanded in registers and every child's
+    // legal moves are bulk-counted, so the widest materialised level is ply depth-2 (depth >= 3).
+    const bool fused = depth >= 3;
+    const int tail_ply = fused ? depth - 2 : depth - 1;
+    const int shard_ply = tail_ply < 2 ? tail_ply : 2; // units = frontier nodes at this ply
     u64 root_count = 0;
     size_t l = 0;
     bool sharded = shard_world == 1;
@@ -543,8 +555,18 @@ extern "C" int ll_perft(ll_ctx *ctx, const ll_world_t *root, int depth, int shar
             sharded = true;
         }
         Frontier &f = ctx->levels[l];
-        if (ply == depth - 1) { // frontier reached: bulk-count the leaves
-            if (f.n) {
+        if (ply == tail_ply) { // frontier reached: bulk-count the leaves
+            if (f.n && fused) {
+                ExpandArgs a{};
+                a.in = f.soa();
+                a.n = f.n;
+                a.root_in = (const u32 *)f.root.ptr;
+                a.per_root = sc + SC_PER_ROOT;
+                a.total = sc + SC_LEAVES;
+                Timed t(ctx, "perft_tail");
+                k_expand<false, MODE_PERFT><<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(a);
+                LL_TRY(check_launch("k_expand<PERFT>"));
+            } else if (f.n) {
                 Timed t(ctx, "count_leaves");
                 k_count_leaves<<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(f.soa(), f.n, ply == 0 ? nullptr : (const u32 *)f.root.ptr,
                                                                                  ply == 0 ? nullptr : sc + SC_PER_ROOT, sc + SC_LEAVES);

@@ -1,15 +1,34 @@
-// ll_device.cuh -- device-side position type, bitboard primitives and the canonical move generator.
+// ll_device.cuh -- device-side position type, bitboard primitives, the canonical move generator,
+// the set-wise legal-move counter and the static evaluator.
 //
 // Everything here is hand-written for sm_100a.  A position lives in registers as 12 u64 planes
 // (the reference's Pinfields, src/space.rs:127-200) plus a u32 of metadata; in HBM it is stored
-// structure-of-arrays (see Soa below).  The canonical generator emits commits in exactly the
-// reference's order (src/life.rs:1052-1084); legality is decided by building the
-// child and testing whether the mover's figurehead square is attacked, which on well-formed
-// positions equals the reference's "run the opponent's full reckless_lookahead and look for a
-// figurehead hospitalization" (src/life.rs:678-699).
+// structure-of-arrays (see Soa below).
+//
+// Legality.  The reference decides legality by making the move and running the opponent's full
+// reckless_lookahead, looking for a figurehead hospitalization (src/life.rs:678-699).  On
+// well-formed positions (include/leafline_b200.h, domain W: disjoint planes, at most one
+// figurehead per team) that is exactly "the mover's figurehead square is attacked afterwards", so
+// it is decided here once per position instead of once per move:
+//   check mask  -- squares a non-figurehead move must land on (capture the single checker or block it);
+//   pinned set  -- own pieces that may only move along the line they share with their figurehead;
+//   danger map  -- squares the opposition attacks once the figurehead is lifted off the board.
+// Passing-by captures and secret service keep the make-the-move-and-test path (two pieces leave a
+// rank at once; phantom cops / figureheads).
+//
+// The header also compiles as plain C++ (LL_HOST_CHECK) so that tests/hostcheck can run the very
+// same generator logic against the oracle on the CPU box.  That build is test infrastructure: the
+// shipped library contains device code only and has no CPU path.
 #pragma once
 #include <cstdint>
+#ifdef __CUDACC__
 #include <cuda_runtime.h>
+#define LL_HD __device__ __forceinline__
+#define LL_HDM __device__ __forceinline__ // member functions
+#else
+#define LL_HD static inline
+#define LL_HDM inline
+#endif
 
 typedef unsigned long long u64;
 typedef unsigned int u32;
@@ -25,6 +44,32 @@ constexpr u64 RANK_1 = 0xFFull;
 constexpr u64 MAIN_DIAG = 0x8040201008040201ull;
 constexpr u64 MAIN_ANTI = 0x0102040810204080ull;
 
+// ---- intrinsics (device) / builtins (host check) ---------------------------------------------------
+#ifdef __CUDACC__
+LL_HD int popc64(u64 x) { return __popcll(x); }
+LL_HD int lsb64(u64 x) { return __ffsll((long long)x) - 1; } // x != 0
+LL_HD int msb64(u64 x) { return 63 - __clzll((long long)x); } // x != 0
+LL_HD u64 brev64(u64 x) { return __brevll(x); }
+LL_HD int lsb32(u32 x) { return __ffs((int)x) - 1; }
+template <class V> LL_HD V ldg(const V *p) { return __ldg(p); }
+LL_HD float fmul(float a, float b) { return __fmul_rn(a, b); } // never contracted into an FMA
+LL_HD float fadd(float a, float b) { return __fadd_rn(a, b); }
+#else
+LL_HD int popc64(u64 x) { return __builtin_popcountll(x); }
+LL_HD int lsb64(u64 x) { return __builtin_ctzll(x); }
+LL_HD int msb64(u64 x) { return 63 - __builtin_clzll(x); }
+LL_HD u64 brev64(u64 x) {
+    x = ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+    x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+    return __builtin_bswap64(x);
+}
+LL_HD int lsb32(u32 x) { return __builtin_ctz(x); }
+template <class V> LL_HD V ldg(const V *p) { return *p; }
+LL_HD float fmul(float a, float b) { return a * b; } // built with -ffp-contract=off
+LL_HD float fadd(float a, float b) { return a + b; }
+#endif
+
 // meta: bit0 initiative (0 Orange, 1 Blue); bits 1-4 service_eligibility (life.rs:178-181);
 // bits 8-15 passing_by Locale byte (rank<<4|file, 0xFF = None) -- same byte as ll_world_t.
 struct Pos {
@@ -32,12 +77,16 @@ struct Pos {
     u32 meta;
 };
 
-__device__ __forceinline__ u32 meta_stm(u32 m) { return m & 1u; }
-__device__ __forceinline__ u32 meta_elig(u32 m) { return (m >> 1) & 0xFu; }
-__device__ __forceinline__ u32 meta_pb(u32 m) { return (m >> 8) & 0xFFu; }
-__device__ __forceinline__ u32 make_meta(u32 stm, u32 elig, u32 pb) { return stm | (elig << 1) | (pb << 8); }
-__device__ __forceinline__ int loc_to_sq(u32 loc) { return (int)(((loc >> 4) << 3) | (loc & 7u)); }
-__device__ __forceinline__ u32 sq_to_loc(int sq) { return (u32)(((sq >> 3) << 4) | (sq & 7)); }
+LL_HD u32 meta_stm(u32 m) { return m & 1u; }
+LL_HD u32 meta_elig(u32 m) { return (m >> 1) & 0xFu; }
+LL_HD u32 meta_pb(u32 m) { return (m >> 8) & 0xFFu; }
+LL_HD u32 make_meta(u32 stm, u32 elig, u32 pb) { return stm | (elig << 1) | (pb << 8); }
+LL_HD int loc_to_sq(u32 loc) { return (int)(((loc >> 4) << 3) | (loc & 7u)); }
+LL_HD u32 sq_to_loc(int sq) { return (u32)(((sq >> 3) << 4) | (sq & 7)); }
+LL_HD u64 passing_by_bit(u32 meta) { // the square a servant may stun "in passing", 0 if none
+    const u32 pb = meta_pb(meta);
+    return pb != 0xFFu ? 1ull << loc_to_sq(pb) : 0ull;
+}
 
 // ---- structure-of-arrays storage in HBM -------------------------------------------------------
 // plane j of position i at pl[j*stride + i]; stride % 2 == 0 keeps every plane 16-byte aligned so a
@@ -48,62 +97,84 @@ struct Soa {
     size_t stride;
 };
 
-__device__ __forceinline__ Pos soa_load(const Soa &s, size_t i) {
+LL_HD Pos soa_load(const Soa &s, size_t i) {
     Pos p;
 #pragma unroll
-    for (int j = 0; j < 12; j++) p.pl[j] = __ldg(s.pl + (size_t)j * s.stride + i);
-    p.meta = __ldg(s.meta + i);
+    for (int j = 0; j < 12; j++) p.pl[j] = ldg(s.pl + (size_t)j * s.stride + i);
+    p.meta = ldg(s.meta + i);
     return p;
 }
-__device__ __forceinline__ void soa_store(const Soa &s, size_t i, const Pos &p) {
+LL_HD void soa_store(const Soa &s, size_t i, const Pos &p) {
 #pragma unroll
     for (int j = 0; j < 12; j++) s.pl[(size_t)j * s.stride + i] = p.pl[j];
     s.meta[i] = p.meta;
 }
 
 // ---- generated tables (furniture/tablemaker.py:41-62), filled by the host at ll_init ----------
+#ifdef __CUDACC__
 __device__ u64 d_pony_table[64];
 __device__ u64 d_figurehead_table[64];
+#else
+static u64 d_pony_table[64];
+static u64 d_figurehead_table[64];
+#endif
+LL_HD u64 pony_moves(int sq) { return ldg(&d_pony_table[sq]); }
+LL_HD u64 figurehead_moves(int sq) { return ldg(&d_figurehead_table[sq]); }
 
-__device__ __forceinline__ u64 pony_moves(int sq) { return __ldg(&d_pony_table[sq]); }
-__device__ __forceinline__ u64 figurehead_moves(int sq) { return __ldg(&d_figurehead_table[sq]); }
-
-// ---- sliding attacks: hyperbola quintessence with a full 64-bit bit reversal (works for ranks,
-// files and both diagonals; no tables, no memory traffic) ---------------------------------------
-__device__ __forceinline__ u64 line_attacks(u64 occ, u64 bit, u64 mask_ex) {
+// ---- one piece's sliding attacks: hyperbola quintessence with a full 64-bit bit reversal (works
+// for ranks, files and both diagonals; no tables, no memory traffic) -----------------------------
+LL_HD u64 line_attacks(u64 occ, u64 bit, u64 mask_ex) {
     u64 f = occ & mask_ex;
-    u64 r = __brevll(f);
+    u64 r = brev64(f);
     f -= bit;
-    r -= __brevll(bit);
-    f ^= __brevll(r);
+    r -= brev64(bit);
+    f ^= brev64(r);
     return f & mask_ex;
 }
-__device__ __forceinline__ u64 rank_mask(int sq) { return RANK_1 << (sq & 56); }
-__device__ __forceinline__ u64 file_mask(int sq) { return FILE_A << (sq & 7); }
-__device__ __forceinline__ u64 diag_mask(int sq) { // squares with file - rank constant (step 9)
+LL_HD u64 rank_mask(int sq) { return RANK_1 << (sq & 56); }
+LL_HD u64 file_mask(int sq) { return FILE_A << (sq & 7); }
+LL_HD u64 diag_mask(int sq) { // squares with file - rank constant (step 9)
     int d = (sq & 7) - (sq >> 3);
     return d >= 0 ? MAIN_DIAG >> (8 * d) : MAIN_DIAG << (-8 * d);
 }
-__device__ __forceinline__ u64 anti_mask(int sq) { // squares with file + rank constant (step 7)
+LL_HD u64 anti_mask(int sq) { // squares with file + rank constant (step 7)
     int s = (sq & 7) + (sq >> 3) - 7;
     return s >= 0 ? MAIN_ANTI << (8 * s) : MAIN_ANTI >> (-8 * s);
 }
-__device__ __forceinline__ u64 diag_attacks(int sq, u64 occ) {
+LL_HD u64 diag_attacks(int sq, u64 occ) {
     u64 bit = 1ull << sq;
     return line_attacks(occ, bit, diag_mask(sq) & ~bit) | line_attacks(occ, bit, anti_mask(sq) & ~bit);
 }
-__device__ __forceinline__ u64 orth_attacks(int sq, u64 occ) {
+LL_HD u64 orth_attacks(int sq, u64 occ) {
     u64 bit = 1ull << sq;
     return line_attacks(occ, bit, rank_mask(sq) & ~bit) | line_attacks(occ, bit, file_mask(sq) & ~bit);
 }
 
+// ---- all sliders of a kind at once: Kogge-Stone occluded fills (branch-free, no divergence).
+// Each returns the squares attacked in that direction, first blocker included. --------------------
+LL_HD u64 ks_north(u64 g, u64 e) { g |= e & (g << 8); e &= e << 8; g |= e & (g << 16); e &= e << 16; g |= e & (g << 32); return g << 8; }
+LL_HD u64 ks_south(u64 g, u64 e) { g |= e & (g >> 8); e &= e >> 8; g |= e & (g >> 16); e &= e >> 16; g |= e & (g >> 32); return g >> 8; }
+LL_HD u64 ks_east(u64 g, u64 e) { e &= ~FILE_A; g |= e & (g << 1); e &= e << 1; g |= e & (g << 2); e &= e << 2; g |= e & (g << 4); return (g << 1) & ~FILE_A; }
+LL_HD u64 ks_west(u64 g, u64 e) { e &= ~FILE_H; g |= e & (g >> 1); e &= e >> 1; g |= e & (g >> 2); e &= e >> 2; g |= e & (g >> 4); return (g >> 1) & ~FILE_H; }
+LL_HD u64 ks_ne(u64 g, u64 e) { e &= ~FILE_A; g |= e & (g << 9); e &= e << 9; g |= e & (g << 18); e &= e << 18; g |= e & (g << 36); return (g << 9) & ~FILE_A; }
+LL_HD u64 ks_nw(u64 g, u64 e) { e &= ~FILE_H; g |= e & (g << 7); e &= e << 7; g |= e & (g << 14); e &= e << 14; g |= e & (g << 28); return (g << 7) & ~FILE_H; }
+LL_HD u64 ks_se(u64 g, u64 e) { e &= ~FILE_A; g |= e & (g >> 7); e &= e >> 7; g |= e & (g >> 14); e &= e >> 14; g |= e & (g >> 28); return (g >> 7) & ~FILE_A; }
+LL_HD u64 ks_sw(u64 g, u64 e) { e &= ~FILE_H; g |= e & (g >> 9); e &= e >> 9; g |= e & (g >> 18); e &= e >> 18; g |= e & (g >> 36); return (g >> 9) & ~FILE_H; }
+LL_HD u64 ks_diag_attacks(u64 sliders, u64 empty) { return ks_ne(sliders, empty) | ks_nw(sliders, empty) | ks_se(sliders, empty) | ks_sw(sliders, empty); }
+LL_HD u64 ks_orth_attacks(u64 sliders, u64 empty) { return ks_north(sliders, empty) | ks_south(sliders, empty) | ks_east(sliders, empty) | ks_west(sliders, empty); }
+
 // squares from which a servant of team A attacks `bit` (life.rs:759, 765: stun offsets (+-1 rank, +-1 file))
-template <int A> __device__ __forceinline__ u64 servant_attackers_of(u64 bit) {
+template <int A> LL_HD u64 servant_attackers_of(u64 bit) {
     if (A == 0) return ((bit >> 7) & ~FILE_A) | ((bit >> 9) & ~FILE_H); // Orange servants stun upwards
     return ((bit << 7) & ~FILE_H) | ((bit << 9) & ~FILE_A);             // Blue servants stun downwards
 }
+// squares the servants `s` of team A stun towards
+template <int A> LL_HD u64 servant_attacks(u64 s) {
+    if (A == 0) return ((s << 7) & ~FILE_H) | ((s << 9) & ~FILE_A);
+    return ((s >> 9) & ~FILE_H) | ((s >> 7) & ~FILE_A);
+}
 
-template <int T> __device__ __forceinline__ u64 occupied_by(const Pos &p) { // life.rs:521-540
+template <int T> LL_HD u64 occupied_by(const Pos &p) { // life.rs:521-540
     return p.pl[6 * T] | p.pl[6 * T + 1] | p.pl[6 * T + 2] | p.pl[6 * T + 3] | p.pl[6 * T + 4] | p.pl[6 * T + 5];
 }
 
@@ -112,7 +183,7 @@ template <int T> __device__ __forceinline__ u64 occupied_by(const Pos &p) { // l
 // (life.rs:284-291) ask once their full movegen is boiled down, given that `sq` is occupied by the
 // defender: servant stuns need only the defender on sq (life.rs:808); every other piece must not
 // find one of its own team on sq (life.rs:840-844, 890-893).
-template <int A> __device__ __forceinline__ bool attacked_by(const Pos &p, int sq, u64 occ, u64 attacker_occ) {
+template <int A> LL_HD bool attacked_by(const Pos &p, int sq, u64 occ, u64 attacker_occ) {
     u64 bit = 1ull << sq;
     if (servant_attackers_of<A>(bit) & p.pl[6 * A + SERVANT]) return true;
     if (bit & attacker_occ) return false;
@@ -124,191 +195,359 @@ template <int A> __device__ __forceinline__ bool attacked_by(const Pos &p, int s
 }
 
 // life.rs:678-690 on a well-formed position: is any figurehead of team T attacked by team 1-T?
-template <int T> __device__ __forceinline__ bool in_critical_endangerment(const Pos &p) {
+template <int T> LL_HD bool in_critical_endangerment(const Pos &p) {
     u64 k = p.pl[6 * T + FIGUREHEAD];
     if (!k) return false;
     u64 own = occupied_by<T>(p), opp = occupied_by<1 - T>(p);
     u64 occ = own | opp;
     while (k) {
-        int sq = __ffsll((long long)k) - 1;
+        int sq = lsb64(k);
         k &= k - 1;
         if (attacked_by<1 - T>(p, sq, occ, opp)) return true;
     }
     return false;
 }
 
-// ---- make-move (life.rs:569-676) ----------------------------------------------------------------
-// T = mover (== initiative), JOB compile-time so that every plane index is static (no local memory).
-// Returns the hospitalized job (JOB_NONE if nobody was stunned).
-template <int T, int JOB> __device__ __forceinline__ u32 apply_move(const Pos &p, int from, int to, Pos &c) {
+// ---- move descriptors -------------------------------------------------------------------------------
+// One generated move, 32 bits: whence sq | whither sq<<6 | job<<12 | ascension job<<15 (7 = none) |
+// passing-by flag<<18 | secret-service flag<<19 | parent slot<<20 (filled by the expansion kernels).
+constexpr u32 ASC_NONE = 7;
+constexpr u32 MV_PASSING_BY = 1u << 18, MV_SERVICE = 1u << 19;
+LL_HD u32 mv_pack(u32 job, int from, int to, u32 asc, u32 flags) { return (u32)from | ((u32)to << 6) | (job << 12) | (asc << 15) | flags; }
+LL_HD int mv_from(u32 m) { return (int)(m & 63u); }
+LL_HD int mv_to(u32 m) { return (int)((m >> 6) & 63u); }
+LL_HD u32 mv_job(u32 m) { return (m >> 12) & 7u; }
+LL_HD u32 mv_asc(u32 m) { return (m >> 15) & 7u; }
+LL_HD u32 mv_slot(u32 m) { return m >> 20; }
+
+// ---- make-move (life.rs:569-676 + ascension life.rs:701-726) ----------------------------------------
+// T = mover (== initiative).  Returns the hospitalized job (JOB_NONE if nobody was stunned).
+template <int T> LL_HD u32 make_child_as(const Pos &p, u32 m, Pos &c) {
+    constexpr int E = 1 - T;
+    const int from = mv_from(m), to = mv_to(m);
+    const u32 job = mv_job(m), asc = mv_asc(m);
     const u64 fb = 1ull << from, tb = 1ull << to;
-    c = p;
-    c.pl[6 * T + JOB] = (p.pl[6 * T + JOB] & ~fb) | tb; // transit: quench then alight (space.rs:169-173)
-    u32 elig = meta_elig(p.meta);
-    if (JOB == FIGUREHEAD) { // life.rs:577-588
-        elig &= T == 0 ? ~0x3u : ~0xCu;
-        int df = (to & 7) - (from & 7);
-        if (df == 2 || df == -2) { // secret service, life.rs:610-629: hop the cop plane whether or not a cop is there
-            int rank8 = to & 56;
-            u64 start = 1ull << (rank8 + (df == 2 ? 7 : 0)), end = 1ull << (rank8 + (df == 2 ? 5 : 3));
-            c.pl[6 * T + COP] = (c.pl[6 * T + COP] & ~start) | end;
-        }
+    const u32 landing = asc != ASC_NONE ? asc : job; // the plane the star ends up on
+    // transit: quench whence, alight whither (space.rs:169-173); an ascending servant alights as its new job
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        u64 v = p.pl[6 * T + j];
+        if ((u32)j == job) v &= ~fb;
+        if ((u32)j == landing) v |= tb;
+        c.pl[6 * T + j] = v;
     }
-    if (JOB == COP) { // life.rs:589-605: file of whence only
-        int f = from & 7;
+    u32 elig = meta_elig(p.meta);
+    if (job == FIGUREHEAD) elig &= T == 0 ? ~0x3u : ~0xCu; // life.rs:577-588
+    if (m & MV_SERVICE) { // secret service, life.rs:610-629: hop the cop plane whether or not a cop is there
+        const int rank8 = to & 56;
+        const bool east = (to & 7) == 6;
+        const u64 start = 1ull << (rank8 + (east ? 7 : 0)), end = 1ull << (rank8 + (east ? 5 : 3));
+        c.pl[6 * T + COP] = (c.pl[6 * T + COP] & ~start) | end;
+    }
+    if (job == COP) { // life.rs:589-605: file of whence only, any rank
+        const int f = from & 7;
         if (f == 0) elig &= T == 0 ? ~0x1u : ~0x4u;
         if (f == 7) elig &= T == 0 ? ~0x2u : ~0x8u;
     }
-    // life.rs:631-657: victim looked up on the pre-move board
-    constexpr int E = 1 - T;
-    u64 victim = tb;
-    u32 pb = meta_pb(p.meta);
-    if (JOB == SERVANT && !(tb & occupied_by<E>(p)) && pb != 0xFFu && loc_to_sq(pb) == to)
-        victim = T == 0 ? tb >> 8 : tb << 8; // passing by: the servant one rank "behind" the passed square
+    // life.rs:631-657: victim looked up on the pre-move board; passing by removes the servant one
+    // rank "behind" the passed square
+    const u64 victim = (m & MV_PASSING_BY) ? (T == 0 ? tb >> 8 : tb << 8) : tb;
     u32 hosp = JOB_NONE;
 #pragma unroll
     for (int j = 5; j >= 0; j--)
-        if (p.pl[6 * E + j] & victim) hosp = j; // first in dramatis_personae order wins (life.rs:550-557)
+        if (p.pl[6 * E + j] & victim) hosp = (u32)j; // first in dramatis_personae order wins (life.rs:550-557)
 #pragma unroll
     for (int j = 0; j < 6; j++) c.pl[6 * E + j] = p.pl[6 * E + j] & ~victim; // W: planes are disjoint
     u32 new_pb = 0xFFu; // life.rs:660-669
-    if (JOB == SERVANT) {
-        int dr = (to >> 3) - (from >> 3);
+    if (job == SERVANT) {
+        const int dr = (to >> 3) - (from >> 3);
         if (dr == 2 || dr == -2) new_pb = sq_to_loc(T == 0 ? from + 8 : from - 8);
     }
     c.meta = make_meta(E, elig, new_pb);
     return hosp;
 }
-
-// life.rs:701-726: replace the servant on `to` by `job`
-template <int T> __device__ __forceinline__ void ascend(Pos &c, int to, int job) {
-    const u64 tb = 1ull << to;
-    c.pl[6 * T + SERVANT] &= ~tb;
-    if (job == PONY) c.pl[6 * T + PONY] |= tb;
-    if (job == SCHOLAR) c.pl[6 * T + SCHOLAR] |= tb;
-    if (job == COP) c.pl[6 * T + COP] |= tb;
-    if (job == PRINCESS) c.pl[6 * T + PRINCESS] |= tb;
+LL_HD u32 make_child(const Pos &p, u32 m, Pos &c) {
+    return meta_stm(p.meta) == 0 ? make_child_as<0>(p, m, c) : make_child_as<1>(p, m, c);
 }
 
-// packed commit metadata: bit0 team | job<<1 | whence sq<<4 | whither sq<<10 | hosp job<<16 | ascension job<<20
-__device__ __forceinline__ u32 pack_commit(int team, int job, int from, int to, u32 hosp, u32 asc) {
-    return (u32)team | ((u32)job << 1) | ((u32)from << 4) | ((u32)to << 10) | (hosp << 16) | (asc << 20);
+// packed commit metadata handed to k_commits_to_aos: bit0 team | job<<1 | whence sq<<4 | whither sq<<10 |
+// hosp job<<16 | ascension job<<20 (0xF = none)
+LL_HD u32 pack_commit(u32 team, u32 m, u32 hosp) {
+    const u32 asc = mv_asc(m) == ASC_NONE ? JOB_NONE : mv_asc(m);
+    return team | (mv_job(m) << 1) | ((u32)mv_from(m) << 4) | ((u32)mv_to(m) << 10) | (hosp << 16) | (asc << 20);
 }
 
-// ---- the canonical generator ---------------------------------------------------------------------
-// Sink: void operator()(const Pos& child, u32 packed_commit).  NIHIL = reckless (pseudo-legal).
-template <int T, int JOB, bool NIHIL, class Sink>
-__device__ __forceinline__ void predict(const Pos &p, int from, int to, Sink &sink) { // life.rs:728-739
-    Pos c;
-    u32 hosp = apply_move<T, JOB>(p, from, to, c);
-    if (!NIHIL && in_critical_endangerment<T>(c)) return; // careful_apply, life.rs:692-699
-    if (JOB == SERVANT && (to >> 3) == (T == 0 ? 7 : 0)) { // subpredict, life.rs:701-726
-#pragma unroll 1
-        for (int job = PONY; job <= PRINCESS; job++) {
-            Pos a = c;
-            ascend<T>(a, to, job);
-            sink(a, pack_commit(T, JOB, from, to, hosp, (u32)job));
+// ---- legality context of one position (see the header comment) ---------------------------------------
+struct Legal {
+    u64 check;      // ~0: not in check; one checker: its square + the squares between; two: 0
+    u64 pinned;     // own pieces pinned against the figurehead
+    u64 danger;     // squares the figurehead may not step onto
+    u64 kd, ka, kf, kr; // the four lines through the figurehead's square
+};
+LL_HD u64 pin_line(const Legal &L, u64 bit) { return (L.kd & bit) ? L.kd : (L.ka & bit) ? L.ka : (L.kf & bit) ? L.kf : L.kr; }
+// may the piece on `fb` land on `tb`?  (not for the figurehead itself)
+LL_HD bool lands_legally(const Legal &L, u64 fb, u64 tb) {
+    if (!(tb & L.check)) return false;
+    return !(fb & L.pinned) || (tb & pin_line(L, fb));
+}
+LL_HD u64 between_on(u64 line, u64 a, u64 b) { return ((a - 1) ^ (b - 1)) & line & ~(a | b); } // a, b on `line`
+
+template <int T> LL_HD Legal legal_context(const Pos &p, u64 own, u64 opp) {
+    constexpr int E = 1 - T;
+    Legal L;
+    L.check = ~0ull;
+    L.pinned = 0;
+    L.danger = 0;
+    L.kd = L.ka = L.kf = L.kr = 0;
+    const u64 k = p.pl[6 * T + FIGUREHEAD];
+    if (!k) return L; // nothing to endanger: every pseudo-legal move is legal (life.rs:678-690)
+    const int ksq = lsb64(k);
+    const u64 occ = own | opp;
+    const u64 e_diag = p.pl[6 * E + SCHOLAR] | p.pl[6 * E + PRINCESS], e_orth = p.pl[6 * E + COP] | p.pl[6 * E + PRINCESS];
+    // danger map: the opposition's attacks with our figurehead lifted (it cannot hide behind itself)
+    const u64 empty_wo_k = ~(occ ^ k);
+    u64 danger = servant_attacks<E>(p.pl[6 * E + SERVANT]);
+    for (u64 s = p.pl[6 * E + PONY]; s; s &= s - 1) danger |= pony_moves(lsb64(s));
+    if (p.pl[6 * E + FIGUREHEAD]) danger |= figurehead_moves(lsb64(p.pl[6 * E + FIGUREHEAD]));
+    danger |= ks_diag_attacks(e_diag, empty_wo_k) | ks_orth_attacks(e_orth, empty_wo_k);
+    L.danger = danger;
+    // checkers and pins along the four lines through the figurehead
+    L.kd = diag_mask(ksq) & ~k;
+    L.ka = anti_mask(ksq) & ~k;
+    L.kf = file_mask(ksq) & ~k;
+    L.kr = rank_mask(ksq) & ~k;
+    u64 checkers = (servant_attackers_of<E>(k) & p.pl[6 * E + SERVANT]) | (pony_moves(ksq) & p.pl[6 * E + PONY]) |
+                   (figurehead_moves(ksq) & p.pl[6 * E + FIGUREHEAD]);
+    u64 pinned = 0;
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+        const u64 line = l == 0 ? L.kd : l == 1 ? L.ka : l == 2 ? L.kf : L.kr;
+        const u64 snipers = (l < 2 ? e_diag : e_orth) & line;
+        if (!snipers) continue;
+        const u64 seen = line_attacks(occ, k, line);
+        checkers |= seen & snipers;
+        const u64 blockers = seen & own;
+        if (blockers) {
+            u64 pinners = line_attacks(occ ^ blockers, k, line) & ~seen & snipers;
+            for (; pinners; pinners &= pinners - 1) pinned |= between_on(line, k, pinners & (0 - pinners)) & blockers;
         }
-    } else {
-        sink(c, pack_commit(T, JOB, from, to, hosp, JOB_NONE));
     }
+    L.pinned = pinned;
+    if (checkers) {
+        if (checkers & (checkers - 1)) {
+            L.check = 0; // two checkers: only the figurehead can move
+        } else {
+            L.check = checkers | between_on(pin_line(L, checkers), k, checkers); // ponies / servants: nothing between
+            if (!((L.kd | L.ka | L.kf | L.kr) & checkers)) L.check = checkers;   // a pony is on none of the lines
+        }
+    }
+    return L;
 }
 
-template <int T, int JOB, bool NIHIL, bool DESC, class Sink>
-__device__ __forceinline__ void predict_each(const Pos &p, int from, u64 targets, Sink &sink) {
-    while (targets) {
-        int to = DESC ? 63 - __clzll((long long)targets) : __ffsll((long long)targets) - 1;
-        targets ^= 1ull << to;
-        predict<T, JOB, NIHIL>(p, from, to, sink);
-    }
-}
-
-// one slider's rays in the reference's direction order, nearest square first (life.rs:857-914)
-template <int T, int JOB, bool NIHIL, bool DIAGONAL, class Sink>
-__device__ __forceinline__ void slider_rays(const Pos &p, int from, u64 occ, u64 own, Sink &sink) {
-    const u64 bit = 1ull << from;
-    const u64 below = bit - 1, above = ~(bit | below);
-    if (DIAGONAL) { // SCHOLAR_OFFSETS (-1,-1), (-1,1), (1,-1), (1,1)  (life.rs:10)
-        u64 d = line_attacks(occ, bit, diag_mask(from) & ~bit) & ~own;
-        u64 a = line_attacks(occ, bit, anti_mask(from) & ~bit) & ~own;
-        predict_each<T, JOB, NIHIL, true>(p, from, d & below, sink);
-        predict_each<T, JOB, NIHIL, true>(p, from, a & below, sink);
-        predict_each<T, JOB, NIHIL, false>(p, from, a & above, sink);
-        predict_each<T, JOB, NIHIL, false>(p, from, d & above, sink);
-    } else { // COP_OFFSETS (-1,0), (1,0), (0,-1), (0,1)  (life.rs:11)
-        u64 f = line_attacks(occ, bit, file_mask(from) & ~bit) & ~own;
-        u64 r = line_attacks(occ, bit, rank_mask(from) & ~bit) & ~own;
-        predict_each<T, JOB, NIHIL, true>(p, from, f & below, sink);
-        predict_each<T, JOB, NIHIL, false>(p, from, f & above, sink);
-        predict_each<T, JOB, NIHIL, true>(p, from, r & below, sink);
-        predict_each<T, JOB, NIHIL, false>(p, from, r & above, sink);
-    }
-}
-
-// life.rs:980-1050.  `leered` is is_being_leered_at_by boiled down (see attacked_by).
-template <int T, bool NIHIL, class Sink> __device__ __forceinline__ void service_lookahead(const Pos &p, Sink &sink) {
+// ---- secret service (life.rs:980-1050) --------------------------------------------------------------
+// `leered` is is_being_leered_at_by boiled down (see attacked_by).  Sink: move(job, from, to, asc, flags).
+template <int T, bool NIHIL, class Sink> LL_HD void service_lookahead(const Pos &p, u64 own, u64 opp, Sink &sink) {
     const u32 elig = meta_elig(p.meta);
     const bool west = elig & (T == 0 ? 0x1u : 0x4u), east = elig & (T == 0 ? 0x2u : 0x8u);
     if (!(west || east)) return;
     const int home = T == 0 ? 0 : 56;
-    const u64 own = occupied_by<T>(p), opp = occupied_by<1 - T>(p), occ = own | opp;
+    const u64 occ = own | opp;
     const bool west_clear = west && !(occ & (0x0Eull << home)), east_clear = east && !(occ & (0x60ull << home));
     if (!(west_clear || east_clear)) return;
     if (attacked_by<1 - T>(p, home + 4, occ, opp)) return; // life.rs:1034-1043
-    if (west_clear && !attacked_by<1 - T>(p, home + 1, occ, opp) && !attacked_by<1 - T>(p, home + 2, occ, opp) &&
-        !attacked_by<1 - T>(p, home + 3, occ, opp))
-        predict<T, FIGUREHEAD, NIHIL>(p, home + 4, home + 2, sink);
-    if (east_clear && !attacked_by<1 - T>(p, home + 5, occ, opp) && !attacked_by<1 - T>(p, home + 6, occ, opp))
-        predict<T, FIGUREHEAD, NIHIL>(p, home + 4, home + 6, sink);
-}
-
-// life.rs:1052-1084: servants, ponies, scholars, cops, princesses, figurehead, then secret service
-template <int T, bool NIHIL, class Sink> __device__ void lookahead_as(const Pos &p, Sink &sink) {
-    const u64 own = occupied_by<T>(p), opp = occupied_by<1 - T>(p), occ = own | opp, empty = ~occ;
-    { // life.rs:749-830
-        const u32 pb = meta_pb(p.meta);
-        const u64 pb_bit = pb != 0xFFu ? 1ull << loc_to_sq(pb) : 0ull;
-        for (u64 s = p.pl[6 * T + SERVANT]; s; s &= s - 1) {
-            const int from = __ffsll((long long)s) - 1;
-            const u64 fb = 1ull << from;
-            const u64 one = T == 0 ? fb << 8 : fb >> 8;
-            if (one & empty) predict<T, SERVANT, NIHIL>(p, from, T == 0 ? from + 8 : from - 8, sink);
-            if ((from >> 3) == (T == 0 ? 1 : 6)) {
-                const u64 two = T == 0 ? fb << 16 : fb >> 16;
-                if ((two & empty) && (one & empty)) predict<T, SERVANT, NIHIL>(p, from, T == 0 ? from + 16 : from - 16, sink);
-            }
-            const u64 west = T == 0 ? (fb << 7) & ~FILE_H : (fb >> 9) & ~FILE_H;
-            const u64 east = T == 0 ? (fb << 9) & ~FILE_A : (fb >> 7) & ~FILE_A;
-            if (west && ((west & opp) || west == pb_bit)) predict<T, SERVANT, NIHIL>(p, from, T == 0 ? from + 7 : from - 9, sink);
-            if (east && ((east & opp) || east == pb_bit)) predict<T, SERVANT, NIHIL>(p, from, T == 0 ? from + 9 : from - 7, sink);
+#pragma unroll 1
+    for (int side = 0; side < 2; side++) { // West is asked first (life.rs:1009-1033)
+        if (side == 0 ? !west_clear : !east_clear) continue;
+        bool leered;
+        if (side == 0)
+            leered = attacked_by<1 - T>(p, home + 1, occ, opp) || attacked_by<1 - T>(p, home + 2, occ, opp) ||
+                     attacked_by<1 - T>(p, home + 3, occ, opp); // the b-file square too: SURVEY.md 8(a) quirk 1
+        else
+            leered = attacked_by<1 - T>(p, home + 5, occ, opp) || attacked_by<1 - T>(p, home + 6, occ, opp);
+        if (leered) continue;
+        const int to = home + (side == 0 ? 2 : 6);
+        if (!NIHIL) { // careful_apply, life.rs:692-699
+            Pos c;
+            make_child_as<T>(p, mv_pack(FIGUREHEAD, home + 4, to, ASC_NONE, MV_SERVICE), c);
+            if (in_critical_endangerment<T>(c)) continue;
         }
+        sink.move(FIGUREHEAD, home + 4, to, ASC_NONE, MV_SERVICE);
     }
-    for (u64 s = p.pl[6 * T + PONY]; s; s &= s - 1) { // life.rs:832-855
-        const int from = __ffsll((long long)s) - 1;
-        predict_each<T, PONY, NIHIL, false>(p, from, pony_moves(from) & ~own, sink);
-    }
-    for (u64 s = p.pl[6 * T + SCHOLAR]; s; s &= s - 1)
-        slider_rays<T, SCHOLAR, NIHIL, true>(p, __ffsll((long long)s) - 1, occ, own, sink);
-    for (u64 s = p.pl[6 * T + COP]; s; s &= s - 1)
-        slider_rays<T, COP, NIHIL, false>(p, __ffsll((long long)s) - 1, occ, own, sink);
-    for (u64 s = p.pl[6 * T + PRINCESS]; s; s &= s - 1) // life.rs:955-969: all diagonals first ...
-        slider_rays<T, PRINCESS, NIHIL, true>(p, __ffsll((long long)s) - 1, occ, own, sink);
-    for (u64 s = p.pl[6 * T + PRINCESS]; s; s &= s - 1) // ... then all orthogonals
-        slider_rays<T, PRINCESS, NIHIL, false>(p, __ffsll((long long)s) - 1, occ, own, sink);
-    for (u64 s = p.pl[6 * T + FIGUREHEAD]; s; s &= s - 1) { // life.rs:973-978
-        const int from = __ffsll((long long)s) - 1;
-        predict_each<T, FIGUREHEAD, NIHIL, false>(p, from, figurehead_moves(from) & ~own, sink);
-    }
-    service_lookahead<T, NIHIL>(p, sink);
 }
 
-template <bool NIHIL, class Sink> __device__ __forceinline__ void lookahead(const Pos &p, Sink &sink) {
+// passing by (life.rs:800-822): the make-the-move-and-test path
+template <int T> LL_HD bool passing_by_is_legal(const Pos &p, int from, int to) {
+    Pos c;
+    make_child_as<T>(p, mv_pack(SERVANT, from, to, ASC_NONE, MV_PASSING_BY), c);
+    return !in_critical_endangerment<T>(c);
+}
+
+// ---- the canonical generator (life.rs:1052-1084) -----------------------------------------------------
+// servants, ponies, scholars, cops, princesses (all diagonals, then all orthogonals), figurehead, then
+// secret service West, East; pieces by ascending square; NIHIL = reckless (pseudo-legal).
+template <int T, bool NIHIL, class Sink> LL_HD void servant_move(const Legal &L, Sink &sink, int from, int to, u32 flags) {
+    if (!NIHIL && !lands_legally(L, 1ull << from, 1ull << to)) return; // predict / careful_apply, life.rs:728-739
+    if ((to >> 3) == (T == 0 ? 7 : 0)) { // subpredict, life.rs:701-726: Pony, Scholar, Cop, Princess
+#pragma unroll
+        for (u32 job = PONY; job <= PRINCESS; job++) sink.move(SERVANT, from, to, job, flags);
+    } else {
+        sink.move(SERVANT, from, to, ASC_NONE, flags);
+    }
+}
+template <bool DESC, class Sink> LL_HD void each_target(Sink &sink, u32 job, int from, u64 targets) {
+    while (targets) {
+        const int to = DESC ? msb64(targets) : lsb64(targets);
+        targets ^= 1ull << to;
+        sink.move(job, from, to, ASC_NONE, 0);
+    }
+}
+// one slider's rays in the reference's direction order, nearest square first (life.rs:857-914)
+template <bool NIHIL, bool DIAGONAL, class Sink> LL_HD void slider_rays(const Legal &L, Sink &sink, u32 job, int from, u64 occ, u64 own) {
+    const u64 bit = 1ull << from;
+    u64 allowed = ~own;
+    if (!NIHIL) {
+        allowed &= L.check;
+        if (bit & L.pinned) allowed &= pin_line(L, bit);
+        if (!allowed) return;
+    }
+    const u64 below = bit - 1, above = ~(bit | below);
+    if (DIAGONAL) { // SCHOLAR_OFFSETS (-1,-1), (-1,1), (1,-1), (1,1)  (life.rs:10)
+        const u64 d = line_attacks(occ, bit, diag_mask(from) & ~bit) & allowed;
+        const u64 a = line_attacks(occ, bit, anti_mask(from) & ~bit) & allowed;
+        each_target<true>(sink, job, from, d & below);
+        each_target<true>(sink, job, from, a & below);
+        each_target<false>(sink, job, from, a & above);
+        each_target<false>(sink, job, from, d & above);
+    } else { // COP_OFFSETS (-1,0), (1,0), (0,-1), (0,1)  (life.rs:11)
+        const u64 f = line_attacks(occ, bit, file_mask(from) & ~bit) & allowed;
+        const u64 r = line_attacks(occ, bit, rank_mask(from) & ~bit) & allowed;
+        each_target<true>(sink, job, from, f & below);
+        each_target<false>(sink, job, from, f & above);
+        each_target<true>(sink, job, from, r & below);
+        each_target<false>(sink, job, from, r & above);
+    }
+}
+
+template <int T, bool NIHIL, class Sink> LL_HD void lookahead_as(const Pos &p, Sink &sink) {
+    const u64 own = occupied_by<T>(p), opp = occupied_by<1 - T>(p), occ = own | opp, empty = ~occ;
+    Legal L;
+    if (!NIHIL) L = legal_context<T>(p, own, opp);
+    const bool others_may_move = NIHIL || L.check != 0;
+    if (others_may_move) {
+        { // life.rs:749-830
+            const u64 pb_bit = passing_by_bit(p.meta);
+            for (u64 s = p.pl[6 * T + SERVANT]; s; s &= s - 1) {
+                const int from = lsb64(s);
+                const u64 fb = 1ull << from;
+                const u64 one = T == 0 ? fb << 8 : fb >> 8;
+                if (one & empty) servant_move<T, NIHIL>(L, sink, from, T == 0 ? from + 8 : from - 8, 0);
+                if ((from >> 3) == (T == 0 ? 1 : 6)) {
+                    const u64 two = T == 0 ? fb << 16 : fb >> 16;
+                    if ((two & empty) && (one & empty)) servant_move<T, NIHIL>(L, sink, from, T == 0 ? from + 16 : from - 16, 0);
+                }
+                const u64 west = T == 0 ? (fb << 7) & ~FILE_H : (fb >> 9) & ~FILE_H;
+                const u64 east = T == 0 ? (fb << 9) & ~FILE_A : (fb >> 7) & ~FILE_A;
+#pragma unroll
+                for (int side = 0; side < 2; side++) {
+                    const u64 dest = side == 0 ? west : east;
+                    const int to = side == 0 ? (T == 0 ? from + 7 : from - 9) : (T == 0 ? from + 9 : from - 7);
+                    if (!dest) continue;
+                    if (dest & opp) servant_move<T, NIHIL>(L, sink, from, to, 0);
+                    else if (dest == pb_bit && (NIHIL || passing_by_is_legal<T>(p, from, to))) sink.move(SERVANT, from, to, ASC_NONE, MV_PASSING_BY);
+                }
+            }
+        }
+        for (u64 s = p.pl[6 * T + PONY]; s; s &= s - 1) { // life.rs:832-855
+            const int from = lsb64(s);
+            u64 targets = pony_moves(from) & ~own;
+            if (!NIHIL) targets = ((1ull << from) & L.pinned) ? 0 : targets & L.check; // a pinned pony never stays on its line
+            each_target<false>(sink, PONY, from, targets);
+        }
+        for (u64 s = p.pl[6 * T + SCHOLAR]; s; s &= s - 1) slider_rays<NIHIL, true>(L, sink, SCHOLAR, lsb64(s), occ, own);
+        for (u64 s = p.pl[6 * T + COP]; s; s &= s - 1) slider_rays<NIHIL, false>(L, sink, COP, lsb64(s), occ, own);
+        for (u64 s = p.pl[6 * T + PRINCESS]; s; s &= s - 1) slider_rays<NIHIL, true>(L, sink, PRINCESS, lsb64(s), occ, own); // life.rs:955-969
+        for (u64 s = p.pl[6 * T + PRINCESS]; s; s &= s - 1) slider_rays<NIHIL, false>(L, sink, PRINCESS, lsb64(s), occ, own);
+    }
+    for (u64 s = p.pl[6 * T + FIGUREHEAD]; s; s &= s - 1) { // life.rs:973-978
+        const int from = lsb64(s);
+        u64 targets = figurehead_moves(from) & ~own;
+        if (!NIHIL) targets &= ~L.danger;
+        each_target<false>(sink, FIGUREHEAD, from, targets);
+    }
+    if (NIHIL || L.check == ~0ull) service_lookahead<T, NIHIL>(p, own, opp, sink); // never out of check (life.rs:1034-1043)
+}
+
+template <bool NIHIL, class Sink> LL_HD void lookahead(const Pos &p, Sink &sink) {
     if (meta_stm(p.meta) == 0) lookahead_as<0, NIHIL>(p, sink);
     else lookahead_as<1, NIHIL>(p, sink);
 }
 
+// ---- set-wise move count: the number of commits lookahead() / reckless_lookahead() would produce,
+// by popcounts over whole piece sets (no per-move work) ---------------------------------------------------
+struct CountSink {
+    u32 n = 0;
+    LL_HDM void move(u32, int, int, u32, u32) { n++; }
+};
+
+template <int T, bool NIHIL> LL_HD u32 count_moves_as(const Pos &p) {
+    const u64 own = occupied_by<T>(p), opp = occupied_by<1 - T>(p), occ = own | opp, empty = ~occ;
+    Legal L;
+    if (!NIHIL) L = legal_context<T>(p, own, opp);
+    else { L.check = ~0ull; L.pinned = 0; L.danger = 0; L.kd = L.ka = L.kf = L.kr = 0; }
+    u32 n = 0;
+    if (p.pl[6 * T + FIGUREHEAD]) n += popc64(figurehead_moves(lsb64(p.pl[6 * T + FIGUREHEAD])) & ~own & ~L.danger);
+    if (L.check == 0) return n;
+    const u64 cm = L.check, free = ~L.pinned;
+    { // servants: a pinned servant may still push along a file pin / stun along a diagonal pin
+        const u64 s = p.pl[6 * T + SERVANT];
+        const u64 pushers = s & (free | L.kf);
+        const u64 west_stunners = s & (free | (T == 0 ? L.ka : L.kd)), east_stunners = s & (free | (T == 0 ? L.kd : L.ka));
+        const u64 last = T == 0 ? RANK_1 << 56 : RANK_1;
+        const u64 one = (T == 0 ? pushers << 8 : pushers >> 8) & empty;
+        const u64 two = (T == 0 ? (one & (RANK_1 << 16)) << 8 : (one & (RANK_1 << 40)) >> 8) & empty & cm;
+        const u64 west = (T == 0 ? (west_stunners << 7) : (west_stunners >> 9)) & ~FILE_H & opp & cm;
+        const u64 east = (T == 0 ? (east_stunners << 9) : (east_stunners >> 7)) & ~FILE_A & opp & cm;
+        const u64 one_ok = one & cm;
+        n += popc64(one_ok) + popc64(two) + popc64(west) + popc64(east);
+        n += 3 * (popc64(one_ok & last) + popc64(west & last) + popc64(east & last)); // ascension x4
+        const u64 pb_bit = passing_by_bit(p.meta);
+        if (pb_bit)
+            for (u64 c = servant_attackers_of<T>(pb_bit) & s; c; c &= c - 1)
+                if (NIHIL || passing_by_is_legal<T>(p, lsb64(c), lsb64(pb_bit))) n++;
+    }
+    for (u64 s = p.pl[6 * T + PONY] & free; s; s &= s - 1) n += popc64(pony_moves(lsb64(s)) & ~own & cm);
+    {
+        const u64 diag = p.pl[6 * T + SCHOLAR] | p.pl[6 * T + PRINCESS], orth = p.pl[6 * T + COP] | p.pl[6 * T + PRINCESS];
+        const u64 ok = ~own & cm;
+        const u64 df = diag & free, of = orth & free;
+        // rays of different pieces in one direction never overlap (a ray stops at the next piece)
+        n += popc64(ks_ne(df, empty) & ok) + popc64(ks_nw(df, empty) & ok) + popc64(ks_se(df, empty) & ok) + popc64(ks_sw(df, empty) & ok);
+        n += popc64(ks_north(of, empty) & ok) + popc64(ks_south(of, empty) & ok) + popc64(ks_east(of, empty) & ok) + popc64(ks_west(of, empty) & ok);
+        if (!NIHIL) { // pinned sliders slide along the pin only
+            const u64 k = p.pl[6 * T + FIGUREHEAD];
+            for (u64 s = diag & L.pinned & (L.kd | L.ka); s; s &= s - 1) {
+                const u64 bit = s & (0 - s);
+                n += popc64(line_attacks(occ, bit, (pin_line(L, bit) | k) & ~bit) & ok);
+            }
+            for (u64 s = orth & L.pinned & (L.kf | L.kr); s; s &= s - 1) {
+                const u64 bit = s & (0 - s);
+                n += popc64(line_attacks(occ, bit, (pin_line(L, bit) | k) & ~bit) & ok);
+            }
+        }
+    }
+    if (cm == ~0ull) {
+        CountSink sink;
+        service_lookahead<T, NIHIL>(p, own, opp, sink);
+        n += sink.n;
+    }
+    return n;
+}
+template <bool NIHIL> LL_HD u32 count_moves(const Pos &p) {
+    return meta_stm(p.meta) == 0 ? count_moves_as<0, NIHIL>(p) : count_moves_as<1, NIHIL>(p);
+}
+
 // ---- well-formedness (domain W, include/leafline_b200.h) ----------------------------------------
-__device__ __forceinline__ bool well_formed(const Pos &p) {
+LL_HD bool well_formed(const Pos &p) {
     u64 acc = 0, overlap = 0;
 #pragma unroll
     for (int j = 0; j < 12; j++) {
@@ -316,7 +555,7 @@ __device__ __forceinline__ bool well_formed(const Pos &p) {
         acc |= p.pl[j];
     }
     if (overlap) return false;
-    if (__popcll(p.pl[FIGUREHEAD]) > 1 || __popcll(p.pl[6 + FIGUREHEAD]) > 1) return false;
+    if (popc64(p.pl[FIGUREHEAD]) > 1 || popc64(p.pl[6 + FIGUREHEAD]) > 1) return false;
     const u32 elig = meta_elig(p.meta);
     if ((elig & 0x3u) && (p.pl[FIGUREHEAD] & ~(1ull << 4))) return false;
     if ((elig & 0xCu) && (p.pl[6 + FIGUREHEAD] & ~(1ull << 60))) return false;
@@ -336,25 +575,25 @@ __device__ __forceinline__ bool well_formed(const Pos &p) {
 }
 
 // ---- static evaluation (mind.rs:50-143): strict f32, one rounded multiply and one rounded add per
-// reference statement, in the reference's order; __fmul_rn/__fadd_rn are never contracted to FMA ----
-__device__ __forceinline__ float score(const Pos &p) {
+// reference statement, in the reference's order; fmul/fadd are never contracted to FMA -----------------
+LL_HD float score(const Pos &p) {
     const float values[6] = {1.0f, 3.2f, 3.3f, 5.1f, 8.8f, 20000.0f}; // mind.rs:36-48
     float v = 0.0f;
-    v = __fadd_rn(v, __fmul_rn(0.5f, meta_stm(p.meta) ? -1.0f : 1.0f)); // mind.rs:53
+    v = fadd(v, fmul(0.5f, meta_stm(p.meta) ? -1.0f : 1.0f)); // mind.rs:53
 #pragma unroll
     for (int team = 0; team < 2; team++) { // mind.rs:55-68
         const float orient = team ? -1.0f : 1.0f;
 #pragma unroll
         for (int job = 0; job < 6; job++)
-            v = __fadd_rn(v, __fmul_rn((float)__popcll(p.pl[6 * team + job]), __fmul_rn(orient, values[job])));
-        if (__popcll(p.pl[6 * team + SCHOLAR]) >= 2) v = __fadd_rn(v, __fmul_rn(orient, 0.5f));
+            v = fadd(v, fmul((float)popc64(p.pl[6 * team + job]), fmul(orient, values[job])));
+        if (popc64(p.pl[6 * team + SCHOLAR]) >= 2) v = fadd(v, fmul(orient, 0.5f));
     }
     const u64 center = 0x00003C3C3C3C0000ull; // mind.rs:70-81
-    const int oc = __popcll((p.pl[SERVANT] | p.pl[PONY]) & center), bc = __popcll((p.pl[6 + SERVANT] | p.pl[6 + PONY]) & center);
-    v = __fadd_rn(v, __fmul_rn(0.1f, (float)(oc - bc)));
+    const int oc = popc64((p.pl[SERVANT] | p.pl[PONY]) & center), bc = popc64((p.pl[6 + SERVANT] | p.pl[6 + PONY]) & center);
+    v = fadd(v, fmul(0.1f, (float)(oc - bc)));
     const u64 high_seventh = 0xFFull << 48, low_seventh = 0xFFull << 8; // mind.rs:83-89
-    v = __fadd_rn(v, __fmul_rn(0.5f, (float)__popcll(p.pl[COP] & high_seventh)));
-    v = __fadd_rn(v, -__fmul_rn(0.5f, (float)__popcll(p.pl[6 + COP] & low_seventh)));
+    v = fadd(v, fmul(0.5f, (float)popc64(p.pl[COP] & high_seventh)));
+    v = fadd(v, -fmul(0.5f, (float)popc64(p.pl[6 + COP] & low_seventh)));
     // mind.rs:91-111: doubled servants, file by file, Orange then Blue.  Files without a second
     // servant contribute nothing, so only those files are visited (ascending, same add order).
     {
@@ -370,22 +609,22 @@ __device__ __forceinline__ float score(const Pos &p) {
         }
         u32 files = o_twice | b_twice;
         while (files) {
-            const int f = __ffs((int)files) - 1;
+            const int f = lsb32(files);
             files &= files - 1;
             const u64 file = FILE_A << f;
-            const int o = __popcll(os & file), b = __popcll(bs & file);
-            if (o > 1) v = __fadd_rn(v, -__fmul_rn(0.5f, (float)(o - 1)));
-            if (b > 1) v = __fadd_rn(v, __fmul_rn(0.5f, (float)(b - 1)));
+            const int o = popc64(os & file), b = popc64(bs & file);
+            if (o > 1) v = fadd(v, -fmul(0.5f, (float)(o - 1)));
+            if (b > 1) v = fadd(v, fmul(0.5f, (float)(b - 1)));
         }
     }
     // mind.rs:113-131
-    v = __fadd_rn(v, __fmul_rn(1.8f, (float)__popcll(p.pl[SERVANT] & high_seventh)));
-    v = __fadd_rn(v, __fmul_rn(0.6f, (float)__popcll(p.pl[SERVANT] & (0xFFull << 40))));
-    v = __fadd_rn(v, -__fmul_rn(1.8f, (float)__popcll(p.pl[6 + SERVANT] & low_seventh)));
-    v = __fadd_rn(v, -__fmul_rn(0.6f, (float)__popcll(p.pl[6 + SERVANT] & (0xFFull << 16))));
+    v = fadd(v, fmul(1.8f, (float)popc64(p.pl[SERVANT] & high_seventh)));
+    v = fadd(v, fmul(0.6f, (float)popc64(p.pl[SERVANT] & (0xFFull << 40))));
+    v = fadd(v, -fmul(1.8f, (float)popc64(p.pl[6 + SERVANT] & low_seventh)));
+    v = fadd(v, -fmul(0.6f, (float)popc64(p.pl[6 + SERVANT] & (0xFFull << 16))));
     const u32 elig = meta_elig(p.meta); // mind.rs:133-140
-    if (elig & 0x3u) v = __fadd_rn(v, 0.1f);
-    if (elig & 0xCu) v = __fadd_rn(v, -0.1f);
+    if (elig & 0x3u) v = fadd(v, 0.1f);
+    if (elig & 0xCu) v = fadd(v, -0.1f);
     return v;
 }
 

@@ -1,49 +1,22 @@
 // ll_kernels.cuh -- the CUDA kernels of the leaf layer (sm_100a).  See DESIGN.md for the roofline
 // that bounds each one.  Host-side launch wrappers live in ll_api.cu.
+//
+// The work-horse is k_expand: a block takes a tile of BLOCK parent positions.  Phase 1: one thread
+// per parent runs the canonical generator and writes 32-bit move descriptors into a shared-memory
+// list at the parent's exclusive-scan offset (so the list is in the reference's order).  Phase 2:
+// the whole block walks that list, one CHILD per thread per step: rebuild the child from the parent
+// tile in shared memory, then either store it (coalesced: neighbouring threads write neighbouring
+// children), bulk-count its legal moves (perft tail) or score it (horizon).  Phase 2 is where the
+// time goes and it is perfectly balanced however uneven the parents' move counts are.
 #pragma once
 #include "ll_device.cuh"
 
 namespace ll {
 
 constexpr int BLOCK = 128;
+constexpr int DESC_CAP = 6144; // move descriptors per window (24 KiB); a tile with more moves takes several windows
 
-// ---- sinks for the canonical generator -----------------------------------------------------------
-struct CountSink {
-    u32 n = 0;
-    __device__ __forceinline__ void operator()(const Pos &, u32) { n++; }
-};
-struct EmitSink { // writes children (and optionally their commit metadata / root ids) at out[idx++]
-    Soa out;
-    u32 *cmeta;
-    u32 *root_out;
-    size_t idx;
-    u32 root;
-    bool root_is_index;
-    __device__ __forceinline__ void operator()(const Pos &c, u32 m) {
-        soa_store(out, idx, c);
-        if (cmeta) cmeta[idx] = m;
-        if (root_out) root_out[idx] = root_is_index ? (u32)idx : root;
-        idx++;
-    }
-};
-struct SelectSink { // keeps the k-th commit
-    u32 n = 0, k;
-    Pos chosen;
-    __device__ __forceinline__ void operator()(const Pos &c, u32) {
-        if (n == k) chosen = c;
-        n++;
-    }
-};
-struct LeafMaxSink { // mind.rs:279-287 one ply above the horizon: max over children of -(orientation * score)
-    float best = -INFINITY;
-    u32 n = 0;
-    __device__ __forceinline__ void operator()(const Pos &c, u32) {
-        const float s = score(c);
-        const float child_value = meta_stm(c.meta) ? -s : s; // orientation(initiative) * score, mind.rs:283
-        best = fmaxf(best, -child_value);
-        n++;
-    }
-};
+enum { MODE_EMIT = 0, MODE_PERFT = 1, MODE_HORIZON = 2 };
 
 // ---- block-level helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ u32 warp_inclusive_scan(u32 v) {
@@ -72,6 +45,12 @@ __device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32 *total) {
     *total = sum;
     return base + inc - v;
 }
+// order-preserving f32 <-> i32 map (no NaNs on this path), so that a float max can be an integer atomicMax
+__device__ __forceinline__ int float_key(float f) {
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7FFFFFFF;
+}
+__device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7FFFFFFF); }
 
 // ---- layout kernels: ll_world_t (array of 104-byte structs) <-> SoA planes -------------------------
 // The 104-byte struct is 13 u64 words; word 12 holds initiative | eligibility<<8 | passing_by<<16.
@@ -161,22 +140,21 @@ __global__ void __launch_bounds__(256) k_score(Soa in, size_t n, float *__restri
     }
 }
 
-// ---- movegen: count / offsets / emit -------------------------------------------------------------------
+// ---- movegen: set-wise count -> scan -> expand ---------------------------------------------------------
 template <bool NIHIL> __global__ void __launch_bounds__(BLOCK) k_count(Soa in, size_t n, u32 *__restrict__ counts, u32 *__restrict__ block_sums) {
     const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
-    CountSink sink;
+    u32 c = 0;
     if (i < n) {
-        const Pos p = soa_load(in, i);
-        lookahead<NIHIL>(p, sink);
-        counts[i] = sink.n;
+        c = count_moves<NIHIL>(soa_load(in, i));
+        counts[i] = c;
     }
     u32 total;
-    block_exclusive_scan(sink.n, &total);
+    block_exclusive_scan(c, &total);
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
 
-// single block: block_sums[0..nb) -> exclusive prefix in place (u64 running total written to *total)
-__global__ void __launch_bounds__(1024) k_scan_block_sums(u32 *block_sums, u64 *block_base, size_t nb, u64 *total) {
+// single block: block_sums[0..nb) -> exclusive prefix (u64 running total written to *total)
+__global__ void __launch_bounds__(1024) k_scan_block_sums(const u32 *block_sums, u64 *block_base, size_t nb, u64 *total) {
     __shared__ u64 warp_sums[32];
     __shared__ u64 carry_s;
     if (threadIdx.x == 0) carry_s = 0;
@@ -214,17 +192,142 @@ __global__ void __launch_bounds__(BLOCK) k_offsets(const u32 *__restrict__ count
     if (i == n - 1) offsets[n] = (u32)(base + ex + c);
 }
 
-template <bool NIHIL>
-__global__ void __launch_bounds__(BLOCK) k_emit(Soa in, size_t n, const u32 *__restrict__ counts, const u64 *__restrict__ block_base, Soa out,
-                                                u32 *__restrict__ cmeta, const u32 *__restrict__ root_in, u32 *__restrict__ root_out, int root_is_index) {
-    const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
-    const u32 c = i < n ? counts[i] : 0;
+// phase-1 sink: descriptors of one parent into the current window of the shared list
+struct DescSink {
+    u32 *buf;
+    u32 idx, lo, hi, slot_bits;
+    LL_HDM void move(u32 job, int from, int to, u32 asc, u32 flags) {
+        if (idx >= lo && idx < hi) buf[idx - lo] = mv_pack(job, from, to, asc, flags) | slot_bits;
+        idx++;
+    }
+};
+
+struct ExpandArgs {
+    Soa in;
+    size_t n;
+    const u32 *counts;      // per-parent commit counts (nullptr: counted here)
+    const u64 *block_base;  // EMIT: first child index of each tile
+    const u32 *root_in;     // root-move id of each parent (nullable)
+    // MODE_EMIT
+    Soa out;
+    u32 *cmeta;             // packed commit metadata (nullable)
+    u32 *root_out;          // nullable
+    int root_is_index;      // children become the roots: root id = own index
+    // MODE_PERFT
+    u64 *per_root, *total;
+    // MODE_HORIZON
+    float *values;
+    u64 *scored;
+};
+
+#ifndef LL_EXPAND_MIN_BLOCKS
+#define LL_EXPAND_MIN_BLOCKS 5
+#endif
+LL_HD Pos tile_load(const u64 (*tile_pl)[BLOCK], const u32 *tile_meta, u32 slot) {
+    Pos p;
+#pragma unroll
+    for (int j = 0; j < 12; j++) p.pl[j] = tile_pl[j][slot];
+    p.meta = tile_meta[slot];
+    return p;
+}
+template <bool NIHIL, int MODE> __global__ void __launch_bounds__(BLOCK, LL_EXPAND_MIN_BLOCKS) k_expand(const ExpandArgs a) {
+    __shared__ u64 tile_pl[12][BLOCK];
+    __shared__ u32 tile_meta[BLOCK];
+    __shared__ u32 descs[DESC_CAP];
+    __shared__ int acc[BLOCK]; // PERFT: leaves below each parent; HORIZON: best child key of each parent
+
+    const int tid = threadIdx.x;
+    const size_t i = (size_t)blockIdx.x * BLOCK + tid;
+    u32 cnt = 0;
+    if (i < a.n) { // the parent lives in the shared tile from here on, not in registers
+        const Pos p = soa_load(a.in, i);
+        cnt = a.counts ? a.counts[i] : count_moves<NIHIL>(p);
+#pragma unroll
+        for (int j = 0; j < 12; j++) tile_pl[j][tid] = p.pl[j];
+        tile_meta[tid] = p.meta;
+    }
+    if (MODE == MODE_PERFT) acc[tid] = 0;
+    if (MODE == MODE_HORIZON) acc[tid] = float_key(-INFINITY);
     u32 total;
-    const u32 ex = block_exclusive_scan(c, &total);
-    if (i >= n || c == 0) return;
-    EmitSink sink{out, cmeta, root_out, (size_t)(block_base[blockIdx.x] + ex), root_in ? root_in[i] : 0u, root_is_index != 0};
-    const Pos p = soa_load(in, i);
-    lookahead<NIHIL>(p, sink);
+    const u32 ex = block_exclusive_scan(cnt, &total); // also orders the tile writes before phase 2
+    const size_t out_base = MODE == MODE_EMIT ? (size_t)a.block_base[blockIdx.x] : 0;
+
+    for (u32 w0 = 0; w0 < total; w0 += DESC_CAP) {
+        if (cnt && ex < w0 + DESC_CAP && ex + cnt > w0) { // phase 1: this parent's commits into the window
+            DescSink sink{descs, ex, w0, w0 + DESC_CAP, (u32)tid << 20};
+            lookahead<NIHIL>(tile_load(tile_pl, tile_meta, tid), sink);
+        }
+        __syncthreads();
+        const u32 wn = min((u32)DESC_CAP, total - w0);
+        for (u32 k0 = 0; k0 < wn; k0 += BLOCK) { // phase 2: one child per thread
+            const u32 k = k0 + tid;
+            const bool live = k < wn;
+            u32 slot = 0;
+            Pos c;
+            u32 m = 0, hosp = JOB_NONE;
+            if (live) {
+                m = descs[k];
+                slot = mv_slot(m);
+                hosp = make_child(tile_load(tile_pl, tile_meta, slot), m, c);
+            }
+            if (MODE == MODE_EMIT) {
+                if (live) {
+                    const size_t o = out_base + w0 + k;
+                    soa_store(a.out, o, c);
+                    if (a.cmeta) a.cmeta[o] = pack_commit(meta_stm(c.meta) ^ 1u, m, hosp);
+                    if (a.root_out) a.root_out[o] = a.root_is_index ? (u32)o : a.root_in[(size_t)blockIdx.x * BLOCK + slot];
+                }
+            } else {
+                int v = 0;
+                if (MODE == MODE_PERFT) {
+                    if (live) v = (int)count_moves<false>(c);
+                } else {
+                    v = float_key(-INFINITY);
+                    if (live) {
+                        const float s = score(c);
+                        v = float_key(meta_stm(c.meta) ? s : -s); // -(orientation(child) * score(child)), mind.rs:283, 331-336
+                    }
+                }
+                // children of one parent are neighbours in the list: reduce per parent inside the warp first
+                const unsigned peers = __match_any_sync(0xffffffffu, live ? slot : 0xFFFFFFFFu);
+                const int r = MODE == MODE_PERFT ? __reduce_add_sync(peers, v) : __reduce_max_sync(peers, v);
+                if (live && (tid & 31) == __ffs((int)peers) - 1) {
+                    if (MODE == MODE_PERFT) atomicAdd(&acc[slot], r);
+                    else atomicMax(&acc[slot], r);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    if (MODE == MODE_PERFT) {
+        // tile order keeps a root's nodes contiguous, so a warp sees very few distinct roots
+        const u32 root = i < a.n ? (a.root_in ? a.root_in[i] : 0u) : 0xFFFFFFFFu;
+        const u32 mine = i < a.n ? (u32)acc[tid] : 0u;
+        const unsigned peers = __match_any_sync(0xffffffffu, root);
+        const u32 sum = __reduce_add_sync(peers, mine);
+        if ((tid & 31) == __ffs((int)peers) - 1 && root != 0xFFFFFFFFu && sum) {
+            if (a.per_root) atomicAdd(a.per_root + root, (u64)sum);
+            atomicAdd(a.total, (u64)sum);
+        }
+    }
+    if (MODE == MODE_HORIZON) {
+        u32 scored = 0;
+        if (i < a.n) {
+            float v;
+            if (cnt == 0) { // no pseudo-legal move: the node is itself a leaf (mind.rs:281-283)
+                const Pos p = tile_load(tile_pl, tile_meta, tid);
+                const float s = score(p);
+                v = meta_stm(p.meta) ? -s : s;
+            } else {
+                v = key_float(acc[tid]);
+            }
+            a.values[i] = v;
+            scored = cnt ? cnt : 1u;
+        }
+        scored = __reduce_add_sync(0xffffffffu, scored);
+        if ((tid & 31) == 0 && scored && a.scored) atomicAdd(a.scored, (u64)scored);
+    }
 }
 
 // keep the units u with u % world == rank (frontier sharding by subtree)
@@ -233,22 +336,19 @@ __global__ void __launch_bounds__(BLOCK) k_shard_filter(Soa in, const u32 *__res
     const size_t i = (size_t)rank + o * (size_t)world;
     if (i >= n) return;
     soa_store(out, o, soa_load(in, i));
-    root_out[o] = root_in[i];
+    root_out[o] = root_in ? root_in[i] : 0u;
 }
 
-// ---- perft tail: count the legal moves of every frontier node, accumulate per root --------------------
+// ---- perft tail on an already materialised frontier: count the legal moves of every node ---------------
 __global__ void __launch_bounds__(BLOCK) k_count_leaves(Soa in, size_t n, const u32 *__restrict__ root_in, u64 *__restrict__ per_root, u64 *__restrict__ total) {
     const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
-    CountSink sink;
-    u32 root = 0xFFFFFFFFu;
+    u32 c = 0, root = 0xFFFFFFFFu;
     if (i < n) {
-        const Pos p = soa_load(in, i);
-        lookahead<false>(p, sink);
+        c = count_moves<false>(soa_load(in, i));
         root = root_in ? root_in[i] : 0u;
     }
-    // frontier order keeps a root's nodes contiguous, so a warp sees very few distinct roots
     const unsigned peers = __match_any_sync(0xffffffffu, root);
-    const u32 sum = __reduce_add_sync(peers, sink.n);
+    const u32 sum = __reduce_add_sync(peers, c);
     if ((threadIdx.x & 31) == __ffs((int)peers) - 1 && root != 0xFFFFFFFFu && sum) {
         if (per_root) atomicAdd(per_root + root, (u64)sum);
         atomicAdd(total, (u64)sum);
@@ -256,26 +356,6 @@ __global__ void __launch_bounds__(BLOCK) k_count_leaves(Soa in, size_t n, const 
 }
 
 // ---- horizon (mind.rs:279-287) -------------------------------------------------------------------------
-// value[i] of frontier node i one ply above the leaves: children generated, scored and reduced in
-// registers -- the leaves never touch HBM.  No pseudo-legal children -> the node is itself a leaf.
-__global__ void __launch_bounds__(BLOCK) k_horizon_last_ply(Soa in, size_t n, float *__restrict__ values, u64 *__restrict__ leaves_scored) {
-    const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
-    u32 scored = 0;
-    if (i < n) {
-        const Pos p = soa_load(in, i);
-        LeafMaxSink sink;
-        lookahead<true>(p, sink);
-        float v = sink.best;
-        if (sink.n == 0) {
-            const float s = score(p);
-            v = meta_stm(p.meta) ? -s : s;
-        }
-        values[i] = v;
-        scored = sink.n ? sink.n : 1u;
-    }
-    scored = __reduce_add_sync(0xffffffffu, scored);
-    if ((threadIdx.x & 31) == 0 && scored) atomicAdd(leaves_scored, (u64)scored);
-}
 // plies == 0: value = orientation * score
 __global__ void __launch_bounds__(BLOCK) k_leaf_values(Soa in, size_t n, float *__restrict__ values) {
     const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
@@ -304,10 +384,6 @@ __global__ void __launch_bounds__(BLOCK) k_backup(Soa parents, size_t n, const u
     }
     values[i] = v;
 }
-__global__ void __launch_bounds__(BLOCK) k_negate(const float *__restrict__ in, size_t n, float *__restrict__ out) {
-    const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
-    if (i < n) out[i] = -in[i];
-}
 
 // ---- life.rs:678-690 for an explicit team ------------------------------------------------------------
 __global__ void __launch_bounds__(BLOCK) k_endangered(Soa in, size_t n, const unsigned char *__restrict__ teams, unsigned char *__restrict__ out) {
@@ -332,6 +408,13 @@ __device__ __forceinline__ Pos opening_position() { // life.rs:184-215
     p.meta = make_meta(0, 0xF, 0xFF);
     return p;
 }
+struct SelectSink { // keeps the k-th commit's descriptor
+    u32 n = 0, k = 0, chosen = 0;
+    LL_HDM void move(u32 job, int from, int to, u32 asc, u32 flags) {
+        if (n == k) chosen = mv_pack(job, from, to, asc, flags);
+        n++;
+    }
+};
 __global__ void __launch_bounds__(BLOCK) k_playout(u64 seed, u64 first_index, size_t n, Soa out) {
     const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
     if (i >= n) return;
@@ -343,14 +426,15 @@ __global__ void __launch_bounds__(BLOCK) k_playout(u64 seed, u64 first_index, si
         const int plies = 16 + (int)(((mix64(h1) >> 32) * 45ull) >> 32);
         int k = 0;
         for (; k < plies; k++) {
-            CountSink counter;
-            lookahead<false>(p, counter);
-            if (counter.n == 0) break;
+            const u32 count = count_moves<false>(p);
+            if (count == 0) break;
             const u64 r = mix64(h1 + (u64)(k + 1) * 0x9E3779B97F4A7C15ull) >> 32;
             SelectSink select;
-            select.k = (u32)((r * (u64)counter.n) >> 32);
+            select.k = (u32)((r * (u64)count) >> 32);
             lookahead<false>(p, select);
-            p = select.chosen;
+            Pos c;
+            make_child(p, select.chosen, c);
+            p = c;
         }
         if (k == plies) break;
     }

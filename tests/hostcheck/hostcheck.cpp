@@ -1,0 +1,81 @@
+// hostcheck.cpp -- TEST INFRASTRUCTURE.  Compiles leafline_b200/csrc/ll_device.cuh as plain C++ so that the
+// generator / legality logic the CUDA kernels are built from can be compared with the oracle on the CPU
+// box, over far more positions than a GPU call affords.  Nothing in the product links or loads this.
+#include "../../include/leafline_b200.h"
+#include "../../leafline_b200/csrc/ll_device.cuh"
+
+using namespace ll;
+
+static Pos to_pos(const ll_world_t *w) {
+    Pos p;
+    for (int j = 0; j < 12; j++) p.pl[j] = w->plane[j];
+    p.meta = make_meta(w->initiative & 1u, w->service_eligibility & 0xFu, w->passing_by);
+    return p;
+}
+static void from_pos(const Pos &p, ll_world_t *w) {
+    for (int j = 0; j < 12; j++) w->plane[j] = p.pl[j];
+    w->initiative = (uint8_t)meta_stm(p.meta);
+    w->service_eligibility = (uint8_t)meta_elig(p.meta);
+    w->passing_by = (uint8_t)meta_pb(p.meta);
+    for (int j = 0; j < 5; j++) w->pad[j] = 0;
+}
+
+struct ListSink {
+    u32 moves[1024];
+    u32 n = 0;
+    void move(u32 job, int from, int to, u32 asc, u32 flags) {
+        if (n < 1024) moves[n] = mv_pack(job, from, to, asc, flags);
+        n++;
+    }
+};
+
+extern "C" void hc_init(void) {
+    static const int pony_opt[8][2] = {{1, 2}, {-1, 2}, {1, -2}, {-1, -2}, {2, 1}, {-2, 1}, {2, -1}, {-2, -1}};
+    for (int r = 0; r < 8; r++)
+        for (int f = 0; f < 8; f++) {
+            u64 a = 0, b = 0;
+            for (int k = 0; k < 8; k++) {
+                int rr = r + pony_opt[k][0], ff = f + pony_opt[k][1];
+                if (rr >= 0 && rr < 8 && ff >= 0 && ff < 8) a |= 1ull << (8 * rr + ff);
+            }
+            for (int i = -1; i <= 1; i++)
+                for (int j = -1; j <= 1; j++) {
+                    int rr = r + i, ff = f + j;
+                    if ((i || j) && rr >= 0 && rr < 8 && ff >= 0 && ff < 8) b |= 1ull << (8 * rr + ff);
+                }
+            d_pony_table[8 * r + f] = a;
+            d_figurehead_table[8 * r + f] = b;
+        }
+}
+
+extern "C" int hc_count(const ll_world_t *w, int nihil) {
+    const Pos p = to_pos(w);
+    return (int)(nihil ? count_moves<true>(p) : count_moves<false>(p));
+}
+
+extern "C" int hc_lookahead(const ll_world_t *w, int nihil, ll_commit_t *out, int cap) {
+    const Pos p = to_pos(w);
+    static thread_local ListSink sink;
+    sink.n = 0;
+    if (nihil) lookahead<true>(p, sink);
+    else lookahead<false>(p, sink);
+    const u32 team = meta_stm(p.meta);
+    for (u32 i = 0; i < sink.n && (int)i < cap; i++) {
+        const u32 m = sink.moves[i];
+        Pos c;
+        const u32 hosp = make_child(p, m, c);
+        ll_commit_t *o = out + i;
+        o->team = (uint8_t)team;
+        o->job = (uint8_t)mv_job(m);
+        o->whence = (uint8_t)sq_to_loc(mv_from(m));
+        o->whither = (uint8_t)sq_to_loc(mv_to(m));
+        o->hospitalization = hosp == JOB_NONE ? 0xFF : (uint8_t)(((team ^ 1u) << 3) | hosp);
+        o->ascension = mv_asc(m) == ASC_NONE ? 0xFF : (uint8_t)((team << 3) | mv_asc(m));
+        o->pad[0] = o->pad[1] = 0;
+        from_pos(c, &o->tree);
+    }
+    return (int)sink.n;
+}
+
+extern "C" float hc_score(const ll_world_t *w) { return score(to_pos(w)); }
+extern "C" int hc_well_formed(const ll_world_t *w) { return well_formed(to_pos(w)) ? 1 : 0; }

@@ -1,0 +1,95 @@
+"""Host-side logic check of the move generator the CUDA kernels are built from.
+
+tests/hostcheck/hostcheck.cpp compiles leafline_b200/csrc/ll_device.cuh as plain C++ (test
+infrastructure only -- the shipped library has no CPU path) so the legality-by-masks generator, the
+set-wise move counter, make-move and the scorer can be compared with the oracle over tens of
+thousands of positions without a GPU.  The GPU parity tests (test_gpu_parity.py) then check the very
+same code compiled for sm_100a."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle as O
+from positions import named_worlds, reckless_walk_worlds
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "hostcheck", "hostcheck.cpp")
+SO = os.path.join(HERE, "hostcheck", "_hostcheck.so")
+HDR = os.path.join(HERE, "..", "leafline_b200", "csrc", "ll_device.cuh")
+
+
+@pytest.fixture(scope="module")
+def hc():
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-o", SO, SRC], check=True)
+    lib = C.CDLL(SO)
+    lib.hc_count.argtypes = [C.c_void_p, C.c_int]
+    lib.hc_lookahead.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.hc_score.argtypes = [C.c_void_p]
+    lib.hc_score.restype = C.c_float
+    lib.hc_well_formed.argtypes = [C.c_void_p]
+    lib.hc_init()
+    return lib
+
+
+def check(hc, worlds):
+    buf = np.zeros(1024, dtype=O.COMMIT_DTYPE)
+    for w in worlds:
+        w = np.ascontiguousarray(w)
+        ptr = w.ctypes.data_as(C.c_void_p)
+        assert hc.hc_well_formed(ptr) == 1
+        for nihil, ref in ((0, O.lookahead), (1, O.reckless_lookahead)):
+            want = ref(w)
+            n = hc.hc_lookahead(ptr, nihil, buf.ctypes.data_as(C.c_void_p), 1024)
+            assert n == len(want), (O.preserve(w), nihil, n, len(want))
+            assert buf[:n].tobytes() == want.tobytes(), (O.preserve(w), nihil)
+            assert hc.hc_count(ptr, nihil) == n, (O.preserve(w), nihil)
+        assert np.float32(hc.hc_score(ptr)).tobytes() == np.float32(O.score(w)).tobytes()
+
+
+def test_named_positions(hc):
+    check(hc, named_worlds())
+
+
+def test_playout_positions(hc):
+    check(hc, O.playout_batch(0x1EAF11E, 0, 3000))
+
+
+def test_reckless_walk_positions(hc):
+    check(hc, reckless_walk_worlds(seed=23, games=60, plies=70))
+
+
+def test_checks_pins_and_passing_by_corners(hc):
+    fens = [
+        "4k3/8/8/8/8/8/4r3/4K3 w - -",          # adjacent checker, capture by the figurehead only
+        "4k3/8/8/8/7b/8/5P2/4K3 w - -",         # servant pinned on a diagonal
+        "4k3/4r3/8/8/8/8/4P3/4K3 w - -",        # servant pinned on a file: may still push
+        "4k3/8/8/8/1b6/8/3P4/4K3 w - -",        # pinned servant, nothing to stun
+        "4k3/8/8/8/1b6/2p5/3P4/4K3 w - -",      # pinned servant may stun along the pin
+        "8/8/8/8/k2Pp2R/8/8/4K3 b - d3",        # passing by would uncover the cop on the rank
+        "8/8/8/2k5/3Pp3/8/8/4K3 b - d3",        # the double-stepped servant gives check: passing by answers it
+        "4k3/8/8/8/8/2n5/8/R3K2R w KQ -",       # pony check: no secret service, block impossible
+        "4k3/8/8/8/8/8/3n1n2/R3K2R w KQ -",     # double check
+        "r3k2r/8/8/8/8/8/8/R3K2R w KQkq -", "r3k2r/8/8/8/8/8/8/R3K2R b KQkq -",
+        "4k3/8/8/8/8/8/8/RN2K2R w KQ -", "4k2r/8/8/8/8/8/8/4K2R w Kk -",
+        "3rk3/8/8/8/8/8/8/R3K2R w KQ -",        # d1 leered at: West refused, East fine
+        "1r2k3/8/8/8/8/8/8/R3K2R w KQ -",       # b1 leered at: West refused (quirk 1)
+        "4k3/1P6/8/8/8/8/8/4K3 w - -", "n1n1k3/1P6/8/8/8/8/8/4K3 w - -", "4k3/8/8/8/8/8/1p6/N1N1K3 b - -",
+        "4k3/8/8/8/8/8/8/4K2n w K -", "4k3/8/8/8/8/8/8/7R w K -", "4k3/8/8/8/8/8/8/4r2R w K -",
+        "Q3k3/8/8/8/8/8/8/q3K3 w - -", "7k/6Q1/8/8/8/8/8/K7 b - -", "7k/5KQ1/8/8/8/8/8/8 b - -",
+        "8/8/8/8/8/1k6/8/K7 w - -", "8/8/8/8/8/8/1k6/K7 w - -",  # adjacent figureheads (reckless lines get there)
+        "k7/8/8/3q4/8/8/3R4/3K4 w - -", "k7/8/8/3q4/8/3B4/8/3K4 w - -", "k7/8/8/q7/8/2Q5/8/4K3 w - -",
+    ]
+    worlds = [O.reconstruct(f) for f in fens]
+    check(hc, worlds)
+    # and everything one and two plies below them (reckless: figureheads get stunned, phantom service)
+    deeper = []
+    for w in worlds:
+        for c in O.reckless_lookahead(w):
+            deeper.append(c["tree"].copy())
+            for d in O.reckless_lookahead(c["tree"])[:12]:
+                deeper.append(d["tree"].copy())
+    check(hc, deeper)
