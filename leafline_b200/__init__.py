@@ -118,11 +118,28 @@ class Engine:
         _abi.check(self._lib.ll_timing_query(self._ctx, kernel.encode(), C.byref(ms), C.byref(launches)))
         return ms.value, launches.value
 
+    def force_synced(self, on=True):
+        """Testing aid: make perft() take the level-by-level path instead of the single launch chain."""
+        _abi.check(self._lib.ll_debug_force_synced(self._ctx, int(on)))
+
+    def measure_int_peak(self, kind=0):
+        """Sustained thread-level integer instructions/s (0: LOP3 stream, 1: LOP3+IMAD) for the integer roofline."""
+        v = C.c_double(0)
+        _abi.check(self._lib.ll_measure_int_peak(self._ctx, kind, C.byref(v)))
+        return v.value
+
     # ---- the leaf layer on host buffers
     def score(self, worlds):
         """mind::score for every world (mind.rs:50-143) -> float32[n]."""
         w = _worlds(worlds)
         out = np.empty(len(w), dtype=np.float32)
+        _abi.check(self._lib.ll_score_batch(self._ctx, _ptr(w), len(w), _ptr(out)))
+        return out
+
+    def score_into(self, worlds, out):
+        """score() into a caller-owned float32 host buffer (e.g. pinned memory): no allocation, no copy of the input."""
+        w = _worlds(worlds)
+        assert out.dtype == np.float32 and out.flags["C_CONTIGUOUS"] and len(out) >= len(w)
         _abi.check(self._lib.ll_score_batch(self._ctx, _ptr(w), len(w), _ptr(out)))
         return out
 

@@ -3,6 +3,7 @@
 #include "../../include/leafline_b200.h"
 #include "ll_kernels.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -66,6 +67,7 @@ struct ll_ctx {
     void *pinned = nullptr; // small host staging
     size_t pinned_cap = 0;
     bool timing = false;
+    bool force_synced = false; // tests: always take the level-by-level path
     std::vector<TimedLaunch> timed;
     uint64_t launches = 0;
 };
@@ -151,7 +153,8 @@ int pinned(ll_ctx *ctx, size_t bytes) {
 
 // scalars buffer layout (u64 slots): 0 = first bad index, 1 = scan total, 2 = leaf total, 3 = leaves scored,
 // 8.. = per-root counts
-constexpr size_t SC_BAD = 0, SC_TOTAL = 1, SC_LEAVES = 2, SC_SCORED = 3, SC_PER_ROOT = 8, SC_SLOTS = 8 + 1024;
+constexpr size_t SC_BAD = 0, SC_TOTAL = 1, SC_LEAVES = 2, SC_SCORED = 3, SC_PER_ROOT = 8, SC_SPARE = 8 + 1024,
+                 SC_N = 1040 /* 64 device-resident level sizes */, SC_TILEQ = 1104 /* 64 u32 tile queues */, SC_OVERFLOW = 1136, SC_SLOTS = 1152;
 
 int upload_worlds(ll_ctx *ctx, const ll_world_t *worlds, size_t n, size_t level) {
     LL_TRY(reserve_level(ctx, level, n, false, false));
@@ -417,6 +420,37 @@ extern "C" int ll_timing_query(ll_ctx *ctx, const char *kernel, double *ms, uint
     return LL_OK;
 }
 extern "C" uint64_t ll_launch_count(ll_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int ll_debug_force_synced(ll_ctx *ctx, int on) {
+    LL_TRY(check_ctx(ctx));
+    ctx->force_synced = on != 0;
+    return LL_OK;
+}
+
+extern "C" int ll_measure_int_peak(ll_ctx *ctx, int kind, double *thread_ops_per_sec) {
+    LL_TRY(check_ctx(ctx));
+    if (!thread_ops_per_sec || kind < 0 || kind > 1) return fail(LL_ERR_INVALID_ARG, "bad argument");
+    const int iters = 4096, blocks = ctx->sm_count * 8, threads = 256;
+    u32 *out = (u32 *)((u64 *)ctx->scalars.ptr + SC_SPARE); // never written (see the kernel)
+    cudaEvent_t a, b;
+    CUDA_TRY(cudaEventCreate(&a));
+    CUDA_TRY(cudaEventCreate(&b));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        CUDA_TRY(cudaEventRecord(a, ctx->stream));
+        ctx->launches++;
+        if (kind == 0) k_int_peak<0><<<blocks, threads, 0, ctx->stream>>>(out, iters, 12345u + rep);
+        else k_int_peak<1><<<blocks, threads, 0, ctx->stream>>>(out, iters, 12345u + rep);
+        CUDA_TRY(cudaEventRecord(b, ctx->stream));
+        CUDA_TRY(cudaEventSynchronize(b));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+        if (rep && ms < best) best = ms;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *thread_ops_per_sec = (double)blocks * threads * iters * 16.0 / (best * 1e-3);
+    return LL_OK;
+}
 
 // ---- scoring -----------------------------------------------------------------------------------------
 
@@ -513,20 +547,116 @@ extern "C" int ll_in_critical_endangerment_batch(ll_ctx *ctx, const ll_world_t *
 
 // ---- perft -------------------------------------------------------------------------------------------
 
-extern "C" int ll_perft(ll_ctx *ctx, const ll_world_t *root, int depth, int shard_rank, int shard_world, uint64_t *leaves,
-                        uint64_t *per_root, uint32_t root_cap, uint32_t *n_roots) {
-    LL_TRY(check_ctx(ctx));
-    if (!root || !leaves) return fail(LL_ERR_INVALID_ARG, "null argument");
-    if (depth < 0 || depth > 32) return fail(LL_ERR_INVALID_ARG, "depth %d out of range", depth);
-    if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) return fail(LL_ERR_INVALID_ARG, "bad shard %d/%d", shard_rank, shard_world);
-    *leaves = 0;
-    if (n_roots) *n_roots = 0;
-    LL_TRY(upload_worlds(ctx, root, 1, 0));
-    LL_TRY(validate_level(ctx, ctx->levels[0].soa(), 1));
-    if (depth == 0) {
-        *leaves = shard_rank == 0 ? 1 : 0;
-        return LL_OK;
+
+// host-side argument check of a single root (domain W of the header); the batch entry points validate on the device
+static bool host_well_formed(const ll_world_t *w) {
+    uint64_t acc = 0;
+    for (int j = 0; j < 12; j++) {
+        if (acc & w->plane[j]) return false;
+        acc |= w->plane[j];
     }
+    if (__builtin_popcountll(w->plane[5]) > 1 || __builtin_popcountll(w->plane[11]) > 1) return false;
+    if (w->initiative > 1 || w->service_eligibility > 0xF) return false;
+    if ((w->service_eligibility & 0x3) && (w->plane[5] & ~(1ull << 4))) return false;
+    if ((w->service_eligibility & 0xC) && (w->plane[11] & ~(1ull << 60))) return false;
+    if (w->passing_by != 0xFF) {
+        const unsigned r = w->passing_by >> 4, f = w->passing_by & 0xF;
+        if (r > 7 || f > 7) return false;
+        const uint64_t bit = 1ull << (8 * r + f);
+        if (acc & bit) return false;
+        if (w->initiative == 0) {
+            if (r != 5 || !(w->plane[6] & (bit >> 8)) || (acc & (bit << 8))) return false;
+        } else {
+            if (r != 2 || !(w->plane[0] & (bit << 8)) || (acc & (bit >> 8))) return false;
+        }
+    }
+    return true;
+}
+
+// The chained path: the same levels, but every level's size stays on the device (ExpandArgs::n_in / n_out),
+// the kernels are persistent tile loops and children are placed by an atomic claim per tile (perft needs no
+// order) -- one launch chain, one synchronisation.  It runs inside the capacities the synced path has grown;
+// *done = false (nothing returned) when a level would not fit.
+static int perft_chained(ll_ctx *ctx, int depth, int shard_rank, int shard_world, uint64_t *leaves, uint64_t *per_root, uint32_t root_cap,
+                         uint32_t *n_roots, bool *done) {
+    *done = false;
+    const int tail_ply = depth - 2;
+    const int shard_ply = tail_ply < 2 ? tail_ply : 2;
+    const size_t need = (size_t)tail_ply + (shard_world > 1 ? 2 : 1);
+    if (ctx->levels.size() < need) return LL_OK;
+    for (size_t l = 0; l < need; l++)
+        if (!ctx->levels[l].cap) return LL_OK;
+    u64 *sc = (u64 *)ctx->scalars.ptr;
+    CUDA_TRY(cudaMemsetAsync(sc + SC_LEAVES, 0, (SC_SLOTS - SC_LEAVES) * sizeof(u64), ctx->stream));
+    u64 *N = sc + SC_N;
+    u32 *tileq = (u32 *)(sc + SC_TILEQ);
+    u32 *overflow = (u32 *)(sc + SC_OVERFLOW);
+    const unsigned resident = (unsigned)ctx->sm_count * LL_EXPAND_MIN_BLOCKS;
+    size_t l = 0;
+    int q = 0;
+    bool sharded = shard_world == 1;
+    for (int ply = 0; ply <= tail_ply; ply++) {
+        if (!sharded && ply == shard_ply) { // keep this rank's units (ply >= 1 here)
+            Frontier &f = ctx->levels[l];
+            Frontier &g = ctx->levels[l + 1];
+            const unsigned grid = (unsigned)std::min<size_t>(nblocks(f.cap), resident);
+            Timed t(ctx, "shard_filter");
+            k_shard_filter<<<grid, BLOCK, 0, ctx->stream>>>(f.soa(), (const u32 *)f.root.ptr, 0, N + l, g.soa(), (u32 *)g.root.ptr, N + l + 1, g.cap, overflow, shard_rank, shard_world);
+            LL_TRY(check_launch("k_shard_filter"));
+            l++;
+            sharded = true;
+        }
+        Frontier &f = ctx->levels[l];
+        ExpandArgs a{};
+        a.in = f.soa();
+        a.n = 1;
+        a.n_in = l == 0 ? nullptr : N + l;
+        a.tile_counter = tileq + q++;
+        a.root_in = ply == 0 ? nullptr : (const u32 *)f.root.ptr;
+        a.overflow = overflow;
+        const unsigned grid = l == 0 ? 1u : (unsigned)std::min<size_t>(nblocks(f.cap), resident);
+        if (ply == tail_ply) {
+            a.per_root = sc + SC_PER_ROOT;
+            a.total = sc + SC_LEAVES;
+            Timed t(ctx, "perft_tail");
+            k_expand<false, MODE_PERFT><<<grid, BLOCK, 0, ctx->stream>>>(a);
+            LL_TRY(check_launch("k_expand<PERFT>"));
+            break;
+        }
+        Frontier &g = ctx->levels[l + 1];
+        a.out = g.soa();
+        a.root_out = (u32 *)g.root.ptr;
+        a.root_is_index = ply == 0;
+        a.n_out = N + l + 1;
+        a.out_cap = g.cap;
+        a.overflow = overflow;
+        {
+            Timed t(ctx, "emit_legal");
+            k_expand<false, MODE_EMIT><<<grid, BLOCK, 0, ctx->stream>>>(a);
+        }
+        LL_TRY(check_launch("k_expand<EMIT>"));
+        l++;
+    }
+    LL_TRY(pinned(ctx, SC_SLOTS * sizeof(u64)));
+    u64 *host = (u64 *)ctx->pinned;
+    CUDA_TRY(cudaMemcpyAsync(host, sc, SC_SLOTS * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (*(u32 *)(host + SC_OVERFLOW)) return LL_OK; // a level outgrew its buffer: let the synced path size it
+    const u64 root_count = host[SC_N + 1];
+    if (root_count > 1024) return fail(LL_ERR_CAPACITY, "more than 1024 root moves");
+    *leaves = host[SC_LEAVES];
+    if (n_roots) *n_roots = (uint32_t)root_count;
+    if (per_root) {
+        if (root_count > root_cap) return fail(LL_ERR_CAPACITY, "%llu root moves do not fit root_cap %u", (unsigned long long)root_count, root_cap);
+        for (u64 i = 0; i < root_count; i++) per_root[i] = host[SC_PER_ROOT + i];
+    }
+    *done = true;
+    return LL_OK;
+}
+
+// the level-by-level path: every level's size comes back to the host, which sizes the next level exactly
+static int perft_synced(ll_ctx *ctx, int depth, int shard_rank, int shard_world, uint64_t *leaves, uint64_t *per_root, uint32_t root_cap,
+                        uint32_t *n_roots) {
     u64 *sc = (u64 *)ctx->scalars.ptr;
     CUDA_TRY(cudaMemsetAsync(sc + SC_LEAVES, 0, sizeof(u64), ctx->stream));
     CUDA_TRY(cudaMemsetAsync(sc + SC_PER_ROOT, 0, 1024 * sizeof(u64), ctx->stream));
@@ -547,7 +677,7 @@ extern "C" int ll_perft(ll_ctx *ctx, const ll_world_t *root, int depth, int shar
             if (kept) {
                 Timed t(ctx, "shard_filter");
                 k_shard_filter<<<(unsigned)nblocks(kept), BLOCK, 0, ctx->stream>>>(ctx->levels[l].soa(), (const u32 *)ctx->levels[l].root.ptr, ctx->levels[l].n,
-                                                                                  g.soa(), (u32 *)g.root.ptr, shard_rank, shard_world);
+                                                                                  nullptr, g.soa(), (u32 *)g.root.ptr, nullptr, 0, nullptr, shard_rank, shard_world);
                 LL_TRY(check_launch("k_shard_filter"));
             }
             g.n = kept;
@@ -599,6 +729,31 @@ extern "C" int ll_perft(ll_ctx *ctx, const ll_world_t *root, int depth, int shar
         for (u64 i = 0; i < root_count; i++) per_root[i] = depth == 1 ? 1 : host[1 + i];
     }
     return LL_OK;
+}
+
+extern "C" int ll_perft(ll_ctx *ctx, const ll_world_t *root, int depth, int shard_rank, int shard_world, uint64_t *leaves,
+                        uint64_t *per_root, uint32_t root_cap, uint32_t *n_roots) {
+    LL_TRY(check_ctx(ctx));
+    if (!root || !leaves) return fail(LL_ERR_INVALID_ARG, "null argument");
+    if (depth < 0 || depth > 32) return fail(LL_ERR_INVALID_ARG, "depth %d out of range", depth);
+    if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) return fail(LL_ERR_INVALID_ARG, "bad shard %d/%d", shard_rank, shard_world);
+    *leaves = 0;
+    if (n_roots) *n_roots = 0;
+    if (!host_well_formed(root)) return fail(LL_ERR_DOMAIN, "position 0 is not well-formed (see include/leafline_b200.h, domain W)");
+    LL_TRY(upload_worlds(ctx, root, 1, 0));
+    if (depth == 0) {
+        *leaves = shard_rank == 0 ? 1 : 0;
+        return LL_OK;
+    }
+    if (depth >= 3 && !ctx->force_synced) {
+        bool done = false;
+        LL_TRY(perft_chained(ctx, depth, shard_rank, shard_world, leaves, per_root, root_cap, n_roots, &done));
+        if (done) return LL_OK;
+        *leaves = 0;
+        if (n_roots) *n_roots = 0;
+        LL_TRY(upload_worlds(ctx, root, 1, 0)); // level 0 again: a failed chain may have left the scratch levels half-written
+    }
+    return perft_synced(ctx, depth, shard_rank, shard_world, leaves, per_root, root_cap, n_roots);
 }
 
 // ---- horizon / kickoff -------------------------------------------------------------------------------
@@ -681,7 +836,7 @@ extern "C" int ll_kickoff(ll_ctx *ctx, const ll_world_t *root, int depth, int ni
         if (kept) {
             Timed t(ctx, "shard_filter");
             k_shard_filter<<<(unsigned)nblocks(kept), BLOCK, 0, ctx->stream>>>(ctx->levels[1].soa(), (const u32 *)ctx->levels[1].root.ptr, ctx->levels[1].n,
-                                                                              h.soa(), (u32 *)h.root.ptr, shard_rank, shard_world);
+                                                                              nullptr, h.soa(), (u32 *)h.root.ptr, nullptr, 0, nullptr, shard_rank, shard_world);
             LL_TRY(check_launch("k_shard_filter"));
         }
         h.n = kept;

@@ -204,15 +204,20 @@ struct DescSink {
 
 struct ExpandArgs {
     Soa in;
-    size_t n;
+    size_t n;               // parents (ignored when n_in is set)
+    const u64 *n_in;        // device-resident parent count: the launch needs no host round trip
+    u32 *tile_counter;      // persistent blocks pull tiles from this queue (nullptr: tile = blockIdx.x)
     const u32 *counts;      // per-parent commit counts (nullptr: counted here)
-    const u64 *block_base;  // EMIT: first child index of each tile
+    const u64 *block_base;  // EMIT, canonical order: first child index of each tile (from the scan)
     const u32 *root_in;     // root-move id of each parent (nullable)
     // MODE_EMIT
     Soa out;
     u32 *cmeta;             // packed commit metadata (nullable)
     u32 *root_out;          // nullable
     int root_is_index;      // children become the roots: root id = own index
+    u64 *n_out;             // EMIT without block_base: tiles claim their output range here (order-free)
+    size_t out_cap;         // ... and raise *overflow instead of writing past this many children
+    u32 *overflow;
     // MODE_PERFT
     u64 *per_root, *total;
     // MODE_HORIZON
@@ -235,108 +240,146 @@ template <bool NIHIL, int MODE> __global__ void __launch_bounds__(BLOCK, LL_EXPA
     __shared__ u32 tile_meta[BLOCK];
     __shared__ u32 descs[DESC_CAP];
     __shared__ int acc[BLOCK]; // PERFT: leaves below each parent; HORIZON: best child key of each parent
+    __shared__ u64 claim_s;    // next tile / claimed output base
 
     const int tid = threadIdx.x;
-    const size_t i = (size_t)blockIdx.x * BLOCK + tid;
-    u32 cnt = 0;
-    if (i < a.n) { // the parent lives in the shared tile from here on, not in registers
-        const Pos p = soa_load(a.in, i);
-        cnt = a.counts ? a.counts[i] : count_moves<NIHIL>(p);
-#pragma unroll
-        for (int j = 0; j < 12; j++) tile_pl[j][tid] = p.pl[j];
-        tile_meta[tid] = p.meta;
-    }
-    if (MODE == MODE_PERFT) acc[tid] = 0;
-    if (MODE == MODE_HORIZON) acc[tid] = float_key(-INFINITY);
-    u32 total;
-    const u32 ex = block_exclusive_scan(cnt, &total); // also orders the tile writes before phase 2
-    const size_t out_base = MODE == MODE_EMIT ? (size_t)a.block_base[blockIdx.x] : 0;
-
-    for (u32 w0 = 0; w0 < total; w0 += DESC_CAP) {
-        if (cnt && ex < w0 + DESC_CAP && ex + cnt > w0) { // phase 1: this parent's commits into the window
-            DescSink sink{descs, ex, w0, w0 + DESC_CAP, (u32)tid << 20};
-            lookahead<NIHIL>(tile_load(tile_pl, tile_meta, tid), sink);
+    // chained launches: once a level has outgrown its buffer, its recorded size says nothing about what was
+    // written -- everything downstream stands down and the host redoes the call level by level
+    if (a.n_in && a.overflow && *(volatile u32 *)a.overflow) return;
+    const size_t n = a.n_in ? (size_t)*a.n_in : a.n;
+    for (;;) {
+        size_t tile = blockIdx.x;
+        if (a.tile_counter) {
+            if (tid == 0) claim_s = atomicAdd(a.tile_counter, 1u);
+            __syncthreads();
+            tile = (size_t)claim_s;
         }
-        __syncthreads();
-        const u32 wn = min((u32)DESC_CAP, total - w0);
-        for (u32 k0 = 0; k0 < wn; k0 += BLOCK) { // phase 2: one child per thread
-            const u32 k = k0 + tid;
-            const bool live = k < wn;
-            u32 slot = 0;
-            Pos c;
-            u32 m = 0, hosp = JOB_NONE;
-            if (live) {
-                m = descs[k];
-                slot = mv_slot(m);
-                hosp = make_child(tile_load(tile_pl, tile_meta, slot), m, c);
+        if (tile * BLOCK >= n) break;
+        const size_t i = tile * BLOCK + tid;
+        u32 cnt = 0;
+        if (i < n) { // the parent lives in the shared tile from here on, not in registers
+            const Pos p = soa_load(a.in, i);
+            cnt = a.counts ? a.counts[i] : count_moves<NIHIL>(p);
+#pragma unroll
+            for (int j = 0; j < 12; j++) tile_pl[j][tid] = p.pl[j];
+            tile_meta[tid] = p.meta;
+        }
+        if (MODE == MODE_PERFT) acc[tid] = 0;
+        if (MODE == MODE_HORIZON) acc[tid] = float_key(-INFINITY);
+        u32 total;
+        const u32 ex = block_exclusive_scan(cnt, &total); // also orders the tile writes before phase 2
+        size_t out_base = 0;
+        bool writable = true;
+        if (MODE == MODE_EMIT) {
+            if (a.block_base) {
+                out_base = (size_t)a.block_base[tile];
+            } else { // order-free: claim a contiguous range for this tile's children
+                if (tid == 0) claim_s = atomicAdd((unsigned long long *)a.n_out, (unsigned long long)total);
+                __syncthreads();
+                out_base = (size_t)claim_s;
+                writable = out_base + total <= a.out_cap;
+                if (!writable && tid == 0) atomicExch(a.overflow, 1u);
             }
-            if (MODE == MODE_EMIT) {
+        }
+
+        for (u32 w0 = 0; w0 < total && writable; w0 += DESC_CAP) {
+            if (cnt && ex < w0 + DESC_CAP && ex + cnt > w0) { // phase 1: this parent's commits into the window
+                DescSink sink{descs, ex, w0, w0 + DESC_CAP, (u32)tid << 20};
+                lookahead<NIHIL>(tile_load(tile_pl, tile_meta, tid), sink);
+            }
+            __syncthreads();
+            const u32 wn = min((u32)DESC_CAP, total - w0);
+            for (u32 k0 = 0; k0 < wn; k0 += BLOCK) { // phase 2: one child per thread
+                const u32 k = k0 + tid;
+                const bool live = k < wn;
+                u32 slot = 0;
+                Pos c;
+                u32 m = 0, hosp = JOB_NONE;
                 if (live) {
-                    const size_t o = out_base + w0 + k;
-                    soa_store(a.out, o, c);
-                    if (a.cmeta) a.cmeta[o] = pack_commit(meta_stm(c.meta) ^ 1u, m, hosp);
-                    if (a.root_out) a.root_out[o] = a.root_is_index ? (u32)o : a.root_in[(size_t)blockIdx.x * BLOCK + slot];
+                    m = descs[k];
+                    slot = mv_slot(m);
+                    hosp = make_child(tile_load(tile_pl, tile_meta, slot), m, c);
                 }
-            } else {
-                int v = 0;
-                if (MODE == MODE_PERFT) {
-                    if (live) v = (int)count_moves<false>(c);
-                } else {
-                    v = float_key(-INFINITY);
+                if (MODE == MODE_EMIT) {
                     if (live) {
-                        const float s = score(c);
-                        v = float_key(meta_stm(c.meta) ? s : -s); // -(orientation(child) * score(child)), mind.rs:283, 331-336
+                        const size_t o = out_base + w0 + k;
+                        soa_store(a.out, o, c);
+                        if (a.cmeta) a.cmeta[o] = pack_commit(meta_stm(c.meta) ^ 1u, m, hosp);
+                        if (a.root_out) a.root_out[o] = a.root_is_index ? (u32)o : a.root_in[tile * BLOCK + slot];
+                    }
+                } else {
+                    int v = 0;
+                    if (MODE == MODE_PERFT) {
+                        if (live) v = (int)count_moves<false>(c);
+                    } else {
+                        v = float_key(-INFINITY);
+                        if (live) {
+                            const float s = score(c);
+                            v = float_key(meta_stm(c.meta) ? s : -s); // -(orientation(child) * score(child)), mind.rs:283, 331-336
+                        }
+                    }
+                    // children of one parent are neighbours in the list: reduce per parent inside the warp first
+                    const unsigned peers = __match_any_sync(0xffffffffu, live ? slot : 0xFFFFFFFFu);
+                    const int r = MODE == MODE_PERFT ? __reduce_add_sync(peers, v) : __reduce_max_sync(peers, v);
+                    if (live && (tid & 31) == __ffs((int)peers) - 1) {
+                        if (MODE == MODE_PERFT) atomicAdd(&acc[slot], r);
+                        else atomicMax(&acc[slot], r);
                     }
                 }
-                // children of one parent are neighbours in the list: reduce per parent inside the warp first
-                const unsigned peers = __match_any_sync(0xffffffffu, live ? slot : 0xFFFFFFFFu);
-                const int r = MODE == MODE_PERFT ? __reduce_add_sync(peers, v) : __reduce_max_sync(peers, v);
-                if (live && (tid & 31) == __ffs((int)peers) - 1) {
-                    if (MODE == MODE_PERFT) atomicAdd(&acc[slot], r);
-                    else atomicMax(&acc[slot], r);
-                }
             }
+            __syncthreads();
         }
-        __syncthreads();
-    }
 
-    if (MODE == MODE_PERFT) {
-        // tile order keeps a root's nodes contiguous, so a warp sees very few distinct roots
-        const u32 root = i < a.n ? (a.root_in ? a.root_in[i] : 0u) : 0xFFFFFFFFu;
-        const u32 mine = i < a.n ? (u32)acc[tid] : 0u;
-        const unsigned peers = __match_any_sync(0xffffffffu, root);
-        const u32 sum = __reduce_add_sync(peers, mine);
-        if ((tid & 31) == __ffs((int)peers) - 1 && root != 0xFFFFFFFFu && sum) {
-            if (a.per_root) atomicAdd(a.per_root + root, (u64)sum);
-            atomicAdd(a.total, (u64)sum);
-        }
-    }
-    if (MODE == MODE_HORIZON) {
-        u32 scored = 0;
-        if (i < a.n) {
-            float v;
-            if (cnt == 0) { // no pseudo-legal move: the node is itself a leaf (mind.rs:281-283)
-                const Pos p = tile_load(tile_pl, tile_meta, tid);
-                const float s = score(p);
-                v = meta_stm(p.meta) ? -s : s;
-            } else {
-                v = key_float(acc[tid]);
+        if (MODE == MODE_PERFT) {
+            // tile order keeps a root's nodes contiguous, so a warp sees very few distinct roots
+            const u32 root = i < n ? (a.root_in ? a.root_in[i] : 0u) : 0xFFFFFFFFu;
+            const u32 mine = i < n ? (u32)acc[tid] : 0u;
+            const unsigned peers = __match_any_sync(0xffffffffu, root);
+            const u32 sum = __reduce_add_sync(peers, mine);
+            if ((tid & 31) == __ffs((int)peers) - 1 && root != 0xFFFFFFFFu && sum) {
+                if (a.per_root) atomicAdd((unsigned long long *)a.per_root + root, (unsigned long long)sum);
+                atomicAdd((unsigned long long *)a.total, (unsigned long long)sum);
             }
-            a.values[i] = v;
-            scored = cnt ? cnt : 1u;
         }
-        scored = __reduce_add_sync(0xffffffffu, scored);
-        if ((tid & 31) == 0 && scored && a.scored) atomicAdd(a.scored, (u64)scored);
+        if (MODE == MODE_HORIZON) {
+            u32 scored = 0;
+            if (i < n) {
+                float v;
+                if (cnt == 0) { // no pseudo-legal move: the node is itself a leaf (mind.rs:281-283)
+                    const Pos p = tile_load(tile_pl, tile_meta, tid);
+                    const float s = score(p);
+                    v = meta_stm(p.meta) ? -s : s;
+                } else {
+                    v = key_float(acc[tid]);
+                }
+                a.values[i] = v;
+                scored = cnt ? cnt : 1u;
+            }
+            scored = __reduce_add_sync(0xffffffffu, scored);
+            if ((tid & 31) == 0 && scored && a.scored) atomicAdd((unsigned long long *)a.scored, (unsigned long long)scored);
+        }
+        if (!a.tile_counter) break;
+        __syncthreads(); // the tile and the claim slot are reused by the next round
     }
 }
 
-// keep the units u with u % world == rank (frontier sharding by subtree)
-__global__ void __launch_bounds__(BLOCK) k_shard_filter(Soa in, const u32 *__restrict__ root_in, size_t n, Soa out, u32 *__restrict__ root_out, int rank, int world) {
-    const size_t o = (size_t)blockIdx.x * BLOCK + threadIdx.x; // o-th kept unit = unit rank + o*world
-    const size_t i = (size_t)rank + o * (size_t)world;
-    if (i >= n) return;
-    soa_store(out, o, soa_load(in, i));
-    root_out[o] = root_in ? root_in[i] : 0u;
+// keep the units u with u % world == rank (frontier sharding by subtree).  n_in / n_out
+// (nullable) are device-resident counts for the launch chain that never returns to the host.
+__global__ void __launch_bounds__(BLOCK) k_shard_filter(Soa in, const u32 *__restrict__ root_in, size_t n, const u64 *n_in, Soa out,
+                                                        u32 *__restrict__ root_out, u64 *n_out, size_t out_cap, u32 *overflow, int rank, int world) {
+    if (n_in && overflow && *(volatile u32 *)overflow) return;
+    if (n_in) n = (size_t)*n_in;
+    size_t kept = n > (size_t)rank ? (n - rank + world - 1) / world : 0;
+    if (overflow && kept > out_cap) { // the chained path: report instead of writing past the level
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(overflow, 1u);
+        kept = 0;
+    }
+    if (n_out && blockIdx.x == 0 && threadIdx.x == 0) *n_out = kept;
+    for (size_t o = (size_t)blockIdx.x * BLOCK + threadIdx.x; o < kept; o += (size_t)gridDim.x * BLOCK) { // o-th kept unit = unit rank + o*world
+        const size_t i = (size_t)rank + o * (size_t)world;
+        soa_store(out, o, soa_load(in, i));
+        root_out[o] = root_in ? root_in[i] : 0u;
+    }
 }
 
 // ---- perft tail on an already materialised frontier: count the legal moves of every node ---------------
@@ -441,4 +484,28 @@ __global__ void __launch_bounds__(BLOCK) k_playout(u64 seed, u64 first_index, si
     soa_store(out, i, p);
 }
 
+} // namespace ll
+
+// ---- integer-issue microbenchmark (measurement utility for bench.py's integer roofline) ---------------
+// 16 independent chains per thread; KIND 0: one LOP3 per chain step (ALU pipe only), KIND 1: LOP3 + IMAD
+// alternating (ALU + FMA pipes, the best case for the issue port).  Returns nothing useful in `out`.
+namespace ll {
+template <int KIND> __global__ void __launch_bounds__(256) k_int_peak(u32 *out, int iters, u32 seed) {
+    u32 a[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) a[j] = seed * (threadIdx.x + 1) + j * 0x9E3779B9u;
+    const u32 b = seed | 0x10001u, c = ~seed;
+#pragma unroll 8
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) { // exactly one SASS instruction per chain step
+            if (KIND == 0 || (j & 1) == 0) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[j]) : "r"(a[(j + 1) & 15]), "r"(b));
+            else asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[j]) : "r"(c), "r"(a[(j + 1) & 15]));
+        }
+    }
+    u32 r = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) r ^= a[j];
+    if (r == 0x12345678u) out[0] = r; // keeps the chains alive
+}
 } // namespace ll
