@@ -169,6 +169,7 @@ def main():
     if world > 1:
         dist.barrier()
     import leafline_b200 as ll
+    from leafline_b200 import sharding
 
     eng = ll.Engine(local_rank)
     # a real (non-default) stream: the engine launches on it, so the CUDA events below see its kernels
@@ -181,15 +182,10 @@ def main():
     expected = PERFT_OPENING.get(depth)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     counts = torch.zeros(1024, dtype=torch.int64, device="cuda")
-    pinned_counts = torch.zeros(1024, dtype=torch.int64).pin_memory()
 
     def reduce_counts(per_root):
-        """u64 all-reduce (sum) of the per-root leaf counts; two's-complement i64 on the wire"""
-        pinned_counts.zero_()
-        pinned_counts[: len(per_root)] = torch.from_numpy(per_root.view(np.int64))
-        counts.copy_(pinned_counts, non_blocking=True)
-        dist.all_reduce(counts)
-        return int(counts.sum().item())
+        """u64 all-reduce (sum) of the per-root leaf counts over NCCL (leafline_b200/sharding.py)"""
+        return sharding.reduce_leaf_counts(per_root, dist, torch, device="cuda", scratch=counts)[0]
 
     def step():
         """one perft per GPU (this rank's root of the batch) + the count all-reduce"""
