@@ -187,10 +187,21 @@ def main():
         """u64 all-reduce (sum) of the per-root leaf counts over NCCL (leafline_b200/sharding.py)"""
         return sharding.reduce_leaf_counts(per_root, dist, torch, device="cuda", scratch=counts)[0]
 
+    d_out = torch.zeros(ll.PERFT_DEVICE_WORDS, dtype=torch.int64, device="cuda")
+    h_out = torch.zeros(ll.PERFT_DEVICE_WORDS, dtype=torch.int64).pin_memory()
+
     def step():
         """one perft per GPU (this rank's root of the batch) + the count all-reduce"""
-        leaves, per_root = eng.perft(root, depth)
-        return reduce_counts(per_root) if world > 1 else leaves
+        if world == 1:
+            return eng.perft(root, depth)[0]
+        # counts stay on the device: launch chain -> NCCL u64 sum -> one D2H read of the reduced table
+        eng.perft_device(root, depth, d_out.data_ptr())
+        dist.all_reduce(d_out)
+        h_out.copy_(d_out, non_blocking=True)
+        stream.synchronize()
+        if int(h_out[2]) != 0:  # some rank's level outgrew its buffer: redo through the re-sizing host path
+            return reduce_counts(eng.perft(root, depth)[1])
+        return int(h_out[0])
 
     for _ in range(args.warmup):
         total = step()
@@ -261,6 +272,31 @@ def main():
         ms7 = float(t7.item())
         result["perft7_strong"] = {"leaves": PERFT_OPENING[7], "ms": ms7, "leaf_positions_per_sec": PERFT_OPENING[7] / (ms7 * 1e-3),
                                    "scaling": "strong", "sharding": f"2-ply prefixes round-robin over {world} rank(s)"}
+
+    # configs[3]: depth-5 search from the opening (TT-free exact negamax below every root move), root moves
+    # dealt to the ranks, per-root scores gathered with a max over NCCL
+    if not args.no_extras:
+        def kickoff5():
+            roots, scores, scored = eng.kickoff(root, 5, shard=(rank, world))
+            if world > 1:
+                scores = sharding.gather_root_scores(scores, dist, torch, device="cuda")
+            return scores, scored
+
+        scores5, scored5 = kickoff5()
+        if world > 1:
+            dist.barrier()
+        ms5 = timed(stream, kickoff5, 3, torch)
+        t5 = torch.tensor([ms5, float(scored5)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            tmax = t5.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t5, op=dist.ReduceOp.SUM)
+            ms5, scored_all = float(tmax[0].item()), int(t5[1].item())
+        else:
+            scored_all = scored5
+        result["kickoff5"] = {"depth": 5, "root_moves": len(scores5), "best_score": float(np.max(scores5)), "leaves_scored": scored_all,
+                              "ms": ms5, "leaf_positions_per_sec": scored_all / (ms5 * 1e-3), "scaling": "strong",
+                              "sharding": f"root moves round-robin over {world} rank(s); max-gather of per-root f32 scores"}
 
     if rank == 0 and world == 1 and not args.no_extras:
         peaks, peak_src = measured_peaks()

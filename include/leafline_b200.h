@@ -103,6 +103,14 @@ int ll_in_critical_endangerment_batch(ll_ctx *ctx, const ll_world_t *worlds, con
 int ll_perft(ll_ctx *ctx, const ll_world_t *root, int depth, int shard_rank, int shard_world, uint64_t *leaves,
              uint64_t *per_root, uint32_t root_cap, uint32_t *n_roots);
 
+/* ll_perft without the host round trip, for callers that reduce the counts on the device (NCCL): the whole
+ * launch chain is enqueued on the context's stream and the results are left in DEVICE memory,
+ * d_out[LL_PERFT_DEVICE_WORDS] u64: [0] leaves, [1] number of root moves, [2] non-zero if a level outgrew
+ * its buffer (the other words are then meaningless: call ll_perft, which re-sizes), [8 + i] leaves below root
+ * move i.  Asynchronous.  depth >= 3; needs one earlier ll_perft call of this depth (LL_ERR_CAPACITY otherwise). */
+#define LL_PERFT_DEVICE_WORDS (8 + 1024)
+int ll_perft_device(ll_ctx *ctx, const ll_world_t *root, int depth, int shard_rank, int shard_world, uint64_t *d_out);
+
 /* replaces the leaf / horizon rule of `α_β_negamax_search` (src/mind.rs:279-287, quiet = None) for
  * n frontier nodes: values[i] = exact negamax value of frontier[i] for its side to move over
  * `plies` plies of reckless_lookahead() children with orientation * score leaves. */

@@ -31,6 +31,7 @@ ORANGE, BLUE = 0, 1
 SERVANT, PONY, SCHOLAR, COP, PRINCESS, FIGUREHEAD = range(6)
 NONE = 0xFF
 PLAYOUT_SEED = 0x1EAF11E
+PERFT_DEVICE_WORDS = 8 + 1024
 
 
 def locale(rank, file):
@@ -181,6 +182,12 @@ class Engine:
             self._lib.ll_perft(self._ctx, _ptr(w), depth, shard[0], shard[1], C.byref(leaves), _ptr(per_root), 1024, C.byref(n_roots))
         )
         return int(leaves.value), per_root[: n_roots.value].copy()
+
+    def perft_device(self, world, depth, d_out_ptr, shard=(0, 1)):
+        """Asynchronous perft whose counts stay in DEVICE memory (u64[PERFT_DEVICE_WORDS] at d_out_ptr:
+        [0] leaves, [1] root moves, [2] overflow flag, [8+i] per-root) -- for an on-device all-reduce."""
+        w = _worlds(world)
+        _abi.check(self._lib.ll_perft_device(self._ctx, _ptr(w), depth, shard[0], shard[1], C.c_void_p(d_out_ptr)))
 
     def horizon(self, worlds, plies):
         """Exact negamax value of each frontier node over `plies` reckless plies (mind.rs:279-287)."""

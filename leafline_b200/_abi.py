@@ -47,6 +47,7 @@ SIGNATURES = {
     "ll_lookahead_batch": ([_vp, _vp, _sz, _i, _vp, _vp, _sz], _i),
     "ll_in_critical_endangerment_batch": ([_vp, _vp, _vp, _sz, _vp], _i),
     "ll_perft": ([_vp, _vp, _i, _i, _i, C.POINTER(_u64), _vp, C.c_uint32, C.POINTER(C.c_uint32)], _i),
+    "ll_perft_device": ([_vp, _vp, _i, _i, _i, _vp], _i),
     "ll_horizon_batch": ([_vp, _vp, _sz, _i, _vp], _i),
     "ll_kickoff": ([_vp, _vp, _i, _i, _i, _i, _vp, _vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(_u64)], _i),
     "ll_soa_alloc": ([_vp, _sz, C.POINTER(Soa)], _i),

@@ -577,9 +577,8 @@ static bool host_well_formed(const ll_world_t *w) {
 // the kernels are persistent tile loops and children are placed by an atomic claim per tile (perft needs no
 // order) -- one launch chain, one synchronisation.  It runs inside the capacities the synced path has grown;
 // *done = false (nothing returned) when a level would not fit.
-static int perft_chained(ll_ctx *ctx, int depth, int shard_rank, int shard_world, uint64_t *leaves, uint64_t *per_root, uint32_t root_cap,
-                         uint32_t *n_roots, bool *done) {
-    *done = false;
+static int perft_chain_launch(ll_ctx *ctx, int depth, int shard_rank, int shard_world, bool *launched) {
+    *launched = false;
     const int tail_ply = depth - 2;
     const int shard_ply = tail_ply < 2 ? tail_ply : 2;
     const size_t need = (size_t)tail_ply + (shard_world > 1 ? 2 : 1);
@@ -637,6 +636,17 @@ static int perft_chained(ll_ctx *ctx, int depth, int shard_rank, int shard_world
         LL_TRY(check_launch("k_expand<EMIT>"));
         l++;
     }
+    *launched = true;
+    return LL_OK;
+}
+
+static int perft_chained(ll_ctx *ctx, int depth, int shard_rank, int shard_world, uint64_t *leaves, uint64_t *per_root, uint32_t root_cap,
+                         uint32_t *n_roots, bool *done) {
+    *done = false;
+    bool launched = false;
+    LL_TRY(perft_chain_launch(ctx, depth, shard_rank, shard_world, &launched));
+    if (!launched) return LL_OK;
+    u64 *sc = (u64 *)ctx->scalars.ptr;
     LL_TRY(pinned(ctx, SC_SLOTS * sizeof(u64)));
     u64 *host = (u64 *)ctx->pinned;
     CUDA_TRY(cudaMemcpyAsync(host, sc, SC_SLOTS * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
@@ -754,6 +764,24 @@ extern "C" int ll_perft(ll_ctx *ctx, const ll_world_t *root, int depth, int shar
         LL_TRY(upload_worlds(ctx, root, 1, 0)); // level 0 again: a failed chain may have left the scratch levels half-written
     }
     return perft_synced(ctx, depth, shard_rank, shard_world, leaves, per_root, root_cap, n_roots);
+}
+
+extern "C" int ll_perft_device(ll_ctx *ctx, const ll_world_t *root, int depth, int shard_rank, int shard_world, uint64_t *d_out) {
+    LL_TRY(check_ctx(ctx));
+    if (!root || !d_out) return fail(LL_ERR_INVALID_ARG, "null argument");
+    if (depth < 3 || depth > 32) return fail(LL_ERR_INVALID_ARG, "depth %d out of range (3..32)", depth);
+    if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) return fail(LL_ERR_INVALID_ARG, "bad shard %d/%d", shard_rank, shard_world);
+    if (!host_well_formed(root)) return fail(LL_ERR_DOMAIN, "position 0 is not well-formed (see include/leafline_b200.h, domain W)");
+    LL_TRY(upload_worlds(ctx, root, 1, 0));
+    bool launched = false;
+    LL_TRY(perft_chain_launch(ctx, depth, shard_rank, shard_world, &launched));
+    if (!launched) return fail(LL_ERR_CAPACITY, "level buffers are not sized yet: call ll_perft once for this depth first");
+    u64 *sc = (u64 *)ctx->scalars.ptr;
+    {
+        Timed t(ctx, "pack_perft_result");
+        k_pack_perft_result<<<1, 1024, 0, ctx->stream>>>(sc + SC_LEAVES, sc + SC_N + 1, (const u32 *)(sc + SC_OVERFLOW), sc + SC_PER_ROOT, (u64 *)d_out);
+    }
+    return check_launch("k_pack_perft_result");
 }
 
 // ---- horizon / kickoff -------------------------------------------------------------------------------

@@ -382,6 +382,13 @@ __global__ void __launch_bounds__(BLOCK) k_shard_filter(Soa in, const u32 *__res
     }
 }
 
+// ll_perft_device: gather the chain's results into the caller's device buffer (see the header for the layout)
+__global__ void __launch_bounds__(1024) k_pack_perft_result(const u64 *leaves, const u64 *n_roots, const u32 *overflow, const u64 *per_root, u64 *out) {
+    const int t = threadIdx.x;
+    out[8 + t] = per_root[t];
+    if (t < 8) out[t] = t == 0 ? *leaves : t == 1 ? *n_roots : t == 2 ? (u64)*overflow : 0ull;
+}
+
 // ---- perft tail on an already materialised frontier: count the legal moves of every node ---------------
 __global__ void __launch_bounds__(BLOCK) k_count_leaves(Soa in, size_t n, const u32 *__restrict__ root_in, u64 *__restrict__ per_root, u64 *__restrict__ total) {
     const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;

@@ -254,6 +254,24 @@ def test_perft_launch_chain_equals_level_by_level_path(eng):
     assert eng.perft(ll.reconstruct(KIWIPETE), 3)[0] == 97814
 
 
+def test_perft_device_resident_counts(eng):
+    import torch
+
+    import leafline_b200 as ll
+
+    out = torch.zeros(ll.PERFT_DEVICE_WORDS, dtype=torch.int64, device="cuda")
+    for fen, depth, shard in ((OPENING, 5, (0, 1)), (KIWIPETE, 4, (0, 1)), (KIWIPETE, 4, (1, 2))):
+        w = ll.reconstruct(fen)
+        leaves, per_root = eng.perft(w, depth, shard=shard)  # also sizes the level buffers
+        eng.perft_device(w, depth, out.data_ptr(), shard=shard)
+        eng.synchronize()
+        got = out.cpu().numpy().view(np.uint64)
+        assert got[2] == 0 and got[0] == leaves and got[1] == len(per_root)
+        assert list(got[8:8 + len(per_root)]) == list(per_root)
+    with pytest.raises(ll.LeaflineError):
+        ll.Engine(0).perft_device(ll.new_world(), 5, out.data_ptr())  # a fresh context has no level buffers yet
+
+
 @pytest.mark.parametrize("world_size", [2, 3, 8])
 def test_perft_shards_sum_to_the_whole(eng, world_size):
     import leafline_b200 as ll
