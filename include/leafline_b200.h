@@ -111,16 +111,19 @@ int ll_perft(ll_ctx *ctx, const ll_world_t *root, int depth, int shard_rank, int
 #define LL_PERFT_DEVICE_WORDS (8 + 1024)
 int ll_perft_device(ll_ctx *ctx, const ll_world_t *root, int depth, int shard_rank, int shard_world, uint64_t *d_out);
 
-/* replaces the leaf / horizon rule of `α_β_negamax_search` (src/mind.rs:279-287, quiet = None) for
- * n frontier nodes: values[i] = exact negamax value of frontier[i] for its side to move over
- * `plies` plies of reckless_lookahead() children with orientation * score leaves. */
-int ll_horizon_batch(ll_ctx *ctx, const ll_world_t *frontier, size_t n, int plies, float *values);
+/* replaces the leaf / horizon rule of `α_β_negamax_search` (src/mind.rs:279-301) for n frontier nodes:
+ * values[i] = exact negamax value of frontier[i] for its side to move over `plies` plies of
+ * reckless_lookahead() children with orientation * score leaves.  quiet_extension < 0 is `quiet = None`;
+ * quiet_extension = e >= 0 is `quiet = Some(e)`: below depth 0 the search continues for up to e plies over the
+ * commits that hospitalize somebody, every such node being free to stand pat (src/mind.rs:288-300). */
+int ll_horizon_batch(ll_ctx *ctx, const ll_world_t *frontier, size_t n, int plies, int quiet_extension, float *values);
 
-/* replaces `kickoff` (src/mind.rs:375-448) without TT / history / threads: roots = lookahead()
+/* replaces `kickoff(world, depth, extension, nihilistically, ..)` (src/mind.rs:375-448) without TT / history /
+ * threads (quiet_extension as in ll_horizon_batch): roots = lookahead()
  * (or reckless_lookahead() if nihilistically), scores[i] = -value(child_i, depth-1), canonical
  * (unsorted) order.  With shard_world > 1 only roots i % shard_world == shard_rank are searched;
  * the others get -INFINITY (gather with a max). */
-int ll_kickoff(ll_ctx *ctx, const ll_world_t *root, int depth, int nihilistically, int shard_rank, int shard_world,
+int ll_kickoff(ll_ctx *ctx, const ll_world_t *root, int depth, int quiet_extension, int nihilistically, int shard_rank, int shard_world,
                ll_commit_t *roots, float *scores, uint32_t root_cap, uint32_t *n_roots, uint64_t *leaves_scored);
 
 /* ---- device-resident positions (structure-of-arrays u64 planes in HBM) ---------------------- */
@@ -142,7 +145,7 @@ int ll_soa_download(ll_ctx *ctx, const ll_soa_t *src, size_t first, size_t n, ll
 /* scores[i] for the positions already resident in HBM; d_scores is a DEVICE pointer. Asynchronous. */
 int ll_score_soa(ll_ctx *ctx, const ll_soa_t *soa, float *d_scores);
 /* horizon values for resident positions; d_values is a DEVICE pointer. */
-int ll_horizon_soa(ll_ctx *ctx, const ll_soa_t *soa, int plies, float *d_values, uint64_t *leaves_scored);
+int ll_horizon_soa(ll_ctx *ctx, const ll_soa_t *soa, int plies, int quiet_extension, float *d_values, uint64_t *leaves_scored);
 /* seeded random-playout positions first_index .. first_index+n-1 of the set defined in DESIGN.md
  * (SURVEY.md 8(d) config 3), generated on the device. */
 int ll_playout_soa(ll_ctx *ctx, uint64_t seed, uint64_t first_index, size_t n, ll_soa_t *dst);

@@ -189,14 +189,15 @@ class Engine:
         w = _worlds(world)
         _abi.check(self._lib.ll_perft_device(self._ctx, _ptr(w), depth, shard[0], shard[1], C.c_void_p(d_out_ptr)))
 
-    def horizon(self, worlds, plies):
-        """Exact negamax value of each frontier node over `plies` reckless plies (mind.rs:279-287)."""
+    def horizon(self, worlds, plies, quiet=None):
+        """Exact negamax value of each frontier node over `plies` reckless plies (mind.rs:279-301);
+        quiet = None or the quiescence extension (mind.rs:284-300)."""
         w = _worlds(worlds)
         out = np.empty(len(w), dtype=np.float32)
-        _abi.check(self._lib.ll_horizon_batch(self._ctx, _ptr(w), len(w), plies, _ptr(out)))
+        _abi.check(self._lib.ll_horizon_batch(self._ctx, _ptr(w), len(w), plies, -1 if quiet is None else int(quiet), _ptr(out)))
         return out
 
-    def kickoff(self, world, depth, nihilistically=False, shard=(0, 1)):
+    def kickoff(self, world, depth, nihilistically=False, shard=(0, 1), quiet=None):
         """mind::kickoff without TT/history: (root commits, root scores, leaves scored), canonical order."""
         w = _worlds(world)
         roots = np.zeros(1024, dtype=COMMIT_DTYPE)
@@ -204,7 +205,7 @@ class Engine:
         n_roots, scored = C.c_uint32(0), C.c_uint64(0)
         _abi.check(
             self._lib.ll_kickoff(
-                self._ctx, _ptr(w), depth, int(nihilistically), shard[0], shard[1], _ptr(roots), _ptr(scores), 1024,
+                self._ctx, _ptr(w), depth, -1 if quiet is None else int(quiet), int(nihilistically), shard[0], shard[1], _ptr(roots), _ptr(scores), 1024,
                 C.byref(n_roots), C.byref(scored),
             )
         )
@@ -236,9 +237,9 @@ class Engine:
         """Asynchronous: scores of resident positions into the DEVICE buffer at d_scores_ptr."""
         _abi.check(self._lib.ll_score_soa(self._ctx, C.byref(soa), C.c_void_p(d_scores_ptr)))
 
-    def horizon_soa(self, soa, plies, d_values_ptr):
+    def horizon_soa(self, soa, plies, d_values_ptr, quiet=None):
         scored = C.c_uint64(0)
-        _abi.check(self._lib.ll_horizon_soa(self._ctx, C.byref(soa), plies, C.c_void_p(d_values_ptr), C.byref(scored)))
+        _abi.check(self._lib.ll_horizon_soa(self._ctx, C.byref(soa), plies, -1 if quiet is None else int(quiet), C.c_void_p(d_values_ptr), C.byref(scored)))
         return int(scored.value)
 
     def playout_soa(self, n, seed=PLAYOUT_SEED, first_index=0, soa=None):

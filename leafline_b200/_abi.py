@@ -48,14 +48,14 @@ SIGNATURES = {
     "ll_in_critical_endangerment_batch": ([_vp, _vp, _vp, _sz, _vp], _i),
     "ll_perft": ([_vp, _vp, _i, _i, _i, C.POINTER(_u64), _vp, C.c_uint32, C.POINTER(C.c_uint32)], _i),
     "ll_perft_device": ([_vp, _vp, _i, _i, _i, _vp], _i),
-    "ll_horizon_batch": ([_vp, _vp, _sz, _i, _vp], _i),
-    "ll_kickoff": ([_vp, _vp, _i, _i, _i, _i, _vp, _vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(_u64)], _i),
+    "ll_horizon_batch": ([_vp, _vp, _sz, _i, _i, _vp], _i),
+    "ll_kickoff": ([_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(_u64)], _i),
     "ll_soa_alloc": ([_vp, _sz, C.POINTER(Soa)], _i),
     "ll_soa_free": ([_vp, C.POINTER(Soa)], _i),
     "ll_soa_upload": ([_vp, _vp, _sz, C.POINTER(Soa)], _i),
     "ll_soa_download": ([_vp, C.POINTER(Soa), _sz, _sz, _vp], _i),
     "ll_score_soa": ([_vp, C.POINTER(Soa), _vp], _i),
-    "ll_horizon_soa": ([_vp, C.POINTER(Soa), _i, _vp, C.POINTER(_u64)], _i),
+    "ll_horizon_soa": ([_vp, C.POINTER(Soa), _i, _i, _vp, C.POINTER(_u64)], _i),
     "ll_playout_soa": ([_vp, _u64, _u64, _sz, C.POINTER(Soa)], _i),
     "ll_timing_enable": ([_vp, _i], _i),
     "ll_timing_reset": ([_vp], _i),

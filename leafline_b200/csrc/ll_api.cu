@@ -188,7 +188,7 @@ int validate_level(ll_ctx *ctx, const Soa &soa, size_t n) {
 }
 
 // count the commits of every node of level l (counts + block bases stay on the device); returns the total
-int count_level(ll_ctx *ctx, size_t l, bool nihil, u64 *total_out) {
+int count_level(ll_ctx *ctx, size_t l, bool nihil, u64 *total_out, bool stuns_only = false) {
     Frontier &f = ctx->levels[l];
     *total_out = 0;
     if (!f.n) return LL_OK;
@@ -196,8 +196,8 @@ int count_level(ll_ctx *ctx, size_t l, bool nihil, u64 *total_out) {
     u64 *sc = (u64 *)ctx->scalars.ptr;
     {
         Timed t(ctx, nihil ? "count_reckless" : "count_legal");
-        if (nihil) k_count<true><<<(unsigned)nb, BLOCK, 0, ctx->stream>>>(f.soa(), f.n, (u32 *)f.counts.ptr, (u32 *)f.block_sums.ptr);
-        else k_count<false><<<(unsigned)nb, BLOCK, 0, ctx->stream>>>(f.soa(), f.n, (u32 *)f.counts.ptr, (u32 *)f.block_sums.ptr);
+        if (nihil) k_count<true><<<(unsigned)nb, BLOCK, 0, ctx->stream>>>(f.soa(), f.n, (u32 *)f.counts.ptr, (u32 *)f.block_sums.ptr, stuns_only);
+        else k_count<false><<<(unsigned)nb, BLOCK, 0, ctx->stream>>>(f.soa(), f.n, (u32 *)f.counts.ptr, (u32 *)f.block_sums.ptr, stuns_only);
     }
     LL_TRY(check_launch("k_count"));
     {
@@ -211,7 +211,7 @@ int count_level(ll_ctx *ctx, size_t l, bool nihil, u64 *total_out) {
 }
 
 // expand level l into level l+1 (count_level(l) must have run).  root_mode: 0 none, 1 inherit, 2 own index
-int emit_level(ll_ctx *ctx, size_t l, bool nihil, u64 total, bool with_cmeta, int root_mode) {
+int emit_level(ll_ctx *ctx, size_t l, bool nihil, u64 total, bool with_cmeta, int root_mode, bool stuns_only = false) {
     LL_TRY(reserve_level(ctx, l + 1, (size_t)total, with_cmeta, false));
     Frontier &f = ctx->levels[l];
     Frontier &g = ctx->levels[l + 1];
@@ -227,6 +227,7 @@ int emit_level(ll_ctx *ctx, size_t l, bool nihil, u64 total, bool with_cmeta, in
     a.cmeta = with_cmeta ? (u32 *)g.cmeta.ptr : nullptr;
     a.root_out = root_mode ? (u32 *)g.root.ptr : nullptr;
     a.root_is_index = root_mode == 2;
+    a.stuns_only = stuns_only;
     {
         Timed t(ctx, nihil ? "emit_reckless" : "emit_legal");
         if (nihil) k_expand<true, MODE_EMIT><<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(a);
@@ -241,35 +242,44 @@ int check_ctx(ll_ctx *ctx) {
     return LL_OK;
 }
 
-// horizon values of level `l` nodes (n of them) into levels[l].values; uses levels l+1.. as scratch
-int horizon_levels(ll_ctx *ctx, size_t l, int plies, uint64_t *scored_total) {
+// horizon values of level `l` nodes (n of them) into levels[l].values; uses levels l+1.. as scratch.
+// The node at level l has `plies` plies of full-width reckless search left; with quiet_ext > 0 the search
+// goes on below depth 0 for up to quiet_ext plies over the stunning commits only, every such node being
+// free to stand pat (mind.rs:284-301).  quiet_ext <= 0: no extension (quiet = None, or Some(0)).
+int horizon_levels(ll_ctx *ctx, size_t l, int plies, int quiet_ext, uint64_t *scored_total) {
     Frontier &f0 = ctx->levels[l];
     LL_TRY(reserve_level(ctx, l, f0.n, false, true));
     u64 *sc = (u64 *)ctx->scalars.ptr;
     if (!f0.n) return LL_OK;
-    if (plies <= 0) {
+    if (plies < 0) plies = 0;
+    const int expanding = plies + (quiet_ext > 0 ? quiet_ext : 0); // levels whose children are generated
+    if (expanding == 0) {
         Timed t(ctx, "leaf_values");
         k_leaf_values<<<(unsigned)nblocks(f0.n), BLOCK, 0, ctx->stream>>>(f0.soa(), f0.n, (float *)f0.values.ptr);
         if (scored_total) *scored_total += f0.n;
         return check_launch("k_leaf_values");
     }
-    // expand plies-1 levels of reckless children
+    // level l + j has plies - j plies left; at <= 0 it is a quiescence level
     size_t bottom = l;
-    for (int p = 0; p < plies - 1; p++) {
+    for (int j = 0; j < expanding - 1; j++) {
+        const bool quiet = plies - j <= 0;
         u64 total = 0;
-        LL_TRY(count_level(ctx, bottom, true, &total));
-        LL_TRY(emit_level(ctx, bottom, true, total, false, 0));
+        LL_TRY(count_level(ctx, bottom, true, &total, quiet));
+        LL_TRY(emit_level(ctx, bottom, true, total, false, 0, quiet));
         bottom++;
     }
     Frontier &fb = ctx->levels[bottom];
     LL_TRY(reserve_level(ctx, bottom, fb.n, false, true));
     CUDA_TRY(cudaMemsetAsync(sc + SC_SCORED, 0, sizeof(u64), ctx->stream));
     if (fb.n) {
+        const bool quiet = plies - (expanding - 1) <= 0;
         ExpandArgs a{};
         a.in = fb.soa();
         a.n = fb.n;
         a.values = (float *)fb.values.ptr;
         a.scored = sc + SC_SCORED;
+        a.stuns_only = quiet;
+        a.stand_pat = quiet;
         Timed t(ctx, "horizon_last_ply");
         k_expand<true, MODE_HORIZON><<<(unsigned)nblocks(fb.n), BLOCK, 0, ctx->stream>>>(a);
     }
@@ -278,9 +288,10 @@ int horizon_levels(ll_ctx *ctx, size_t l, int plies, uint64_t *scored_total) {
         Frontier &par = ctx->levels[lev - 1];
         Frontier &chi = ctx->levels[lev];
         LL_TRY(reserve_level(ctx, lev - 1, par.n, false, true));
+        const bool quiet = plies - (int)(lev - 1 - l) <= 0;
         Timed t(ctx, "backup");
         k_backup<<<(unsigned)nblocks(par.n), BLOCK, 0, ctx->stream>>>(par.soa(), par.n, (const u32 *)par.counts.ptr, (const u64 *)par.block_base.ptr,
-                                                                     (const float *)chi.values.ptr, (float *)par.values.ptr);
+                                                                     (const float *)chi.values.ptr, (float *)par.values.ptr, quiet);
         LL_TRY(check_launch("k_backup"));
     }
     if (scored_total) {
@@ -786,20 +797,21 @@ extern "C" int ll_perft_device(ll_ctx *ctx, const ll_world_t *root, int depth, i
 
 // ---- horizon / kickoff -------------------------------------------------------------------------------
 
-extern "C" int ll_horizon_batch(ll_ctx *ctx, const ll_world_t *frontier, size_t n, int plies, float *values) {
+extern "C" int ll_horizon_batch(ll_ctx *ctx, const ll_world_t *frontier, size_t n, int plies, int quiet_extension, float *values) {
     LL_TRY(check_ctx(ctx));
     if (n && (!frontier || !values)) return fail(LL_ERR_INVALID_ARG, "null buffer");
     if (plies < 0 || plies > 8) return fail(LL_ERR_INVALID_ARG, "plies %d out of range", plies);
     if (!n) return LL_OK;
     LL_TRY(upload_worlds(ctx, frontier, n, 0));
     LL_TRY(validate_level(ctx, ctx->levels[0].soa(), n));
-    LL_TRY(horizon_levels(ctx, 0, plies, nullptr));
+    if (quiet_extension > 8) return fail(LL_ERR_INVALID_ARG, "quiet extension %d out of range", quiet_extension);
+    LL_TRY(horizon_levels(ctx, 0, plies, quiet_extension, nullptr));
     CUDA_TRY(cudaMemcpyAsync(values, ctx->levels[0].values.ptr, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return LL_OK;
 }
 
-extern "C" int ll_horizon_soa(ll_ctx *ctx, const ll_soa_t *soa, int plies, float *d_values, uint64_t *leaves_scored) {
+extern "C" int ll_horizon_soa(ll_ctx *ctx, const ll_soa_t *soa, int plies, int quiet_extension, float *d_values, uint64_t *leaves_scored) {
     LL_TRY(check_ctx(ctx));
     if (!soa || !d_values) return fail(LL_ERR_INVALID_ARG, "null argument");
     if (plies < 0 || plies > 8) return fail(LL_ERR_INVALID_ARG, "plies %d out of range", plies);
@@ -821,7 +833,7 @@ extern "C" int ll_horizon_soa(ll_ctx *ctx, const ll_soa_t *soa, int plies, float
     view.cap = soa->stride;
     view.n = soa->n;
     ctx->levels[0] = view;
-    int rc = horizon_levels(ctx, 0, plies, leaves_scored);
+    int rc = horizon_levels(ctx, 0, plies, quiet_extension, leaves_scored);
     if (rc == LL_OK && cudaMemcpyAsync(d_values, ctx->levels[0].values.ptr, soa->n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess)
         rc = fail(LL_ERR_CUDA, "copy of horizon values failed");
     if (rc == LL_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(LL_ERR_CUDA, "synchronize failed");
@@ -829,7 +841,7 @@ extern "C" int ll_horizon_soa(ll_ctx *ctx, const ll_soa_t *soa, int plies, float
     return rc;
 }
 
-extern "C" int ll_kickoff(ll_ctx *ctx, const ll_world_t *root, int depth, int nihilistically, int shard_rank, int shard_world,
+extern "C" int ll_kickoff(ll_ctx *ctx, const ll_world_t *root, int depth, int quiet_extension, int nihilistically, int shard_rank, int shard_world,
                           ll_commit_t *roots, float *scores, uint32_t root_cap, uint32_t *n_roots, uint64_t *leaves_scored) {
     LL_TRY(check_ctx(ctx));
     if (!root || !scores || !n_roots) return fail(LL_ERR_INVALID_ARG, "null argument");
@@ -871,7 +883,7 @@ extern "C" int ll_kickoff(ll_ctx *ctx, const ll_world_t *root, int depth, int ni
         search_level = 2;
     }
     uint64_t scored = 0;
-    LL_TRY(horizon_levels(ctx, search_level, depth - 1, &scored)); // mind.rs:406-411: full window per root
+    LL_TRY(horizon_levels(ctx, search_level, depth - 1, quiet_extension, &scored)); // mind.rs:406-411: full window per root
     if (leaves_scored) *leaves_scored = scored;
     std::vector<float> vals(kept);
     if (kept) CUDA_TRY(cudaMemcpyAsync(vals.data(), ctx->levels[search_level].values.ptr, kept * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));

@@ -140,12 +140,27 @@ __global__ void __launch_bounds__(256) k_score(Soa in, size_t n, float *__restri
     }
 }
 
+struct StunCountSink { // commits with hospitalization.is_some()
+    u64 onto;
+    u32 n = 0;
+    LL_HDM void move(u32, int, int to, u32, u32 flags) {
+        if (((1ull << to) & onto) || (flags & MV_PASSING_BY)) n++;
+    }
+};
+LL_HD u64 opposition_squares(const Pos &p) { return meta_stm(p.meta) == 0 ? occupied_by<1>(p) : occupied_by<0>(p); }
+template <bool NIHIL> LL_HD u32 count_stuns(const Pos &p) {
+    StunCountSink sink{opposition_squares(p)};
+    lookahead<NIHIL>(p, sink);
+    return sink.n;
+}
+
 // ---- movegen: set-wise count -> scan -> expand ---------------------------------------------------------
-template <bool NIHIL> __global__ void __launch_bounds__(BLOCK) k_count(Soa in, size_t n, u32 *__restrict__ counts, u32 *__restrict__ block_sums) {
+template <bool NIHIL> __global__ void __launch_bounds__(BLOCK) k_count(Soa in, size_t n, u32 *__restrict__ counts, u32 *__restrict__ block_sums, int stuns_only) {
     const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
     u32 c = 0;
     if (i < n) {
-        c = count_moves<NIHIL>(soa_load(in, i));
+        const Pos p = soa_load(in, i);
+        c = stuns_only ? count_stuns<NIHIL>(p) : count_moves<NIHIL>(p);
         counts[i] = c;
     }
     u32 total;
@@ -196,12 +211,13 @@ __global__ void __launch_bounds__(BLOCK) k_offsets(const u32 *__restrict__ count
 struct DescSink {
     u32 *buf;
     u32 idx, lo, hi, slot_bits;
+    u64 only_onto; // ~0, or the opposition's squares: keep stuns only (quiescence, mind.rs:292-294)
     LL_HDM void move(u32 job, int from, int to, u32 asc, u32 flags) {
+        if (!((1ull << to) & only_onto) && !(flags & MV_PASSING_BY)) return;
         if (idx >= lo && idx < hi) buf[idx - lo] = mv_pack(job, from, to, asc, flags) | slot_bits;
         idx++;
     }
 };
-
 struct ExpandArgs {
     Soa in;
     size_t n;               // parents (ignored when n_in is set)
@@ -210,6 +226,8 @@ struct ExpandArgs {
     const u32 *counts;      // per-parent commit counts (nullptr: counted here)
     const u64 *block_base;  // EMIT, canonical order: first child index of each tile (from the scan)
     const u32 *root_in;     // root-move id of each parent (nullable)
+    int stuns_only;         // quiescence levels: expand only the commits that hospitalize somebody (mind.rs:292-294)
+    int stand_pat;          // ... and a parent may decline them all: value = max(orientation*score, children) (mind.rs:298)
     // MODE_EMIT
     Soa out;
     u32 *cmeta;             // packed commit metadata (nullable)
@@ -259,7 +277,7 @@ template <bool NIHIL, int MODE> __global__ void __launch_bounds__(BLOCK, LL_EXPA
         u32 cnt = 0;
         if (i < n) { // the parent lives in the shared tile from here on, not in registers
             const Pos p = soa_load(a.in, i);
-            cnt = a.counts ? a.counts[i] : count_moves<NIHIL>(p);
+            cnt = a.counts ? a.counts[i] : a.stuns_only ? count_stuns<NIHIL>(p) : count_moves<NIHIL>(p);
 #pragma unroll
             for (int j = 0; j < 12; j++) tile_pl[j][tid] = p.pl[j];
             tile_meta[tid] = p.meta;
@@ -284,8 +302,9 @@ template <bool NIHIL, int MODE> __global__ void __launch_bounds__(BLOCK, LL_EXPA
 
         for (u32 w0 = 0; w0 < total && writable; w0 += DESC_CAP) {
             if (cnt && ex < w0 + DESC_CAP && ex + cnt > w0) { // phase 1: this parent's commits into the window
-                DescSink sink{descs, ex, w0, w0 + DESC_CAP, (u32)tid << 20};
-                lookahead<NIHIL>(tile_load(tile_pl, tile_meta, tid), sink);
+                const Pos p = tile_load(tile_pl, tile_meta, tid);
+                DescSink sink{descs, ex, w0, w0 + DESC_CAP, (u32)tid << 20, a.stuns_only ? opposition_squares(p) : ~0ull};
+                lookahead<NIHIL>(p, sink);
             }
             __syncthreads();
             const u32 wn = min((u32)DESC_CAP, total - w0);
@@ -344,13 +363,11 @@ template <bool NIHIL, int MODE> __global__ void __launch_bounds__(BLOCK, LL_EXPA
         if (MODE == MODE_HORIZON) {
             u32 scored = 0;
             if (i < n) {
-                float v;
-                if (cnt == 0) { // no pseudo-legal move: the node is itself a leaf (mind.rs:281-283)
+                float v = cnt ? key_float(acc[tid]) : -INFINITY;
+                if (cnt == 0 || a.stand_pat) { // nothing to play: the node is itself a leaf (mind.rs:281-283, 295-299)
                     const Pos p = tile_load(tile_pl, tile_meta, tid);
                     const float s = score(p);
-                    v = meta_stm(p.meta) ? -s : s;
-                } else {
-                    v = key_float(acc[tid]);
+                    v = fmaxf(v, meta_stm(p.meta) ? -s : s);
                 }
                 a.values[i] = v;
                 scored = cnt ? cnt : 1u;
@@ -416,20 +433,20 @@ __global__ void __launch_bounds__(BLOCK) k_leaf_values(Soa in, size_t n, float *
 }
 // negamax back-up of one level: parent = max over its children of -child; childless parent -> leaf rule
 __global__ void __launch_bounds__(BLOCK) k_backup(Soa parents, size_t n, const u32 *__restrict__ counts, const u64 *__restrict__ block_base,
-                                                  const float *__restrict__ child_values, float *__restrict__ values) {
+                                                  const float *__restrict__ child_values, float *__restrict__ values, int stand_pat) {
     const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
     const u32 c = i < n ? counts[i] : 0;
     u32 total;
     const u32 ex = block_exclusive_scan(c, &total);
     if (i >= n) return;
-    float v;
-    if (c == 0) {
+    float v = -INFINITY;
+    if (c == 0 || stand_pat) {
         const Pos p = soa_load(parents, i);
         const float s = score(p);
         v = meta_stm(p.meta) ? -s : s;
-    } else {
+    }
+    if (c) {
         const size_t first = (size_t)(block_base[blockIdx.x] + ex);
-        v = -INFINITY;
         for (u32 k = 0; k < c; k++) v = fmaxf(v, -child_values[first + k]);
     }
     values[i] = v;

@@ -67,6 +67,9 @@ def lib():
         L.lo_negamax.argtypes = [vp, i32]
         L.lo_negamax.restype = C.c_float
         L.lo_kickoff.argtypes = [vp, i32, i32, vp, vp, i32]
+        L.lo_kickoff_quiet.argtypes = [vp, i32, i32, i32, vp, vp, i32]
+        L.lo_negamax_quiet.argtypes = [vp, i32, i32]
+        L.lo_negamax_quiet.restype = C.c_float
         L.lo_mix64.argtypes = [u64]
         L.lo_mix64.restype = u64
         L.lo_playout.argtypes = [u64, u64, vp, C.POINTER(i32)]
@@ -202,16 +205,17 @@ def perft_divide(w, depth, threads=1):
     return per_root[:n].copy()
 
 
-def negamax(w, depth):
+def negamax(w, depth, quiet=None):
+    """mind.rs:271-364 TT-free; quiet = None or the quiescence extension (mind.rs:284-301)."""
     w = np.ascontiguousarray(w)
-    return np.float32(lib().lo_negamax(_ptr(w), depth))
+    return np.float32(lib().lo_negamax_quiet(_ptr(w), depth, -1 if quiet is None else quiet))
 
 
-def kickoff(w, depth, nihilistically, threads=1):
+def kickoff(w, depth, nihilistically, threads=1, quiet=None):
     w = np.ascontiguousarray(w)
     roots = np.zeros(MAX_COMMITS, dtype=COMMIT_DTYPE)
     scores = np.zeros(MAX_COMMITS, dtype=np.float32)
-    n = _check(lib().lo_kickoff(_ptr(w), depth, int(nihilistically), _ptr(roots), _ptr(scores), threads))
+    n = _check(lib().lo_kickoff_quiet(_ptr(w), depth, -1 if quiet is None else quiet, int(nihilistically), _ptr(roots), _ptr(scores), threads))
     return roots[:n].copy(), scores[:n].copy()
 
 

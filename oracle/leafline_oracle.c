@@ -653,8 +653,10 @@ typedef struct {
     int next;
     pthread_mutex_t lock;
     int mode; /* 0 perft, 1 negamax */
+    int quiet;
 } lo_job_t;
 
+float lo_negamax_quiet(const lo_world_t *w, int depth, int quiet);
 static void *root_worker(void *arg) {
     lo_job_t *job = (lo_job_t *)arg;
     for (;;) {
@@ -663,7 +665,7 @@ static void *root_worker(void *arg) {
         pthread_mutex_unlock(&job->lock);
         if (i >= job->n_roots) break;
         if (job->mode == 0) job->per_root[i] = lo_perft(&job->roots[i].tree, job->depth - 1);
-        else job->scores[i] = -lo_negamax(&job->roots[i].tree, job->depth - 1); /* mind.rs:425 */
+        else job->scores[i] = -lo_negamax_quiet(&job->roots[i].tree, job->depth - 1, job->quiet); /* mind.rs:425 */
     }
     return NULL;
 }
@@ -695,7 +697,7 @@ int lo_perft_divide(const lo_world_t *w, int depth, uint64_t *per_root, int cap,
         free(roots);
         return n < 0 ? n : LO_PANIC;
     }
-    lo_job_t job = {roots, n, depth, per_root, NULL, 0, PTHREAD_MUTEX_INITIALIZER, 0};
+    lo_job_t job = {roots, n, depth, per_root, NULL, 0, PTHREAD_MUTEX_INITIALIZER, 0, -1};
     if (depth >= 1) run_root_job(&job, threads);
     free(roots);
     return n;
@@ -711,15 +713,25 @@ static float mvv_lva(const lo_commit_t *c) {
     return patient - star;
 }
 
-/* mind.rs:271-364 without the transposition table, the history table and quiescence:
- * fail-soft alpha-beta; with a full window the value is the exact negamax value. */
-static float alpha_beta(const lo_world_t *w, int depth, float alpha, float beta) {
+/* mind.rs:271-364 without the transposition table and the history table: fail-soft alpha-beta; with a
+ * full window the value is the exact negamax value.  quiet < 0 is `quiet: None`, else Some(quiet). */
+static float alpha_beta(const lo_world_t *w, int depth, float alpha, float beta, int quiet) {
     lo_commit_t *prems = (lo_commit_t *)malloc(sizeof(lo_commit_t) * LO_MAX_COMMITS);
     int n = lo_reckless_lookahead(w, prems); /* :279 -- also at depth <= 0, like the reference */
     float optimum = -INFINITY;
-    if (depth <= 0 || n <= 0) { /* :282-287 */
-        free(prems);
-        return lo_orientation(w->initiative) * lo_score(w);
+    if (depth <= 0 || n <= 0) { /* :282-301 */
+        float potential_score = lo_orientation(w->initiative) * lo_score(w);
+        int stuns = 0;
+        if (quiet >= 0 && abs(depth) < quiet) { /* :289-294: keep the commits that hospitalize somebody */
+            for (int i = 0; i < n; i++)
+                if (prems[i].hospitalization != LO_NONE) prems[stuns++] = prems[i];
+        }
+        if (stuns == 0) {
+            free(prems);
+            return potential_score;
+        }
+        n = stuns;
+        optimum = potential_score; /* :298 stand pat */
     }
     /* stable insertion sort by MVV-LVA, descending */
     int order[LO_MAX_COMMITS];
@@ -736,7 +748,7 @@ static float alpha_beta(const lo_world_t *w, int depth, float alpha, float beta)
         order[j] = i;
     }
     for (int i = 0; i < n; i++) { /* :312-362 */
-        float value = -alpha_beta(&prems[order[i]].tree, depth - 1, -beta, -alpha);
+        float value = -alpha_beta(&prems[order[i]].tree, depth - 1, -beta, -alpha, quiet);
         if (value > optimum) optimum = value;
         if (value > alpha) alpha = value;
         if (alpha >= beta) break;
@@ -745,16 +757,20 @@ static float alpha_beta(const lo_world_t *w, int depth, float alpha, float beta)
     return optimum;
 }
 
-float lo_negamax(const lo_world_t *w, int depth) { return alpha_beta(w, depth, -INFINITY, INFINITY); }
+float lo_negamax(const lo_world_t *w, int depth) { return alpha_beta(w, depth, -INFINITY, INFINITY, -1); }
+float lo_negamax_quiet(const lo_world_t *w, int depth, int quiet) { return alpha_beta(w, depth, -INFINITY, INFINITY, quiet); }
 
 /* mind.rs:375-448: root moves legal unless nihilistically (388-392); each child searched with a
  * full window (406-411); root value = -child value (425). */
-int lo_kickoff(const lo_world_t *w, int depth, int nihilistically, lo_commit_t *roots, float *scores, int threads) {
+int lo_kickoff_quiet(const lo_world_t *w, int depth, int quiet, int nihilistically, lo_commit_t *roots, float *scores, int threads) {
     int n = nihilistically ? lo_reckless_lookahead(w, roots) : lo_lookahead(w, roots);
     if (n <= 0) return n;
-    lo_job_t job = {roots, n, depth, NULL, scores, 0, PTHREAD_MUTEX_INITIALIZER, 1};
+    lo_job_t job = {roots, n, depth, NULL, scores, 0, PTHREAD_MUTEX_INITIALIZER, 1, quiet};
     run_root_job(&job, threads);
     return n;
+}
+int lo_kickoff(const lo_world_t *w, int depth, int nihilistically, lo_commit_t *roots, float *scores, int threads) {
+    return lo_kickoff_quiet(w, depth, -1, nihilistically, roots, scores, threads);
 }
 
 /* ---------------------------------------------------------------- seeded random playouts */

@@ -96,10 +96,14 @@ int lo_perft_divide(const lo_world_t *w, int depth, uint64_t *per_root, int cap,
 /* TT-free exact negamax with the leaf rule of mind.rs:279-287 (quiet = None): value of `w` for the
  * side to move, searching `depth` plies of reckless children. */
 float lo_negamax(const lo_world_t *w, int depth);
+/* the same with the quiescence extension of mind.rs:284-301: quiet < 0 is None, else Some(quiet) */
+float lo_negamax_quiet(const lo_world_t *w, int depth, int quiet);
 /* mind.rs:375-448 kickoff without TT/history/threads: root moves = lookahead() (or reckless if
  * nihilistically), score[i] = -negamax(child_i, depth-1).  Canonical (unsorted) order. */
 int lo_kickoff(const lo_world_t *w, int depth, int nihilistically, lo_commit_t *roots, float *scores,
                int threads);
+int lo_kickoff_quiet(const lo_world_t *w, int depth, int quiet, int nihilistically, lo_commit_t *roots, float *scores,
+                     int threads);
 
 /* Seeded random-playout positions (defined by this build). */
 uint64_t lo_mix64(uint64_t z);

@@ -305,6 +305,27 @@ def test_horizon_depth_3_on_a_few(eng, playouts):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("plies,quiet", [(0, 1), (0, 2), (1, 1), (1, 3), (2, 2), (0, 0), (1, 0)])
+def test_horizon_with_quiescence_extension(eng, playouts, reckless_worlds, plies, quiet):
+    # mind.rs:284-301: below depth 0 only stunning commits are searched and every node may stand pat
+    n = 40 if plies + quiet <= 3 else 10
+    for worlds in (playouts[100:100 + n], reckless_worlds[50:50 + n], named_worlds()[:n]):
+        got = eng.horizon(worlds, plies, quiet=quiet)
+        want = np.array([O.negamax(w, plies, quiet) for w in worlds], dtype=np.float32)
+        assert np.array_equal(got, want), (plies, quiet, np.nonzero(got != want))
+
+
+def test_kickoff_with_quiescence_extension(eng):
+    import leafline_b200 as ll
+
+    for fen, depth, quiet in ((KIWIPETE, 2, 2), (POSITION_5, 2, 1), (OPENING, 3, 2), ("8/q1P1k/8/8/8/8/6PP/7K w - -", 3, 3)):
+        w = ll.reconstruct(fen)
+        roots, scores, scored = eng.kickoff(w, depth, quiet=quiet)
+        want_roots, want_scores = O.kickoff(w, depth, False, threads=8, quiet=quiet)
+        assert roots.tobytes() == want_roots.tobytes()
+        assert np.array_equal(scores, want_scores), (fen, depth, quiet)
+
+
 def check_kickoff(eng, world, depth, nihilistically):
     roots, scores, scored = eng.kickoff(world, depth, nihilistically=nihilistically)
     want_roots, want_scores = O.kickoff(world, depth, nihilistically, threads=8)
