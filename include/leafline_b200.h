@@ -126,6 +126,30 @@ int ll_horizon_batch(ll_ctx *ctx, const ll_world_t *frontier, size_t n, int plie
 int ll_kickoff(ll_ctx *ctx, const ll_world_t *root, int depth, int quiet_extension, int nihilistically, int shard_rank, int shard_world,
                ll_commit_t *roots, float *scores, uint32_t root_cap, uint32_t *n_roots, uint64_t *leaves_scored);
 
+/* ---- the kickoff family as the reference's callers see it (src/mind.rs:441-490) ----------------------- */
+#define LL_MAX_VARIATION 16
+typedef struct ll_patch_t { /* `Patch` (src/life.rs:15-20) */
+    uint8_t team, job, whence, whither;
+} ll_patch_t;
+/* one element of the `Vec<(Commit, f32, Variation)>` the kickoff functions return */
+typedef struct ll_forecast_t {
+    ll_commit_t commit; /* the root move */
+    float score;
+    uint32_t variation_len;                  /* >= 1: variation[0] is the root move's patch (mind.rs:426-427) */
+    ll_patch_t variation[LL_MAX_VARIATION];  /* principal variation; ties go to the first commit in canonical order */
+} ll_forecast_t;
+
+/* replaces `kickoff::<Variation>(world, depth, extension, nihilistically, _)` (src/mind.rs:441-448): forecasts
+ * sorted by score, best first (mind.rs:436).  The search is TT-free and full-width on the device. */
+int ll_forecast(ll_ctx *ctx, const ll_world_t *root, int depth, int quiet_extension, int nihilistically, ll_forecast_t *forecasts,
+                uint32_t cap, uint32_t *n_forecasts, uint64_t *leaves_scored);
+/* replaces `fixed_depth_sequence_kickoff` (src/mind.rs:473-490) */
+int ll_fixed_depth_sequence_forecast(ll_ctx *ctx, const ll_world_t *root, const uint8_t *depths, uint32_t n_depths, int nihilistically,
+                                     ll_forecast_t *forecasts, uint32_t cap, uint32_t *n_forecasts);
+/* replaces `iterative_deepening_kickoff` (src/mind.rs:451-469): the deepest iteration that finished inside the timeout */
+int ll_iterative_deepening_forecast(ll_ctx *ctx, const ll_world_t *root, double timeout_seconds, int nihilistically, ll_forecast_t *forecasts,
+                                    uint32_t cap, uint32_t *n_forecasts, uint32_t *depth_reached);
+
 /* ---- device-resident positions (structure-of-arrays u64 planes in HBM) ---------------------- */
 
 /* 12 planes of `stride` u64 each (plane j of position i at planes[j*stride + i]; stride is a

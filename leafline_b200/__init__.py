@@ -24,7 +24,7 @@ import ctypes as C
 import numpy as np
 
 from . import _abi
-from ._abi import COMMIT_DTYPE, WORLD_DTYPE, LeaflineError, Soa  # noqa: F401
+from ._abi import COMMIT_DTYPE, FORECAST_DTYPE, WORLD_DTYPE, LeaflineError, Soa  # noqa: F401
 from .runes import preserve, reconstruct  # noqa: F401
 
 ORANGE, BLUE = 0, 1
@@ -51,6 +51,12 @@ def to_algebraic(loc):
 
 def agent(team, job):
     return (team << 3) | job
+
+
+def pagan_variation(forecast):
+    """The variation of one forecast as "e2e4 e7e5 ..." (cf. pagan_variation_format, mind.rs:174-180)."""
+    n = int(forecast["variation_len"])
+    return " ".join(to_algebraic(p["whence"]) + to_algebraic(p["whither"]) for p in forecast["variation"][:n])
 
 
 def new_world():
@@ -210,6 +216,35 @@ class Engine:
             )
         )
         return roots[: n_roots.value].copy(), scores[: n_roots.value].copy(), int(scored.value)
+
+    # ---- the kickoff family as the reference's callers see it (mind.rs:441-490)
+    def forecast(self, world, depth, nihilistically=False, quiet=None):
+        """kickoff::<Variation>: FORECAST_DTYPE records (commit, score, variation) sorted by score, best first."""
+        w = _worlds(world)
+        out = np.zeros(1024, dtype=FORECAST_DTYPE)
+        n, scored = C.c_uint32(0), C.c_uint64(0)
+        _abi.check(self._lib.ll_forecast(self._ctx, _ptr(w), depth, -1 if quiet is None else int(quiet), int(nihilistically),
+                                         _ptr(out), 1024, C.byref(n), C.byref(scored)))
+        return out[: n.value].copy()
+
+    def fixed_depth_sequence_kickoff(self, world, depth_sequence, nihilistically=False):
+        """mind.rs:473-490."""
+        w = _worlds(world)
+        depths = np.ascontiguousarray(depth_sequence, dtype=np.uint8)
+        out = np.zeros(1024, dtype=FORECAST_DTYPE)
+        n = C.c_uint32(0)
+        _abi.check(self._lib.ll_fixed_depth_sequence_forecast(self._ctx, _ptr(w), _ptr(depths), len(depths), int(nihilistically),
+                                                              _ptr(out), 1024, C.byref(n)))
+        return out[: n.value].copy()
+
+    def iterative_deepening_kickoff(self, world, timeout_seconds, nihilistically=False):
+        """mind.rs:451-469 -> (forecasts of the deepest iteration that finished in time, its depth)."""
+        w = _worlds(world)
+        out = np.zeros(1024, dtype=FORECAST_DTYPE)
+        n, depth = C.c_uint32(0), C.c_uint32(0)
+        _abi.check(self._lib.ll_iterative_deepening_forecast(self._ctx, _ptr(w), float(timeout_seconds), int(nihilistically),
+                                                             _ptr(out), 1024, C.byref(n), C.byref(depth)))
+        return out[: n.value].copy(), int(depth.value)
 
     # ---- positions resident in HBM (SoA planes)
     def soa_alloc(self, n):

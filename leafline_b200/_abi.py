@@ -21,7 +21,12 @@ COMMIT_DTYPE = np.dtype(
     [("team", "u1"), ("job", "u1"), ("whence", "u1"), ("whither", "u1"), ("hospitalization", "u1"),
      ("ascension", "u1"), ("pad", "u1", (2,)), ("tree", WORLD_DTYPE)]
 )
-assert WORLD_DTYPE.itemsize == 104 and COMMIT_DTYPE.itemsize == 112
+MAX_VARIATION = 16
+PATCH_DTYPE = np.dtype([("team", "u1"), ("job", "u1"), ("whence", "u1"), ("whither", "u1")])
+FORECAST_DTYPE = np.dtype(
+    [("commit", COMMIT_DTYPE), ("score", "<f4"), ("variation_len", "<u4"), ("variation", PATCH_DTYPE, (MAX_VARIATION,))]
+)
+assert WORLD_DTYPE.itemsize == 104 and COMMIT_DTYPE.itemsize == 112 and FORECAST_DTYPE.itemsize == 184
 
 
 class Soa(C.Structure):
@@ -50,6 +55,9 @@ SIGNATURES = {
     "ll_perft_device": ([_vp, _vp, _i, _i, _i, _vp], _i),
     "ll_horizon_batch": ([_vp, _vp, _sz, _i, _i, _vp], _i),
     "ll_kickoff": ([_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(_u64)], _i),
+    "ll_forecast": ([_vp, _vp, _i, _i, _i, _vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(_u64)], _i),
+    "ll_fixed_depth_sequence_forecast": ([_vp, _vp, _vp, C.c_uint32, _i, _vp, C.c_uint32, C.POINTER(C.c_uint32)], _i),
+    "ll_iterative_deepening_forecast": ([_vp, _vp, C.c_double, _i, _vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)], _i),
     "ll_soa_alloc": ([_vp, _sz, C.POINTER(Soa)], _i),
     "ll_soa_free": ([_vp, C.POINTER(Soa)], _i),
     "ll_soa_upload": ([_vp, _vp, _sz, C.POINTER(Soa)], _i),

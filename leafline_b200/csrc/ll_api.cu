@@ -4,6 +4,7 @@
 #include "ll_kernels.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -246,13 +247,14 @@ int check_ctx(ll_ctx *ctx) {
 // The node at level l has `plies` plies of full-width reckless search left; with quiet_ext > 0 the search
 // goes on below depth 0 for up to quiet_ext plies over the stunning commits only, every such node being
 // free to stand pat (mind.rs:284-301).  quiet_ext <= 0: no extension (quiet = None, or Some(0)).
-int horizon_levels(ll_ctx *ctx, size_t l, int plies, int quiet_ext, uint64_t *scored_total) {
+int horizon_levels(ll_ctx *ctx, size_t l, int plies, int quiet_ext, uint64_t *scored_total, bool with_cmeta = false, size_t *bottom_out = nullptr) {
     Frontier &f0 = ctx->levels[l];
     LL_TRY(reserve_level(ctx, l, f0.n, false, true));
     u64 *sc = (u64 *)ctx->scalars.ptr;
     if (!f0.n) return LL_OK;
     if (plies < 0) plies = 0;
     const int expanding = plies + (quiet_ext > 0 ? quiet_ext : 0); // levels whose children are generated
+    if (bottom_out) *bottom_out = l;
     if (expanding == 0) {
         Timed t(ctx, "leaf_values");
         k_leaf_values<<<(unsigned)nblocks(f0.n), BLOCK, 0, ctx->stream>>>(f0.soa(), f0.n, (float *)f0.values.ptr);
@@ -265,10 +267,11 @@ int horizon_levels(ll_ctx *ctx, size_t l, int plies, int quiet_ext, uint64_t *sc
         const bool quiet = plies - j <= 0;
         u64 total = 0;
         LL_TRY(count_level(ctx, bottom, true, &total, quiet));
-        LL_TRY(emit_level(ctx, bottom, true, total, false, 0, quiet));
+        LL_TRY(emit_level(ctx, bottom, true, total, with_cmeta, 0, quiet));
         bottom++;
     }
     Frontier &fb = ctx->levels[bottom];
+    if (bottom_out) *bottom_out = bottom;
     LL_TRY(reserve_level(ctx, bottom, fb.n, false, true));
     CUDA_TRY(cudaMemsetAsync(sc + SC_SCORED, 0, sizeof(u64), ctx->stream));
     if (fb.n) {
@@ -841,11 +844,13 @@ extern "C" int ll_horizon_soa(ll_ctx *ctx, const ll_soa_t *soa, int plies, int q
     return rc;
 }
 
-extern "C" int ll_kickoff(ll_ctx *ctx, const ll_world_t *root, int depth, int quiet_extension, int nihilistically, int shard_rank, int shard_world,
-                          ll_commit_t *roots, float *scores, uint32_t root_cap, uint32_t *n_roots, uint64_t *leaves_scored) {
+// variations (nullable): [root_cap][PV_MAX + 1] u32 -- length, then the packed commits of the line BELOW each root move
+static int kickoff_core(ll_ctx *ctx, const ll_world_t *root, int depth, int quiet_extension, int nihilistically, int shard_rank, int shard_world,
+                        ll_commit_t *roots, float *scores, uint32_t root_cap, uint32_t *n_roots, uint64_t *leaves_scored, u32 *variations) {
     LL_TRY(check_ctx(ctx));
     if (!root || !scores || !n_roots) return fail(LL_ERR_INVALID_ARG, "null argument");
     if (depth < 1 || depth > 9) return fail(LL_ERR_INVALID_ARG, "depth %d out of range (1..9)", depth);
+    if (quiet_extension > 8) return fail(LL_ERR_INVALID_ARG, "quiet extension %d out of range", quiet_extension);
     if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) return fail(LL_ERR_INVALID_ARG, "bad shard %d/%d", shard_rank, shard_world);
     *n_roots = 0;
     if (leaves_scored) *leaves_scored = 0;
@@ -883,13 +888,118 @@ extern "C" int ll_kickoff(ll_ctx *ctx, const ll_world_t *root, int depth, int qu
         search_level = 2;
     }
     uint64_t scored = 0;
-    LL_TRY(horizon_levels(ctx, search_level, depth - 1, quiet_extension, &scored)); // mind.rs:406-411: full window per root
+    size_t bottom = search_level;
+    LL_TRY(horizon_levels(ctx, search_level, depth - 1, quiet_extension, &scored, variations != nullptr, &bottom)); // mind.rs:406-411: full window per root
     if (leaves_scored) *leaves_scored = scored;
+    std::vector<u32> pv;
+    const int expanding = (depth - 1) + (quiet_extension > 0 ? quiet_extension : 0);
+    if (variations && kept && expanding > 0) {
+        if (bottom - search_level + 1 > (size_t)PV_LEVELS) return fail(LL_ERR_CAPACITY, "variation deeper than %d levels", PV_LEVELS);
+        PvArgs pa{};
+        pa.n_levels = (int)(bottom - search_level + 1);
+        for (int L = 0; L < pa.n_levels; L++) {
+            Frontier &f = ctx->levels[search_level + L];
+            pa.lev[L] = PvLevel{f.soa(), (const u32 *)f.counts.ptr, (const u64 *)f.block_base.ptr, (const float *)f.values.ptr, (const u32 *)f.cmeta.ptr,
+                                (depth - 1) - L <= 0};
+        }
+        pa.n = kept;
+        LL_TRY(ensure(ctx, ctx->flags, kept * (PV_MAX + 1) * sizeof(u32)));
+        pa.out = (u32 *)ctx->flags.ptr;
+        {
+            Timed t(ctx, "variation");
+            k_variation<<<(unsigned)nblocks(kept), BLOCK, 0, ctx->stream>>>(pa);
+        }
+        LL_TRY(check_launch("k_variation"));
+        pv.resize(kept * (PV_MAX + 1));
+        CUDA_TRY(cudaMemcpyAsync(pv.data(), ctx->flags.ptr, pv.size() * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     std::vector<float> vals(kept);
     if (kept) CUDA_TRY(cudaMemcpyAsync(vals.data(), ctx->levels[search_level].values.ptr, kept * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     for (u64 i = 0; i < total; i++) scores[i] = -INFINITY;
     for (size_t o = 0; o < kept; o++) scores[(size_t)shard_rank + o * (size_t)shard_world] = -vals[o]; // mind.rs:425
+    if (variations) {
+        for (u64 i = 0; i < total; i++) variations[i * (PV_MAX + 1)] = 0;
+        if (!pv.empty())
+            for (size_t o = 0; o < kept; o++)
+                memcpy(variations + ((size_t)shard_rank + o * (size_t)shard_world) * (PV_MAX + 1), pv.data() + o * (PV_MAX + 1), (PV_MAX + 1) * sizeof(u32));
+    }
+    return LL_OK;
+}
+
+extern "C" int ll_kickoff(ll_ctx *ctx, const ll_world_t *root, int depth, int quiet_extension, int nihilistically, int shard_rank, int shard_world,
+                          ll_commit_t *roots, float *scores, uint32_t root_cap, uint32_t *n_roots, uint64_t *leaves_scored) {
+    return kickoff_core(ctx, root, depth, quiet_extension, nihilistically, shard_rank, shard_world, roots, scores, root_cap, n_roots, leaves_scored, nullptr);
+}
+
+// ---- the kickoff family as the reference's callers see it (mind.rs:441-490): forecasts sorted by score ------
+static void unpack_patch(u32 m, ll_patch_t *p) {
+    p->team = (uint8_t)(m & 1u);
+    p->job = (uint8_t)((m >> 1) & 7u);
+    const u32 from = (m >> 4) & 63u, to = (m >> 10) & 63u;
+    p->whence = (uint8_t)(((from >> 3) << 4) | (from & 7u));
+    p->whither = (uint8_t)(((to >> 3) << 4) | (to & 7u));
+}
+
+extern "C" int ll_forecast(ll_ctx *ctx, const ll_world_t *root, int depth, int quiet_extension, int nihilistically, ll_forecast_t *forecasts,
+                           uint32_t cap, uint32_t *n_forecasts, uint64_t *leaves_scored) {
+    if (!forecasts || !n_forecasts) return fail(LL_ERR_INVALID_ARG, "null argument");
+    static_assert(PV_MAX == LL_MAX_VARIATION, "variation capacity");
+    std::vector<ll_commit_t> roots(1024);
+    std::vector<float> scores(1024);
+    std::vector<u32> pv((size_t)1024 * (PV_MAX + 1));
+    uint32_t n = 0;
+    LL_TRY(kickoff_core(ctx, root, depth, quiet_extension, nihilistically, 0, 1, roots.data(), scores.data(), 1024, &n, leaves_scored, pv.data()));
+    *n_forecasts = n;
+    if (n > cap) return fail(LL_ERR_CAPACITY, "%u forecasts do not fit the capacity of %u", n, cap);
+    std::vector<uint32_t> order(n);
+    for (uint32_t i = 0; i < n; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return scores[x] > scores[y]; }); // mind.rs:436
+    for (uint32_t k = 0; k < n; k++) {
+        const uint32_t i = order[k];
+        ll_forecast_t &f = forecasts[k];
+        memset(&f, 0, sizeof f);
+        f.commit = roots[i];
+        f.score = scores[i];
+        const u32 *line = pv.data() + (size_t)i * (PV_MAX + 1);
+        f.variation[0] = ll_patch_t{roots[i].team, roots[i].job, roots[i].whence, roots[i].whither}; // T::flash(premonition.patch), mind.rs:426
+        uint32_t len = 1;
+        for (u32 j = 0; j < line[0] && len < LL_MAX_VARIATION; j++) unpack_patch(line[1 + j], &f.variation[len++]);
+        f.variation_len = len;
+    }
+    return LL_OK;
+}
+
+extern "C" int ll_fixed_depth_sequence_forecast(ll_ctx *ctx, const ll_world_t *root, const uint8_t *depths, uint32_t n_depths, int nihilistically,
+                                                ll_forecast_t *forecasts, uint32_t cap, uint32_t *n_forecasts) {
+    if (!depths || !n_depths) return fail(LL_ERR_INVALID_ARG, "`depth_sequence` should be nonempty"); // mind.rs:480
+    for (uint32_t k = 0; k < n_depths; k++) LL_TRY(ll_forecast(ctx, root, depths[k], -1, nihilistically, forecasts, cap, n_forecasts, nullptr));
+    return LL_OK;
+}
+
+extern "C" int ll_iterative_deepening_forecast(ll_ctx *ctx, const ll_world_t *root, double timeout_seconds, int nihilistically, ll_forecast_t *forecasts,
+                                               uint32_t cap, uint32_t *n_forecasts, uint32_t *depth_reached) {
+    if (!forecasts || !n_forecasts || !depth_reached) return fail(LL_ERR_INVALID_ARG, "null argument");
+    const auto t0 = std::chrono::steady_clock::now();
+    auto elapsed = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
+    // mind.rs:451-469: depth 1 always completes; then deepen while an iteration finishes before the deadline
+    LL_TRY(ll_forecast(ctx, root, 1, -1, nihilistically, forecasts, cap, n_forecasts, nullptr));
+    *depth_reached = 1;
+    std::vector<ll_forecast_t> next(cap);
+    for (int depth = 2; depth <= 9; depth++) {
+        const double before = elapsed();
+        if (before >= timeout_seconds) break;
+        uint32_t n = 0;
+        const int rc = ll_forecast(ctx, root, depth, -1, nihilistically, next.data(), cap, &n, nullptr);
+        if (rc == LL_ERR_OOM) break; // the full-width tree no longer fits HBM: keep the previous iteration
+        LL_TRY(rc);
+        if (elapsed() > timeout_seconds) break; // finished late: discarded, like the reference's `None` (mind.rs:416-420)
+        memcpy(forecasts, next.data(), n * sizeof(ll_forecast_t));
+        *n_forecasts = n;
+        *depth_reached = (uint32_t)depth;
+        const double took = elapsed() - before;
+        if (elapsed() + took * 20.0 > timeout_seconds) break; // the next ply is ~30x wider: it cannot finish in time
+    }
     return LL_OK;
 }
 

@@ -452,6 +452,77 @@ __global__ void __launch_bounds__(BLOCK) k_backup(Soa parents, size_t n, const u
     values[i] = v;
 }
 
+// ---- principal variation (the `Variation` memory of mind.rs:208-224) -------------------------------------
+// After the back-up every materialised level holds its nodes' values; the variation below a root child is
+// re-traced by following, at each node, the FIRST child (canonical order) whose negated value equals the
+// node's value -- a quiescence node stands pat on ties (mind.rs:298, 346: `value > optimum` is strict).
+// The reference breaks ties in its MVV-LVA / history order (unstable sort), so only the values along the
+// line, not the line itself, are comparable with it.
+constexpr int PV_MAX = 16;       // == LL_MAX_VARIATION
+constexpr int PV_LEVELS = 12;
+struct PvLevel {
+    Soa soa;
+    const u32 *counts;
+    const u64 *block_base;
+    const float *values;
+    const u32 *cmeta;
+    int quiet;
+};
+struct PvArgs {
+    PvLevel lev[PV_LEVELS];
+    int n_levels;   // materialised levels, the root children's level first
+    size_t n;       // root children on this rank
+    u32 *out;       // [n][PV_MAX + 1]: length, then packed commits (pack_commit)
+};
+struct BestChildSink {
+    const Pos &par;
+    float target;
+    u64 only_onto;
+    u32 found;
+    LL_HDM void move(u32 job, int from, int to, u32 asc, u32 flags) {
+        if (found != 0xFFFFFFFFu) return;
+        if (!((1ull << to) & only_onto) && !(flags & MV_PASSING_BY)) return;
+        const u32 m = mv_pack(job, from, to, asc, flags);
+        Pos c;
+        const u32 hosp = make_child(par, m, c);
+        const float s = score(c);
+        if ((meta_stm(c.meta) ? s : -s) == target) found = pack_commit(meta_stm(par.meta), m, hosp);
+    }
+};
+__global__ void __launch_bounds__(BLOCK) k_variation(const PvArgs a) {
+    const size_t r = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (r >= a.n) return;
+    u32 *out = a.out + r * (PV_MAX + 1);
+    u32 len = 0;
+    size_t node = r;
+    for (int L = 0; L < a.n_levels && len < PV_MAX; L++) {
+        const PvLevel &lv = a.lev[L];
+        const Pos p = soa_load(lv.soa, node);
+        const float v = lv.values[node];
+        if (lv.quiet) { // stand pat wins ties
+            const float s = score(p);
+            if ((meta_stm(p.meta) ? -s : s) == v) break;
+        }
+        if (L == a.n_levels - 1) { // the children of the bottom level were scored in registers, never stored
+            BestChildSink sink{p, v, lv.quiet ? opposition_squares(p) : ~0ull, 0xFFFFFFFFu};
+            lookahead<true>(p, sink);
+            if (sink.found != 0xFFFFFFFFu) out[1 + len++] = sink.found;
+            break;
+        }
+        const u32 c = lv.counts[node];
+        if (c == 0) break;
+        const size_t tile0 = (node / BLOCK) * BLOCK;
+        size_t first = (size_t)lv.block_base[node / BLOCK];
+        for (size_t j = tile0; j < node; j++) first += lv.counts[j];
+        const PvLevel &nx = a.lev[L + 1];
+        u32 k = 0;
+        while (k + 1 < c && -nx.values[first + k] != v) k++;
+        out[1 + len++] = nx.cmeta[first + k];
+        node = first + k;
+    }
+    out[0] = len;
+}
+
 // ---- life.rs:678-690 for an explicit team ------------------------------------------------------------
 __global__ void __launch_bounds__(BLOCK) k_endangered(Soa in, size_t n, const unsigned char *__restrict__ teams, unsigned char *__restrict__ out) {
     const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;

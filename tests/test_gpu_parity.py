@@ -350,6 +350,57 @@ def test_kickoff_known_answers_of_the_reference(eng):
         assert roots[int(np.argmax(scores))]["whither"] == ll.locale(0, 0)
 
 
+def oracle_variation_values(world, depth, quiet):
+    """value of every node along a variation must equal the exact negamax value of that node (sign-alternating)"""
+    return O.negamax(world, depth, quiet)
+
+
+@pytest.mark.parametrize("fen,depth,quiet", [(KIWIPETE, 3, None), ("8/q1P1k/8/8/8/8/6PP/7K w - -", 3, None), (POSITION_5, 2, 2),
+                                             (OPENING, 4, None), (POSITION_4, 3, 1)])
+def test_forecasts_are_sorted_and_their_variations_are_principal(eng, fen, depth, quiet):
+    import leafline_b200 as ll
+
+    w = ll.reconstruct(fen)
+    fc = eng.forecast(w, depth, quiet=quiet)
+    roots, scores, _ = eng.kickoff(w, depth, quiet=quiet)
+    assert len(fc) == len(roots)
+    assert list(fc["score"]) == sorted(scores, reverse=True)  # mind.rs:436
+    # stable: equal scores keep the canonical order
+    order = sorted(range(len(scores)), key=lambda i: -scores[i])
+    assert [bytes(f["commit"].tobytes()) for f in fc] == [roots[i].tobytes() for i in order]
+    for f in fc[:6]:
+        n = int(f["variation_len"])
+        assert 1 <= n <= depth + (quiet or 0)
+        assert f["variation"][0]["whence"] == f["commit"]["whence"] and f["variation"][0]["whither"] == f["commit"]["whither"]
+        # replay the line with the oracle: every step must be a reckless commit of the node, and the value must carry along it
+        node, remaining, value = f["commit"]["tree"].copy(), depth - 1, -np.float32(f["score"])
+        for step in f["variation"][1:n]:
+            assert O.negamax(node, remaining, quiet) == value
+            kids = [c for c in O.reckless_lookahead(node) if c["whence"] == step["whence"] and c["whither"] == step["whither"] and c["job"] == step["job"]]
+            assert kids, "variation step is not a move of the node"
+            vals = [-O.negamax(c["tree"], remaining - 1, quiet) for c in kids]
+            k = int(np.argmax([v == value for v in vals]))
+            assert vals[k] == value, "variation step does not carry the node's value"
+            node, remaining, value = kids[k]["tree"].copy(), remaining - 1, -value
+        assert O.negamax(node, remaining, quiet) == value
+
+
+def test_kickoff_family(eng):
+    import leafline_b200 as ll
+
+    w = ll.reconstruct("8/q1P1k/8/8/8/8/6PP/7K w - -")  # mind.rs:662-675
+    fc = eng.fixed_depth_sequence_kickoff(w, [1, 2, 3], nihilistically=True)
+    assert ll.preserve(fc[0]["commit"]["tree"]) == "2N5/q3k3/8/8/8/8/6PP/7K b - -" and fc[0]["score"] > 0
+    assert ll.pagan_variation(fc[0]).startswith("c7c8")
+    best, depth = eng.iterative_deepening_kickoff(ll.new_world(), 0.5)
+    assert depth >= 3 and len(best) == 20
+    assert np.array_equal(np.sort(best["score"])[::-1], best["score"])
+    same = eng.forecast(ll.new_world(), depth)
+    assert best.tobytes() == same.tobytes()
+    with pytest.raises(ll.LeaflineError):
+        eng.fixed_depth_sequence_kickoff(w, [])
+
+
 @pytest.mark.parametrize("depth", [1, 2, 3])
 def test_kickoff_opening_matches_oracle(eng, depth):
     import leafline_b200 as ll
