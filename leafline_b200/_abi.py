@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libleafline_b200.so")
+LIB_PATH = os.environ.get("LEAFLINE_B200_LIB") or os.path.join(_HERE, "libleafline_b200.so")  # the env override is for A/B builds
 
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_CAPACITY, ERR_DOMAIN, ERR_NO_DEVICE, ERR_OOM = 0, -1, -2, -3, -4, -5, -6
 

@@ -14,6 +14,10 @@
 
 using namespace ll;
 
+#ifndef LL_SMALL_TILE_PLIES
+#define LL_SMALL_TILE_PLIES 4 // plies of the perft launch chain expanded with 32-parent tiles
+#endif
+
 static thread_local char g_error[512] = "";
 
 static int fail(int code, const char *fmt, ...) {
@@ -228,10 +232,11 @@ int emit_level(ll_ctx *ctx, size_t l, bool nihil, u64 total, bool with_cmeta, in
     a.cmeta = with_cmeta ? (u32 *)g.cmeta.ptr : nullptr;
     a.root_out = root_mode ? (u32 *)g.root.ptr : nullptr;
     a.root_is_index = root_mode == 2;
-    a.stuns_only = stuns_only;
     {
         Timed t(ctx, nihil ? "emit_reckless" : "emit_legal");
-        if (nihil) k_expand<true, MODE_EMIT><<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(a);
+        if (stuns_only && !nihil) return fail(LL_ERR_INVALID_ARG, "quiescence levels are reckless");
+        if (stuns_only) k_expand<true, MODE_EMIT, BLOCK, true><<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(a);
+        else if (nihil) k_expand<true, MODE_EMIT><<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(a);
         else k_expand<false, MODE_EMIT><<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(a);
     }
     return check_launch("k_expand<EMIT>");
@@ -281,10 +286,10 @@ int horizon_levels(ll_ctx *ctx, size_t l, int plies, int quiet_ext, uint64_t *sc
         a.n = fb.n;
         a.values = (float *)fb.values.ptr;
         a.scored = sc + SC_SCORED;
-        a.stuns_only = quiet;
         a.stand_pat = quiet;
         Timed t(ctx, "horizon_last_ply");
-        k_expand<true, MODE_HORIZON><<<(unsigned)nblocks(fb.n), BLOCK, 0, ctx->stream>>>(a);
+        if (quiet) k_expand<true, MODE_HORIZON, BLOCK, true><<<(unsigned)nblocks(fb.n), BLOCK, 0, ctx->stream>>>(a);
+        else k_expand<true, MODE_HORIZON><<<(unsigned)nblocks(fb.n), BLOCK, 0, ctx->stream>>>(a);
     }
     LL_TRY(check_launch("k_expand<HORIZON>"));
     for (size_t lev = bottom; lev > l; lev--) {
@@ -614,7 +619,8 @@ static int perft_chain_launch(ll_ctx *ctx, int depth, int shard_rank, int shard_
             Frontier &g = ctx->levels[l + 1];
             const unsigned grid = (unsigned)std::min<size_t>(nblocks(f.cap), resident);
             Timed t(ctx, "shard_filter");
-            k_shard_filter<<<grid, BLOCK, 0, ctx->stream>>>(f.soa(), (const u32 *)f.root.ptr, 0, N + l, g.soa(), (u32 *)g.root.ptr, N + l + 1, g.cap, overflow, shard_rank, shard_world);
+            k_shard_filter<<<grid, BLOCK, 0, ctx->stream>>>(f.soa(), (const u32 *)f.root.ptr, 0, N + l, g.soa(), (u32 *)g.root.ptr, N + l + 1, g.cap, overflow, shard_rank, shard_world,
+                                                            shard_ply == 2 ? N + 1 : nullptr);
             LL_TRY(check_launch("k_shard_filter"));
             l++;
             sharded = true;
@@ -645,7 +651,16 @@ static int perft_chain_launch(ll_ctx *ctx, int depth, int shard_rank, int shard_
         a.overflow = overflow;
         {
             Timed t(ctx, "emit_legal");
-            k_expand<false, MODE_EMIT><<<grid, BLOCK, 0, ctx->stream>>>(a);
+#if LL_SMALL_TILE_PLIES > 0
+            // the first plies are narrow (1, ~30, ~900, ~27 000 nodes): 32-parent tiles reach more SMs and finish sooner
+            // (not above the shard ply: the units dealt to the ranks must be in canonical order, which a level keeps only
+            // while its parents fit ONE tile -- k_shard_filter checks that)
+            if (ply < LL_SMALL_TILE_PLIES && (shard_world == 1 || ply >= shard_ply)) {
+                const unsigned small_grid = l == 0 ? 1u : (unsigned)std::min<size_t>(nblocks(f.cap, 32), resident);
+                k_expand<false, MODE_EMIT, 32><<<small_grid, BLOCK, 0, ctx->stream>>>(a);
+            } else
+#endif
+                k_expand<false, MODE_EMIT><<<grid, BLOCK, 0, ctx->stream>>>(a);
         }
         LL_TRY(check_launch("k_expand<EMIT>"));
         l++;
@@ -701,7 +716,7 @@ static int perft_synced(ll_ctx *ctx, int depth, int shard_rank, int shard_world,
             if (kept) {
                 Timed t(ctx, "shard_filter");
                 k_shard_filter<<<(unsigned)nblocks(kept), BLOCK, 0, ctx->stream>>>(ctx->levels[l].soa(), (const u32 *)ctx->levels[l].root.ptr, ctx->levels[l].n,
-                                                                                  nullptr, g.soa(), (u32 *)g.root.ptr, nullptr, 0, nullptr, shard_rank, shard_world);
+                                                                                  nullptr, g.soa(), (u32 *)g.root.ptr, nullptr, 0, nullptr, shard_rank, shard_world, nullptr);
                 LL_TRY(check_launch("k_shard_filter"));
             }
             g.n = kept;
@@ -881,7 +896,7 @@ static int kickoff_core(ll_ctx *ctx, const ll_world_t *root, int depth, int quie
         if (kept) {
             Timed t(ctx, "shard_filter");
             k_shard_filter<<<(unsigned)nblocks(kept), BLOCK, 0, ctx->stream>>>(ctx->levels[1].soa(), (const u32 *)ctx->levels[1].root.ptr, ctx->levels[1].n,
-                                                                              nullptr, h.soa(), (u32 *)h.root.ptr, nullptr, 0, nullptr, shard_rank, shard_world);
+                                                                              nullptr, h.soa(), (u32 *)h.root.ptr, nullptr, 0, nullptr, shard_rank, shard_world, nullptr);
             LL_TRY(check_launch("k_shard_filter"));
         }
         h.n = kept;

@@ -14,7 +14,10 @@
 namespace ll {
 
 constexpr int BLOCK = 128;
-constexpr int DESC_CAP = 6144; // move descriptors per window (24 KiB); a tile with more moves takes several windows
+#ifndef LL_DESC_CAP
+#define LL_DESC_CAP 5120
+#endif
+constexpr int DESC_CAP = LL_DESC_CAP; // move descriptors per window (24 KiB); a tile with more moves takes several windows
 
 enum { MODE_EMIT = 0, MODE_PERFT = 1, MODE_HORIZON = 2 };
 
@@ -208,12 +211,12 @@ __global__ void __launch_bounds__(BLOCK) k_offsets(const u32 *__restrict__ count
 }
 
 // phase-1 sink: descriptors of one parent into the current window of the shared list
-struct DescSink {
+template <bool STUNS> struct DescSink {
     u32 *buf;
     u32 idx, lo, hi, slot_bits;
-    u64 only_onto; // ~0, or the opposition's squares: keep stuns only (quiescence, mind.rs:292-294)
+    u64 onto; // STUNS: the opposition's squares -- keep only the commits that hospitalize somebody (quiescence, mind.rs:292-294)
     LL_HDM void move(u32 job, int from, int to, u32 asc, u32 flags) {
-        if (!((1ull << to) & only_onto) && !(flags & MV_PASSING_BY)) return;
+        if (STUNS && !((1ull << to) & onto) && !(flags & MV_PASSING_BY)) return;
         if (idx >= lo && idx < hi) buf[idx - lo] = mv_pack(job, from, to, asc, flags) | slot_bits;
         idx++;
     }
@@ -226,8 +229,7 @@ struct ExpandArgs {
     const u32 *counts;      // per-parent commit counts (nullptr: counted here)
     const u64 *block_base;  // EMIT, canonical order: first child index of each tile (from the scan)
     const u32 *root_in;     // root-move id of each parent (nullable)
-    int stuns_only;         // quiescence levels: expand only the commits that hospitalize somebody (mind.rs:292-294)
-    int stand_pat;          // ... and a parent may decline them all: value = max(orientation*score, children) (mind.rs:298)
+    int stand_pat;          // quiescence levels (STUNS): a parent may decline every stun: value = max(orientation*score, children) (mind.rs:298)
     // MODE_EMIT
     Soa out;
     u32 *cmeta;             // packed commit metadata (nullable)
@@ -244,20 +246,23 @@ struct ExpandArgs {
 };
 
 #ifndef LL_EXPAND_MIN_BLOCKS
-#define LL_EXPAND_MIN_BLOCKS 5
+#define LL_EXPAND_MIN_BLOCKS 6
 #endif
-LL_HD Pos tile_load(const u64 (*tile_pl)[BLOCK], const u32 *tile_meta, u32 slot) {
+template <int P> LL_HD Pos tile_load(const u64 (*tile_pl)[P], const u32 *tile_meta, u32 slot) {
     Pos p;
 #pragma unroll
     for (int j = 0; j < 12; j++) p.pl[j] = tile_pl[j][slot];
     p.meta = tile_meta[slot];
     return p;
 }
-template <bool NIHIL, int MODE> __global__ void __launch_bounds__(BLOCK, LL_EXPAND_MIN_BLOCKS) k_expand(const ExpandArgs a) {
-    __shared__ u64 tile_pl[12][BLOCK];
-    __shared__ u32 tile_meta[BLOCK];
+// P = parents per tile (BLOCK, or fewer for narrow levels: shorter tiles spread over more SMs; canonical-order
+// emission needs P == BLOCK because the scan works on BLOCK-sized groups)
+// STUNS = quiescence level: only stunning commits are expanded (a.stand_pat says whether the parent may decline them)
+template <bool NIHIL, int MODE, int P = BLOCK, bool STUNS = false> __global__ void __launch_bounds__(BLOCK, LL_EXPAND_MIN_BLOCKS) k_expand(const ExpandArgs a) {
+    __shared__ u64 tile_pl[12][P];
+    __shared__ u32 tile_meta[P];
     __shared__ u32 descs[DESC_CAP];
-    __shared__ int acc[BLOCK]; // PERFT: leaves below each parent; HORIZON: best child key of each parent
+    __shared__ int acc[P]; // PERFT: leaves below each parent; HORIZON: best child key of each parent
     __shared__ u64 claim_s;    // next tile / claimed output base
 
     const int tid = threadIdx.x;
@@ -272,18 +277,19 @@ template <bool NIHIL, int MODE> __global__ void __launch_bounds__(BLOCK, LL_EXPA
             __syncthreads();
             tile = (size_t)claim_s;
         }
-        if (tile * BLOCK >= n) break;
-        const size_t i = tile * BLOCK + tid;
+        if (tile * P >= n) break;
+        const size_t i = tile * P + tid;
+        const bool mine = tid < P && i < n; // this thread owns a parent of the tile
         u32 cnt = 0;
-        if (i < n) { // the parent lives in the shared tile from here on, not in registers
+        if (mine) { // the parent lives in the shared tile from here on, not in registers
             const Pos p = soa_load(a.in, i);
-            cnt = a.counts ? a.counts[i] : a.stuns_only ? count_stuns<NIHIL>(p) : count_moves<NIHIL>(p);
+            cnt = a.counts ? a.counts[i] : STUNS ? count_stuns<NIHIL>(p) : count_moves<NIHIL>(p);
 #pragma unroll
             for (int j = 0; j < 12; j++) tile_pl[j][tid] = p.pl[j];
             tile_meta[tid] = p.meta;
         }
-        if (MODE == MODE_PERFT) acc[tid] = 0;
-        if (MODE == MODE_HORIZON) acc[tid] = float_key(-INFINITY);
+        if (MODE == MODE_PERFT && tid < P) acc[tid] = 0;
+        if (MODE == MODE_HORIZON && tid < P) acc[tid] = float_key(-INFINITY);
         u32 total;
         const u32 ex = block_exclusive_scan(cnt, &total); // also orders the tile writes before phase 2
         size_t out_base = 0;
@@ -303,7 +309,7 @@ template <bool NIHIL, int MODE> __global__ void __launch_bounds__(BLOCK, LL_EXPA
         for (u32 w0 = 0; w0 < total && writable; w0 += DESC_CAP) {
             if (cnt && ex < w0 + DESC_CAP && ex + cnt > w0) { // phase 1: this parent's commits into the window
                 const Pos p = tile_load(tile_pl, tile_meta, tid);
-                DescSink sink{descs, ex, w0, w0 + DESC_CAP, (u32)tid << 20, a.stuns_only ? opposition_squares(p) : ~0ull};
+                DescSink<STUNS> sink{descs, ex, w0, w0 + DESC_CAP, (u32)tid << 20, STUNS ? opposition_squares(p) : 0ull};
                 lookahead<NIHIL>(p, sink);
             }
             __syncthreads();
@@ -324,7 +330,7 @@ template <bool NIHIL, int MODE> __global__ void __launch_bounds__(BLOCK, LL_EXPA
                         const size_t o = out_base + w0 + k;
                         soa_store(a.out, o, c);
                         if (a.cmeta) a.cmeta[o] = pack_commit(meta_stm(c.meta) ^ 1u, m, hosp);
-                        if (a.root_out) a.root_out[o] = a.root_is_index ? (u32)o : a.root_in[tile * BLOCK + slot];
+                        if (a.root_out) a.root_out[o] = a.root_is_index ? (u32)o : a.root_in[tile * P + slot];
                     }
                 } else {
                     int v = 0;
@@ -351,10 +357,10 @@ template <bool NIHIL, int MODE> __global__ void __launch_bounds__(BLOCK, LL_EXPA
 
         if (MODE == MODE_PERFT) {
             // tile order keeps a root's nodes contiguous, so a warp sees very few distinct roots
-            const u32 root = i < n ? (a.root_in ? a.root_in[i] : 0u) : 0xFFFFFFFFu;
-            const u32 mine = i < n ? (u32)acc[tid] : 0u;
+            const u32 root = mine ? (a.root_in ? a.root_in[i] : 0u) : 0xFFFFFFFFu;
+            const u32 below = mine ? (u32)acc[tid] : 0u;
             const unsigned peers = __match_any_sync(0xffffffffu, root);
-            const u32 sum = __reduce_add_sync(peers, mine);
+            const u32 sum = __reduce_add_sync(peers, below);
             if ((tid & 31) == __ffs((int)peers) - 1 && root != 0xFFFFFFFFu && sum) {
                 if (a.per_root) atomicAdd((unsigned long long *)a.per_root + root, (unsigned long long)sum);
                 atomicAdd((unsigned long long *)a.total, (unsigned long long)sum);
@@ -362,9 +368,9 @@ template <bool NIHIL, int MODE> __global__ void __launch_bounds__(BLOCK, LL_EXPA
         }
         if (MODE == MODE_HORIZON) {
             u32 scored = 0;
-            if (i < n) {
+            if (mine) {
                 float v = cnt ? key_float(acc[tid]) : -INFINITY;
-                if (cnt == 0 || a.stand_pat) { // nothing to play: the node is itself a leaf (mind.rs:281-283, 295-299)
+                if (cnt == 0 || (STUNS && a.stand_pat)) { // nothing to play: the node is itself a leaf (mind.rs:281-283, 295-299)
                     const Pos p = tile_load(tile_pl, tile_meta, tid);
                     const float s = score(p);
                     v = fmaxf(v, meta_stm(p.meta) ? -s : s);
@@ -383,11 +389,14 @@ template <bool NIHIL, int MODE> __global__ void __launch_bounds__(BLOCK, LL_EXPA
 // keep the units u with u % world == rank (frontier sharding by subtree).  n_in / n_out
 // (nullable) are device-resident counts for the launch chain that never returns to the host.
 __global__ void __launch_bounds__(BLOCK) k_shard_filter(Soa in, const u32 *__restrict__ root_in, size_t n, const u64 *n_in, Soa out,
-                                                        u32 *__restrict__ root_out, u64 *n_out, size_t out_cap, u32 *overflow, int rank, int world) {
+                                                        u32 *__restrict__ root_out, u64 *n_out, size_t out_cap, u32 *overflow, int rank, int world,
+                                                        const u64 *single_tile_guard) {
     if (n_in && overflow && *(volatile u32 *)overflow) return;
     if (n_in) n = (size_t)*n_in;
     size_t kept = n > (size_t)rank ? (n - rank + world - 1) / world : 0;
-    if (overflow && kept > out_cap) { // the chained path: report instead of writing past the level
+    // order-free placement keeps the canonical order only below a level that fitted one tile; with more root moves
+    // than that the unit numbering is not reproducible across ranks -- hand the call to the level-by-level path
+    if (overflow && ((single_tile_guard && *single_tile_guard > BLOCK) || kept > out_cap)) {
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(overflow, 1u);
         kept = 0;
     }

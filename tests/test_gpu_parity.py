@@ -470,3 +470,27 @@ def test_full_size_score_batch_properties(eng):
     eng.synchronize()
     assert torch.equal(out, out2)
     eng.soa_free(soa)
+
+
+# ---------------------------------------------------------------- --correspond wire format (main.rs:182-244)
+def test_correspondence_wire_format(eng):
+    import json
+
+    from leafline_b200 import correspondence as co
+
+    # main.rs:461-469: the reference's own end-to-end test
+    assert co.correspondence(eng, "R6k/6pp/8/8/8/8/8/8 b - -", co.Depth(2)) == '{"the_triumphant":"Orange"}'
+    # stalemate of the side to move -> nobody triumphs
+    assert co.correspondence(eng, "7k/5Q2/6K1/8/8/8/8/8 b - -", co.Depth(1)) == '{"the_triumphant":null}'
+    card = co.correspondence(eng, "8/q1P1k/8/8/8/8/6PP/7K w - -", co.DepthSequence.from_depiction("1,2,3"))
+    d = json.loads(card)
+    assert list(d) == ["world", "patch", "hospitalization", "thinking_time", "depth", "counterreplies", "rosetta_stone"]
+    assert d["world"] == "2N5/q3k3/8/8/8/8/6PP/7K b - -" and d["depth"] == 3 and d["hospitalization"] is None
+    assert d["patch"] == {"star": {"team": "Orange", "job_description": "Servant"}, "whence": {"rank": 6, "file": 2}, "whither": {"rank": 7, "file": 2}}
+    assert d["rosetta_stone"] == "c8" and len(d["counterreplies"]) == len(O.lookahead(O.reconstruct(d["world"])))
+    assert ", " not in card and "\": " not in card  # compact, like rustc-serialize
+    # a capture reports its patient; Seconds bound runs the iterative deepening
+    d = json.loads(co.correspondence(eng, "1p6/8/2N5/8/6p1/2B5/8/n7 w - -", co.Depth(2)))
+    assert d["hospitalization"] == {"team": "Blue", "job_description": "Pony"} and d["rosetta_stone"] == "Ba1"
+    d = json.loads(co.correspondence(eng, "rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq -", co.Seconds(1)))
+    assert d["depth"] >= 3 and len(d["counterreplies"]) == 20
