@@ -203,6 +203,7 @@ def main():
             return reduce_counts(eng.perft(root, depth)[1])
         return int(h_out[0])
 
+    eng.perft(root, depth)  # the first call sizes the level buffers (level-by-level path); the steps run the launch chain
     for _ in range(args.warmup):
         total = step()
         assert expected is None or total == expected * world, total
@@ -253,7 +254,8 @@ def main():
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 104, "d2h_bytes_per_step": 8 + 8 * 1024,
                 "ms_per_step": host_ms / args.steps,
-                "note": "host clock around the C-ABI call ll_perft (host root in, host leaf counts out, both copies inside)"},
+                "note": ("host clock around the C-ABI call ll_perft (host root in, host leaf counts out, both copies inside)" if world == 1 else
+                         "host clock around ll_perft_device (host root in) + NCCL u64 all-reduce of the count table + its D2H read")},
     }
 
     # strong-scaling companion: ONE perft(7) tree dealt to the ranks by 2-ply prefixes + u64 all-reduce
