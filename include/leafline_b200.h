@@ -182,7 +182,7 @@ int ll_timing_query(ll_ctx *ctx, const char *kernel, double *ms, uint64_t *launc
 /* total number of this library's kernel launches since ll_init (for bench.py's gpu_launches) */
 uint64_t ll_launch_count(ll_ctx *ctx);
 /* testing aid: on != 0 makes ll_perft take its level-by-level path (sizes every level on the host) instead of the
- * single launch chain; both give identical results */
+ * launch chain with device-resident level sizes; both give identical results */
 int ll_debug_force_synced(ll_ctx *ctx, int on);
 /* measurement utility for the integer roofline: sustained thread-level integer instructions per second
  * of a dependency-free stream; kind 0 = LOP3 only (ALU pipe), 1 = LOP3 + IMAD (ALU + FMA pipes) */

@@ -126,7 +126,7 @@ class Engine:
         return ms.value, launches.value
 
     def force_synced(self, on=True):
-        """Testing aid: make perft() take the level-by-level path instead of the single launch chain."""
+        """Testing aid: make perft() take the level-by-level path instead of the launch chain."""
         _abi.check(self._lib.ll_debug_force_synced(self._ctx, int(on)))
 
     def measure_int_peak(self, kind=0):

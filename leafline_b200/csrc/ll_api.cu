@@ -610,36 +610,42 @@ static int perft_chain_launch(ll_ctx *ctx, int depth, int shard_rank, int shard_
     u32 *tileq = (u32 *)(sc + SC_TILEQ);
     u32 *overflow = (u32 *)(sc + SC_OVERFLOW);
     const unsigned resident = (unsigned)ctx->sm_count * LL_EXPAND_MIN_BLOCKS;
+    // the plan: one step per ply (+ the shard filter); each step reads its level's size from the device
+    ExpandArgs steps[CHAIN_MAX_STEPS] = {};
+    int kinds[CHAIN_MAX_STEPS] = {};
+    unsigned grids[CHAIN_MAX_STEPS] = {};
+    ShardArgs shard{};
     size_t l = 0;
-    int q = 0;
-    bool sharded = shard_world == 1;
+    int q = 0, n_steps = 0;
+    bool sharded = shard_world == 1, too_deep = false;
     for (int ply = 0; ply <= tail_ply; ply++) {
+        if (n_steps + 2 > CHAIN_MAX_STEPS) {
+            too_deep = true;
+            break;
+        }
         if (!sharded && ply == shard_ply) { // keep this rank's units (ply >= 1 here)
             Frontier &f = ctx->levels[l];
             Frontier &g = ctx->levels[l + 1];
-            const unsigned grid = (unsigned)std::min<size_t>(nblocks(f.cap), resident);
-            Timed t(ctx, "shard_filter");
-            k_shard_filter<<<grid, BLOCK, 0, ctx->stream>>>(f.soa(), (const u32 *)f.root.ptr, 0, N + l, g.soa(), (u32 *)g.root.ptr, N + l + 1, g.cap, overflow, shard_rank, shard_world,
-                                                            shard_ply == 2 ? N + 1 : nullptr);
-            LL_TRY(check_launch("k_shard_filter"));
+            shard = ShardArgs{f.soa(), (const u32 *)f.root.ptr, 0, N + l, g.soa(), (u32 *)g.root.ptr, N + l + 1, g.cap, overflow, shard_rank, shard_world,
+                              shard_ply == 2 ? N + 1 : nullptr};
+            grids[n_steps] = (unsigned)std::min<size_t>(nblocks(f.cap), resident);
+            kinds[n_steps++] = STEP_SHARD;
             l++;
             sharded = true;
         }
         Frontier &f = ctx->levels[l];
-        ExpandArgs a{};
+        ExpandArgs &a = steps[n_steps];
         a.in = f.soa();
         a.n = 1;
         a.n_in = l == 0 ? nullptr : N + l;
         a.tile_counter = tileq + q++;
         a.root_in = ply == 0 ? nullptr : (const u32 *)f.root.ptr;
         a.overflow = overflow;
-        const unsigned grid = l == 0 ? 1u : (unsigned)std::min<size_t>(nblocks(f.cap), resident);
+        grids[n_steps] = l == 0 ? 1u : (unsigned)std::min<size_t>(nblocks(f.cap), resident);
         if (ply == tail_ply) {
             a.per_root = sc + SC_PER_ROOT;
             a.total = sc + SC_LEAVES;
-            Timed t(ctx, "perft_tail");
-            k_expand<false, MODE_PERFT><<<grid, BLOCK, 0, ctx->stream>>>(a);
-            LL_TRY(check_launch("k_expand<PERFT>"));
+            kinds[n_steps++] = STEP_TAIL;
             break;
         }
         Frontier &g = ctx->levels[l + 1];
@@ -648,22 +654,24 @@ static int perft_chain_launch(ll_ctx *ctx, int depth, int shard_rank, int shard_
         a.root_is_index = ply == 0;
         a.n_out = N + l + 1;
         a.out_cap = g.cap;
-        a.overflow = overflow;
-        {
-            Timed t(ctx, "emit_legal");
-#if LL_SMALL_TILE_PLIES > 0
-            // the first plies are narrow (1, ~30, ~900, ~27 000 nodes): 32-parent tiles reach more SMs and finish sooner
-            // (not above the shard ply: the units dealt to the ranks must be in canonical order, which a level keeps only
-            // while its parents fit ONE tile -- k_shard_filter checks that)
-            if (ply < LL_SMALL_TILE_PLIES && (shard_world == 1 || ply >= shard_ply)) {
-                const unsigned small_grid = l == 0 ? 1u : (unsigned)std::min<size_t>(nblocks(f.cap, 32), resident);
-                k_expand<false, MODE_EMIT, 32><<<small_grid, BLOCK, 0, ctx->stream>>>(a);
-            } else
-#endif
-                k_expand<false, MODE_EMIT><<<grid, BLOCK, 0, ctx->stream>>>(a);
-        }
-        LL_TRY(check_launch("k_expand<EMIT>"));
+        // the first plies are narrow (1, ~30, ~900, ~27 000 nodes): 32-parent tiles reach more SMs and finish sooner
+        // (not above the shard ply: the units dealt to the ranks must be in canonical order, which a level keeps only
+        // while its parents fit ONE tile -- the shard filter checks that)
+        const bool small = ply < LL_SMALL_TILE_PLIES && (shard_world == 1 || ply >= shard_ply);
+        if (small && l != 0) grids[n_steps] = (unsigned)std::min<size_t>(nblocks(f.cap, 32), resident);
+        kinds[n_steps++] = small ? STEP_EMIT_SMALL : STEP_EMIT;
         l++;
+    }
+    if (too_deep) return LL_OK; // deeper than the plan holds: the level-by-level path takes it
+    // (a single cooperative launch with grid-wide barriers between the plies was measured: no faster -- DESIGN.md)
+    for (int s = 0; s < n_steps; s++) {
+        const int kind = kinds[s];
+        Timed t(ctx, kind == STEP_TAIL ? "perft_tail" : kind == STEP_SHARD ? "shard_filter" : "emit_legal");
+        if (kind == STEP_SHARD) k_shard_filter<<<grids[s], BLOCK, 0, ctx->stream>>>(shard);
+        else if (kind == STEP_TAIL) k_expand<false, MODE_PERFT><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
+        else if (kind == STEP_EMIT_SMALL) k_expand<false, MODE_EMIT, 32><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
+        else k_expand<false, MODE_EMIT><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
+        LL_TRY(check_launch("perft chain step"));
     }
     *launched = true;
     return LL_OK;
@@ -715,8 +723,8 @@ static int perft_synced(ll_ctx *ctx, int depth, int shard_rank, int shard_world,
             Frontier &g = ctx->levels[l + 1];
             if (kept) {
                 Timed t(ctx, "shard_filter");
-                k_shard_filter<<<(unsigned)nblocks(kept), BLOCK, 0, ctx->stream>>>(ctx->levels[l].soa(), (const u32 *)ctx->levels[l].root.ptr, ctx->levels[l].n,
-                                                                                  nullptr, g.soa(), (u32 *)g.root.ptr, nullptr, 0, nullptr, shard_rank, shard_world, nullptr);
+                k_shard_filter<<<(unsigned)nblocks(kept), BLOCK, 0, ctx->stream>>>(ShardArgs{ctx->levels[l].soa(), (const u32 *)ctx->levels[l].root.ptr, ctx->levels[l].n,
+                                                                                            nullptr, g.soa(), (u32 *)g.root.ptr, nullptr, 0, nullptr, shard_rank, shard_world, nullptr});
                 LL_TRY(check_launch("k_shard_filter"));
             }
             g.n = kept;
@@ -895,8 +903,8 @@ static int kickoff_core(ll_ctx *ctx, const ll_world_t *root, int depth, int quie
         Frontier &h = ctx->levels[2];
         if (kept) {
             Timed t(ctx, "shard_filter");
-            k_shard_filter<<<(unsigned)nblocks(kept), BLOCK, 0, ctx->stream>>>(ctx->levels[1].soa(), (const u32 *)ctx->levels[1].root.ptr, ctx->levels[1].n,
-                                                                              nullptr, h.soa(), (u32 *)h.root.ptr, nullptr, 0, nullptr, shard_rank, shard_world, nullptr);
+            k_shard_filter<<<(unsigned)nblocks(kept), BLOCK, 0, ctx->stream>>>(ShardArgs{ctx->levels[1].soa(), (const u32 *)ctx->levels[1].root.ptr, ctx->levels[1].n,
+                                                                                        nullptr, h.soa(), (u32 *)h.root.ptr, nullptr, 0, nullptr, shard_rank, shard_world, nullptr});
             LL_TRY(check_launch("k_shard_filter"));
         }
         h.n = kept;

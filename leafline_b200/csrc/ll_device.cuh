@@ -174,6 +174,13 @@ template <int A> LL_HD u64 servant_attacks(u64 s) {
     return ((s >> 9) & ~FILE_H) | ((s >> 7) & ~FILE_A);
 }
 
+// squares the ponies `s` jump to, all of them at once (the union of PONY_MOVEMENT_TABLE rows, furniture/tablemaker.py:41-50)
+LL_HD u64 pony_attacks(u64 s) {
+    const u64 h1 = ((s >> 1) & ~FILE_H) | ((s << 1) & ~FILE_A);
+    const u64 h2 = ((s >> 2) & ~(FILE_H | (FILE_H >> 1))) | ((s << 2) & ~(FILE_A | (FILE_A << 1)));
+    return (h1 << 16) | (h1 >> 16) | (h2 << 8) | (h2 >> 8);
+}
+
 template <int T> LL_HD u64 occupied_by(const Pos &p) { // life.rs:521-540
     return p.pl[6 * T] | p.pl[6 * T + 1] | p.pl[6 * T + 2] | p.pl[6 * T + 3] | p.pl[6 * T + 4] | p.pl[6 * T + 5];
 }
@@ -304,13 +311,15 @@ template <int T> LL_HD Legal legal_context(const Pos &p, u64 own, u64 opp) {
     const int ksq = lsb64(k);
     const u64 occ = own | opp;
     const u64 e_diag = p.pl[6 * E + SCHOLAR] | p.pl[6 * E + PRINCESS], e_orth = p.pl[6 * E + COP] | p.pl[6 * E + PRINCESS];
-    // danger map: the opposition's attacks with our figurehead lifted (it cannot hide behind itself)
-    const u64 empty_wo_k = ~(occ ^ k);
-    u64 danger = servant_attacks<E>(p.pl[6 * E + SERVANT]);
-    for (u64 s = p.pl[6 * E + PONY]; s; s &= s - 1) danger |= pony_moves(lsb64(s));
-    if (p.pl[6 * E + FIGUREHEAD]) danger |= figurehead_moves(lsb64(p.pl[6 * E + FIGUREHEAD]));
-    danger |= ks_diag_attacks(e_diag, empty_wo_k) | ks_orth_attacks(e_orth, empty_wo_k);
-    L.danger = danger;
+    // danger map: the opposition's attacks with our figurehead lifted (it cannot hide behind itself).  Only the
+    // figurehead's own steps consult it, so a boxed-in figurehead (siblings in a perft frontier share that) skips it.
+    if (figurehead_moves(ksq) & ~own) {
+        const u64 empty_wo_k = ~(occ ^ k);
+        u64 danger = servant_attacks<E>(p.pl[6 * E + SERVANT]) | pony_attacks(p.pl[6 * E + PONY]);
+        if (p.pl[6 * E + FIGUREHEAD]) danger |= figurehead_moves(lsb64(p.pl[6 * E + FIGUREHEAD]));
+        danger |= ks_diag_attacks(e_diag, empty_wo_k) | ks_orth_attacks(e_orth, empty_wo_k);
+        L.danger = danger;
+    }
     // checkers and pins along the four lines through the figurehead
     L.kd = diag_mask(ksq) & ~k;
     L.ka = anti_mask(ksq) & ~k;

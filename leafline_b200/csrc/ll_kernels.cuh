@@ -248,34 +248,36 @@ struct ExpandArgs {
 #ifndef LL_EXPAND_MIN_BLOCKS
 #define LL_EXPAND_MIN_BLOCKS 6
 #endif
-template <int P> LL_HD Pos tile_load(const u64 (*tile_pl)[P], const u32 *tile_meta, u32 slot) {
+// shared memory of one expansion block (33.8 KiB: six blocks per SM)
+struct ExpandShared {
+    u64 tile_pl[12][BLOCK];
+    u32 tile_meta[BLOCK];
+    u32 descs[DESC_CAP];
+    int acc[BLOCK]; // PERFT: leaves below each parent; HORIZON: best child key of each parent
+    u64 claim;      // next tile / claimed output base
+};
+LL_HD Pos tile_load(const ExpandShared &sh, u32 slot) {
     Pos p;
 #pragma unroll
-    for (int j = 0; j < 12; j++) p.pl[j] = tile_pl[j][slot];
-    p.meta = tile_meta[slot];
+    for (int j = 0; j < 12; j++) p.pl[j] = sh.tile_pl[j][slot];
+    p.meta = sh.tile_meta[slot];
     return p;
 }
 // P = parents per tile (BLOCK, or fewer for narrow levels: shorter tiles spread over more SMs; canonical-order
 // emission needs P == BLOCK because the scan works on BLOCK-sized groups)
 // STUNS = quiescence level: only stunning commits are expanded (a.stand_pat says whether the parent may decline them)
-template <bool NIHIL, int MODE, int P = BLOCK, bool STUNS = false> __global__ void __launch_bounds__(BLOCK, LL_EXPAND_MIN_BLOCKS) k_expand(const ExpandArgs a) {
-    __shared__ u64 tile_pl[12][P];
-    __shared__ u32 tile_meta[P];
-    __shared__ u32 descs[DESC_CAP];
-    __shared__ int acc[P]; // PERFT: leaves below each parent; HORIZON: best child key of each parent
-    __shared__ u64 claim_s;    // next tile / claimed output base
-
+template <bool NIHIL, int MODE, int P, bool STUNS> __device__ __forceinline__ void expand_tiles(const ExpandArgs &a, ExpandShared &sh) {
     const int tid = threadIdx.x;
     // chained launches: once a level has outgrown its buffer, its recorded size says nothing about what was
     // written -- everything downstream stands down and the host redoes the call level by level
     if (a.n_in && a.overflow && *(volatile u32 *)a.overflow) return;
-    const size_t n = a.n_in ? (size_t)*a.n_in : a.n;
+    const size_t n = a.n_in ? (size_t)*(volatile const u64 *)a.n_in : a.n;
     for (;;) {
         size_t tile = blockIdx.x;
         if (a.tile_counter) {
-            if (tid == 0) claim_s = atomicAdd(a.tile_counter, 1u);
+            if (tid == 0) sh.claim = atomicAdd(a.tile_counter, 1u);
             __syncthreads();
-            tile = (size_t)claim_s;
+            tile = (size_t)sh.claim;
         }
         if (tile * P >= n) break;
         const size_t i = tile * P + tid;
@@ -285,11 +287,11 @@ template <bool NIHIL, int MODE, int P = BLOCK, bool STUNS = false> __global__ vo
             const Pos p = soa_load(a.in, i);
             cnt = a.counts ? a.counts[i] : STUNS ? count_stuns<NIHIL>(p) : count_moves<NIHIL>(p);
 #pragma unroll
-            for (int j = 0; j < 12; j++) tile_pl[j][tid] = p.pl[j];
-            tile_meta[tid] = p.meta;
+            for (int j = 0; j < 12; j++) sh.tile_pl[j][tid] = p.pl[j];
+            sh.tile_meta[tid] = p.meta;
         }
-        if (MODE == MODE_PERFT && tid < P) acc[tid] = 0;
-        if (MODE == MODE_HORIZON && tid < P) acc[tid] = float_key(-INFINITY);
+        if (MODE == MODE_PERFT && tid < P) sh.acc[tid] = 0;
+        if (MODE == MODE_HORIZON && tid < P) sh.acc[tid] = float_key(-INFINITY);
         u32 total;
         const u32 ex = block_exclusive_scan(cnt, &total); // also orders the tile writes before phase 2
         size_t out_base = 0;
@@ -298,9 +300,9 @@ template <bool NIHIL, int MODE, int P = BLOCK, bool STUNS = false> __global__ vo
             if (a.block_base) {
                 out_base = (size_t)a.block_base[tile];
             } else { // order-free: claim a contiguous range for this tile's children
-                if (tid == 0) claim_s = atomicAdd((unsigned long long *)a.n_out, (unsigned long long)total);
+                if (tid == 0) sh.claim = atomicAdd((unsigned long long *)a.n_out, (unsigned long long)total);
                 __syncthreads();
-                out_base = (size_t)claim_s;
+                out_base = (size_t)sh.claim;
                 writable = out_base + total <= a.out_cap;
                 if (!writable && tid == 0) atomicExch(a.overflow, 1u);
             }
@@ -308,8 +310,8 @@ template <bool NIHIL, int MODE, int P = BLOCK, bool STUNS = false> __global__ vo
 
         for (u32 w0 = 0; w0 < total && writable; w0 += DESC_CAP) {
             if (cnt && ex < w0 + DESC_CAP && ex + cnt > w0) { // phase 1: this parent's commits into the window
-                const Pos p = tile_load(tile_pl, tile_meta, tid);
-                DescSink<STUNS> sink{descs, ex, w0, w0 + DESC_CAP, (u32)tid << 20, STUNS ? opposition_squares(p) : 0ull};
+                const Pos p = tile_load(sh, tid);
+                DescSink<STUNS> sink{sh.descs, ex, w0, w0 + DESC_CAP, (u32)tid << 20, STUNS ? opposition_squares(p) : 0ull};
                 lookahead<NIHIL>(p, sink);
             }
             __syncthreads();
@@ -321,9 +323,9 @@ template <bool NIHIL, int MODE, int P = BLOCK, bool STUNS = false> __global__ vo
                 Pos c;
                 u32 m = 0, hosp = JOB_NONE;
                 if (live) {
-                    m = descs[k];
+                    m = sh.descs[k];
                     slot = mv_slot(m);
-                    hosp = make_child(tile_load(tile_pl, tile_meta, slot), m, c);
+                    hosp = make_child(tile_load(sh, slot), m, c);
                 }
                 if (MODE == MODE_EMIT) {
                     if (live) {
@@ -347,8 +349,8 @@ template <bool NIHIL, int MODE, int P = BLOCK, bool STUNS = false> __global__ vo
                     const unsigned peers = __match_any_sync(0xffffffffu, live ? slot : 0xFFFFFFFFu);
                     const int r = MODE == MODE_PERFT ? __reduce_add_sync(peers, v) : __reduce_max_sync(peers, v);
                     if (live && (tid & 31) == __ffs((int)peers) - 1) {
-                        if (MODE == MODE_PERFT) atomicAdd(&acc[slot], r);
-                        else atomicMax(&acc[slot], r);
+                        if (MODE == MODE_PERFT) atomicAdd(&sh.acc[slot], r);
+                        else atomicMax(&sh.acc[slot], r);
                     }
                 }
             }
@@ -358,7 +360,7 @@ template <bool NIHIL, int MODE, int P = BLOCK, bool STUNS = false> __global__ vo
         if (MODE == MODE_PERFT) {
             // tile order keeps a root's nodes contiguous, so a warp sees very few distinct roots
             const u32 root = mine ? (a.root_in ? a.root_in[i] : 0u) : 0xFFFFFFFFu;
-            const u32 below = mine ? (u32)acc[tid] : 0u;
+            const u32 below = mine ? (u32)sh.acc[tid] : 0u;
             const unsigned peers = __match_any_sync(0xffffffffu, root);
             const u32 sum = __reduce_add_sync(peers, below);
             if ((tid & 31) == __ffs((int)peers) - 1 && root != 0xFFFFFFFFu && sum) {
@@ -369,9 +371,9 @@ template <bool NIHIL, int MODE, int P = BLOCK, bool STUNS = false> __global__ vo
         if (MODE == MODE_HORIZON) {
             u32 scored = 0;
             if (mine) {
-                float v = cnt ? key_float(acc[tid]) : -INFINITY;
+                float v = cnt ? key_float(sh.acc[tid]) : -INFINITY;
                 if (cnt == 0 || (STUNS && a.stand_pat)) { // nothing to play: the node is itself a leaf (mind.rs:281-283, 295-299)
-                    const Pos p = tile_load(tile_pl, tile_meta, tid);
+                    const Pos p = tile_load(sh, tid);
                     const float s = score(p);
                     v = fmaxf(v, meta_stm(p.meta) ? -s : s);
                 }
@@ -385,28 +387,46 @@ template <bool NIHIL, int MODE, int P = BLOCK, bool STUNS = false> __global__ vo
         __syncthreads(); // the tile and the claim slot are reused by the next round
     }
 }
+template <bool NIHIL, int MODE, int P = BLOCK, bool STUNS = false> __global__ void __launch_bounds__(BLOCK, LL_EXPAND_MIN_BLOCKS) k_expand(const ExpandArgs a) {
+    __shared__ ExpandShared sh;
+    expand_tiles<NIHIL, MODE, P, STUNS>(a, sh);
+}
 
 // keep the units u with u % world == rank (frontier sharding by subtree).  n_in / n_out
 // (nullable) are device-resident counts for the launch chain that never returns to the host.
-__global__ void __launch_bounds__(BLOCK) k_shard_filter(Soa in, const u32 *__restrict__ root_in, size_t n, const u64 *n_in, Soa out,
-                                                        u32 *__restrict__ root_out, u64 *n_out, size_t out_cap, u32 *overflow, int rank, int world,
-                                                        const u64 *single_tile_guard) {
-    if (n_in && overflow && *(volatile u32 *)overflow) return;
-    if (n_in) n = (size_t)*n_in;
-    size_t kept = n > (size_t)rank ? (n - rank + world - 1) / world : 0;
+struct ShardArgs {
+    Soa in;
+    const u32 *root_in;
+    size_t n;
+    const u64 *n_in;
+    Soa out;
+    u32 *root_out;
+    u64 *n_out;
+    size_t out_cap;
+    u32 *overflow;
+    int rank, world;
+    const u64 *single_tile_guard;
+};
+__global__ void __launch_bounds__(BLOCK) k_shard_filter(const ShardArgs a) {
+    if (a.n_in && a.overflow && *(volatile u32 *)a.overflow) return;
+    const size_t n = a.n_in ? (size_t)*(volatile const u64 *)a.n_in : a.n;
+    size_t kept = n > (size_t)a.rank ? (n - a.rank + a.world - 1) / a.world : 0;
     // order-free placement keeps the canonical order only below a level that fitted one tile; with more root moves
     // than that the unit numbering is not reproducible across ranks -- hand the call to the level-by-level path
-    if (overflow && ((single_tile_guard && *single_tile_guard > BLOCK) || kept > out_cap)) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(overflow, 1u);
+    if (a.overflow && ((a.single_tile_guard && *(volatile const u64 *)a.single_tile_guard > BLOCK) || kept > a.out_cap)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(a.overflow, 1u);
         kept = 0;
     }
-    if (n_out && blockIdx.x == 0 && threadIdx.x == 0) *n_out = kept;
+    if (a.n_out && blockIdx.x == 0 && threadIdx.x == 0) *a.n_out = kept;
     for (size_t o = (size_t)blockIdx.x * BLOCK + threadIdx.x; o < kept; o += (size_t)gridDim.x * BLOCK) { // o-th kept unit = unit rank + o*world
-        const size_t i = (size_t)rank + o * (size_t)world;
-        soa_store(out, o, soa_load(in, i));
-        root_out[o] = root_in ? root_in[i] : 0u;
+        const size_t i = (size_t)a.rank + o * (size_t)a.world;
+        soa_store(a.out, o, soa_load(a.in, i));
+        a.root_out[o] = a.root_in ? a.root_in[i] : 0u;
     }
 }
+// ---- the perft launch chain: one step per ply (+ the shard filter), every size resident on the device --------
+constexpr int CHAIN_MAX_STEPS = 12;
+enum { STEP_EMIT_SMALL = 0, STEP_EMIT = 1, STEP_TAIL = 2, STEP_SHARD = 3 };
 
 // ll_perft_device: gather the chain's results into the caller's device buffer (see the header for the layout)
 __global__ void __launch_bounds__(1024) k_pack_perft_result(const u64 *leaves, const u64 *n_roots, const u32 *overflow, const u64 *per_root, u64 *out) {
