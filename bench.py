@@ -72,7 +72,7 @@ class ClockSampler(threading.Thread):
                     ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu_index)],
                     capture_output=True, text=True, timeout=5).stdout.strip().split("\n")[0]
                 parts = [p.strip() for p in out.split(",")]
-                self.samples.append(float(parts[0]))
+                self.samples.append((time.perf_counter(), float(parts[0])))
                 self.sm_max = float(parts[1])
                 for name, val in zip(names, parts[2:]):
                     if val.lower().startswith("active"):
@@ -81,14 +81,21 @@ class ClockSampler(threading.Thread):
                 pass
             self._halt.wait(0.05)
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """median SM clock of the samples taken inside [t_begin, t_end] (the timed region); a region shorter than
+        a few nvidia-smi calls falls back to every sample since the sampler started (warm-up included: same load)"""
         self._halt.set()
         self.join(timeout=10)
+        inside = [mhz for t, mhz in self.samples if t_begin is not None and t_begin <= t <= t_end]
+        window = "timed region"
+        if len(inside) < 3:
+            inside, window = [mhz for _, mhz in self.samples], "warm-up + timed region"
         return {
-            "sm_mhz": statistics.median(self.samples) if self.samples else None,
+            "sm_mhz": statistics.median(inside) if inside else None,
             "sm_max_mhz": self.sm_max,
             "reasons": sorted(self.reasons),
-            "samples": len(self.samples),
+            "samples": len(inside),
+            "window": window,
         }
 
 
@@ -138,13 +145,15 @@ def timed(stream, fn, reps, torch):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--depth", type=int, default=6)
     ap.add_argument("--no-extras", action="store_true", help="skip the cpu baseline and the secondary kernels")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":  # each reference step is ~0.5 s of all-core CPU work: keep the default run to about half a minute
+        args.steps, args.warmup = min(args.steps, 40), min(args.warmup, 3)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -204,16 +213,17 @@ def main():
         return int(h_out[0])
 
     eng.perft(root, depth)  # the first call sizes the level buffers (level-by-level path); the steps run the launch chain
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         total = step()
         assert expected is None or total == expected * world, total
     launches0 = eng.launch_count
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    t_begin = time.perf_counter()
     device_ms = 0.0
     host_s = 0.0
     for _ in range(args.steps):
@@ -230,7 +240,7 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_begin, time.perf_counter())
     launches = eng.launch_count - launches0
     assert expected is None or total == expected * world, total
     t = torch.tensor([device_ms, host_s * 1e3], dtype=torch.float64, device="cuda")
