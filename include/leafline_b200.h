@@ -98,8 +98,11 @@ int ll_in_critical_endangerment_batch(ll_ctx *ctx, const ll_world_t *worlds, con
 /* perft = number of leaves of the legal-move tree (recursive `lookahead()`);
  * depth 0 -> 1.  per_root (nullable, root_cap entries) receives the leaf count below each root
  * move in canonical order and *n_roots their number ("divide").  With shard_world > 1 only the
- * work units u (2-ply prefixes, canonical order) with u % shard_world == shard_rank are counted:
- * summing the results of all ranks (a u64 allreduce) gives the full answer. */
+ * work units u with u % shard_world == shard_rank are counted, the units being the nodes of ply
+ * min(2, depth - 2) in canonical order (2-ply prefixes for depth >= 4; ply 1 for depth 2 and 3; the
+ * whole tree is rank 0's for depth 1): summing the results of all ranks (a u64 allreduce) gives the
+ * full answer.  The frontier is materialised in HBM up to ply depth - 2 (100 B per node + 12 B of ids and
+ * counts); the last two plies are generated and counted on chip.  LL_ERR_OOM if a level does not fit. */
 int ll_perft(ll_ctx *ctx, const ll_world_t *root, int depth, int shard_rank, int shard_world, uint64_t *leaves,
              uint64_t *per_root, uint32_t root_cap, uint32_t *n_roots);
 
