@@ -187,6 +187,11 @@ uint64_t ll_launch_count(ll_ctx *ctx);
 /* testing aid: on != 0 makes ll_perft take its level-by-level path (sizes every level on the host) instead of the
  * launch chain with device-resident level sizes; both give identical results */
 int ll_debug_force_synced(ll_ctx *ctx, int on);
+/* testing aid, full-size property check on resident positions: for every position the set-wise move counter, the
+ * canonical generator (legality by check / pin / danger masks) and the reference's definition (each reckless commit
+ * made, kept iff the mover's figurehead is not endangered afterwards, src/life.rs:692-699) must agree.
+ * result4 = { disagreeing positions, first disagreeing index (~0 if none), legal commits, reckless commits }. */
+int ll_debug_selfcheck_soa(ll_ctx *ctx, const ll_soa_t *soa, uint64_t *result4);
 /* measurement utility for the integer roofline: sustained thread-level integer instructions per second
  * of a dependency-free stream; kind 0 = LOP3 only (ALU pipe), 1 = LOP3 + IMAD (ALU + FMA pipes) */
 int ll_measure_int_peak(ll_ctx *ctx, int kind, double *thread_ops_per_sec);

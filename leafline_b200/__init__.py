@@ -129,6 +129,12 @@ class Engine:
         """Testing aid: make perft() take the level-by-level path instead of the launch chain."""
         _abi.check(self._lib.ll_debug_force_synced(self._ctx, int(on)))
 
+    def selfcheck_soa(self, soa):
+        """Testing aid -> (disagreeing positions, first index or None, legal commits, reckless commits); see the header."""
+        out = np.zeros(4, dtype=np.uint64)
+        _abi.check(self._lib.ll_debug_selfcheck_soa(self._ctx, C.byref(soa), _ptr(out)))
+        return int(out[0]), (None if out[1] == np.uint64(0xFFFFFFFFFFFFFFFF) else int(out[1])), int(out[2]), int(out[3])
+
     def measure_int_peak(self, kind=0):
         """Sustained thread-level integer instructions/s (0: LOP3 stream, 1: LOP3+IMAD) for the integer roofline."""
         v = C.c_double(0)

@@ -70,6 +70,7 @@ SIGNATURES = {
     "ll_timing_query": ([_vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(_u64)], _i),
     "ll_launch_count": ([_vp], _u64),
     "ll_debug_force_synced": ([_vp, _i], _i),
+    "ll_debug_selfcheck_soa": ([_vp, C.POINTER(Soa), _vp], _i),
     "ll_measure_int_peak": ([_vp, _i, C.POINTER(C.c_double)], _i),
 }
 

@@ -445,6 +445,22 @@ extern "C" int ll_debug_force_synced(ll_ctx *ctx, int on) {
     return LL_OK;
 }
 
+extern "C" int ll_debug_selfcheck_soa(ll_ctx *ctx, const ll_soa_t *soa, uint64_t *result4) {
+    LL_TRY(check_ctx(ctx));
+    if (!soa || !result4) return fail(LL_ERR_INVALID_ARG, "null argument");
+    u64 *sc = (u64 *)ctx->scalars.ptr + SC_SPARE;
+    const u64 init[4] = {0, ~0ull, 0, 0};
+    CUDA_TRY(cudaMemcpyAsync(sc, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    if (soa->n) {
+        Timed t(ctx, "selfcheck");
+        k_selfcheck<<<(unsigned)nblocks(soa->n), BLOCK, 0, ctx->stream>>>(Soa{(u64 *)soa->planes, soa->meta, soa->stride}, soa->n, (unsigned long long *)sc);
+    }
+    LL_TRY(check_launch("k_selfcheck"));
+    CUDA_TRY(cudaMemcpyAsync(result4, sc, 4 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return LL_OK;
+}
+
 extern "C" int ll_measure_int_peak(ll_ctx *ctx, int kind, double *thread_ops_per_sec) {
     LL_TRY(check_ctx(ctx));
     if (!thread_ops_per_sec || kind < 0 || kind > 1) return fail(LL_ERR_INVALID_ARG, "bad argument");

@@ -552,6 +552,38 @@ __global__ void __launch_bounds__(BLOCK) k_variation(const PvArgs a) {
     out[0] = len;
 }
 
+// ---- full-size self-consistency check (tests): the three ways this library knows a position's legal moves ------
+// (1) the set-wise counter, (2) the canonical generator with legality by masks, (3) the reference's own definition:
+// every reckless commit made and kept iff the mover's figurehead is not endangered afterwards (life.rs:692-699).
+// out[0] += positions where they disagree, out[1] = first such index, out[2] += legal commits, out[3] += reckless commits.
+struct ExactLegalSink {
+    const Pos &par;
+    u32 n = 0;
+    LL_HDM void move(u32 job, int from, int to, u32 asc, u32 flags) {
+        Pos c;
+        make_child(par, mv_pack(job, from, to, asc, flags), c);
+        const bool endangered = meta_stm(par.meta) == 0 ? in_critical_endangerment<0>(c) : in_critical_endangerment<1>(c);
+        if (!endangered) n++;
+    }
+};
+__global__ void __launch_bounds__(BLOCK) k_selfcheck(Soa in, size_t n, unsigned long long *out) {
+    const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    const Pos p = soa_load(in, i);
+    const u32 fast_legal = count_moves<false>(p), fast_reckless = count_moves<true>(p);
+    CountSink legal, reckless;
+    lookahead<false>(p, legal);
+    lookahead<true>(p, reckless);
+    ExactLegalSink exact{p};
+    lookahead<true>(p, exact);
+    if (fast_legal != legal.n || legal.n != exact.n || fast_reckless != reckless.n) {
+        atomicAdd(out, 1ull);
+        atomicMin(out + 1, (unsigned long long)i);
+    }
+    atomicAdd(out + 2, (unsigned long long)legal.n);
+    atomicAdd(out + 3, (unsigned long long)reckless.n);
+}
+
 // ---- life.rs:678-690 for an explicit team ------------------------------------------------------------
 __global__ void __launch_bounds__(BLOCK) k_endangered(Soa in, size_t n, const unsigned char *__restrict__ teams, unsigned char *__restrict__ out) {
     const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;

@@ -472,6 +472,35 @@ def test_full_size_score_batch_properties(eng):
     eng.soa_free(soa)
 
 
+def test_full_size_movegen_self_consistency(eng):
+    # 2^22 seeded playout positions (and the depth-4 frontier of Kiwipete, rich in checks, pins, ascensions and
+    # secret service): set-wise counter == generator with legality by masks == make-the-move-and-test definition
+    import torch
+
+    n = 1 << 22
+    soa = eng.playout_soa(n)
+    bad, first, legal, reckless = eng.selfcheck_soa(soa)
+    assert bad == 0, (bad, first, O.preserve(eng.soa_download(soa, first, 1)[0]) if first is not None else None)
+    assert 20 * n < legal <= reckless < 60 * n
+    k = 2048  # the totals are anchored to the oracle on a prefix
+    worlds = eng.soa_download(soa, 0, k)
+    sub = eng.soa_upload(worlds)
+    _, _, legal_k, reckless_k = eng.selfcheck_soa(sub)
+    assert legal_k == sum(len(O.lookahead(w)) for w in worlds[:k]) and reckless_k == sum(len(O.reckless_lookahead(w)) for w in worlds[:k])
+    eng.soa_free(sub)
+    eng.soa_free(soa)
+    import leafline_b200 as ll
+
+    frontier = np.array([ll.reconstruct(KIWIPETE)], dtype=ll.WORLD_DTYPE)
+    for _ in range(3):
+        _, commits = eng.reckless_lookahead(frontier)
+        frontier = np.ascontiguousarray(commits["tree"])
+    soa = eng.soa_upload(frontier)
+    bad, first, legal, reckless = eng.selfcheck_soa(soa)
+    assert bad == 0 and len(frontier) > 90000, (bad, first)
+    eng.soa_free(soa)
+
+
 # ---------------------------------------------------------------- --correspond wire format (main.rs:182-244)
 def test_correspondence_wire_format(eng):
     import json
