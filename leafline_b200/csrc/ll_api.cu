@@ -288,10 +288,10 @@ int horizon_levels(ll_ctx *ctx, size_t l, int plies, int quiet_ext, uint64_t *sc
         a.scored = sc + SC_SCORED;
         a.stand_pat = quiet;
         Timed t(ctx, "horizon_last_ply");
-        if (quiet) k_expand<true, MODE_HORIZON, BLOCK, true><<<(unsigned)nblocks(fb.n), BLOCK, 0, ctx->stream>>>(a);
-        else k_expand<true, MODE_HORIZON><<<(unsigned)nblocks(fb.n), BLOCK, 0, ctx->stream>>>(a);
+        if (quiet) k_horizon<true><<<(unsigned)nblocks(fb.n, HP), BLOCK, 0, ctx->stream>>>(a);
+        else k_horizon<false><<<(unsigned)nblocks(fb.n, HP), BLOCK, 0, ctx->stream>>>(a);
     }
-    LL_TRY(check_launch("k_expand<HORIZON>"));
+    LL_TRY(check_launch("k_horizon"));
     for (size_t lev = bottom; lev > l; lev--) {
         Frontier &par = ctx->levels[lev - 1];
         Frontier &chi = ctx->levels[lev];

@@ -555,6 +555,120 @@ template <bool NIHIL> LL_HD u32 count_moves(const Pos &p) {
     return meta_stm(p.meta) == 0 ? count_moves_as<0, NIHIL>(p) : count_moves_as<1, NIHIL>(p);
 }
 
+// ---- reckless commits as (piece or servant-set, target mask) records ------------------------------------
+// For consumers that need every child but not the canonical order (the horizon kernel): one record per piece --
+// and one per KIND of servant step for all servants at once -- instead of one descriptor per move.  The k-th
+// commit of a position is recovered from the records by select-the-k-th-set-bit, so generation costs per piece and
+// decoding runs one child per thread at full lane efficiency.  The commits are exactly those of
+// reckless_lookahead() (life.rs:1082), in another order; with STUNS only those that hospitalize somebody
+// (mind.rs:292-294).  At most 36 records exist: servant sets 18 (3 kinds x (plain + 4 ascensions), double step,
+// 2 passing-by), up to 15 other pieces, 2 secret services, and there are at most 16 pieces.
+constexpr int REC_MAX = 36;
+enum { REC_PIECE = 0, REC_PUSH = 1, REC_DOUBLE = 2, REC_STUN_WEST = 3, REC_STUN_EAST = 4, REC_SERVICE = 5 };
+// info: kind | job<<3 | from<<6 | asc<<12 | passing-by<<15 | first move index of the record<<16
+LL_HD u32 rec_info(u32 kind, u32 job, int from, u32 asc, u32 passing_by, u32 base) {
+    return kind | (job << 3) | ((u32)from << 6) | (asc << 12) | (passing_by << 15) | (base << 16);
+}
+LL_HD u32 rec_base(u32 info) { return info >> 16; }
+LL_HD int select_bit(u64 mask, u32 t) { // index of the t-th (0-based) set bit of mask; t < popc(mask)
+    u32 w = (u32)mask;
+    int at = 0;
+    u32 c = (u32)popc64((u64)w);
+    if (t >= c) { t -= c; w = (u32)(mask >> 32); at = 32; }
+    c = (u32)popc64((u64)(w & 0xFFFFu));
+    if (t >= c) { t -= c; w >>= 16; at += 16; }
+    c = (u32)popc64((u64)(w & 0xFFu));
+    if (t >= c) { t -= c; w >>= 8; at += 8; }
+    c = (u32)popc64((u64)(w & 0xFu));
+    if (t >= c) { t -= c; w >>= 4; at += 4; }
+    c = (u32)popc64((u64)(w & 0x3u));
+    if (t >= c) { t -= c; w >>= 2; at += 2; }
+    if (t >= (w & 1u)) at += 1;
+    return at;
+}
+// the move descriptor of commit number t (0-based) of a record, for mover `team`
+LL_HD u32 rec_move(u64 mask, u32 info, u32 t, u32 team) {
+    const int to = select_bit(mask, t);
+    const u32 kind = info & 7u, job = (info >> 3) & 7u, asc = (info >> 12) & 7u;
+    int from = (int)((info >> 6) & 63u);
+    if (kind == REC_PUSH) from = team == 0 ? to - 8 : to + 8;
+    else if (kind == REC_DOUBLE) from = team == 0 ? to - 16 : to + 16;
+    else if (kind == REC_STUN_WEST) from = team == 0 ? to - 7 : to + 9; // the servant stands one file EAST of its west stun
+    else if (kind == REC_STUN_EAST) from = team == 0 ? to - 9 : to + 7;
+    const u32 flags = ((info >> 15) & 1u ? MV_PASSING_BY : 0u) | (kind == REC_SERVICE ? MV_SERVICE : 0u);
+    return mv_pack(job, from, to, asc, flags);
+}
+struct ServiceBits { // collects the secret-service destinations the exact path admits
+    u64 to_bits = 0;
+    LL_HDM void move(u32, int, int to, u32, u32) { to_bits |= 1ull << to; }
+};
+// Out: void put(u64 mask, u32 info_without_base) -- called only with mask != 0; returns nothing.  The caller keeps
+// the running move count (the record's base) itself.
+template <int T, bool STUNS, class Out> LL_HD void reckless_records_as(const Pos &p, Out &out) {
+    const u64 own = occupied_by<T>(p), opp = occupied_by<1 - T>(p), occ = own | opp, empty = ~occ;
+    const u64 allowed = STUNS ? opp : ~own;
+    const u64 last = T == 0 ? RANK_1 << 56 : RANK_1;
+    { // life.rs:749-830, all servants at once
+        const u64 s = p.pl[6 * T + SERVANT];
+        const u64 one = (T == 0 ? s << 8 : s >> 8) & empty;
+        const u64 two = (T == 0 ? (one & (RANK_1 << 16)) << 8 : (one & (RANK_1 << 40)) >> 8) & empty;
+        const u64 west = (T == 0 ? s << 7 : s >> 9) & ~FILE_H, east = (T == 0 ? s << 9 : s >> 7) & ~FILE_A;
+        const u64 pb_bit = passing_by_bit(p.meta);
+#pragma unroll
+        for (int kind = REC_PUSH; kind <= REC_STUN_EAST; kind++) {
+            if (kind == REC_DOUBLE) {
+                if (!STUNS && two) out.put(two, rec_info(REC_DOUBLE, SERVANT, 0, ASC_NONE, 0, 0));
+                continue;
+            }
+            if (kind == REC_PUSH && STUNS) continue;
+            const u64 targets = kind == REC_PUSH ? one : (kind == REC_STUN_WEST ? west : east) & opp;
+            if (targets & ~last) out.put(targets & ~last, rec_info((u32)kind, SERVANT, 0, ASC_NONE, 0, 0));
+            if (targets & last) {
+#pragma unroll
+                for (u32 asc = PONY; asc <= PRINCESS; asc++) out.put(targets & last, rec_info((u32)kind, SERVANT, 0, asc, 0, 0));
+            }
+            if (kind != REC_PUSH) { // passing by: the passed square is empty, so it is never in `targets`
+                const u64 passing = (kind == REC_STUN_WEST ? west : east) & pb_bit;
+                if (passing) out.put(passing, rec_info((u32)kind, SERVANT, 0, ASC_NONE, 1, 0));
+            }
+        }
+    }
+    for (u64 s = p.pl[6 * T + PONY]; s; s &= s - 1) { // life.rs:832-855
+        const int from = lsb64(s);
+        const u64 targets = pony_moves(from) & allowed;
+        if (targets) out.put(targets, rec_info(REC_PIECE, PONY, from, ASC_NONE, 0, 0));
+    }
+    for (u64 s = p.pl[6 * T + SCHOLAR]; s; s &= s - 1) { // life.rs:857-914
+        const int from = lsb64(s);
+        const u64 targets = diag_attacks(from, occ) & allowed;
+        if (targets) out.put(targets, rec_info(REC_PIECE, SCHOLAR, from, ASC_NONE, 0, 0));
+    }
+    for (u64 s = p.pl[6 * T + COP]; s; s &= s - 1) {
+        const int from = lsb64(s);
+        const u64 targets = orth_attacks(from, occ) & allowed;
+        if (targets) out.put(targets, rec_info(REC_PIECE, COP, from, ASC_NONE, 0, 0));
+    }
+    for (u64 s = p.pl[6 * T + PRINCESS]; s; s &= s - 1) { // life.rs:955-969, both ray families in one record
+        const int from = lsb64(s);
+        const u64 targets = (diag_attacks(from, occ) | orth_attacks(from, occ)) & allowed;
+        if (targets) out.put(targets, rec_info(REC_PIECE, PRINCESS, from, ASC_NONE, 0, 0));
+    }
+    for (u64 s = p.pl[6 * T + FIGUREHEAD]; s; s &= s - 1) { // life.rs:973-978
+        const int from = lsb64(s);
+        const u64 targets = figurehead_moves(from) & allowed;
+        if (targets) out.put(targets, rec_info(REC_PIECE, FIGUREHEAD, from, ASC_NONE, 0, 0));
+    }
+    if (!STUNS) { // life.rs:980-1050: the exact path (leer tests), never a stun
+        ServiceBits service;
+        service_lookahead<T, true>(p, own, opp, service);
+        if (service.to_bits) out.put(service.to_bits, rec_info(REC_SERVICE, FIGUREHEAD, (T == 0 ? 0 : 56) + 4, ASC_NONE, 0, 0));
+    }
+}
+template <bool STUNS, class Out> LL_HD void reckless_records(const Pos &p, Out &out) {
+    if (meta_stm(p.meta) == 0) reckless_records_as<0, STUNS>(p, out);
+    else reckless_records_as<1, STUNS>(p, out);
+}
+
 // ---- well-formedness (domain W, include/leafline_b200.h) ----------------------------------------
 LL_HD bool well_formed(const Pos &p) {
     u64 acc = 0, overlap = 0;

@@ -19,7 +19,7 @@ constexpr int BLOCK = 128;
 #endif
 constexpr int DESC_CAP = LL_DESC_CAP; // move descriptors per window (24 KiB); a tile with more moves takes several windows
 
-enum { MODE_EMIT = 0, MODE_PERFT = 1, MODE_HORIZON = 2 };
+enum { MODE_EMIT = 0, MODE_PERFT = 1 };
 
 // ---- block-level helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ u32 warp_inclusive_scan(u32 v) {
@@ -229,7 +229,7 @@ struct ExpandArgs {
     const u32 *counts;      // per-parent commit counts (nullptr: counted here)
     const u64 *block_base;  // EMIT, canonical order: first child index of each tile (from the scan)
     const u32 *root_in;     // root-move id of each parent (nullable)
-    int stand_pat;          // quiescence levels (STUNS): a parent may decline every stun: value = max(orientation*score, children) (mind.rs:298)
+    int stand_pat;          // k_horizon<STUNS>: a parent may decline every stun: value = max(orientation*score, children) (mind.rs:298)
     // MODE_EMIT
     Soa out;
     u32 *cmeta;             // packed commit metadata (nullable)
@@ -240,7 +240,7 @@ struct ExpandArgs {
     u32 *overflow;
     // MODE_PERFT
     u64 *per_root, *total;
-    // MODE_HORIZON
+    // k_horizon
     float *values;
     u64 *scored;
 };
@@ -253,7 +253,7 @@ struct ExpandShared {
     u64 tile_pl[12][BLOCK];
     u32 tile_meta[BLOCK];
     u32 descs[DESC_CAP];
-    int acc[BLOCK]; // PERFT: leaves below each parent; HORIZON: best child key of each parent
+    int acc[BLOCK]; // PERFT: leaves below each parent
     u64 claim;      // next tile / claimed output base
 };
 LL_HD Pos tile_load(const ExpandShared &sh, u32 slot) {
@@ -265,7 +265,7 @@ LL_HD Pos tile_load(const ExpandShared &sh, u32 slot) {
 }
 // P = parents per tile (BLOCK, or fewer for narrow levels: shorter tiles spread over more SMs; canonical-order
 // emission needs P == BLOCK because the scan works on BLOCK-sized groups)
-// STUNS = quiescence level: only stunning commits are expanded (a.stand_pat says whether the parent may decline them)
+// STUNS = quiescence level: only stunning commits are expanded
 template <bool NIHIL, int MODE, int P, bool STUNS> __device__ __forceinline__ void expand_tiles(const ExpandArgs &a, ExpandShared &sh) {
     const int tid = threadIdx.x;
     // chained launches: once a level has outgrown its buffer, its recorded size says nothing about what was
@@ -291,7 +291,6 @@ template <bool NIHIL, int MODE, int P, bool STUNS> __device__ __forceinline__ vo
             sh.tile_meta[tid] = p.meta;
         }
         if (MODE == MODE_PERFT && tid < P) sh.acc[tid] = 0;
-        if (MODE == MODE_HORIZON && tid < P) sh.acc[tid] = float_key(-INFINITY);
         u32 total;
         const u32 ex = block_exclusive_scan(cnt, &total); // also orders the tile writes before phase 2
         size_t out_base = 0;
@@ -335,23 +334,11 @@ template <bool NIHIL, int MODE, int P, bool STUNS> __device__ __forceinline__ vo
                         if (a.root_out) a.root_out[o] = a.root_is_index ? (u32)o : a.root_in[tile * P + slot];
                     }
                 } else {
-                    int v = 0;
-                    if (MODE == MODE_PERFT) {
-                        if (live) v = (int)count_moves<false>(c);
-                    } else {
-                        v = float_key(-INFINITY);
-                        if (live) {
-                            const float s = score(c);
-                            v = float_key(meta_stm(c.meta) ? s : -s); // -(orientation(child) * score(child)), mind.rs:283, 331-336
-                        }
-                    }
+                    const int v = live ? (int)count_moves<false>(c) : 0;
                     // children of one parent are neighbours in the list: reduce per parent inside the warp first
                     const unsigned peers = __match_any_sync(0xffffffffu, live ? slot : 0xFFFFFFFFu);
-                    const int r = MODE == MODE_PERFT ? __reduce_add_sync(peers, v) : __reduce_max_sync(peers, v);
-                    if (live && (tid & 31) == __ffs((int)peers) - 1) {
-                        if (MODE == MODE_PERFT) atomicAdd(&sh.acc[slot], r);
-                        else atomicMax(&sh.acc[slot], r);
-                    }
+                    const int r = __reduce_add_sync(peers, v);
+                    if (live && (tid & 31) == __ffs((int)peers) - 1) atomicAdd(&sh.acc[slot], r);
                 }
             }
             __syncthreads();
@@ -368,21 +355,6 @@ template <bool NIHIL, int MODE, int P, bool STUNS> __device__ __forceinline__ vo
                 atomicAdd((unsigned long long *)a.total, (unsigned long long)sum);
             }
         }
-        if (MODE == MODE_HORIZON) {
-            u32 scored = 0;
-            if (mine) {
-                float v = cnt ? key_float(sh.acc[tid]) : -INFINITY;
-                if (cnt == 0 || (STUNS && a.stand_pat)) { // nothing to play: the node is itself a leaf (mind.rs:281-283, 295-299)
-                    const Pos p = tile_load(sh, tid);
-                    const float s = score(p);
-                    v = fmaxf(v, meta_stm(p.meta) ? -s : s);
-                }
-                a.values[i] = v;
-                scored = cnt ? cnt : 1u;
-            }
-            scored = __reduce_add_sync(0xffffffffu, scored);
-            if ((tid & 31) == 0 && scored && a.scored) atomicAdd((unsigned long long *)a.scored, (unsigned long long)scored);
-        }
         if (!a.tile_counter) break;
         __syncthreads(); // the tile and the claim slot are reused by the next round
     }
@@ -390,6 +362,106 @@ template <bool NIHIL, int MODE, int P, bool STUNS> __device__ __forceinline__ vo
 template <bool NIHIL, int MODE, int P = BLOCK, bool STUNS = false> __global__ void __launch_bounds__(BLOCK, LL_EXPAND_MIN_BLOCKS) k_expand(const ExpandArgs a) {
     __shared__ ExpandShared sh;
     expand_tiles<NIHIL, MODE, P, STUNS>(a, sh);
+}
+
+// ---- horizon by records (mind.rs:279-301): children decoded from (piece, target mask) records ---------------
+// Phase 1 costs per PIECE, not per move: a parent thread writes at most REC_MAX records (ll_device.cuh) into shared
+// memory.  Phase 2 runs one CHILD per thread: binary-search the parent by the prefix sums, the record by its base,
+// select the t-th set bit, rebuild the child from the parent tile, score it, max-reduce per parent.
+constexpr int HP = 64; // parents per horizon tile
+struct HorizonShared {
+    u64 tile_pl[12][HP];
+    u32 tile_meta[HP];
+    u64 rec_mask[REC_MAX][HP]; // transposed: neighbouring parents write neighbouring words
+    u32 rec_info[REC_MAX][HP];
+    u32 ex[HP + 1]; // exclusive prefix of the parents' commit counts
+    u32 n_rec[HP];
+    int acc[HP];
+};
+struct SharedRecordOut {
+    HorizonShared &sh;
+    int slot;
+    u32 n_rec = 0, n_moves = 0;
+    LL_HDM void put(u64 mask, u32 info) {
+        sh.rec_mask[n_rec][slot] = mask;
+        sh.rec_info[n_rec][slot] = info | (n_moves << 16);
+        n_rec++;
+        n_moves += (u32)__popcll(mask);
+    }
+};
+template <bool STUNS> __global__ void __launch_bounds__(BLOCK, 6) k_horizon(const ExpandArgs a) {
+    __shared__ HorizonShared sh;
+    const int tid = threadIdx.x;
+    const size_t tile = blockIdx.x;
+    const size_t i = tile * HP + tid;
+    const bool mine = tid < HP && i < a.n;
+    u32 cnt = 0;
+    if (mine) {
+        const Pos p = soa_load(a.in, i);
+#pragma unroll
+        for (int j = 0; j < 12; j++) sh.tile_pl[j][tid] = p.pl[j];
+        sh.tile_meta[tid] = p.meta;
+        SharedRecordOut out{sh, tid};
+        reckless_records<STUNS>(p, out);
+        cnt = out.n_moves;
+        sh.n_rec[tid] = out.n_rec;
+        sh.acc[tid] = float_key(-INFINITY);
+    }
+    u32 total;
+    const u32 ex = block_exclusive_scan(cnt, &total);
+    if (tid < HP) sh.ex[tid] = ex;
+    if (tid == 0) sh.ex[HP] = total;
+    __syncthreads();
+    for (u32 k0 = 0; k0 < total; k0 += BLOCK) {
+        const u32 k = k0 + tid;
+        const bool live = k < total;
+        u32 slot = 0;
+        int v = float_key(-INFINITY);
+        if (live) {
+            u32 hi = HP;
+#pragma unroll
+            for (int step = 0; step < 6; step++) { // HP = 2^6: the last parent whose prefix is <= k
+                const u32 mid = (slot + hi) >> 1;
+                if (sh.ex[mid] <= k) slot = mid;
+                else hi = mid;
+            }
+            const u32 j = k - sh.ex[slot];
+            u32 r = 0, rhi = sh.n_rec[slot];
+            while (rhi - r > 1) { // the last record whose base is <= j
+                const u32 mid = (r + rhi) >> 1;
+                if (rec_base(sh.rec_info[mid][slot]) <= j) r = mid;
+                else rhi = mid;
+            }
+            const u32 info = sh.rec_info[r][slot];
+            Pos par, c;
+#pragma unroll
+            for (int q = 0; q < 12; q++) par.pl[q] = sh.tile_pl[q][slot];
+            par.meta = sh.tile_meta[slot];
+            make_child(par, rec_move(sh.rec_mask[r][slot], info, j - rec_base(info), meta_stm(par.meta)), c);
+            const float s = score(c);
+            v = float_key(meta_stm(c.meta) ? s : -s); // -(orientation(child) * score(child)), mind.rs:283, 331-336
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, live ? slot : 0xFFFFFFFFu);
+        const int best = __reduce_max_sync(peers, v);
+        if (live && (tid & 31) == __ffs((int)peers) - 1) atomicMax(&sh.acc[slot], best);
+    }
+    __syncthreads();
+    u32 scored = 0;
+    if (mine) {
+        float v = cnt ? key_float(sh.acc[tid]) : -INFINITY;
+        if (cnt == 0 || (STUNS && a.stand_pat)) { // nothing to play: the node is itself a leaf (mind.rs:281-283, 295-299)
+            Pos p;
+#pragma unroll
+            for (int q = 0; q < 12; q++) p.pl[q] = sh.tile_pl[q][tid];
+            p.meta = sh.tile_meta[tid];
+            const float s = score(p);
+            v = fmaxf(v, meta_stm(p.meta) ? -s : s);
+        }
+        a.values[i] = v;
+        scored = cnt ? cnt : 1u;
+    }
+    scored = __reduce_add_sync(0xffffffffu, scored);
+    if ((tid & 31) == 0 && scored && a.scored) atomicAdd((unsigned long long *)a.scored, (unsigned long long)scored);
 }
 
 // keep the units u with u % world == rank (frontier sharding by subtree).  n_in / n_out

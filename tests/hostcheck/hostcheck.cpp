@@ -79,3 +79,48 @@ extern "C" int hc_lookahead(const ll_world_t *w, int nihil, ll_commit_t *out, in
 
 extern "C" float hc_score(const ll_world_t *w) { return score(to_pos(w)); }
 extern "C" int hc_well_formed(const ll_world_t *w) { return well_formed(to_pos(w)) ? 1 : 0; }
+
+// the reckless commits decoded from the (piece / servant-set, target mask) records, as the horizon kernel decodes them
+struct RecordList {
+    u64 mask[REC_MAX];
+    u32 info[REC_MAX];
+    u32 n_rec = 0, n_moves = 0;
+    void put(u64 m, u32 i) {
+        if (n_rec < REC_MAX) {
+            mask[n_rec] = m;
+            info[n_rec] = i | (n_moves << 16);
+        }
+        n_rec++;
+        n_moves += (u32)popc64(m);
+    }
+};
+extern "C" int hc_record_moves(const ll_world_t *w, int stuns, uint32_t *moves, int cap, int *n_records) {
+    const Pos p = to_pos(w);
+    RecordList rl;
+    if (stuns) reckless_records<true>(p, rl);
+    else reckless_records<false>(p, rl);
+    *n_records = (int)rl.n_rec;
+    if (rl.n_rec > REC_MAX) return -1;
+    const u32 team = meta_stm(p.meta);
+    for (u32 k = 0; k < rl.n_moves && (int)k < cap; k++) {
+        u32 r = 0;
+        while (r + 1 < rl.n_rec && rec_base(rl.info[r + 1]) <= k) r++;
+        moves[k] = rec_move(rl.mask[r], rl.info[r], k - rec_base(rl.info[r]), team);
+    }
+    return (int)rl.n_moves;
+}
+extern "C" int hc_generator_moves(const ll_world_t *w, int stuns, uint32_t *moves, int cap) {
+    const Pos p = to_pos(w);
+    static thread_local ListSink sink;
+    sink.n = 0;
+    lookahead<true>(p, sink);
+    const u64 opp = meta_stm(p.meta) == 0 ? occupied_by<1>(p) : occupied_by<0>(p);
+    int n = 0;
+    for (u32 i = 0; i < sink.n; i++) {
+        const u32 m = sink.moves[i];
+        if (stuns && !((1ull << mv_to(m)) & opp) && !(m & MV_PASSING_BY)) continue;
+        if (n < cap) moves[n] = m;
+        n++;
+    }
+    return n;
+}

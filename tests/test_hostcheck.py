@@ -31,6 +31,8 @@ def hc():
     lib.hc_score.argtypes = [C.c_void_p]
     lib.hc_score.restype = C.c_float
     lib.hc_well_formed.argtypes = [C.c_void_p]
+    lib.hc_record_moves.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    lib.hc_generator_moves.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.hc_init()
     return lib
 
@@ -48,6 +50,13 @@ def check(hc, worlds):
             assert buf[:n].tobytes() == want.tobytes(), (O.preserve(w), nihil)
             assert hc.hc_count(ptr, nihil) == n, (O.preserve(w), nihil)
         assert np.float32(hc.hc_score(ptr)).tobytes() == np.float32(O.score(w)).tobytes()
+        # the record form of the reckless commits (horizon kernel) holds exactly the generator's commits, in another order
+        a, b, nrec = np.zeros(1024, dtype=np.uint32), np.zeros(1024, dtype=np.uint32), C.c_int(0)
+        for stuns in (0, 1):
+            na = hc.hc_record_moves(ptr, stuns, a.ctypes.data_as(C.c_void_p), 1024, C.byref(nrec))
+            nb = hc.hc_generator_moves(ptr, stuns, b.ctypes.data_as(C.c_void_p), 1024)
+            assert 0 <= nrec.value <= 36 and na == nb, (O.preserve(w), stuns, na, nb, nrec.value)
+            assert sorted(a[:na]) == sorted(b[:nb]), (O.preserve(w), stuns)
 
 
 def test_named_positions(hc):
