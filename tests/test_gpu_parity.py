@@ -523,3 +523,36 @@ def test_correspondence_wire_format(eng):
     assert d["hospitalization"] == {"team": "Blue", "job_description": "Pony"} and d["rosetta_stone"] == "Ba1"
     d = json.loads(co.correspondence(eng, "rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq -", co.Seconds(1)))
     assert d["depth"] >= 3 and len(d["counterreplies"]) == 20
+
+
+def test_uci_daemon_and_command_line(eng):
+    import io
+    import json
+    import subprocess
+    import sys
+
+    from leafline_b200 import uci
+
+    # uci.rs:13-104: the same dialogue the reference holds
+    script = "uci\nisready\nucinewgame\nposition startpos moves e2e4\ngo depth 2\nposition startpos moves e2e4 x g1f3\ngo wtime 4000 btime 4000 movestogo 2\nquit\n"
+    out = io.StringIO()
+    uci.dæmon(engine=eng, stdin=io.StringIO(script), stdout=out)
+    lines = out.getvalue().splitlines()
+    assert lines[0].startswith("id name Leafline") and lines[2] == "uciok" and lines[3] == "readyok"
+    best = [l for l in lines if l.startswith("bestmove ")]
+    assert len(best) == 2 and all(len(b.split()[1]) == 4 for b in best)
+    assert any(l.startswith("info depth ") and " score cp " in l for l in lines)
+    # the first reply answers 1.e4 at depth 2 with the move exact negamax ranks first (stable order)
+    import leafline_b200 as ll
+
+    after_e4 = [c for c in eng.lookahead(ll.new_world())[1] if ll.to_algebraic(c["whence"]) + ll.to_algebraic(c["whither"]) == "e2e4"][0]["tree"]
+    top = eng.forecast(after_e4, 2)[0]["commit"]
+    assert best[0] == "bestmove " + ll.to_algebraic(top["whence"]) + ll.to_algebraic(top["whither"])
+    # main.rs: `leafline --correspond --depth 2 --from <runes>` as the web client runs it (main.rs:461-469 for the answer)
+    root = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+    run = subprocess.run([sys.executable, "-m", "leafline_b200", "--correspond", "--depth", "2", "--from", "R6k/6pp/8/8/8/8/8/8 b - -"],
+                         capture_output=True, text=True, cwd=root, timeout=300)
+    assert run.returncode == 0 and run.stdout.strip() == '{"the_triumphant":"Orange"}', run.stderr
+    run = subprocess.run([sys.executable, "-m", "leafline_b200", "--correspond", "--depth", "2", "--seconds", "1", "--from", "x"],
+                         capture_output=True, text=True, cwd=root, timeout=300)
+    assert run.returncode != 0 and "more than one of" in run.stderr
