@@ -354,6 +354,8 @@ def main():
                     "unit": "T thread-inst/s", "frac": rate / int_peak["lop3_imad_thread_inst_per_sec"],
                     "frac_of_alu_pipe": rate / int_peak["lop3_thread_inst_per_sec"],
                     "thread_inst_per_launch": inst, "leaves_per_launch": expected,
+                    "ncu": {"alu_pipe_busy_pct": consts.get("perft6_tail_alu_pipe_pct"), "issue_slots_busy_pct": consts.get("perft6_tail_issue_active_pct"),
+                            "lanes_active_of_32": consts.get("perft6_tail_lanes_active_of_32")},
                     "note": "thread-level instructions per launch from the committed ncu capture (profiles/constants.json); "
                             "peak = dependency-free LOP3+IMAD stream measured in this run (issue port), frac_of_alu_pipe = vs LOP3 only",
                 }
@@ -363,9 +365,17 @@ def main():
         vals = torch.empty(n_h, dtype=torch.float32, device="cuda")
         scored = eng.horizon_soa(soa, 1, vals.data_ptr())
         h_ms = timed(stream, lambda: eng.horizon_soa(soa, 1, vals.data_ptr()), 5, torch)
+        h_inst = consts.get("horizon_2p20_thread_inst")
         result["horizon"] = {
             "frontier_positions": n_h, "plies": 1, "leaf_positions": scored, "ms": h_ms,
             "leaf_positions_per_sec": scored / (h_ms * 1e-3),
+            "int_roofline": None if not h_inst else {
+                "kernel": "k_horizon", "bound": "int-issue", "achieved": h_inst * (n_h / (1 << 20)) / (h_ms * 1e-3) / 1e12,
+                "peak": int_peak["lop3_imad_thread_inst_per_sec"] / 1e12, "unit": "T thread-inst/s",
+                "frac": h_inst * (n_h / (1 << 20)) / (h_ms * 1e-3) / int_peak["lop3_imad_thread_inst_per_sec"],
+                "ncu": {"alu_pipe_busy_pct": consts.get("horizon_2p20_alu_pipe_pct"), "issue_slots_busy_pct": consts.get("horizon_2p20_issue_active_pct"),
+                        "lanes_active_of_32": consts.get("horizon_2p20_lanes_active_of_32")},
+                "note": "thread instructions of the committed ncu capture (2^20 parents) scaled to this run's parents"},
             "what": "reckless movegen of every frontier node + static score of every child + negamax max; leaves never leave the SM",
         }
         eng.soa_free(soa)

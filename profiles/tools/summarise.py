@@ -102,6 +102,9 @@ with open(os.path.join(OUT, f"{tag}_kernels.csv"), "w", newline="") as f:
             consts[f"{key}_thread_inst"] = tinst
             consts[f"{key}_warp_inst"] = float(r[hdr.index("smsp__inst_executed.sum")])
             consts[f"{key}_ncu_seconds"] = val("gpu__time_duration.sum")
+            consts[f"{key}_alu_pipe_pct"] = float(r[hdr.index("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active")])
+            consts[f"{key}_issue_active_pct"] = float(r[hdr.index("smsp__issue_active.avg.pct_of_peak_sustained_active")])
+            consts[f"{key}_lanes_active_of_32"] = float(r[hdr.index("smsp__thread_inst_executed_per_inst_executed.ratio")])
 consts["source"] = f"profiles/{tag}_kernels.csv (ncu --set full of profiles/workload.py)"
 json.dump(consts, open(os.path.join(OUT, "constants.json"), "w"), indent=1)
 print(json.dumps(consts, indent=1))
