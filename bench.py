@@ -379,6 +379,13 @@ def main():
             "what": "reckless movegen of every frontier node + static score of every child + negamax max; leaves never leave the SM",
         }
         eng.soa_free(soa)
+        # the reference's search structure: host alpha-beta (MVV-LVA + history, full window per root move) over device
+        # frontier batches -- depth 8 from the opening, beyond what a full-width tree fits in HBM
+        t0 = time.perf_counter()
+        fc8, host_nodes, handed_off = eng.alpha_beta_forecast(root, 8, device_plies=4)
+        result["alpha_beta_depth8"] = {"seconds": time.perf_counter() - t0, "best_score": float(fc8[0]["score"]), "host_nodes_expanded": host_nodes,
+                                       "frontier_nodes_handed_to_device": handed_off, "device_plies": 4,
+                                       "what": "ll_alpha_beta_forecast: exact root scores (alpha-beta prunes work, not values)"}
         # batched static scoring of 2^24 seeded playout positions (configs[2])
         n = 1 << 24
         soa = eng.playout_soa(n)

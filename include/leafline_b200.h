@@ -146,6 +146,14 @@ typedef struct ll_forecast_t {
  * sorted by score, best first (mind.rs:436).  The search is TT-free and full-width on the device. */
 int ll_forecast(ll_ctx *ctx, const ll_world_t *root, int depth, int quiet_extension, int nihilistically, ll_forecast_t *forecasts,
                 uint32_t cap, uint32_t *n_forecasts, uint64_t *leaves_scored);
+/* the same forecasts with the reference's search STRUCTURE (src/mind.rs:145-169, 271-364): negamax with alpha-beta
+ * cut-offs, MVV-LVA + history ordering and a full window below every root move run on the HOST; a node with
+ * `device_plies` plies left is handed to the device, which returns its exact full-width value (quiet_extension as in
+ * ll_horizon_batch).  Scores equal ll_forecast's (alpha-beta is exact at the root); only the work is pruned, so
+ * depths beyond ll_forecast's HBM limit are reachable.  variation holds the root move only.  No transposition table.
+ * stats3 (nullable): { nodes expanded on the host, frontier nodes handed to the device, 0 }. */
+int ll_alpha_beta_forecast(ll_ctx *ctx, const ll_world_t *root, int depth, int device_plies, int quiet_extension, int nihilistically,
+                           ll_forecast_t *forecasts, uint32_t cap, uint32_t *n_forecasts, uint64_t *stats3);
 /* replaces `fixed_depth_sequence_kickoff` (src/mind.rs:473-490) */
 int ll_fixed_depth_sequence_forecast(ll_ctx *ctx, const ll_world_t *root, const uint8_t *depths, uint32_t n_depths, int nihilistically,
                                      ll_forecast_t *forecasts, uint32_t cap, uint32_t *n_forecasts);

@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <tuple>
+#include <unordered_map>
 #include <vector>
 
 using namespace ll;
@@ -1005,6 +1007,151 @@ extern "C" int ll_forecast(ll_ctx *ctx, const ll_world_t *root, int depth, int q
         uint32_t len = 1;
         for (u32 j = 0; j < line[0] && len < LL_MAX_VARIATION; j++) unpack_patch(line[1 + j], &f.variation[len++]);
         f.variation_len = len;
+    }
+    return LL_OK;
+}
+
+// ---- the host alpha-beta driver (mind.rs:145-169, 271-364) over device frontier batches -----------------------
+// The branchy part of the search stays on the host, as in the reference: negamax with alpha-beta cut-offs, MVV-LVA +
+// history move ordering, a full window below every root move (mind.rs:406-411).  Where the remaining depth reaches
+// `device_plies` the node is handed to the device, which returns its EXACT full-width value (horizon_levels), so
+// the root scores equal TT-free exact negamax -- only the work is pruned.  The children of a node one ply above
+// the hand-off are valued in two batches ("young brothers wait"): the first commit alone, then -- unless it
+// already caused a cut-off -- all the others at once.  No transposition table: the reference's stores bound
+// values as exact ones (mind.rs:340-343), which this driver does not reproduce.
+namespace {
+
+struct AlphaBeta {
+    ll_ctx *ctx;
+    int device_plies, quiet_extension;
+    std::unordered_map<uint32_t, uint32_t> intuition; // the "intuition bank": Patch -> credit (mind.rs:353-359)
+    uint64_t expanded = 0, handed_off = 0, leaves_scored = 0;
+    int rc = LL_OK;
+
+    static uint32_t patch_key(const ll_commit_t &c) { return (uint32_t)c.team | ((uint32_t)c.job << 1) | ((uint32_t)c.whence << 8) | ((uint32_t)c.whither << 16); }
+    static float figurine_valuation(uint8_t agent) { // mind.rs:36-48
+        static const float value[6] = {1.0f, 3.2f, 3.3f, 5.1f, 8.8f, 20000.0f};
+        return ((agent >> 3) ? -1.0f : 1.0f) * value[agent & 7];
+    }
+    static float mvv_lva(const ll_commit_t &c) { // mind.rs:145-153
+        if (c.hospitalization == LL_NONE) return 0.0f;
+        return figurine_valuation(c.hospitalization) - figurine_valuation((uint8_t)((c.team << 3) | c.job));
+    }
+    void order(std::vector<ll_commit_t> &commits) { // mind.rs:155-169 (history first, then MVV-LVA; stable here)
+        std::vector<std::tuple<uint32_t, float, uint32_t>> keys(commits.size());
+        for (uint32_t i = 0; i < commits.size(); i++) {
+            auto it = intuition.find(patch_key(commits[i]));
+            keys[i] = {it == intuition.end() ? 0u : it->second + 1u, mvv_lva(commits[i]), i};
+        }
+        std::stable_sort(keys.begin(), keys.end(), [](const auto &a, const auto &b) {
+            if (std::get<0>(a) != std::get<0>(b)) return std::get<0>(a) > std::get<0>(b);
+            return std::get<1>(a) > std::get<1>(b);
+        });
+        std::vector<ll_commit_t> sorted(commits.size());
+        for (uint32_t i = 0; i < commits.size(); i++) sorted[i] = commits[std::get<2>(keys[i])];
+        commits.swap(sorted);
+    }
+    bool children(const ll_world_t &node, std::vector<ll_commit_t> &out) {
+        uint32_t offsets[2] = {0, 0};
+        out.resize(1024);
+        rc = ll_lookahead_batch(ctx, &node, 1, 1, offsets, out.data(), out.size()); // reckless, mind.rs:279
+        if (rc != LL_OK) return false;
+        out.resize(offsets[1]);
+        expanded++;
+        return true;
+    }
+    bool device_values(const ll_world_t *nodes, size_t n, float *values) {
+        rc = ll_horizon_batch(ctx, nodes, n, device_plies, quiet_extension, values);
+        handed_off += n;
+        return rc == LL_OK;
+    }
+    // value of `node` for its side to move with `depth` plies left, window (alpha, beta); fail-soft
+    float search(const ll_world_t &node, int depth, float alpha, float beta) {
+        if (rc != LL_OK) return 0.0f;
+        if (depth <= device_plies) {
+            float v = 0.0f;
+            device_values(&node, 1, &v);
+            return v;
+        }
+        std::vector<ll_commit_t> premonitions;
+        if (!children(node, premonitions)) return 0.0f;
+        if (premonitions.empty()) { // mind.rs:282-287 at depth > 0: the node is its own leaf
+            float v = 0.0f;
+            rc = ll_horizon_batch(ctx, &node, 1, 0, -1, &v);
+            return v;
+        }
+        order(premonitions);
+        float optimum = -INFINITY;
+        auto consider = [&](const ll_commit_t &c, float value) { // mind.rs:346-361
+            if (value > optimum) optimum = value;
+            if (value > alpha) alpha = value;
+            if (alpha >= beta) {
+                intuition[patch_key(c)] += 1u << (depth > 30 ? 30 : depth);
+                return true;
+            }
+            return false;
+        };
+        if (depth - 1 <= device_plies) { // the children are frontier nodes: first alone, then the rest in one batch
+            float first = 0.0f;
+            if (!device_values(&premonitions[0].tree, 1, &first)) return 0.0f;
+            if (consider(premonitions[0], -first)) return optimum;
+            const size_t rest = premonitions.size() - 1;
+            if (rest) {
+                std::vector<ll_world_t> trees(rest);
+                std::vector<float> values(rest);
+                for (size_t i = 0; i < rest; i++) trees[i] = premonitions[i + 1].tree;
+                if (!device_values(trees.data(), rest, values.data())) return 0.0f;
+                for (size_t i = 0; i < rest; i++)
+                    if (consider(premonitions[i + 1], -values[i])) break;
+            }
+            return optimum;
+        }
+        for (const ll_commit_t &c : premonitions) {
+            const float value = -search(c.tree, depth - 1, -beta, -alpha);
+            if (rc != LL_OK) return 0.0f;
+            if (consider(c, value)) break;
+        }
+        return optimum;
+    }
+};
+
+} // namespace
+
+extern "C" int ll_alpha_beta_forecast(ll_ctx *ctx, const ll_world_t *root, int depth, int device_plies, int quiet_extension, int nihilistically,
+                                      ll_forecast_t *forecasts, uint32_t cap, uint32_t *n_forecasts, uint64_t *stats3) {
+    LL_TRY(check_ctx(ctx));
+    if (!root || !forecasts || !n_forecasts) return fail(LL_ERR_INVALID_ARG, "null argument");
+    if (depth < 1 || depth > 32) return fail(LL_ERR_INVALID_ARG, "depth %d out of range (1..32)", depth);
+    if (device_plies < 0 || device_plies > 8) return fail(LL_ERR_INVALID_ARG, "device_plies %d out of range (0..8)", device_plies);
+    if (quiet_extension > 8) return fail(LL_ERR_INVALID_ARG, "quiet extension %d out of range", quiet_extension);
+    uint32_t offsets[2] = {0, 0};
+    std::vector<ll_commit_t> roots(1024);
+    LL_TRY(ll_lookahead_batch(ctx, root, 1, nihilistically, offsets, roots.data(), roots.size())); // mind.rs:388-392
+    roots.resize(offsets[1]);
+    *n_forecasts = offsets[1];
+    if (offsets[1] > cap) return fail(LL_ERR_CAPACITY, "%u forecasts do not fit the capacity of %u", offsets[1], cap);
+    AlphaBeta ab{ctx, device_plies, quiet_extension};
+    std::vector<float> scores(roots.size());
+    for (size_t i = 0; i < roots.size(); i++) { // every root move gets the full window (mind.rs:406-411)
+        scores[i] = -ab.search(roots[i].tree, depth - 1, -INFINITY, INFINITY);
+        if (ab.rc != LL_OK) return ab.rc;
+    }
+    std::vector<uint32_t> order(roots.size());
+    for (uint32_t i = 0; i < roots.size(); i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return scores[x] > scores[y]; }); // mind.rs:436
+    for (uint32_t k = 0; k < roots.size(); k++) {
+        const uint32_t i = order[k];
+        ll_forecast_t &f = forecasts[k];
+        memset(&f, 0, sizeof f);
+        f.commit = roots[i];
+        f.score = scores[i];
+        f.variation[0] = ll_patch_t{roots[i].team, roots[i].job, roots[i].whence, roots[i].whither};
+        f.variation_len = 1;
+    }
+    if (stats3) {
+        stats3[0] = ab.expanded;
+        stats3[1] = ab.handed_off;
+        stats3[2] = 0;
     }
     return LL_OK;
 }

@@ -385,6 +385,26 @@ def test_forecasts_are_sorted_and_their_variations_are_principal(eng, fen, depth
         assert O.negamax(node, remaining, quiet) == value
 
 
+@pytest.mark.parametrize("fen,depth,device_plies,quiet", [(KIWIPETE, 4, 2, None), (OPENING, 5, 3, None), (POSITION_5, 4, 1, None),
+                                                          (POSITION_4, 4, 2, 1), (KIWIPETE, 3, 0, None), ("8/q1P1k/8/8/8/8/6PP/7K w - -", 5, 2, None)])
+def test_host_alpha_beta_driver_equals_full_width_search(eng, fen, depth, device_plies, quiet):
+    # mind.rs:271-364 on the host over device frontier batches: cut-offs prune work, never the root scores
+    import leafline_b200 as ll
+
+    w = ll.reconstruct(fen)
+    pruned, expanded, handed_off = eng.alpha_beta_forecast(w, depth, device_plies=device_plies, quiet=quiet)
+    full = eng.forecast(w, depth, quiet=quiet)
+    assert pruned["score"].tobytes() == full["score"].tobytes()
+    assert pruned["commit"].tobytes() == full["commit"].tobytes()
+    assert handed_off > 0
+    if depth - device_plies >= 3:  # cut-offs happened: fewer frontier nodes than the full-width tree has at that ply
+        frontier = np.array([w], dtype=ll.WORLD_DTYPE)
+        frontier = np.ascontiguousarray(eng.lookahead(frontier)[1]["tree"])
+        for _ in range(depth - device_plies - 1):
+            frontier = np.ascontiguousarray(eng.reckless_lookahead(frontier)[1]["tree"])
+        assert handed_off < len(frontier)
+
+
 def test_kickoff_family(eng):
     import leafline_b200 as ll
 
