@@ -218,6 +218,14 @@ class Mind {
         check(ll_forecast(ctx_, &w.raw, depth, extension ? (int)*extension : -1, nihilistically, raw.data(), 1024, &n, nullptr));
         return convert(raw, n);
     }
+    // the reference's search structure for depths beyond the device's full-width reach: alpha-beta with MVV-LVA +
+    // history ordering on the host, frontier nodes with `device_plies` plies left valued exactly on the device
+    std::vector<Forecast> alpha_beta_kickoff(const WorldState &w, uint8_t depth, uint8_t device_plies, std::optional<uint8_t> extension, bool nihilistically) {
+        std::vector<ll_forecast_t> raw(1024);
+        uint32_t n = 0;
+        check(ll_alpha_beta_forecast(ctx_, &w.raw, depth, device_plies, extension ? (int)*extension : -1, nihilistically, raw.data(), 1024, &n, nullptr));
+        return convert(raw, n);
+    }
     std::pair<std::vector<Forecast>, uint8_t> iterative_deepening_kickoff(const WorldState &w, double timeout_seconds, bool nihilistically) { // mind.rs:451-469
         std::vector<ll_forecast_t> raw(1024);
         uint32_t n = 0, depth = 0;

@@ -76,6 +76,9 @@ int main() {
     EXPECT(!forecasts.empty() && std::get<1>(forecasts[0]) > 0.0f);
     EXPECT(std::get<0>(forecasts[0]).tree.preserve() == "2N5/q3k3/8/8/8/8/6PP/7K b - -");
     EXPECT(std::get<2>(forecasts[0]).size() >= 1 && std::get<2>(forecasts[0])[0].abbreviated_pagan_movement_rune() == "c8");
+    auto pruned = mind.alpha_beta_kickoff(WorldState::reconstruct("8/q1P1k/8/8/8/8/6PP/7K w - -"), 3, 1, std::nullopt, true);
+    EXPECT(pruned.size() == forecasts.size() && std::get<1>(pruned[0]) == std::get<1>(forecasts[0]) &&
+           std::get<0>(pruned[0]).tree == std::get<0>(forecasts[0]).tree);
     auto [deep, depth] = mind.iterative_deepening_kickoff(opening, 0.3, false);
     EXPECT(depth >= 3 && deep.size() == 20);
     puts("host selfcheck ok");
