@@ -79,7 +79,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._halt.wait(0.05)
+            self._halt.wait(0.1)
 
     def stop(self, t_begin=None, t_end=None):
         """median SM clock of the samples taken inside [t_begin, t_end] (the timed region); a region shorter than
@@ -218,7 +218,8 @@ def main():
 
     eng.perft(root, depth)  # the first call sizes the level buffers (level-by-level path); the steps run the launch chain
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:  # one nvidia-smi poller per job: the clocks reported are rank 0's GPU
+        sampler.start()
     for _ in range(args.warmup):
         total = step()
         assert expected is None or total == expected * world, total
@@ -244,7 +245,7 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop(t_begin, time.perf_counter())
+    clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
     launches = eng.launch_count - launches0
     assert expected is None or total == expected * world, total
     t = torch.tensor([device_ms, host_s * 1e3], dtype=torch.float64, device="cuda")
