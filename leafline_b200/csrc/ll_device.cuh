@@ -160,6 +160,29 @@ LL_HD u64 ks_ne(u64 g, u64 e) { e &= ~FILE_A; g |= e & (g << 9); e &= e << 9; g 
 LL_HD u64 ks_nw(u64 g, u64 e) { e &= ~FILE_H; g |= e & (g << 7); e &= e << 7; g |= e & (g << 14); e &= e << 14; g |= e & (g << 28); return (g << 7) & ~FILE_H; }
 LL_HD u64 ks_se(u64 g, u64 e) { e &= ~FILE_A; g |= e & (g >> 7); e &= e >> 7; g |= e & (g >> 14); e &= e >> 14; g |= e & (g >> 28); return (g >> 7) & ~FILE_A; }
 LL_HD u64 ks_sw(u64 g, u64 e) { e &= ~FILE_H; g |= e & (g >> 9); e &= e >> 9; g |= e & (g >> 18); e &= e >> 18; g |= e & (g >> 36); return (g >> 9) & ~FILE_H; }
+// The four "up" fills (left shifts) and, on the bit-reversed board, the four "down" fills: brev maps square s to
+// 63 - s (south <-> north, west <-> east, sw <-> ne, se <-> nw, FILE_A <-> FILE_H).  A 64-bit left shift costs one
+// IMAD.SHL (FMA pipe) + one SHF (ALU pipe), a right shift two SHF: keeping every fill a left fill takes work off the
+// ALU pipe that bounds the perft tail (-3 %).  (Going further -- IMAD.WIDE + IMAD for the whole shift, no ALU
+// instruction at all -- was measured slower: DESIGN.md.)
+template <int S> LL_HD u64 ks_up(u64 g, u64 e, u64 keep) {
+    e &= keep;
+    g |= e & (g << S);
+    e &= e << S;
+    g |= e & (g << (2 * S));
+    e &= e << (2 * S);
+    g |= e & (g << (4 * S));
+    return (g << S) & keep;
+}
+// attacks of the orthogonal sliders `orth` and the diagonal sliders `diag` in the four up directions (north, east,
+// ne, nw); called with bit-reversed arguments it yields the bit-reversed attacks in the four down directions
+LL_HD u64 ks_up_attacks(u64 orth, u64 diag, u64 empty) {
+    return ks_up<8>(orth, empty, ~0ull) | ks_up<1>(orth, empty, ~FILE_A) | ks_up<9>(diag, empty, ~FILE_A) | ks_up<7>(diag, empty, ~FILE_H);
+}
+LL_HD u32 ks_up_count(u64 orth, u64 diag, u64 empty, u64 ok) {
+    return (u32)(popc64(ks_up<8>(orth, empty, ~0ull) & ok) + popc64(ks_up<1>(orth, empty, ~FILE_A) & ok) +
+                 popc64(ks_up<9>(diag, empty, ~FILE_A) & ok) + popc64(ks_up<7>(diag, empty, ~FILE_H) & ok));
+}
 LL_HD u64 ks_diag_attacks(u64 sliders, u64 empty) { return ks_ne(sliders, empty) | ks_nw(sliders, empty) | ks_se(sliders, empty) | ks_sw(sliders, empty); }
 LL_HD u64 ks_orth_attacks(u64 sliders, u64 empty) { return ks_north(sliders, empty) | ks_south(sliders, empty) | ks_east(sliders, empty) | ks_west(sliders, empty); }
 
@@ -317,7 +340,7 @@ template <int T> LL_HD Legal legal_context(const Pos &p, u64 own, u64 opp) {
         const u64 empty_wo_k = ~(occ ^ k);
         u64 danger = servant_attacks<E>(p.pl[6 * E + SERVANT]) | pony_attacks(p.pl[6 * E + PONY]);
         if (p.pl[6 * E + FIGUREHEAD]) danger |= figurehead_moves(lsb64(p.pl[6 * E + FIGUREHEAD]));
-        danger |= ks_diag_attacks(e_diag, empty_wo_k) | ks_orth_attacks(e_orth, empty_wo_k);
+        danger |= ks_up_attacks(e_orth, e_diag, empty_wo_k) | brev64(ks_up_attacks(brev64(e_orth), brev64(e_diag), brev64(empty_wo_k)));
         L.danger = danger;
     }
     // checkers and pins along the four lines through the figurehead
@@ -530,8 +553,7 @@ template <int T, bool NIHIL> LL_HD u32 count_moves_as(const Pos &p) {
         const u64 ok = ~own & cm;
         const u64 df = diag & free, of = orth & free;
         // rays of different pieces in one direction never overlap (a ray stops at the next piece)
-        n += popc64(ks_ne(df, empty) & ok) + popc64(ks_nw(df, empty) & ok) + popc64(ks_se(df, empty) & ok) + popc64(ks_sw(df, empty) & ok);
-        n += popc64(ks_north(of, empty) & ok) + popc64(ks_south(of, empty) & ok) + popc64(ks_east(of, empty) & ok) + popc64(ks_west(of, empty) & ok);
+        n += ks_up_count(of, df, empty, ok) + ks_up_count(brev64(of), brev64(df), brev64(empty), brev64(ok));
         if (!NIHIL) { // pinned sliders slide along the pin only
             const u64 k = p.pl[6 * T + FIGUREHEAD];
             for (u64 s = diag & L.pinned & (L.kd | L.ka); s; s &= s - 1) {
