@@ -152,14 +152,6 @@ LL_HD u64 orth_attacks(int sq, u64 occ) {
 
 // ---- all sliders of a kind at once: Kogge-Stone occluded fills (branch-free, no divergence).
 // Each returns the squares attacked in that direction, first blocker included. --------------------
-LL_HD u64 ks_north(u64 g, u64 e) { g |= e & (g << 8); e &= e << 8; g |= e & (g << 16); e &= e << 16; g |= e & (g << 32); return g << 8; }
-LL_HD u64 ks_south(u64 g, u64 e) { g |= e & (g >> 8); e &= e >> 8; g |= e & (g >> 16); e &= e >> 16; g |= e & (g >> 32); return g >> 8; }
-LL_HD u64 ks_east(u64 g, u64 e) { e &= ~FILE_A; g |= e & (g << 1); e &= e << 1; g |= e & (g << 2); e &= e << 2; g |= e & (g << 4); return (g << 1) & ~FILE_A; }
-LL_HD u64 ks_west(u64 g, u64 e) { e &= ~FILE_H; g |= e & (g >> 1); e &= e >> 1; g |= e & (g >> 2); e &= e >> 2; g |= e & (g >> 4); return (g >> 1) & ~FILE_H; }
-LL_HD u64 ks_ne(u64 g, u64 e) { e &= ~FILE_A; g |= e & (g << 9); e &= e << 9; g |= e & (g << 18); e &= e << 18; g |= e & (g << 36); return (g << 9) & ~FILE_A; }
-LL_HD u64 ks_nw(u64 g, u64 e) { e &= ~FILE_H; g |= e & (g << 7); e &= e << 7; g |= e & (g << 14); e &= e << 14; g |= e & (g << 28); return (g << 7) & ~FILE_H; }
-LL_HD u64 ks_se(u64 g, u64 e) { e &= ~FILE_A; g |= e & (g >> 7); e &= e >> 7; g |= e & (g >> 14); e &= e >> 14; g |= e & (g >> 28); return (g >> 7) & ~FILE_A; }
-LL_HD u64 ks_sw(u64 g, u64 e) { e &= ~FILE_H; g |= e & (g >> 9); e &= e >> 9; g |= e & (g >> 18); e &= e >> 18; g |= e & (g >> 36); return (g >> 9) & ~FILE_H; }
 // The four "up" fills (left shifts) and, on the bit-reversed board, the four "down" fills: brev maps square s to
 // 63 - s (south <-> north, west <-> east, sw <-> ne, se <-> nw, FILE_A <-> FILE_H).  A 64-bit left shift costs one
 // IMAD.SHL (FMA pipe) + one SHF (ALU pipe), a right shift two SHF: keeping every fill a left fill takes work off the
@@ -183,8 +175,6 @@ LL_HD u32 ks_up_count(u64 orth, u64 diag, u64 empty, u64 ok) {
     return (u32)(popc64(ks_up<8>(orth, empty, ~0ull) & ok) + popc64(ks_up<1>(orth, empty, ~FILE_A) & ok) +
                  popc64(ks_up<9>(diag, empty, ~FILE_A) & ok) + popc64(ks_up<7>(diag, empty, ~FILE_H) & ok));
 }
-LL_HD u64 ks_diag_attacks(u64 sliders, u64 empty) { return ks_ne(sliders, empty) | ks_nw(sliders, empty) | ks_se(sliders, empty) | ks_sw(sliders, empty); }
-LL_HD u64 ks_orth_attacks(u64 sliders, u64 empty) { return ks_north(sliders, empty) | ks_south(sliders, empty) | ks_east(sliders, empty) | ks_west(sliders, empty); }
 
 // squares from which a servant of team A attacks `bit` (life.rs:759, 765: stun offsets (+-1 rank, +-1 file))
 template <int A> LL_HD u64 servant_attackers_of(u64 bit) {
