@@ -145,17 +145,17 @@ def timed(stream, fn, reps, torch):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 400; 40 for --impl reference)")
-    ap.add_argument("--warmup", type=int, default=None, help="warm-up steps (default 20; 3 for --impl reference)")
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 2000, about 1.2 s; 40 for --impl reference)")
+    ap.add_argument("--warmup", type=int, default=None, help="warm-up steps (default 50; 3 for --impl reference)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--depth", type=int, default=6)
     ap.add_argument("--no-extras", action="store_true", help="skip the cpu baseline and the secondary kernels")
     args = ap.parse_args()
     # a reference step is ~0.5 s of all-core CPU work, a B200 step ~0.5 ms: different defaults, explicit values are honoured
     if args.steps is None:
-        args.steps = 400 if args.impl == "b200" else 40
+        args.steps = 2000 if args.impl == "b200" else 40
     if args.warmup is None:
-        args.warmup = 20 if args.impl == "b200" else 3
+        args.warmup = 50 if args.impl == "b200" else 3
     if args.impl == "b200":
         args.warmup = max(args.warmup, 3)
 
