@@ -332,6 +332,8 @@ def main():
         eng.timing(False)
         eng.timing_reset()
         result["kernels"] = kernels
+        result["kernels_note"] = ("per-kernel durations come from a separate pass of 5 steps with per-launch CUDA events enabled (ll_timing_enable); "
+                                  "the headline loop runs without them")
         int_peak = {"lop3_thread_inst_per_sec": eng.measure_int_peak(0), "lop3_imad_thread_inst_per_sec": eng.measure_int_peak(1)}
         result["int_peak_measured"] = int_peak
         if "perft_tail" in kernels and depth == 6:
