@@ -342,7 +342,7 @@ def main():
             alg_bytes = nodes * 104.0 + 21 * 8  # 100 B position + 4 B root id per expanded node, per-root counts out
             achieved = alg_bytes / (k_ms * 1e-3) / 1e9
             result["roofline"] = {
-                "kernel": "k_expand<legal,PERFT>", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "kernel": "k_expand_records<PERFT>", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": consts.get("perft6_tail_dram_bytes"), "peak_source": peak_src,
                 "ms": k_ms,
                 "note": "the perft tail reads only the ply-4 frontier (197281 positions x 104 B) and builds the 4.87 M ply-5 "
@@ -352,7 +352,7 @@ def main():
             if inst:
                 rate = inst / (k_ms * 1e-3)
                 result["int_roofline"] = {
-                    "kernel": "k_expand<legal,PERFT>", "bound": "int-issue", "achieved": rate / 1e12,
+                    "kernel": "k_expand_records<PERFT>", "bound": "int-issue", "achieved": rate / 1e12,
                     "peak": int_peak["lop3_imad_thread_inst_per_sec"] / 1e12,
                     "unit": "T thread-inst/s", "frac": rate / int_peak["lop3_imad_thread_inst_per_sec"],
                     "frac_of_alu_pipe": rate / int_peak["lop3_thread_inst_per_sec"],

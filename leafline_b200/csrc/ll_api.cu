@@ -631,6 +631,7 @@ static int perft_chain_launch(ll_ctx *ctx, int depth, int shard_rank, int shard_
     // the plan: one step per ply (+ the shard filter); each step reads its level's size from the device
     ExpandArgs steps[CHAIN_MAX_STEPS] = {};
     int kinds[CHAIN_MAX_STEPS] = {};
+    bool canonical[CHAIN_MAX_STEPS] = {}; // expanded by the canonical generator: the plies between the root and the shard ply (unit numbering)
     unsigned grids[CHAIN_MAX_STEPS] = {};
     ShardArgs shard{};
     size_t l = 0;
@@ -677,6 +678,7 @@ static int perft_chain_launch(ll_ctx *ctx, int depth, int shard_rank, int shard_
         // while its parents fit ONE tile -- the shard filter checks that)
         const bool small = ply < LL_SMALL_TILE_PLIES && (shard_world == 1 || ply >= shard_ply);
         if (small && l != 0) grids[n_steps] = (unsigned)std::min<size_t>(nblocks(f.cap, 32), resident);
+        canonical[n_steps] = ply != 0 && shard_world > 1 && ply < shard_ply; // (the root ply sorts its records by canonical key)
         kinds[n_steps++] = small ? STEP_EMIT_SMALL : STEP_EMIT;
         l++;
     }
@@ -686,7 +688,11 @@ static int perft_chain_launch(ll_ctx *ctx, int depth, int shard_rank, int shard_
         const int kind = kinds[s];
         Timed t(ctx, kind == STEP_TAIL ? "perft_tail" : kind == STEP_SHARD ? "shard_filter" : "emit_legal");
         if (kind == STEP_SHARD) k_shard_filter<<<grids[s], BLOCK, 0, ctx->stream>>>(shard);
-        else if (kind == STEP_TAIL) k_expand<false, MODE_PERFT><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
+        // order-free steps expand from legal RECORDS (small code: these launches are bound by instruction fetch and by one
+        // thread's serial latency); the plies whose order matters keep the canonical generator
+        else if (kind == STEP_TAIL) k_expand_records<MODE_PERFT><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
+        else if (kind == STEP_EMIT_SMALL && !canonical[s]) k_expand_records<MODE_EMIT, 32><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
+        else if (kind == STEP_EMIT && !canonical[s]) k_expand_records<MODE_EMIT><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
         else if (kind == STEP_EMIT_SMALL) k_expand<false, MODE_EMIT, 32><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
         else k_expand<false, MODE_EMIT><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
         LL_TRY(check_launch("perft chain step"));
@@ -759,8 +765,8 @@ static int perft_synced(ll_ctx *ctx, int depth, int shard_rank, int shard_world,
                 a.per_root = sc + SC_PER_ROOT;
                 a.total = sc + SC_LEAVES;
                 Timed t(ctx, "perft_tail");
-                k_expand<false, MODE_PERFT><<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(a);
-                LL_TRY(check_launch("k_expand<PERFT>"));
+                k_expand_records<MODE_PERFT><<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(a);
+                LL_TRY(check_launch("k_expand_records<PERFT>"));
             } else if (f.n) {
                 Timed t(ctx, "count_leaves");
                 k_count_leaves<<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(f.soa(), f.n, ply == 0 ? nullptr : (const u32 *)f.root.ptr,

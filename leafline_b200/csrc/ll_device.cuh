@@ -599,17 +599,8 @@ LL_HD int select_bit(u64 mask, u32 t) { // index of the t-th (0-based) set bit o
     return at;
 }
 // the move descriptor of commit number t (0-based) of a record, for mover `team`
-LL_HD u32 rec_move(u64 mask, u32 info, u32 t, u32 team) {
-    const int to = select_bit(mask, t);
-    const u32 kind = info & 7u, job = (info >> 3) & 7u, asc = (info >> 12) & 7u;
-    int from = (int)((info >> 6) & 63u);
-    if (kind == REC_PUSH) from = team == 0 ? to - 8 : to + 8;
-    else if (kind == REC_DOUBLE) from = team == 0 ? to - 16 : to + 16;
-    else if (kind == REC_STUN_WEST) from = team == 0 ? to - 7 : to + 9; // the servant stands one file EAST of its west stun
-    else if (kind == REC_STUN_EAST) from = team == 0 ? to - 9 : to + 7;
-    const u32 flags = ((info >> 15) & 1u ? MV_PASSING_BY : 0u) | (kind == REC_SERVICE ? MV_SERVICE : 0u);
-    return mv_pack(job, from, to, asc, flags);
-}
+LL_HD u32 rec_move_to(u32 info, int to, u32 team);
+LL_HD u32 rec_move(u64 mask, u32 info, u32 t, u32 team) { return rec_move_to(info, select_bit(mask, t), team); }
 struct ServiceBits { // collects the secret-service destinations the exact path admits
     u64 to_bits = 0;
     LL_HDM void move(u32, int, int to, u32, u32) { to_bits |= 1ull << to; }
@@ -679,6 +670,108 @@ template <int T, bool STUNS, class Out> LL_HD void reckless_records_as(const Pos
 template <bool STUNS, class Out> LL_HD void reckless_records(const Pos &p, Out &out) {
     if (meta_stm(p.meta) == 0) reckless_records_as<0, STUNS>(p, out);
     else reckless_records_as<1, STUNS>(p, out);
+}
+
+// ---- legal commits as records (the order-free consumers of lookahead(): perft chain and tail) -----------------
+// The same commits as lookahead() (life.rs:1078), in another order, produced per piece set / per piece with the
+// legality masks applied to whole target sets -- a fraction of the canonical generator's code and instructions
+// (the narrow perft levels are bound by instruction fetch: one thread runs the whole generator once).
+template <int T, class Out> LL_HD void legal_records_as(const Pos &p, Out &out) {
+    const u64 own = occupied_by<T>(p), opp = occupied_by<1 - T>(p), occ = own | opp, empty = ~occ;
+    const Legal L = legal_context<T>(p, own, opp);
+    const u64 k = p.pl[6 * T + FIGUREHEAD];
+    if (k) { // life.rs:973-978
+        const int from = lsb64(k);
+        const u64 targets = figurehead_moves(from) & ~own & ~L.danger;
+        if (targets) out.put(targets, rec_info(REC_PIECE, FIGUREHEAD, from, ASC_NONE, 0, 0));
+    }
+    if (L.check == 0) return; // two checkers: only the figurehead moves
+    const u64 cm = L.check, free = ~L.pinned;
+    { // life.rs:749-830: a pinned servant may still push along a file pin / stun along a diagonal pin
+        const u64 s = p.pl[6 * T + SERVANT];
+        const u64 last = T == 0 ? RANK_1 << 56 : RANK_1;
+        const u64 pushers = s & (free | L.kf);
+        const u64 west_stunners = s & (free | (T == 0 ? L.ka : L.kd)), east_stunners = s & (free | (T == 0 ? L.kd : L.ka));
+        const u64 one = (T == 0 ? pushers << 8 : pushers >> 8) & empty;
+        const u64 two = (T == 0 ? (one & (RANK_1 << 16)) << 8 : (one & (RANK_1 << 40)) >> 8) & empty & cm;
+        if (two) out.put(two, rec_info(REC_DOUBLE, SERVANT, 0, ASC_NONE, 0, 0));
+#pragma unroll
+        for (int kind = REC_PUSH; kind <= REC_STUN_EAST; kind++) {
+            if (kind == REC_DOUBLE) continue;
+            const u64 targets = (kind == REC_PUSH ? one
+                                 : kind == REC_STUN_WEST ? (T == 0 ? west_stunners << 7 : west_stunners >> 9) & ~FILE_H & opp
+                                                         : (T == 0 ? east_stunners << 9 : east_stunners >> 7) & ~FILE_A & opp) & cm;
+            if (targets & ~last) out.put(targets & ~last, rec_info((u32)kind, SERVANT, 0, ASC_NONE, 0, 0));
+            if (targets & last) {
+#pragma unroll
+                for (u32 asc = PONY; asc <= PRINCESS; asc++) out.put(targets & last, rec_info((u32)kind, SERVANT, 0, asc, 0, 0));
+            }
+        }
+        const u64 pb_bit = passing_by_bit(p.meta);
+        if (pb_bit) // passing by: the make-the-move-and-test path
+            for (u64 c = servant_attackers_of<T>(pb_bit) & s; c; c &= c - 1)
+                if (passing_by_is_legal<T>(p, lsb64(c), lsb64(pb_bit))) out.put(pb_bit, rec_info(REC_PIECE, SERVANT, lsb64(c), ASC_NONE, 1, 0));
+    }
+    const u64 ok = ~own & cm;
+    for (u64 s = p.pl[6 * T + PONY] & free; s; s &= s - 1) { // a pinned pony never stays on its line
+        const int from = lsb64(s);
+        const u64 targets = pony_moves(from) & ok;
+        if (targets) out.put(targets, rec_info(REC_PIECE, PONY, from, ASC_NONE, 0, 0));
+    }
+#pragma unroll 1
+    for (int job = SCHOLAR; job <= PRINCESS; job++) { // one loop body for the three sliders: less code to fetch
+        // (the plane is picked by comparisons: a runtime index would push the position out of registers)
+        for (u64 s = job == SCHOLAR ? p.pl[6 * T + SCHOLAR] : job == COP ? p.pl[6 * T + COP] : p.pl[6 * T + PRINCESS]; s; s &= s - 1) {
+            const int from = lsb64(s);
+            const u64 bit = 1ull << from;
+            u64 targets = 0;
+            if (job != COP) targets |= diag_attacks(from, occ);
+            if (job != SCHOLAR) targets |= orth_attacks(from, occ);
+            targets &= ok;
+            if (bit & L.pinned) targets &= pin_line(L, bit);
+            if (targets) out.put(targets, rec_info(REC_PIECE, (u32)job, from, ASC_NONE, 0, 0));
+        }
+    }
+    if (cm == ~0ull) { // never out of check (life.rs:1034-1043)
+        ServiceBits service;
+        service_lookahead<T, false>(p, own, opp, service);
+        if (service.to_bits) out.put(service.to_bits, rec_info(REC_SERVICE, FIGUREHEAD, (T == 0 ? 0 : 56) + 4, ASC_NONE, 0, 0));
+    }
+}
+template <class Out> LL_HD void legal_records(const Pos &p, Out &out) {
+    if (meta_stm(p.meta) == 0) legal_records_as<0>(p, out);
+    else legal_records_as<1>(p, out);
+}
+// the move descriptor of the commit of a record that lands on `to`
+LL_HD u32 rec_move_to(u32 info, int to, u32 team) {
+    const u32 kind = info & 7u, job = (info >> 3) & 7u, asc = (info >> 12) & 7u;
+    int from = (int)((info >> 6) & 63u);
+    if (kind == REC_PUSH) from = team == 0 ? to - 8 : to + 8;
+    else if (kind == REC_DOUBLE) from = team == 0 ? to - 16 : to + 16;
+    else if (kind == REC_STUN_WEST) from = team == 0 ? to - 7 : to + 9;
+    else if (kind == REC_STUN_EAST) from = team == 0 ? to - 9 : to + 7;
+    const u32 flags = ((info >> 15) & 1u ? MV_PASSING_BY : 0u) | (kind == REC_SERVICE ? MV_SERVICE : 0u);
+    return mv_pack(job, from, to, asc, flags);
+}
+
+// The position of a commit in lookahead()'s order among the commits of ONE position, as a sortable key computed from
+// the move alone (life.rs:1052-1084): servants, ponies, scholars, cops, princesses (all diagonal moves, then all
+// orthogonal ones), figurehead, secret service West then East; pieces by ascending square; a servant's push, double
+// push, west stun, east stun, each through Pony, Scholar, Cop, Princess when ascending; table pieces by ascending
+// destination; sliders by the reference's direction lists (life.rs:10-11), nearest square first.
+LL_HD u32 canonical_key(u32 m) {
+    const int from = mv_from(m), to = mv_to(m);
+    const u32 job = mv_job(m), asc = mv_asc(m);
+    const int dr = (to >> 3) - (from >> 3), df = (to & 7) - (from & 7);
+    const u32 dist = (u32)((dr < 0 ? -dr : dr) > (df < 0 ? -df : df) ? (dr < 0 ? -dr : dr) : (df < 0 ? -df : df));
+    const bool diagonal = dr != 0 && df != 0;
+    u32 cls = job <= COP ? job : job == PRINCESS ? (diagonal ? 4u : 5u) : (m & MV_SERVICE) ? 7u : 6u;
+    u32 sub;
+    if (job == SERVANT) sub = ((df == 0 ? (dist == 1 ? 0u : 1u) : df < 0 ? 2u : 3u) << 3) | (asc == ASC_NONE ? 0u : asc);
+    else if (job == PONY || job == FIGUREHEAD) sub = (u32)to;
+    else if (diagonal) sub = ((u32)((dr > 0 ? 2 : 0) + (df > 0 ? 1 : 0)) << 3) | dist; // (-1,-1), (-1,1), (1,-1), (1,1)
+    else sub = ((dr < 0 ? 0u : dr > 0 ? 1u : df < 0 ? 2u : 3u) << 3) | dist;            // (-1,0), (1,0), (0,-1), (0,1)
+    return (cls << 16) | ((u32)from << 8) | sub;
 }
 
 // ---- well-formedness (domain W, include/leafline_b200.h) ----------------------------------------

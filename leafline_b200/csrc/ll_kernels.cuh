@@ -364,6 +364,139 @@ template <bool NIHIL, int MODE, int P = BLOCK, bool STUNS = false> __global__ vo
     expand_tiles<NIHIL, MODE, P, STUNS>(a, sh);
 }
 
+// ---- the order-free legal expansion (perft launch chain and tail): phase 1 by records ------------------------
+// One sink for both passes over a parent's legal records: COUNT adds the popcounts, WRITE expands every record into
+// move descriptors at the parent's offset of the current window.  The record generator is inlined ONCE (a single call
+// site inside a loop) -- the narrow perft levels are bound by instruction fetch, so code size is time here.
+struct RecordSink {
+    u32 *buf;
+    u32 idx, lo, hi, slot_bits, team;
+    bool write;
+    LL_HDM void put(u64 mask, u32 info) {
+        if (!write) {
+            idx += (u32)__popcll(mask);
+            return;
+        }
+        for (; mask; mask &= mask - 1) {
+            if (idx >= lo && idx < hi) buf[idx - lo] = rec_move_to(info, __ffsll((long long)mask) - 1, team) | slot_bits;
+            idx++;
+        }
+    }
+};
+template <int MODE, int P> __device__ __forceinline__ void expand_tiles_records(const ExpandArgs &a, ExpandShared &sh) {
+    const int tid = threadIdx.x;
+    if (a.n_in && a.overflow && *(volatile u32 *)a.overflow) return; // see expand_tiles
+    const size_t n = a.n_in ? (size_t)*(volatile const u64 *)a.n_in : a.n;
+    for (;;) {
+        size_t tile = blockIdx.x;
+        if (a.tile_counter) {
+            if (tid == 0) sh.claim = atomicAdd(a.tile_counter, 1u);
+            __syncthreads();
+            tile = (size_t)sh.claim;
+        }
+        if (tile * P >= n) break;
+        const size_t i = tile * P + tid;
+        const bool mine = tid < P && i < n;
+        if (mine) {
+            const Pos p = soa_load(a.in, i);
+#pragma unroll
+            for (int j = 0; j < 12; j++) sh.tile_pl[j][tid] = p.pl[j];
+            sh.tile_meta[tid] = p.meta;
+        }
+        if (MODE == MODE_PERFT && tid < P) sh.acc[tid] = 0;
+        u32 cnt = 0, ex = 0, total = 0;
+        size_t out_base = 0;
+        bool writable = true;
+        // pass 0 counts; pass 1 + w writes window w of the tile's descriptor list and consumes it
+#pragma unroll 1
+        for (u32 pass = 0;; pass++) {
+            const u32 w0 = pass ? (pass - 1) * DESC_CAP : 0;
+            if (pass && (w0 >= total || !writable)) break;
+            if (mine && (pass == 0 || (cnt && ex < w0 + DESC_CAP && ex + cnt > w0))) {
+                const Pos p = tile_load(sh, tid);
+                RecordSink sink{sh.descs, pass ? ex : 0u, w0, w0 + DESC_CAP, (u32)tid << 20, meta_stm(p.meta), pass != 0};
+                legal_records(p, sink);
+                if (pass == 0) cnt = sink.idx;
+            }
+            if (pass == 0) {
+                ex = block_exclusive_scan(cnt, &total);
+                if (MODE == MODE_EMIT) { // order-free: claim a contiguous range for this tile's children
+                    if (tid == 0) sh.claim = atomicAdd((unsigned long long *)a.n_out, (unsigned long long)total);
+                    __syncthreads();
+                    out_base = (size_t)sh.claim;
+                    writable = out_base + total <= a.out_cap;
+                    if (!writable && tid == 0) atomicExch(a.overflow, 1u);
+                }
+                continue;
+            }
+            __syncthreads();
+            if (MODE == MODE_EMIT && a.root_is_index) {
+                // the root's children become the root moves of the divide table: put the (single) parent's commits into
+                // the reference's order by their canonical keys -- a rank sort over at most a few hundred entries
+                constexpr u32 S = DESC_CAP / 4;
+                if (total > S) { // more root moves than the sort buffer holds: the level-by-level path takes the call
+                    if (tid == 0) atomicExch(a.overflow, 1u);
+                    writable = false;
+                    break;
+                }
+                for (u32 k = tid; k < total; k += BLOCK) sh.descs[S + k] = canonical_key(sh.descs[k]);
+                __syncthreads();
+                for (u32 k = tid; k < total; k += BLOCK) {
+                    const u32 key = sh.descs[S + k];
+                    u32 rank = 0;
+                    for (u32 j = 0; j < total; j++) rank += sh.descs[S + j] < key;
+                    sh.descs[2 * S + rank] = sh.descs[k];
+                }
+                __syncthreads();
+                for (u32 k = tid; k < total; k += BLOCK) sh.descs[k] = sh.descs[2 * S + k];
+                __syncthreads();
+            }
+            const u32 wn = min((u32)DESC_CAP, total - w0);
+            for (u32 k0 = 0; k0 < wn; k0 += BLOCK) { // phase 2: one child per thread
+                const u32 k = k0 + tid;
+                const bool live = k < wn;
+                u32 slot = 0;
+                Pos c;
+                if (live) {
+                    const u32 m = sh.descs[k];
+                    slot = mv_slot(m);
+                    make_child(tile_load(sh, slot), m, c);
+                }
+                if (MODE == MODE_EMIT) {
+                    if (live) {
+                        const size_t o = out_base + w0 + k;
+                        soa_store(a.out, o, c);
+                        if (a.root_out) a.root_out[o] = a.root_is_index ? (u32)o : a.root_in[tile * P + slot];
+                    }
+                } else {
+                    const int v = live ? (int)count_moves<false>(c) : 0;
+                    // children of one parent are neighbours in the list: reduce per parent inside the warp first
+                    const unsigned peers = __match_any_sync(0xffffffffu, live ? slot : 0xFFFFFFFFu);
+                    const int r = __reduce_add_sync(peers, v);
+                    if (live && (tid & 31) == __ffs((int)peers) - 1) atomicAdd(&sh.acc[slot], r);
+                }
+            }
+            __syncthreads();
+        }
+        if (MODE == MODE_PERFT) {
+            const u32 root = mine ? (a.root_in ? a.root_in[i] : 0u) : 0xFFFFFFFFu;
+            const u32 below = mine ? (u32)sh.acc[tid] : 0u;
+            const unsigned peers = __match_any_sync(0xffffffffu, root);
+            const u32 sum = __reduce_add_sync(peers, below);
+            if ((tid & 31) == __ffs((int)peers) - 1 && root != 0xFFFFFFFFu && sum) {
+                if (a.per_root) atomicAdd((unsigned long long *)a.per_root + root, (unsigned long long)sum);
+                atomicAdd((unsigned long long *)a.total, (unsigned long long)sum);
+            }
+        }
+        if (!a.tile_counter) break;
+        __syncthreads();
+    }
+}
+template <int MODE, int P = BLOCK> __global__ void __launch_bounds__(BLOCK, LL_EXPAND_MIN_BLOCKS) k_expand_records(const ExpandArgs a) {
+    __shared__ ExpandShared sh;
+    expand_tiles_records<MODE, P>(a, sh);
+}
+
 // ---- horizon by records (mind.rs:279-301): children decoded from (piece, target mask) records ---------------
 // Phase 1 costs per PIECE, not per move: a parent thread writes at most REC_MAX records (ll_device.cuh) into shared
 // memory.  Phase 2 runs one CHILD per thread: binary-search the parent by the prefix sums, the record by its base,

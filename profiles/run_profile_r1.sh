@@ -3,5 +3,5 @@ set -x
 python profiles/workload.py > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches.csv python profiles/workload.py > gpurun_out/ncu_launch.log 2>&1
 python profiles/workload.py > gpurun_out/plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:"k_expandILb0ELi1|k_horizon|k_score" -o gpurun_out/r01_hot python profiles/workload.py > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:"k_expand_recordsILi1|k_horizon|k_score" -o gpurun_out/r01_hot python profiles/workload.py > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log

@@ -124,3 +124,36 @@ extern "C" int hc_generator_moves(const ll_world_t *w, int stuns, uint32_t *move
     }
     return n;
 }
+
+// the legal commits decoded from legal_records() the way the order-free perft kernels expand them
+struct ExpandList {
+    u32 moves[1024];
+    u32 n = 0, n_rec = 0, team;
+    void put(u64 m, u32 info) {
+        n_rec++;
+        for (; m; m &= m - 1) {
+            if (n < 1024) moves[n] = rec_move_to(info, lsb64(m), team);
+            n++;
+        }
+    }
+};
+extern "C" int hc_legal_record_moves(const ll_world_t *w, uint32_t *moves, int cap, int *n_records) {
+    const Pos p = to_pos(w);
+    static thread_local ExpandList el;
+    el.n = el.n_rec = 0;
+    el.team = meta_stm(p.meta);
+    legal_records(p, el);
+    *n_records = (int)el.n_rec;
+    for (u32 i = 0; i < el.n && (int)i < cap; i++) moves[i] = el.moves[i];
+    return (int)el.n;
+}
+extern "C" int hc_legal_generator_moves(const ll_world_t *w, uint32_t *moves, int cap) {
+    const Pos p = to_pos(w);
+    static thread_local ListSink sink;
+    sink.n = 0;
+    lookahead<false>(p, sink);
+    for (u32 i = 0; i < sink.n && (int)i < cap; i++) moves[i] = sink.moves[i];
+    return (int)sink.n;
+}
+
+extern "C" uint32_t hc_canonical_key(uint32_t move) { return canonical_key(move); }

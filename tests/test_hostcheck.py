@@ -33,6 +33,10 @@ def hc():
     lib.hc_well_formed.argtypes = [C.c_void_p]
     lib.hc_record_moves.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     lib.hc_generator_moves.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.hc_legal_record_moves.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    lib.hc_legal_generator_moves.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.hc_canonical_key.argtypes = [C.c_uint32]
+    lib.hc_canonical_key.restype = C.c_uint32
     lib.hc_init()
     return lib
 
@@ -57,6 +61,17 @@ def check(hc, worlds):
             nb = hc.hc_generator_moves(ptr, stuns, b.ctypes.data_as(C.c_void_p), 1024)
             assert 0 <= nrec.value <= 36 and na == nb, (O.preserve(w), stuns, na, nb, nrec.value)
             assert sorted(a[:na]) == sorted(b[:nb]), (O.preserve(w), stuns)
+        # ... and the legal records (perft chain / tail) hold exactly lookahead()'s commits
+        na = hc.hc_legal_record_moves(ptr, a.ctypes.data_as(C.c_void_p), 1024, C.byref(nrec))
+        nb = hc.hc_legal_generator_moves(ptr, b.ctypes.data_as(C.c_void_p), 1024)
+        assert na == nb and sorted(a[:na]) == sorted(b[:nb]), (O.preserve(w), na, nb)
+        # ... which the canonical key sorts back into the reference's order (the root ply of the perft chain does that)
+        keys = [hc.hc_canonical_key(int(m)) for m in b[:nb]]
+        assert keys == sorted(keys) and len(set(keys)) == nb, O.preserve(w)
+        for stuns in (0,):
+            nr = hc.hc_generator_moves(ptr, 0, b.ctypes.data_as(C.c_void_p), 1024)
+            keys = [hc.hc_canonical_key(int(m)) for m in b[:nr]]
+            assert keys == sorted(keys) and len(set(keys)) == nr, O.preserve(w)
 
 
 def test_named_positions(hc):
