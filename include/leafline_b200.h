@@ -16,7 +16,7 @@
  *  - an ll_ctx is NOT thread-safe; use one ll_ctx per host thread (the reference calls the leaf
  *    layer from one thread per root move, src/mind.rs:405).
  *  - positions must be "well-formed" (domain W: no two planes overlap; at most one
- *    figurehead per team; a set service-eligibility bit implies that team's figurehead, if any,
+ *    figurehead and at most 16 figurines per team; a set service-eligibility bit implies that team's figurehead, if any,
  *    stands on its home e-square; passing_by is None or an empty square directly behind an enemy
  *    servant on its double-step rank).  Every state reachable from a well-formed state by the
  *    reference's own move generator is well-formed.  Other inputs are rejected with

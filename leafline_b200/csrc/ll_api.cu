@@ -593,6 +593,9 @@ static bool host_well_formed(const ll_world_t *w) {
         acc |= w->plane[j];
     }
     if (__builtin_popcountll(w->plane[5]) > 1 || __builtin_popcountll(w->plane[11]) > 1) return false;
+    uint64_t orange = 0, blue = 0;
+    for (int j = 0; j < 6; j++) orange |= w->plane[j], blue |= w->plane[6 + j];
+    if (__builtin_popcountll(orange) > 16 || __builtin_popcountll(blue) > 16) return false;
     if (w->initiative > 1 || w->service_eligibility > 0xF) return false;
     if ((w->service_eligibility & 0x3) && (w->plane[5] & ~(1ull << 4))) return false;
     if ((w->service_eligibility & 0xC) && (w->plane[11] & ~(1ull << 60))) return false;
@@ -867,6 +870,8 @@ extern "C" int ll_horizon_soa(ll_ctx *ctx, const ll_soa_t *soa, int plies, int q
     if (plies < 0 || plies > 8) return fail(LL_ERR_INVALID_ARG, "plies %d out of range", plies);
     if (leaves_scored) *leaves_scored = 0;
     if (!soa->n) return LL_OK;
+    if (soa->stride & 1) return fail(LL_ERR_INVALID_ARG, "stride must be even");
+    LL_TRY(validate_level(ctx, Soa{(u64 *)soa->planes, soa->meta, soa->stride}, soa->n));
     // level 0 aliases the caller's planes for the duration of the call; its scratch arrays persist in ctx->ext
     if (ctx->levels.empty()) ctx->levels.resize(1);
     Frontier &ext = ctx->ext;

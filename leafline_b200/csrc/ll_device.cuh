@@ -784,6 +784,7 @@ LL_HD bool well_formed(const Pos &p) {
     }
     if (overlap) return false;
     if (popc64(p.pl[FIGUREHEAD]) > 1 || popc64(p.pl[6 + FIGUREHEAD]) > 1) return false;
+    if (popc64(occupied_by<0>(p)) > 16 || popc64(occupied_by<1>(p)) > 16) return false; // bounds the record lists (REC_MAX)
     const u32 elig = meta_elig(p.meta);
     if ((elig & 0x3u) && (p.pl[FIGUREHEAD] & ~(1ull << 4))) return false;
     if ((elig & 0xCu) && (p.pl[6 + FIGUREHEAD] & ~(1ull << 60))) return false;

@@ -516,6 +516,7 @@ struct SharedRecordOut {
     int slot;
     u32 n_rec = 0, n_moves = 0;
     LL_HDM void put(u64 mask, u32 info) {
+        if (n_rec >= REC_MAX) return; // cannot happen on a well-formed position (<= 16 figurines a team); never write past the tile
         sh.rec_mask[n_rec][slot] = mask;
         sh.rec_info[n_rec][slot] = info | (n_moves << 16);
         n_rec++;

@@ -67,6 +67,11 @@ def is_well_formed(w):
         acc |= p
     if bin(planes[5]).count("1") > 1 or bin(planes[11]).count("1") > 1:
         return False
+    orange, blue = 0, 0
+    for j in range(6):
+        orange, blue = orange | planes[j], blue | planes[6 + j]
+    if bin(orange).count("1") > 16 or bin(blue).count("1") > 16:
+        return False
     e = int(w["service_eligibility"])
     if e & 3 and planes[5] & ~(1 << 4):
         return False

@@ -161,6 +161,9 @@ def test_domain_errors_are_reported_not_guessed(eng):
     with pytest.raises(ll.LeaflineError) as e:
         eng.lookahead(np.array([ll.new_world(), bad], dtype=ll.WORLD_DTYPE))
     assert e.value.code == -4 and "position 1" in str(e.value)
+    crowd = ll.reconstruct("4k3/8/8/8/NNNNNNNN/NNNNNNNN/8/4K3 w - -")  # 17 orange figurines: beyond the record bound
+    with pytest.raises(ll.LeaflineError):
+        eng.horizon(crowd, 1)
     two_kings = ll.reconstruct("4k3/8/8/8/8/8/8/K3K3 w - -")
     with pytest.raises(ll.LeaflineError):
         eng.perft(two_kings, 2)
