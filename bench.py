@@ -315,6 +315,29 @@ def main():
                               "ms": ms5, "leaf_positions_per_sec": scored_all / (ms5 * 1e-3), "scaling": "strong",
                               "sharding": f"root moves round-robin over {world} rank(s); max-gather of per-root f32 scores"}
 
+        # the same search two plies deeper (3.3 G leaves): large enough for the root-subtree sharding to show
+        def kickoff7():
+            roots, scores, scored = eng.kickoff(root, 7, shard=(rank, world))
+            if world > 1:
+                scores = sharding.gather_root_scores(scores, dist, torch, device="cuda")
+            return scores, scored
+
+        scores7, scored7 = kickoff7()
+        if world > 1:
+            dist.barrier()
+        ms7k = timed(stream, kickoff7, 3, torch)
+        t7k = torch.tensor([ms7k, float(scored7)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            tmax = t7k.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t7k, op=dist.ReduceOp.SUM)
+            ms7k, scored7_all = float(tmax[0].item()), int(t7k[1].item())
+        else:
+            scored7_all = scored7
+        result["kickoff7"] = {"depth": 7, "root_moves": len(scores7), "best_score": float(np.max(scores7)), "leaves_scored": scored7_all,
+                              "ms": ms7k, "leaf_positions_per_sec": scored7_all / (ms7k * 1e-3), "scaling": "strong",
+                              "sharding": f"root moves round-robin over {world} rank(s); max-gather of per-root f32 scores"}
+
     if rank == 0 and world == 1 and not args.no_extras:
         peaks, peak_src = measured_peaks()
         consts = profile_constants()
