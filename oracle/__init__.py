@@ -61,6 +61,7 @@ def lib():
         L.lo_reckless_lookahead.argtypes = [vp, vp]
         L.lo_score.argtypes = [vp]
         L.lo_score.restype = C.c_float
+        L.lo_score_batch.argtypes = [vp, C.c_size_t, vp]
         L.lo_perft.argtypes = [vp, i32]
         L.lo_perft.restype = u64
         L.lo_perft_divide.argtypes = [vp, i32, vp, i32, i32]
@@ -184,12 +185,9 @@ def score(w):
 
 
 def score_batch(worlds):
-    worlds = np.ascontiguousarray(worlds)
+    worlds = np.ascontiguousarray(worlds, dtype=WORLD_DTYPE)
     out = np.empty(len(worlds), dtype=np.float32)
-    base = worlds.ctypes.data
-    f = lib().lo_score
-    for i in range(len(worlds)):
-        out[i] = f(base + 104 * i)
+    lib().lo_score_batch(_ptr(worlds), len(worlds), _ptr(out))
     return out
 
 

@@ -703,6 +703,11 @@ int lo_perft_divide(const lo_world_t *w, int depth, uint64_t *per_root, int cap,
     return n;
 }
 
+/* lo_score over an array of worlds (the full-size parity test scores 2^24 positions) */
+void lo_score_batch(const lo_world_t *worlds, size_t n, float *out) {
+    for (size_t i = 0; i < n; i++) out[i] = lo_score(&worlds[i]);
+}
+
 /* ---------------------------------------------------------------- mind.rs: leaf rule + negamax */
 
 /* mind.rs:145-153 (MVV-LVA); ordering only changes how fast the exact value is found. */

@@ -86,6 +86,7 @@ int lo_reckless_lookahead(const lo_world_t *w, lo_commit_t *out);
 
 float lo_orientation(int team);                                   /* mind.rs:29-34 */
 float lo_score(const lo_world_t *w);                              /* mind.rs:50-143 */
+void lo_score_batch(const lo_world_t *worlds, size_t n, float *out);
 
 /* perft = recursive count of lookahead() leaves; depth 0 -> 1.
  * lo_perft_divide also fills per_root[i] for root move i (canonical order), returns the root count.

@@ -482,11 +482,13 @@ def test_full_size_score_batch_properties(eng):
     worlds = eng.soa_download(soa, 0, k)
     assert worlds.tobytes() == O.playout_batch(0x1EAF11E, 0, k).tobytes()
     assert scores[:k].tobytes() == O.score_batch(worlds).tobytes()
-    # a strided sample across the whole set against the oracle
-    idx = np.arange(0, n, n // 512)
-    for i in idx[:64]:
-        w = eng.soa_download(soa, int(i), 1)
-        assert np.float32(scores[i]) == O.score(w[0])
+    # ALL 2^24 scores against the oracle, bit for bit (tolerance of the north star: 1e-5 relative)
+    chunk = 1 << 21
+    for first in range(0, n, chunk):
+        worlds = eng.soa_download(soa, first, chunk)
+        want = O.score_batch(worlds)
+        np.testing.assert_allclose(scores[first:first + chunk], want, rtol=SCORE_RTOL, atol=0)
+        assert scores[first:first + chunk].tobytes() == want.tobytes(), first
     # idempotence: scoring again gives identical bits
     out2 = torch.empty_like(out)
     eng.score_soa(soa, out2.data_ptr())
