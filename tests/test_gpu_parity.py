@@ -440,6 +440,21 @@ def test_kickoff_depth_4_kiwipete_matches_oracle(eng):
     check_kickoff(eng, ll.reconstruct(POSITION_5), 3, True)
 
 
+def test_kickoff_depth_5_and_6_match_the_oracle(eng):
+    # BASELINE.json configs[3]: depth-5 search from the opening (and one ply deeper), per-root scores equal to TT-free
+    # exact negamax (the oracle prunes with alpha-beta, which is exact at the root; the device searches full width)
+    import leafline_b200 as ll
+
+    for fen, depth in ((OPENING, 5), (OPENING, 6), (KIWIPETE, 4)):
+        w = ll.reconstruct(fen)
+        roots, scores, scored = eng.kickoff(w, depth)
+        want_roots, want_scores = O.kickoff(w, depth, False, threads=16)
+        assert roots.tobytes() == want_roots.tobytes()
+        assert np.array_equal(scores, want_scores), (fen, depth)
+        pruned, _, _ = eng.alpha_beta_forecast(w, depth, device_plies=3)
+        assert sorted(pruned["score"]) == sorted(want_scores)
+
+
 @pytest.mark.parametrize("world_size", [2, 4])
 def test_kickoff_shards_gather_to_the_whole(eng, world_size):
     import leafline_b200 as ll
