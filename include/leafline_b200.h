@@ -192,8 +192,9 @@ int ll_timing_reset(ll_ctx *ctx);
 int ll_timing_query(ll_ctx *ctx, const char *kernel, double *ms, uint64_t *launches);
 /* total number of this library's kernel launches since ll_init (for bench.py's gpu_launches) */
 uint64_t ll_launch_count(ll_ctx *ctx);
-/* testing aid: on != 0 makes ll_perft take its level-by-level path (sizes every level on the host) instead of the
- * launch chain with device-resident level sizes; both give identical results */
+/* testing aid: ll_perft normally replays its launch chain (device-resident level sizes) as a captured CUDA graph.
+ * on == 1 forces the level-by-level path (every level sized on the host), on == 2 issues the chain launch by launch;
+ * 0 restores the default.  All three give identical results. */
 int ll_debug_force_synced(ll_ctx *ctx, int on);
 /* testing aid, full-size property check on resident positions: for every position the set-wise move counter, the
  * canonical generator (legality by check / pin / danger masks) and the reference's definition (each reckless commit

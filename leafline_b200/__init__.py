@@ -126,7 +126,7 @@ class Engine:
         return ms.value, launches.value
 
     def force_synced(self, on=True):
-        """Testing aid: make perft() take the level-by-level path instead of the launch chain."""
+        """Testing aid: True/1 = level-by-level perft, 2 = the launch chain without its CUDA graph, False/0 = default."""
         _abi.check(self._lib.ll_debug_force_synced(self._ctx, int(on)))
 
     def selfcheck_soa(self, soa):

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <string>
 #include <tuple>
+#include <type_traits>
 #include <unordered_map>
 #include <vector>
 
@@ -75,6 +76,10 @@ struct ll_ctx {
     size_t pinned_cap = 0;
     bool timing = false;
     bool force_synced = false; // tests: always take the level-by-level path
+    bool no_graph = false;     // tests: issue the perft launch chain launch by launch instead of replaying its CUDA graph
+    uint64_t chain_sig = 0;    // the captured perft chain (same plan, same buffers, same stream -> replay)
+    cudaGraphExec_t chain_exec = nullptr;
+    cudaStream_t chain_stream = nullptr;
     std::vector<TimedLaunch> timed;
     uint64_t launches = 0;
 };
@@ -388,6 +393,7 @@ extern "C" int ll_shutdown(ll_ctx *ctx) {
         cudaEventDestroy(t.stop);
     }
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->chain_exec) cudaGraphExecDestroy(ctx->chain_exec);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return LL_OK;
@@ -443,7 +449,8 @@ extern "C" int ll_timing_query(ll_ctx *ctx, const char *kernel, double *ms, uint
 extern "C" uint64_t ll_launch_count(ll_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int ll_debug_force_synced(ll_ctx *ctx, int on) {
     LL_TRY(check_ctx(ctx));
-    ctx->force_synced = on != 0;
+    ctx->force_synced = on == 1;
+    ctx->no_graph = on == 2;
     return LL_OK;
 }
 
@@ -626,17 +633,27 @@ static int perft_chain_launch(ll_ctx *ctx, int depth, int shard_rank, int shard_
     for (size_t l = 0; l < need; l++)
         if (!ctx->levels[l].cap) return LL_OK;
     u64 *sc = (u64 *)ctx->scalars.ptr;
-    CUDA_TRY(cudaMemsetAsync(sc + SC_LEAVES, 0, (SC_SLOTS - SC_LEAVES) * sizeof(u64), ctx->stream));
     u64 *N = sc + SC_N;
     u32 *tileq = (u32 *)(sc + SC_TILEQ);
     u32 *overflow = (u32 *)(sc + SC_OVERFLOW);
     const unsigned resident = (unsigned)ctx->sm_count * LL_EXPAND_MIN_BLOCKS;
     // the plan: one step per ply (+ the shard filter); each step reads its level's size from the device
-    ExpandArgs steps[CHAIN_MAX_STEPS] = {};
-    int kinds[CHAIN_MAX_STEPS] = {};
-    bool canonical[CHAIN_MAX_STEPS] = {}; // expanded by the canonical generator: the plies between the root and the shard ply (unit numbering)
-    unsigned grids[CHAIN_MAX_STEPS] = {};
-    ShardArgs shard{};
+    struct Plan { // zero-filled (padding included): its bytes are the signature of the captured graph
+        ExpandArgs steps[CHAIN_MAX_STEPS];
+        ShardArgs shard;
+        int kinds[CHAIN_MAX_STEPS];
+        unsigned grids[CHAIN_MAX_STEPS];
+        bool canonical[CHAIN_MAX_STEPS]; // expanded by the canonical generator: the plies between the root and the shard ply (unit numbering)
+        int n_steps;
+    };
+    static_assert(std::is_trivially_copyable<Plan>::value, "the plan is hashed byte-wise");
+    Plan plan;
+    memset(&plan, 0, sizeof plan);
+    ExpandArgs *steps = plan.steps;
+    int *kinds = plan.kinds;
+    bool *canonical = plan.canonical;
+    unsigned *grids = plan.grids;
+    ShardArgs &shard = plan.shard;
     size_t l = 0;
     int q = 0, n_steps = 0;
     bool sharded = shard_world == 1, too_deep = false;
@@ -686,20 +703,63 @@ static int perft_chain_launch(ll_ctx *ctx, int depth, int shard_rank, int shard_
         l++;
     }
     if (too_deep) return LL_OK; // deeper than the plan holds: the level-by-level path takes it
+    plan.n_steps = n_steps;
     // (a single cooperative launch with grid-wide barriers between the plies was measured: no faster -- DESIGN.md)
-    for (int s = 0; s < n_steps; s++) {
-        const int kind = kinds[s];
-        Timed t(ctx, kind == STEP_TAIL ? "perft_tail" : kind == STEP_SHARD ? "shard_filter" : "emit_legal");
-        if (kind == STEP_SHARD) k_shard_filter<<<grids[s], BLOCK, 0, ctx->stream>>>(shard);
-        // order-free steps expand from legal RECORDS (small code: these launches are bound by instruction fetch and by one
-        // thread's serial latency); the plies whose order matters keep the canonical generator
-        else if (kind == STEP_TAIL) k_expand_records<MODE_PERFT><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
-        else if (kind == STEP_EMIT_SMALL && !canonical[s]) k_expand_records<MODE_EMIT, 32><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
-        else if (kind == STEP_EMIT && !canonical[s]) k_expand_records<MODE_EMIT><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
-        else if (kind == STEP_EMIT_SMALL) k_expand<false, MODE_EMIT, 32><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
-        else k_expand<false, MODE_EMIT><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
-        LL_TRY(check_launch("perft chain step"));
+    auto issue = [&]() -> int {
+        CUDA_TRY(cudaMemsetAsync(sc + SC_LEAVES, 0, (SC_SLOTS - SC_LEAVES) * sizeof(u64), ctx->stream));
+        for (int s = 0; s < n_steps; s++) {
+            const int kind = kinds[s];
+            Timed t(ctx, kind == STEP_TAIL ? "perft_tail" : kind == STEP_SHARD ? "shard_filter" : "emit_legal");
+            if (kind == STEP_SHARD) k_shard_filter<<<grids[s], BLOCK, 0, ctx->stream>>>(shard);
+            // order-free steps expand from legal RECORDS (small code: these launches are bound by instruction fetch and by one
+            // thread's serial latency); the plies whose order matters keep the canonical generator
+            else if (kind == STEP_TAIL) k_expand_records<MODE_PERFT><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
+            else if (kind == STEP_EMIT_SMALL && !canonical[s]) k_expand_records<MODE_EMIT, 32><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
+            else if (kind == STEP_EMIT && !canonical[s]) k_expand_records<MODE_EMIT><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
+            else if (kind == STEP_EMIT_SMALL) k_expand<false, MODE_EMIT, 32><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
+            else k_expand<false, MODE_EMIT><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
+            LL_TRY(check_launch("perft chain step"));
+        }
+        return LL_OK;
+    };
+    if (ctx->timing || ctx->no_graph) { // per-kernel events cannot be recorded into a replayed graph
+        LL_TRY(issue());
+        *launched = true;
+        return LL_OK;
     }
+    // the chain is the same launches with the same arguments call after call: capture it once as a CUDA graph and replay it
+    uint64_t sig = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof plan; i++) sig = (sig ^ ((const unsigned char *)&plan)[i]) * 1099511628211ull;
+    if (!ctx->chain_exec || ctx->chain_sig != sig || ctx->chain_stream != ctx->stream) {
+        if (ctx->chain_exec) cudaGraphExecDestroy(ctx->chain_exec);
+        ctx->chain_exec = nullptr;
+        cudaGraph_t graph = nullptr;
+        const uint64_t launches_before = ctx->launches;
+        CUDA_TRY(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = issue();
+        const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+        ctx->launches = launches_before;
+        if (rc != LL_OK || e != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            LL_TRY(issue()); // capture unavailable: plain launches
+            *launched = true;
+            return LL_OK;
+        }
+        const cudaError_t ei = cudaGraphInstantiate(&ctx->chain_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) {
+            ctx->chain_exec = nullptr;
+            cudaGetLastError();
+            LL_TRY(issue());
+            *launched = true;
+            return LL_OK;
+        }
+        ctx->chain_sig = sig;
+        ctx->chain_stream = ctx->stream;
+    }
+    CUDA_TRY(cudaGraphLaunch(ctx->chain_exec, ctx->stream));
+    ctx->launches += (uint64_t)n_steps;
     *launched = true;
     return LL_OK;
 }

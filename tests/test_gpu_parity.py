@@ -234,23 +234,24 @@ def test_perft_deeper_trees_are_consistent_across_split_depths(eng):
 
 def test_perft_launch_chain_equals_level_by_level_path(eng):
     # ll_perft first sizes the levels on the host (synced path), later calls run as one launch chain with
-    # device-resident level sizes and order-free child placement; both must give the same divide table
+    # device-resident level sizes and order-free child placement, replayed as a CUDA graph; all must give the same divide table
     import leafline_b200 as ll
 
     for fen, depth in ((OPENING, 6), (KIWIPETE, 5), (POSITION_4, 5), (POSITION_3, 6), (OPENING, 3)):
         w = ll.reconstruct(fen)
         eng.force_synced(True)
         want = eng.perft(w, depth)
-        eng.force_synced(False)
-        for _ in range(2):
+        for mode in (2, 0, 0):  # the chain launch by launch, then as a captured CUDA graph (capture, then replay)
+            eng.force_synced(mode)
             got = eng.perft(w, depth)
-            assert got[0] == want[0] and list(got[1]) == list(want[1])
+            assert got[0] == want[0] and list(got[1]) == list(want[1]), (fen, depth, mode)
         for shard in ((1, 3), (0, 2)):
             eng.force_synced(True)
             want_s = eng.perft(w, depth, shard=shard)
-            eng.force_synced(False)
-            got_s = eng.perft(w, depth, shard=shard)
-            assert got_s[0] == want_s[0] and list(got_s[1]) == list(want_s[1])
+            for mode in (2, 0, 0):
+                eng.force_synced(mode)
+                got_s = eng.perft(w, depth, shard=shard)
+                assert got_s[0] == want_s[0] and list(got_s[1]) == list(want_s[1]), (fen, depth, shard, mode)
     # a tree that outgrows the buffers the previous calls left behind falls back and still counts right
     small = ll.reconstruct(POSITION_3)
     eng.perft(small, 3)
