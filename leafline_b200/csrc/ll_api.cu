@@ -697,8 +697,8 @@ static int perft_chain_launch(ll_ctx *ctx, int depth, int shard_rank, int shard_
         // (not above the shard ply: the units dealt to the ranks must be in canonical order, which a level keeps only
         // while its parents fit ONE tile -- the shard filter checks that)
         const bool small = ply < LL_SMALL_TILE_PLIES && (shard_world == 1 || ply >= shard_ply);
-        if (small && l != 0) grids[n_steps] = (unsigned)std::min<size_t>(nblocks(f.cap, 32), resident);
         canonical[n_steps] = ply != 0 && shard_world > 1 && ply < shard_ply; // (the root ply sorts its records by canonical key)
+        if (small && l != 0) grids[n_steps] = (unsigned)std::min<size_t>(nblocks(f.cap, canonical[n_steps] ? 32 : COOP_WARPS), resident);
         kinds[n_steps++] = small ? STEP_EMIT_SMALL : STEP_EMIT;
         l++;
     }
@@ -714,7 +714,7 @@ static int perft_chain_launch(ll_ctx *ctx, int depth, int shard_rank, int shard_
             // order-free steps expand from legal RECORDS (small code: these launches are bound by instruction fetch and by one
             // thread's serial latency); the plies whose order matters keep the canonical generator
             else if (kind == STEP_TAIL) k_expand_records<MODE_PERFT><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
-            else if (kind == STEP_EMIT_SMALL && !canonical[s]) k_expand_records<MODE_EMIT, 32><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
+            else if (kind == STEP_EMIT_SMALL && !canonical[s]) k_expand_coop<<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]); // narrow level: one warp per parent
             else if (kind == STEP_EMIT && !canonical[s]) k_expand_records<MODE_EMIT><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
             else if (kind == STEP_EMIT_SMALL) k_expand<false, MODE_EMIT, 32><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
             else k_expand<false, MODE_EMIT><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);

@@ -497,6 +497,223 @@ template <int MODE, int P = BLOCK> __global__ void __launch_bounds__(BLOCK, LL_E
     expand_tiles_records<MODE, P>(a, sh);
 }
 
+// ---- narrow levels: one WARP per parent (order-free legal expansion) -------------------------------------------
+// A narrow perft level (1 ... ~10^4 parents) cannot fill the machine; with one thread per parent its time is that
+// thread's serial walk through the whole generator.  Here a warp owns the parent and the lanes split it by DATA, so
+// every lane runs the same code: lanes 0-7 one Kogge-Stone direction each of the danger map (the four down directions
+// on the bit-reversed board), lanes 8-11 one line through the figurehead each (checkers and pins), then lanes 0-15 one
+// non-servant piece each, lanes 16-19 one kind of servant step each for all servants at once, lanes 20-21 the
+// passing-by candidates, lane 22 secret service.  The commits are those of lookahead() in another order (the root
+// ply rank-sorts them by canonical key); each lane expands its own target set into the warp's descriptor list, then
+// the 32 lanes build and store the children, 32 at a time.
+constexpr int COOP_WARPS = BLOCK / 32;
+constexpr int COOP_CAP = 256; // commits of one position (the reference's generator never exceeds ~220)
+struct CoopShared {
+    u32 descs[COOP_WARPS][COOP_CAP];
+    u32 keys[COOP_WARPS][COOP_CAP];
+    u64 claim;
+};
+__device__ __forceinline__ u64 warp_or64(u64 v) {
+    const u32 lo = __reduce_or_sync(0xffffffffu, (u32)v), hi = __reduce_or_sync(0xffffffffu, (u32)(v >> 32));
+    return ((u64)hi << 32) | lo;
+}
+// an up fill whose direction is data: shift s in {8, 1, 9, 7} with its wrap mask
+__device__ __forceinline__ u64 ks_up_var(u64 g, u64 e, int s, u64 keep) {
+    e &= keep;
+    g |= e & (g << s);
+    e &= e << s;
+    g |= e & (g << (2 * s));
+    e &= e << (2 * s);
+    g |= e & (g << (4 * s));
+    return (g << s) & keep;
+}
+template <int T> __device__ __forceinline__ void coop_expand_parent(const ExpandArgs &a, const Pos &p, size_t parent, u32 *descs, u32 *keys) {
+    constexpr int E = 1 - T;
+    const int lane = threadIdx.x & 31;
+    const u64 own = occupied_by<T>(p), opp = occupied_by<E>(p), occ = own | opp, empty = ~occ;
+    const u64 k = p.pl[6 * T + FIGUREHEAD];
+    // ---- legality context, cooperatively (cf. legal_context<T>)
+    Legal L;
+    L.check = ~0ull;
+    L.pinned = L.danger = L.kd = L.ka = L.kf = L.kr = 0;
+    if (k) { // warp-uniform
+        const int ksq = lsb64(k);
+        const u64 e_diag = p.pl[6 * E + SCHOLAR] | p.pl[6 * E + PRINCESS], e_orth = p.pl[6 * E + COP] | p.pl[6 * E + PRINCESS];
+        u64 part = 0;
+        if (lane < 8) { // one direction per lane; lanes 4-7 on the bit-reversed board
+            const int d = lane & 3;
+            const int s = d == 0 ? 8 : d == 1 ? 1 : d == 2 ? 9 : 7;
+            const u64 keep = d == 0 ? ~0ull : d == 3 ? ~FILE_H : ~FILE_A;
+            u64 g = d < 2 ? e_orth : e_diag, e = ~(occ ^ k);
+            if (lane >= 4) g = brev64(g), e = brev64(e);
+            part = ks_up_var(g, e, s, keep);
+            if (lane >= 4) part = brev64(part);
+        }
+        u64 danger = warp_or64(part) | servant_attacks<E>(p.pl[6 * E + SERVANT]) | pony_attacks(p.pl[6 * E + PONY]);
+        if (p.pl[6 * E + FIGUREHEAD]) danger |= figurehead_moves(lsb64(p.pl[6 * E + FIGUREHEAD]));
+        L.danger = danger;
+        L.kd = diag_mask(ksq) & ~k;
+        L.ka = anti_mask(ksq) & ~k;
+        L.kf = file_mask(ksq) & ~k;
+        L.kr = rank_mask(ksq) & ~k;
+        u64 chk = 0, pin = 0;
+        if (lane >= 8 && lane < 12) { // one line through the figurehead per lane
+            const int l = lane - 8;
+            const u64 line = l == 0 ? L.kd : l == 1 ? L.ka : l == 2 ? L.kf : L.kr;
+            const u64 snipers = (l < 2 ? e_diag : e_orth) & line;
+            if (snipers) {
+                const u64 seen = line_attacks(occ, k, line);
+                chk = seen & snipers;
+                const u64 blockers = seen & own;
+                if (blockers) {
+                    u64 pinners = line_attacks(occ ^ blockers, k, line) & ~seen & snipers;
+                    for (; pinners; pinners &= pinners - 1) pin |= between_on(line, k, pinners & (0 - pinners)) & blockers;
+                }
+            }
+        }
+        const u64 checkers = warp_or64(chk) | (servant_attackers_of<E>(k) & p.pl[6 * E + SERVANT]) | (pony_moves(ksq) & p.pl[6 * E + PONY]) |
+                             (figurehead_moves(ksq) & p.pl[6 * E + FIGUREHEAD]);
+        L.pinned = warp_or64(pin);
+        if (checkers) {
+            if (checkers & (checkers - 1)) {
+                L.check = 0;
+            } else {
+                L.check = checkers | between_on(pin_line(L, checkers), k, checkers);
+                if (!((L.kd | L.ka | L.kf | L.kr) & checkers)) L.check = checkers;
+            }
+        }
+    }
+    const u64 cm = L.check, free = ~L.pinned;
+    // ---- this lane's target sets: `plain`, and for ascending servants `ascending` (each target counts four times)
+    u64 plain = 0, ascending = 0;
+    u32 info = 0;
+    const u64 others = own & ~p.pl[6 * T + SERVANT];
+    if (lane < 16) { // the lane-th non-servant figurine
+        if (lane < popc64(others)) {
+            const int from = select_bit(others, (u32)lane);
+            const u64 bit = 1ull << from;
+            const u32 job = (p.pl[6 * T + PONY] & bit) ? PONY : (p.pl[6 * T + SCHOLAR] & bit) ? SCHOLAR : (p.pl[6 * T + COP] & bit) ? COP
+                            : (p.pl[6 * T + PRINCESS] & bit) ? PRINCESS : FIGUREHEAD;
+            u64 targets = 0;
+            if (job == PONY) targets = (bit & L.pinned) ? 0ull : pony_moves(from);
+            else if (job == FIGUREHEAD) targets = figurehead_moves(from) & ~L.danger;
+            else {
+                if (job != COP) targets |= diag_attacks(from, occ);
+                if (job != SCHOLAR) targets |= orth_attacks(from, occ);
+                if (bit & L.pinned) targets &= pin_line(L, bit);
+            }
+            targets &= ~own;
+            if (job != FIGUREHEAD) targets &= cm;
+            plain = targets;
+            info = rec_info(REC_PIECE, job, from, ASC_NONE, 0, 0);
+        }
+    } else if (lane < 20) { // one kind of servant step for all servants
+        if (cm) {
+            const u64 s = p.pl[6 * T + SERVANT];
+            const u64 last = T == 0 ? RANK_1 << 56 : RANK_1;
+            const u64 pushers = s & (free | L.kf);
+            const u64 one = (T == 0 ? pushers << 8 : pushers >> 8) & empty;
+            const int kind = lane == 16 ? REC_PUSH : lane == 17 ? REC_DOUBLE : lane == 18 ? REC_STUN_WEST : REC_STUN_EAST;
+            u64 targets;
+            if (kind == REC_PUSH) targets = one;
+            else if (kind == REC_DOUBLE) targets = (T == 0 ? (one & (RANK_1 << 16)) << 8 : (one & (RANK_1 << 40)) >> 8) & empty;
+            else if (kind == REC_STUN_WEST) targets = (T == 0 ? (s & (free | L.ka)) << 7 : (s & (free | L.kd)) >> 9) & ~FILE_H & opp;
+            else targets = (T == 0 ? (s & (free | L.kd)) << 9 : (s & (free | L.ka)) >> 7) & ~FILE_A & opp;
+            targets &= cm;
+            plain = targets & ~last;
+            ascending = targets & last;
+            info = rec_info((u32)kind, SERVANT, 0, ASC_NONE, 0, 0);
+        }
+    } else if (lane < 22) { // passing by: the make-the-move-and-test path, one candidate per lane
+        const u64 pb_bit = passing_by_bit(p.meta);
+        if (pb_bit && cm) {
+            u64 c = servant_attackers_of<T>(pb_bit) & p.pl[6 * T + SERVANT];
+            if (lane == 21) c &= c - 1;
+            if (c && passing_by_is_legal<T>(p, lsb64(c), lsb64(pb_bit))) {
+                plain = pb_bit;
+                info = rec_info(REC_PIECE, SERVANT, lsb64(c), ASC_NONE, 1, 0);
+            }
+        }
+    } else if (lane == 22) { // secret service: the exact path
+        if (cm == ~0ull) {
+            ServiceBits service;
+            service_lookahead<T, false>(p, own, opp, service);
+            plain = service.to_bits;
+            info = rec_info(REC_SERVICE, FIGUREHEAD, (T == 0 ? 0 : 56) + 4, ASC_NONE, 0, 0);
+        }
+    }
+    // ---- the lanes' commits, laid end to end
+    const u32 mine = (u32)popc64(plain) + 4u * (u32)popc64(ascending);
+    u32 at = warp_inclusive_scan(mine);
+    const u32 total = __shfl_sync(0xffffffffu, at, 31);
+    at -= mine;
+    size_t base = 0;
+    if (lane == 0 && total) base = (size_t)atomicAdd((unsigned long long *)a.n_out, (unsigned long long)total);
+    base = (size_t)__shfl_sync(0xffffffffu, (unsigned long long)base, 0);
+    if (total == 0) return;
+    if (total > (u32)COOP_CAP || base + total > a.out_cap) { // cannot happen / the level outgrew its buffer
+        if (lane == 0) atomicExch(a.overflow, 1u);
+        return;
+    }
+    for (u64 m = plain; m; m &= m - 1) descs[at++] = rec_move_to(info, lsb64(m), T);
+    for (u64 m = ascending; m; m &= m - 1)
+        for (u32 asc = PONY; asc <= PRINCESS; asc++) descs[at++] = rec_move_to((info & ~(7u << 12)) | (asc << 12), lsb64(m), T);
+    __syncwarp();
+    if (a.root_is_index) { // the root's children become the divide table's rows: the reference's order
+        for (u32 i = lane; i < total; i += 32) keys[i] = canonical_key(descs[i]);
+        __syncwarp();
+        u32 moved[COOP_CAP / 32], rank[COOP_CAP / 32];
+#pragma unroll
+        for (int r = 0; r < COOP_CAP / 32; r++) {
+            const u32 i = lane + 32 * r;
+            rank[r] = 0;
+            moved[r] = 0;
+            if (i < total) {
+                moved[r] = descs[i];
+                const u32 key = keys[i];
+                for (u32 j = 0; j < total; j++) rank[r] += keys[j] < key;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < COOP_CAP / 32; r++)
+            if (lane + 32 * r < total) descs[rank[r]] = moved[r];
+        __syncwarp();
+    }
+    const u32 root = a.root_is_index ? 0u : a.root_in[parent];
+    for (u32 i = lane; i < total; i += 32) { // 32 children at a time: coalesced plane stores
+        Pos c;
+        make_child_as<T>(p, descs[i], c);
+        const size_t o = base + i;
+        soa_store(a.out, o, c);
+        if (a.root_out) a.root_out[o] = a.root_is_index ? (u32)o : root;
+    }
+    __syncwarp();
+}
+__global__ void __launch_bounds__(BLOCK, LL_EXPAND_MIN_BLOCKS) k_expand_coop(const ExpandArgs a) {
+    __shared__ CoopShared sh;
+    if (a.n_in && a.overflow && *(volatile u32 *)a.overflow) return; // see expand_tiles
+    const size_t n = a.n_in ? (size_t)*(volatile const u64 *)a.n_in : a.n;
+    const int warp = threadIdx.x >> 5;
+    for (;;) {
+        size_t tile = blockIdx.x;
+        if (a.tile_counter) {
+            if (threadIdx.x == 0) sh.claim = atomicAdd(a.tile_counter, 1u);
+            __syncthreads();
+            tile = (size_t)sh.claim;
+            __syncthreads(); // everybody has read the claim before the next round overwrites it
+        }
+        if (tile * COOP_WARPS >= n) break;
+        const size_t parent = tile * COOP_WARPS + warp;
+        if (parent < n) {
+            const Pos p = soa_load(a.in, parent); // every lane holds the whole parent
+            if (meta_stm(p.meta) == 0) coop_expand_parent<0>(a, p, parent, sh.descs[warp], sh.keys[warp]);
+            else coop_expand_parent<1>(a, p, parent, sh.descs[warp], sh.keys[warp]);
+        }
+        if (!a.tile_counter) break;
+    }
+}
+
 // ---- horizon by records (mind.rs:279-301): children decoded from (piece, target mask) records ---------------
 // Phase 1 costs per PIECE, not per move: a parent thread writes at most REC_MAX records (ll_device.cuh) into shared
 // memory.  Phase 2 runs one CHILD per thread: binary-search the parent by the prefix sums, the record by its base,

@@ -258,6 +258,21 @@ def test_perft_launch_chain_equals_level_by_level_path(eng):
     assert eng.perft(ll.reconstruct(KIWIPETE), 3)[0] == 97814
 
 
+def test_narrow_levels_warp_per_parent_expansion_on_many_positions(eng, playouts, reckless_worlds):
+    # the launch chain expands its narrow levels with one warp per parent (k_expand_coop): every lane a piece / a fill
+    # direction / a line through the figurehead.  perft(3) and perft(4) through the chain against the level-by-level
+    # path (canonical generator) on named, playout and reckless-walk roots: divide tables must be identical.
+    worlds = list(named_worlds()) + list(playouts[:300]) + list(reckless_worlds[:200])
+    for depth, sample in ((3, worlds), (4, worlds[::7])):
+        for w in sample:
+            eng.force_synced(True)
+            want = eng.perft(w, depth)
+            eng.force_synced(False)
+            got = eng.perft(w, depth)
+            assert got[0] == want[0] and list(got[1]) == list(want[1]), (O.preserve(w), depth)
+    eng.force_synced(False)
+
+
 def test_perft_device_resident_counts(eng):
     import torch
 
