@@ -69,6 +69,8 @@ struct ll_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_stream = nullptr; // uploads of the next chunk while the current one is being scored (ll_score_batch)
+    cudaEvent_t slot_uploaded[2] = {nullptr, nullptr}, slot_consumed[2] = {nullptr, nullptr};
     std::vector<Frontier> levels;
     Frontier ext; // scratch (counts / scan / values) used when level 0 aliases caller-owned planes
     DevBuf aos_in, aos_out, scalars, scores, teams, flags;
@@ -343,6 +345,11 @@ extern "C" int ll_init(int device, ll_ctx **out) {
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->slot_uploaded[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->slot_consumed[i], cudaEventDisableTiming));
+    }
     ctx->stream = ctx->own_stream;
     // generated tables, furniture/tablemaker.py:41-62
     u64 pony[64], fig[64];
@@ -394,6 +401,11 @@ extern "C" int ll_shutdown(ll_ctx *ctx) {
     }
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->chain_exec) cudaGraphExecDestroy(ctx->chain_exec);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->slot_uploaded[i]) cudaEventDestroy(ctx->slot_uploaded[i]);
+        if (ctx->slot_consumed[i]) cudaEventDestroy(ctx->slot_consumed[i]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return LL_OK;
@@ -509,11 +521,41 @@ extern "C" int ll_score_batch(ll_ctx *ctx, const ll_world_t *worlds, size_t n, f
     LL_TRY(check_ctx(ctx));
     if (n && (!worlds || !scores)) return fail(LL_ERR_INVALID_ARG, "null buffer");
     if (!n) return LL_OK;
-    LL_TRY(upload_worlds(ctx, worlds, n, 0));
-    LL_TRY(ensure(ctx, ctx->scores, (n + 1) * sizeof(float)));
-    LL_TRY(launch_score(ctx, ctx->levels[0].soa(), n, (float *)ctx->scores.ptr));
-    CUDA_TRY(cudaMemcpyAsync(scores, ctx->scores.ptr, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    constexpr size_t CHUNK = (size_t)1 << 20; // 104 MiB of ll_world_t per chunk
+    if (n <= CHUNK) {
+        LL_TRY(upload_worlds(ctx, worlds, n, 0));
+        LL_TRY(ensure(ctx, ctx->scores, (n + 1) * sizeof(float)));
+        LL_TRY(launch_score(ctx, ctx->levels[0].soa(), n, (float *)ctx->scores.ptr));
+        CUDA_TRY(cudaMemcpyAsync(scores, ctx->scores.ptr, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return LL_OK;
+    }
+    // Large batches are PCIe-bound (104 B in, 4 B out per position): stream them in chunks through two staging slots so
+    // that the upload of chunk c+1 (copy stream) overlaps the repack + score + result download of chunk c.
+    LL_TRY(reserve_level(ctx, 0, 2 * CHUNK, false, false));
+    LL_TRY(ensure(ctx, ctx->aos_in, 2 * CHUNK * sizeof(ll_world_t)));
+    LL_TRY(ensure(ctx, ctx->scores, 2 * CHUNK * sizeof(float)));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const Soa level = ctx->levels[0].soa();
+    for (size_t first = 0, c = 0; first < n; first += CHUNK, c++) {
+        const size_t m = std::min(CHUNK, n - first), slot = c & 1;
+        ll_world_t *staging = (ll_world_t *)ctx->aos_in.ptr + slot * CHUNK;
+        if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->slot_consumed[slot], 0)); // the slot's previous chunk has been repacked
+        CUDA_TRY(cudaMemcpyAsync(staging, worlds + first, m * sizeof(ll_world_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+        CUDA_TRY(cudaEventRecord(ctx->slot_uploaded[slot], ctx->copy_stream));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->slot_uploaded[slot], 0));
+        {
+            Timed t(ctx, "aos_to_soa");
+            k_aos_to_soa<<<(unsigned)nblocks(m), BLOCK, 0, ctx->stream>>>((const u64 *)staging, m, level, slot * CHUNK);
+        }
+        LL_TRY(check_launch("k_aos_to_soa"));
+        CUDA_TRY(cudaEventRecord(ctx->slot_consumed[slot], ctx->stream));
+        float *d_scores = (float *)ctx->scores.ptr + slot * CHUNK;
+        LL_TRY(launch_score(ctx, Soa{level.pl + slot * CHUNK, level.meta + slot * CHUNK, level.stride}, m, d_scores));
+        CUDA_TRY(cudaMemcpyAsync(scores + first, d_scores, m * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
     return LL_OK;
 }
 
