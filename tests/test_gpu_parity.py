@@ -612,3 +612,36 @@ def test_uci_daemon_and_command_line(eng):
     run = subprocess.run([sys.executable, "-m", "leafline_b200", "--correspond", "--depth", "2", "--seconds", "1", "--from", "x"],
                          capture_output=True, text=True, cwd=root, timeout=300)
     assert run.returncode != 0 and "more than one of" in run.stderr
+
+
+def test_one_context_per_host_thread():
+    # the reference calls the leaf layer from one thread per root move (mind.rs:405); the ABI's contract is one ll_ctx per
+    # host thread -- four threads, four contexts, concurrent perft / lookahead / score (ctypes releases the GIL)
+    import threading
+
+    import leafline_b200 as ll
+
+    fens = [OPENING, KIWIPETE, POSITION_4, POSITION_5]
+    with ll.Engine(0) as e0:
+        want = {f: e0.perft(ll.reconstruct(f), 5 if f == OPENING else 4) for f in fens}
+    errors = []
+
+    def work(fen):
+        try:
+            with ll.Engine(0) as e:
+                w = ll.reconstruct(fen)
+                for _ in range(6):
+                    got = e.perft(w, 5 if fen == OPENING else 4)
+                    assert got[0] == want[fen][0] and list(got[1]) == list(want[fen][1])
+                    offsets, commits = e.lookahead(w)
+                    assert offsets[1] == len(want[fen][1])
+                    assert e.score(commits["tree"]).tobytes() == O.score_batch(commits["tree"]).tobytes()
+        except Exception as exc:  # noqa: BLE001
+            errors.append((fen, repr(exc)))
+
+    threads = [threading.Thread(target=work, args=(f,)) for f in fens]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
