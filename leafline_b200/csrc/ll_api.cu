@@ -130,7 +130,7 @@ int reserve_level(ll_ctx *ctx, size_t l, size_t n, bool with_cmeta, bool with_va
     return LL_OK;
 }
 
-struct Timed { // RAII-less helper: brackets one launch with events when timing is on
+struct Timed { // scope guard: counts the launch and, when timing is on, brackets it with CUDA events on the launching stream
     ll_ctx *ctx;
     int idx = -1;
     Timed(ll_ctx *c, const char *name) : ctx(c) {

@@ -1,13 +1,16 @@
 // ll_kernels.cuh -- the CUDA kernels of the leaf layer (sm_100a).  See DESIGN.md for the roofline
 // that bounds each one.  Host-side launch wrappers live in ll_api.cu.
 //
-// The work-horse is k_expand: a block takes a tile of BLOCK parent positions.  Phase 1: one thread
-// per parent runs the canonical generator and writes 32-bit move descriptors into a shared-memory
-// list at the parent's exclusive-scan offset (so the list is in the reference's order).  Phase 2:
-// the whole block walks that list, one CHILD per thread per step: rebuild the child from the parent
-// tile in shared memory, then either store it (coalesced: neighbouring threads write neighbouring
-// children), bulk-count its legal moves (perft tail) or score it (horizon).  Phase 2 is where the
-// time goes and it is perfectly balanced however uneven the parents' move counts are.
+// Expansion kernels (all: a block owns a tile of parents; children are rebuilt from the parent tile in shared
+// memory, one CHILD per thread, so the dominant phase is balanced however uneven the parents' move counts are):
+//   k_expand          canonical order (the API's lookahead / kickoff levels): one thread per parent runs the canonical
+//                     generator into a shared descriptor list at its exclusive-scan offset, then the block walks the list
+//                     and stores the children coalesced.
+//   k_expand_records  order-free legal expansion of the perft launch chain, and its tail (children bulk-counted instead
+//                     of stored): phase 1 expands per-piece legal target-mask RECORDS (small code, one inlined generator).
+//   k_expand_coop     narrow perft levels: one WARP per parent, the lanes split the position by data.
+//   k_horizon         the search's bottom ply: children decoded from records by select-the-t-th-bit, scored, max-reduced.
+// k_score is the HBM-bound streaming scorer; the rest are scans, back-ups, repacking and test utilities.
 #pragma once
 #include "ll_device.cuh"
 
