@@ -458,6 +458,19 @@ def main():
             "value": PERFT_OPENING[5] / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"perft(5) from the opening ({PERFT_OPENING[5]} leaves) x{reps_cpu}, one thread per root move over {cores} host threads, {dt:.2f} s each",
         }
+        # beside it: the same on ONE host thread, and the CPU scorer on a 2^20-position prefix
+        t0 = time.perf_counter()
+        assert int(O.perft_divide(w, 5, threads=1).sum()) == PERFT_OPENING[5]
+        dt1 = time.perf_counter() - t0
+        prefix = O.playout_batch(ll.PLAYOUT_SEED, 0, 1 << 14)
+        prefix = np.tile(prefix, 64)
+        t0 = time.perf_counter()
+        O.score_batch(prefix)
+        dts = time.perf_counter() - t0
+        result["cpu_baseline_single_thread"] = {
+            "perft_leaf_positions_per_sec": PERFT_OPENING[5] / dt1, "score_positions_per_sec": len(prefix) / dts, "cores": 1, "kind": "port",
+            "sample": f"perft(5) from the opening once ({dt1:.1f} s); lo_score over 2^20 positions (2^14 playout positions x64, {dts * 1e3:.0f} ms)",
+        }
 
     if rank == 0:
         print(json.dumps(result))
