@@ -278,6 +278,15 @@ template <int T> LL_HD u32 make_child_as(const Pos &p, u32 m, Pos &c) {
         if (p.pl[6 * E + j] & victim) hosp = (u32)j; // first in dramatis_personae order wins (life.rs:550-557)
 #pragma unroll
     for (int j = 0; j < 6; j++) c.pl[6 * E + j] = p.pl[6 * E + j] & ~victim; // W: planes are disjoint
+#ifdef LL_ORTHODOX_COP_CAPTURE
+    // PROBE BUILD ONLY (profiles/tools/orthodox_probe.py): orthodox chess also withdraws the eligibility when something
+    // lands on a cop's home square; the reference does not.  With this switch the counts must
+    // equal the published orthodox perft numbers wherever quirk 1 (b-file leer) cannot matter.
+    if (tb & (1ull << 0)) elig &= ~0x1u;
+    if (tb & (1ull << 7)) elig &= ~0x2u;
+    if (tb & (1ull << 56)) elig &= ~0x4u;
+    if (tb & (1ull << 63)) elig &= ~0x8u;
+#endif
     u32 new_pb = 0xFFu; // life.rs:660-669
     if (job == SERVANT) {
         const int dr = (to >> 3) - (from >> 3);

@@ -184,6 +184,7 @@ def test_in_critical_endangerment(eng, playouts, reckless_worlds):
 # ---------------------------------------------------------------- perft (recursive lookahead() leaf count)
 PERFT = [
     (OPENING, [20, 400, 8902, 197281, 4865609]),
+    (POSITION_5, [44, 1486, 62416, 2104591]),  # phantom cop (quirk 2); orthodox chess: 62 379 / 2 103 487
     (KIWIPETE, [48, 2038, 97814]),
     (POSITION_5, [44, 1486, 62416]),
     (POSITION_4, [6, 258, 9221]),
@@ -204,7 +205,18 @@ def test_perft_counts(eng, fen, counts):
         assert len(per_root) == counts[0] and int(per_root.sum()) == expected
 
 
-@pytest.mark.parametrize("fen,depth", [(OPENING, 4), (KIWIPETE, 3), (POSITION_5, 3), (POSITION_4, 3)])
+def test_perft_depth_7_and_8_of_the_opening(eng):
+    # perft(7) equals orthodox chess (no rule of the reference can differ before ply 8); perft(8) exceeds the orthodox
+    # 84 998 978 956 by the 899 phantom-cop secret services of ply 8 -- the probe build with that ONE rule switched to
+    # orthodox chess reproduces the published numbers exactly (profiles/r01_orthodox_probe.txt)
+    import leafline_b200 as ll
+
+    assert eng.perft(ll.new_world(), 7)[0] == 3195901860
+    leaves, per_root = eng.perft(ll.new_world(), 8)
+    assert leaves == 84998979855 and int(per_root.sum()) == leaves and len(per_root) == 20
+
+
+@pytest.mark.parametrize("fen,depth", [(OPENING, 4), (KIWIPETE, 3), (POSITION_5, 4), (POSITION_4, 3)])
 def test_perft_divide_matches_oracle(eng, fen, depth):
     import leafline_b200 as ll
 
