@@ -266,8 +266,13 @@ template <int T> LL_HD u32 make_child_as(const Pos &p, u32 m, Pos &c) {
     }
     if (job == COP) { // life.rs:589-605: file of whence only, any rank
         const int f = from & 7;
-        if (f == 0) elig &= T == 0 ? ~0x1u : ~0x4u;
-        if (f == 7) elig &= T == 0 ? ~0x2u : ~0x8u;
+#ifdef LL_ORTHODOX_COP_CAPTURE
+        const bool counts = (from >> 3) == (T == 0 ? 0 : 7); // probe build: only a cop leaving its home square (quirk 3)
+#else
+        const bool counts = true;
+#endif
+        if (counts && f == 0) elig &= T == 0 ? ~0x1u : ~0x4u;
+        if (counts && f == 7) elig &= T == 0 ? ~0x2u : ~0x8u;
     }
     // life.rs:631-657: victim looked up on the pre-move board; passing by removes the servant one
     // rank "behind" the passed square
@@ -280,8 +285,8 @@ template <int T> LL_HD u32 make_child_as(const Pos &p, u32 m, Pos &c) {
     for (int j = 0; j < 6; j++) c.pl[6 * E + j] = p.pl[6 * E + j] & ~victim; // W: planes are disjoint
 #ifdef LL_ORTHODOX_COP_CAPTURE
     // PROBE BUILD ONLY (profiles/tools/orthodox_probe.py): orthodox chess also withdraws the eligibility when something
-    // lands on a cop's home square; the reference does not.  With this switch the counts must
-    // equal the published orthodox perft numbers wherever quirk 1 (b-file leer) cannot matter.
+    // lands on a cop's home square; the reference does not.  Together with the two other
+    // switches of this macro (quirks 1 and 3) the counts must equal the published orthodox perft numbers.
     if (tb & (1ull << 0)) elig &= ~0x1u;
     if (tb & (1ull << 7)) elig &= ~0x2u;
     if (tb & (1ull << 56)) elig &= ~0x4u;
@@ -391,8 +396,11 @@ template <int T, bool NIHIL, class Sink> LL_HD void service_lookahead(const Pos 
         if (side == 0 ? !west_clear : !east_clear) continue;
         bool leered;
         if (side == 0)
-            leered = attacked_by<1 - T>(p, home + 1, occ, opp) || attacked_by<1 - T>(p, home + 2, occ, opp) ||
-                     attacked_by<1 - T>(p, home + 3, occ, opp); // the b-file square too: SURVEY.md 8(a) quirk 1
+            leered =
+#ifndef LL_ORTHODOX_COP_CAPTURE
+                attacked_by<1 - T>(p, home + 1, occ, opp) || // the b-file square too: SURVEY.md 8(a) quirk 1 (not in the probe build)
+#endif
+                attacked_by<1 - T>(p, home + 2, occ, opp) || attacked_by<1 - T>(p, home + 3, occ, opp);
         else
             leered = attacked_by<1 - T>(p, home + 5, occ, opp) || attacked_by<1 - T>(p, home + 6, occ, opp);
         if (leered) continue;

@@ -182,9 +182,15 @@ def test_in_critical_endangerment(eng, playouts, reckless_worlds):
 
 
 # ---------------------------------------------------------------- perft (recursive lookahead() leaf count)
+# deeper entries: castling-free positions equal the published orthodox tables; the others are this engine's counts under
+# the reference's rules, whose orthodox-rules probe build reproduces the published tables (profiles/r01_orthodox_probe.txt)
 PERFT = [
     (OPENING, [20, 400, 8902, 197281, 4865609]),
-    (POSITION_5, [44, 1486, 62416, 2104591]),  # phantom cop (quirk 2); orthodox chess: 62 379 / 2 103 487
+    (POSITION_5, [44, 1486, 62416, 2104591, 90060265]),  # phantom cop (quirk 2); orthodox chess: 62 379 / 2 103 487 / 89 941 194
+    (POSITION_3, [14, 191, 2812, 43238, 674624, 11030083, 178633661]),
+    (POSITION_6, [46, 2079, 89890, 3894594, 164075551]),
+    (KIWIPETE, [48, 2038, 97814, 4080840, 193457491]),
+    (POSITION_4, [6, 258, 9221, 405001, 15117015]),
     (KIWIPETE, [48, 2038, 97814]),
     (POSITION_5, [44, 1486, 62416]),
     (POSITION_4, [6, 258, 9221]),
