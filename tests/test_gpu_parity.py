@@ -222,12 +222,12 @@ def test_perft_depth_7_and_8_of_the_opening(eng):
     assert leaves == 84998979855 and int(per_root.sum()) == leaves and len(per_root) == 20
 
 
-@pytest.mark.parametrize("fen,depth", [(OPENING, 4), (KIWIPETE, 3), (POSITION_5, 4), (POSITION_4, 3)])
+@pytest.mark.parametrize("fen,depth", [(OPENING, 4), (KIWIPETE, 4), (POSITION_5, 4), (POSITION_4, 4)])
 def test_perft_divide_matches_oracle(eng, fen, depth):
     import leafline_b200 as ll
 
     _, per_root = eng.perft(ll.reconstruct(fen), depth)
-    assert list(per_root) == list(O.perft_divide(O.reconstruct(fen), depth, threads=8))
+    assert list(per_root) == list(O.perft_divide(O.reconstruct(fen), depth, threads=16))
 
 
 def test_perft_depth_6_opening_bit_exact(eng):
