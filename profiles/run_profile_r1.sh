@@ -5,3 +5,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 python profiles/workload.py > gpurun_out/plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:"k_expand_recordsILi1|k_horizon|k_score" -o gpurun_out/r01_hot python profiles/workload.py > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
+# the narrow-level kernel (one warp per parent): the four plies of one perft(6) chain
+python profiles/workload.py > gpurun_out/plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:"k_expand_coop" -s 4 -c 4 -o gpurun_out/r01_coop python profiles/workload.py > gpurun_out/ncu_coop.log 2>&1
+tail -2 gpurun_out/ncu_coop.log
