@@ -409,7 +409,7 @@ def main():
         # frontier batches -- depth 8 from the opening, beyond what a full-width tree fits in HBM
         t0 = time.perf_counter()
         fc8, host_nodes, handed_off = eng.alpha_beta_forecast(root, 8, device_plies=4)
-        result["alpha_beta_depth8"] = {"seconds": time.perf_counter() - t0, "best_score": float(fc8[0]["score"]), "host_nodes_expanded": host_nodes,
+        result["alpha_beta_depth8"] = {"seconds": time.perf_counter() - t0, "best_score": float(fc8[0]["score"]), "host_nodes_expanded": host_nodes, "values_remembered": eng.last_search_stats["values_remembered"],
                                        "frontier_nodes_handed_to_device": handed_off, "device_plies": 4,
                                        "what": "ll_alpha_beta_forecast: exact root scores (alpha-beta prunes work, not values)"}
         # batched static scoring of 2^24 seeded playout positions (configs[2])

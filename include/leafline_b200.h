@@ -150,8 +150,10 @@ int ll_forecast(ll_ctx *ctx, const ll_world_t *root, int depth, int quiet_extens
  * cut-offs, MVV-LVA + history ordering and a full window below every root move run on the HOST; a node with
  * `device_plies` plies left is handed to the device, which returns its exact full-width value (quiet_extension as in
  * ll_horizon_batch).  Scores equal ll_forecast's (alpha-beta is exact at the root); only the work is pruned, so
- * depths beyond ll_forecast's HBM limit are reachable.  variation holds the root move only.  No transposition table.
- * stats3 (nullable): { nodes expanded on the host, frontier nodes handed to the device, 0 }. */
+ * depths beyond ll_forecast's HBM limit are reachable.  variation holds the root move only.  The memory bank
+ * (mind.rs:312-344) is sound here: entries are keyed by the whole position and the plies left and say whether their
+ * value is exact or a bound, so remembering changes the work, never a root score.
+ * stats3 (nullable): { nodes expanded on the host, frontier nodes handed to the device, values taken from the bank }. */
 int ll_alpha_beta_forecast(ll_ctx *ctx, const ll_world_t *root, int depth, int device_plies, int quiet_extension, int nihilistically,
                            ll_forecast_t *forecasts, uint32_t cap, uint32_t *n_forecasts, uint64_t *stats3);
 /* replaces `fixed_depth_sequence_kickoff` (src/mind.rs:473-490) */
@@ -194,7 +196,8 @@ int ll_timing_query(ll_ctx *ctx, const char *kernel, double *ms, uint64_t *launc
 uint64_t ll_launch_count(ll_ctx *ctx);
 /* testing aid: ll_perft normally replays its launch chain (device-resident level sizes) as a captured CUDA graph.
  * on == 1 forces the level-by-level path (every level sized on the host), on == 2 issues the chain launch by launch;
- * 0 restores the default.  All three give identical results. */
+ * 0 restores the default.  All three give identical results.  on == 1 also makes ll_horizon_batch take its level-by-level
+ * path for small batches (by default <= 4096 nodes with plies >= 2 and no quiet extension run as one launch chain). */
 int ll_debug_force_synced(ll_ctx *ctx, int on);
 /* testing aid, full-size property check on resident positions: for every position the set-wise move counter, the
  * canonical generator (legality by check / pin / danger masks) and the reference's definition (each reckless commit

@@ -235,13 +235,16 @@ class Engine:
 
     def alpha_beta_forecast(self, world, depth, device_plies=4, nihilistically=False, quiet=None):
         """The reference's search structure: alpha-beta with MVV-LVA + history ordering on the host, frontier nodes with
-        `device_plies` plies left valued exactly on the device -> (forecasts, host nodes expanded, frontier nodes handed off)."""
+        `device_plies` plies left valued exactly on the device -> (forecasts, host nodes expanded, frontier nodes handed off);
+        `last_search_stats` also holds how many values the (sound) memory bank supplied."""
         w = _worlds(world)
         out = np.zeros(1024, dtype=FORECAST_DTYPE)
         n = C.c_uint32(0)
         stats = np.zeros(3, dtype=np.uint64)
         _abi.check(self._lib.ll_alpha_beta_forecast(self._ctx, _ptr(w), depth, device_plies, -1 if quiet is None else int(quiet),
                                                     int(nihilistically), _ptr(out), 1024, C.byref(n), _ptr(stats)))
+        self.last_search_stats = {"host_nodes_expanded": int(stats[0]), "frontier_nodes_handed_to_device": int(stats[1]),
+                                  "values_remembered": int(stats[2])}
         return out[: n.value].copy(), int(stats[0]), int(stats[1])
 
     def fixed_depth_sequence_kickoff(self, world, depth_sequence, nihilistically=False):

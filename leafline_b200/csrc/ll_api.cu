@@ -52,7 +52,7 @@ struct DevBuf { // grow-only device allocation
 };
 
 struct Frontier { // one BFS level resident in HBM
-    DevBuf planes, meta, root, counts, block_sums, block_base, cmeta, values;
+    DevBuf planes, meta, root, counts, block_sums, block_base, cmeta, values, child_first;
     size_t cap = 0; // positions
     size_t n = 0;
     Soa soa() const { return Soa{(u64 *)planes.ptr, (u32 *)meta.ptr, cap}; }
@@ -320,6 +320,74 @@ int horizon_levels(ll_ctx *ctx, size_t l, int plies, int quiet_ext, uint64_t *sc
     return LL_OK;
 }
 
+// The same values for a SMALL batch without a host round trip per level: every level is expanded order-free into the
+// capacity it already has (sizes stay on the device, tiles claim their output ranges, every parent records where its
+// children went), the bottom level by k_horizon<CHAIN>, the back-ups by range.  One launch chain, no synchronisation;
+// the caller reads the overflow flag together with the values and, if a level outgrew its buffer, redoes the call
+// level by level (which also grows the buffers).  plies >= 2, no quiescence extension.
+constexpr size_t HORIZON_CHAIN_MAX_BATCH = 4096;
+constexpr size_t HORIZON_CHAIN_MIN_CAP = 1u << 20; // positions per scratch level (100 MB), so that small batches fit from the start
+int horizon_chain(ll_ctx *ctx, int plies, bool *launched) {
+    *launched = false;
+    const size_t bottom = (size_t)plies - 1;
+    if (bottom + 2 > 60) return LL_OK;
+    const size_t n = ctx->levels[0].n;
+    for (size_t j = 1; j <= bottom; j++) LL_TRY(reserve_level(ctx, j, HORIZON_CHAIN_MIN_CAP, false, true));
+    LL_TRY(reserve_level(ctx, 0, n, false, true));
+    for (size_t j = 0; j < bottom; j++) LL_TRY(ensure(ctx, ctx->levels[j].child_first, ctx->levels[j].cap * sizeof(u64)));
+    u64 *sc = (u64 *)ctx->scalars.ptr;
+    u64 *N = sc + SC_N;
+    u32 *tileq = (u32 *)(sc + SC_TILEQ);
+    u32 *overflow = (u32 *)(sc + SC_OVERFLOW);
+    const unsigned resident = (unsigned)ctx->sm_count * LL_EXPAND_MIN_BLOCKS;
+    CUDA_TRY(cudaMemsetAsync(sc + SC_LEAVES, 0, (SC_SLOTS - SC_LEAVES) * sizeof(u64), ctx->stream));
+    int q = 0;
+    for (size_t j = 0; j < bottom; j++) {
+        Frontier &f = ctx->levels[j];
+        Frontier &g = ctx->levels[j + 1];
+        ExpandArgs a{};
+        a.in = f.soa();
+        a.n = n;
+        a.n_in = j == 0 ? nullptr : N + j;
+        a.tile_counter = tileq + q++;
+        a.out = g.soa();
+        a.n_out = N + j + 1;
+        a.out_cap = g.cap;
+        a.overflow = overflow;
+        a.child_first = (u64 *)f.child_first.ptr;
+        a.child_count = (u32 *)f.counts.ptr;
+        const unsigned grid = (unsigned)std::min<size_t>(nblocks(j == 0 ? n : f.cap, 32), resident);
+        Timed t(ctx, "emit_reckless");
+        k_expand<true, MODE_EMIT, 32><<<grid, BLOCK, 0, ctx->stream>>>(a);
+        LL_TRY(check_launch("k_expand<EMIT, 32>"));
+        g.n = 0; // its size lives on the device
+    }
+    {
+        Frontier &fb = ctx->levels[bottom];
+        ExpandArgs a{};
+        a.in = fb.soa();
+        a.n_in = N + bottom;
+        a.tile_counter = tileq + q++;
+        a.overflow = overflow;
+        a.values = (float *)fb.values.ptr;
+        a.scored = sc + SC_SCORED;
+        Timed t(ctx, "horizon_last_ply");
+        k_horizon<false, true><<<(unsigned)std::min<size_t>(nblocks(fb.cap, HP), resident), BLOCK, 0, ctx->stream>>>(a);
+        LL_TRY(check_launch("k_horizon<CHAIN>"));
+    }
+    for (size_t lev = bottom; lev > 0; lev--) {
+        Frontier &par = ctx->levels[lev - 1];
+        Frontier &chi = ctx->levels[lev];
+        Timed t(ctx, "backup");
+        k_backup_ranges<<<(unsigned)std::min<size_t>(nblocks(lev == 1 ? n : par.cap), resident), BLOCK, 0, ctx->stream>>>(
+            par.soa(), n, lev == 1 ? nullptr : N + lev - 1, overflow, (const u64 *)par.child_first.ptr, (const u32 *)par.counts.ptr,
+            (const float *)chi.values.ptr, (float *)par.values.ptr);
+        LL_TRY(check_launch("k_backup_ranges"));
+    }
+    *launched = true;
+    return LL_OK;
+}
+
 } // namespace
 
 // ================================================================================================ ABI
@@ -392,7 +460,7 @@ extern "C" int ll_shutdown(ll_ctx *ctx) {
     };
     drop(ctx->ext.counts); drop(ctx->ext.block_sums); drop(ctx->ext.block_base); drop(ctx->ext.values);
     for (Frontier &f : ctx->levels) {
-        drop(f.planes); drop(f.meta); drop(f.root); drop(f.counts); drop(f.block_sums); drop(f.block_base); drop(f.cmeta); drop(f.values);
+        drop(f.planes); drop(f.meta); drop(f.root); drop(f.counts); drop(f.block_sums); drop(f.block_base); drop(f.cmeta); drop(f.values); drop(f.child_first);
     }
     drop(ctx->aos_in); drop(ctx->aos_out); drop(ctx->scalars); drop(ctx->scores); drop(ctx->teams); drop(ctx->flags);
     for (TimedLaunch &t : ctx->timed) {
@@ -957,9 +1025,27 @@ extern "C" int ll_horizon_batch(ll_ctx *ctx, const ll_world_t *frontier, size_t 
     if (n && (!frontier || !values)) return fail(LL_ERR_INVALID_ARG, "null buffer");
     if (plies < 0 || plies > 8) return fail(LL_ERR_INVALID_ARG, "plies %d out of range", plies);
     if (!n) return LL_OK;
-    LL_TRY(upload_worlds(ctx, frontier, n, 0));
-    LL_TRY(validate_level(ctx, ctx->levels[0].soa(), n));
     if (quiet_extension > 8) return fail(LL_ERR_INVALID_ARG, "quiet extension %d out of range", quiet_extension);
+    const bool small = n <= HORIZON_CHAIN_MAX_BATCH && plies >= 2 && quiet_extension <= 0 && !ctx->force_synced;
+    if (small) { // the alpha-beta driver's hand-offs: check on the host, then one launch chain and ONE synchronisation
+        for (size_t i = 0; i < n; i++)
+            if (!host_well_formed(&frontier[i]))
+                return fail(LL_ERR_DOMAIN, "position %llu is not well-formed (see include/leafline_b200.h, domain W)", (unsigned long long)i);
+    }
+    LL_TRY(upload_worlds(ctx, frontier, n, 0));
+    if (small) {
+        bool launched = false;
+        LL_TRY(horizon_chain(ctx, plies, &launched));
+        if (launched) {
+            u32 outgrown = 0;
+            CUDA_TRY(cudaMemcpyAsync(values, ctx->levels[0].values.ptr, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(&outgrown, (u64 *)ctx->scalars.ptr + SC_OVERFLOW, sizeof outgrown, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            if (!outgrown) return LL_OK;
+        }
+    } else {
+        LL_TRY(validate_level(ctx, ctx->levels[0].soa(), n));
+    }
     LL_TRY(horizon_levels(ctx, 0, plies, quiet_extension, nullptr));
     CUDA_TRY(cudaMemcpyAsync(values, ctx->levels[0].values.ptr, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1130,16 +1216,51 @@ extern "C" int ll_forecast(ll_ctx *ctx, const ll_world_t *root, int depth, int q
 // `device_plies` the node is handed to the device, which returns its EXACT full-width value (horizon_levels), so
 // the root scores equal TT-free exact negamax -- only the work is pruned.  The children of a node one ply above
 // the hand-off are valued in two batches ("young brothers wait"): the first commit alone, then -- unless it
-// already caused a cut-off -- all the others at once.  No transposition table: the reference's stores bound
-// values as exact ones (mind.rs:340-343), which this driver does not reproduce.
+// already caused a cut-off -- all the others at once.
+// The "memory bank" (mind.rs:312-344) is kept, made sound: an entry is keyed by the WHOLE position plus the plies left
+// (no hash collisions, no deeper-entry substitution) and says what its value is -- exact, a lower bound (the node
+// failed high) or an upper bound (it failed low) -- where the reference files every value as exact (mind.rs:340-343).
+// A bound is used only where it settles the window, so the root scores stay those of exact negamax; frontier values
+// are exact by construction and are remembered the same way.
 namespace {
 
 struct AlphaBeta {
     ll_ctx *ctx;
     int device_plies, quiet_extension;
     std::unordered_map<uint32_t, uint32_t> intuition; // the "intuition bank": Patch -> credit (mind.rs:353-359)
-    uint64_t expanded = 0, handed_off = 0, leaves_scored = 0;
+    uint64_t expanded = 0, handed_off = 0, remembered = 0;
     int rc = LL_OK;
+
+    struct Key { // the position and the plies left
+        u64 w[13];
+        bool operator==(const Key &o) const { return memcmp(w, o.w, sizeof w) == 0; }
+    };
+    struct KeyHash {
+        size_t operator()(const Key &k) const {
+            u64 h = 0x9E3779B97F4A7C15ull;
+            for (int i = 0; i < 13; i++) {
+                h = (h ^ k.w[i]) * 0xBF58476D1CE4E5B9ull;
+                h ^= h >> 29;
+            }
+            return (size_t)h;
+        }
+    };
+    enum : uint8_t { EXACT, LOWER, UPPER };
+    struct Memory {
+        float value;
+        uint8_t kind;
+    };
+    static constexpr size_t BANK_MAX = 1u << 22; // ~0.6 GB of host memory at most; past it nothing new is filed
+    std::unordered_map<Key, Memory, KeyHash> bank;
+    static Key key_of(const ll_world_t &w, int plies) {
+        Key k;
+        for (int j = 0; j < 12; j++) k.w[j] = w.plane[j];
+        k.w[12] = (u64)w.initiative | ((u64)w.service_eligibility << 8) | ((u64)w.passing_by << 16) | ((u64)(uint32_t)plies << 32);
+        return k;
+    }
+    void file(const Key &k, float value, uint8_t kind) {
+        if (bank.size() < BANK_MAX) bank[k] = Memory{value, kind};
+    }
 
     static uint32_t patch_key(const ll_commit_t &c) { return (uint32_t)c.team | ((uint32_t)c.job << 1) | ((uint32_t)c.whence << 8) | ((uint32_t)c.whither << 16); }
     static float figurine_valuation(uint8_t agent) { // mind.rs:36-48
@@ -1173,28 +1294,63 @@ struct AlphaBeta {
         expanded++;
         return true;
     }
-    bool device_values(const ll_world_t *nodes, size_t n, float *values) {
-        rc = ll_horizon_batch(ctx, nodes, n, device_plies, quiet_extension, values);
-        handed_off += n;
-        return rc == LL_OK;
+    // exact values of frontier nodes with `plies` plies left: the remembered ones from the bank, the others in ONE device batch
+    bool device_values(const ll_world_t *nodes, size_t n, int plies, float *values) {
+        std::vector<ll_world_t> unknown;
+        std::vector<size_t> where;
+        for (size_t i = 0; i < n; i++) {
+            const auto it = bank.find(key_of(nodes[i], plies));
+            if (it != bank.end()) { // frontier entries are always exact
+                values[i] = it->second.value;
+                remembered++;
+            } else {
+                unknown.push_back(nodes[i]);
+                where.push_back(i);
+            }
+        }
+        if (unknown.empty()) return true;
+        std::vector<float> fresh(unknown.size());
+        rc = ll_horizon_batch(ctx, unknown.data(), unknown.size(), plies, quiet_extension, fresh.data());
+        if (rc != LL_OK) return false;
+        handed_off += unknown.size();
+        for (size_t j = 0; j < unknown.size(); j++) {
+            values[where[j]] = fresh[j];
+            file(key_of(unknown[j], plies), fresh[j], EXACT);
+        }
+        return true;
     }
     // value of `node` for its side to move with `depth` plies left, window (alpha, beta); fail-soft
     float search(const ll_world_t &node, int depth, float alpha, float beta) {
         if (rc != LL_OK) return 0.0f;
         if (depth <= device_plies) {
             float v = 0.0f;
-            device_values(&node, 1, &v);
+            device_values(&node, 1, depth < 0 ? 0 : depth, &v);
             return v;
         }
+        const Key key = key_of(node, depth);
+        const auto seen = bank.find(key);
+        if (seen != bank.end()) { // mind.rs:316-325, with the kinds of value told apart
+            const Memory m = seen->second;
+            if (m.kind == EXACT || (m.kind == LOWER && m.value >= beta) || (m.kind == UPPER && m.value <= alpha)) {
+                remembered++;
+                return m.value;
+            }
+        }
+        const float alpha_in = alpha;
         std::vector<ll_commit_t> premonitions;
         if (!children(node, premonitions)) return 0.0f;
         if (premonitions.empty()) { // mind.rs:282-287 at depth > 0: the node is its own leaf
             float v = 0.0f;
             rc = ll_horizon_batch(ctx, &node, 1, 0, -1, &v);
+            if (rc == LL_OK) file(key, v, EXACT);
             return v;
         }
         order(premonitions);
         float optimum = -INFINITY;
+        auto remember = [&]() { // mind.rs:340-343
+            if (rc == LL_OK) file(key, optimum, optimum <= alpha_in ? UPPER : optimum >= beta ? LOWER : EXACT);
+            return optimum;
+        };
         auto consider = [&](const ll_commit_t &c, float value) { // mind.rs:346-361
             if (value > optimum) optimum = value;
             if (value > alpha) alpha = value;
@@ -1206,25 +1362,25 @@ struct AlphaBeta {
         };
         if (depth - 1 <= device_plies) { // the children are frontier nodes: first alone, then the rest in one batch
             float first = 0.0f;
-            if (!device_values(&premonitions[0].tree, 1, &first)) return 0.0f;
-            if (consider(premonitions[0], -first)) return optimum;
+            if (!device_values(&premonitions[0].tree, 1, depth - 1, &first)) return 0.0f;
+            if (consider(premonitions[0], -first)) return remember();
             const size_t rest = premonitions.size() - 1;
             if (rest) {
                 std::vector<ll_world_t> trees(rest);
                 std::vector<float> values(rest);
                 for (size_t i = 0; i < rest; i++) trees[i] = premonitions[i + 1].tree;
-                if (!device_values(trees.data(), rest, values.data())) return 0.0f;
+                if (!device_values(trees.data(), rest, depth - 1, values.data())) return 0.0f;
                 for (size_t i = 0; i < rest; i++)
                     if (consider(premonitions[i + 1], -values[i])) break;
             }
-            return optimum;
+            return remember();
         }
         for (const ll_commit_t &c : premonitions) {
             const float value = -search(c.tree, depth - 1, -beta, -alpha);
             if (rc != LL_OK) return 0.0f;
             if (consider(c, value)) break;
         }
-        return optimum;
+        return remember();
     }
 };
 
@@ -1264,7 +1420,7 @@ extern "C" int ll_alpha_beta_forecast(ll_ctx *ctx, const ll_world_t *root, int d
     if (stats3) {
         stats3[0] = ab.expanded;
         stats3[1] = ab.handed_off;
-        stats3[2] = 0;
+        stats3[2] = ab.remembered;
     }
     return LL_OK;
 }

@@ -241,6 +241,8 @@ struct ExpandArgs {
     u64 *n_out;             // EMIT without block_base: tiles claim their output range here (order-free)
     size_t out_cap;         // ... and raise *overflow instead of writing past this many children
     u32 *overflow;
+    u64 *child_first;       // EMIT, order-free (nullable): where each parent's children went ...
+    u32 *child_count;       // ... and how many there are (the negamax back-up of the horizon chain reads these)
     // MODE_PERFT
     u64 *per_root, *total;
     // k_horizon
@@ -307,6 +309,10 @@ template <bool NIHIL, int MODE, int P, bool STUNS> __device__ __forceinline__ vo
                 out_base = (size_t)sh.claim;
                 writable = out_base + total <= a.out_cap;
                 if (!writable && tid == 0) atomicExch(a.overflow, 1u);
+                if (mine && a.child_first) {
+                    a.child_first[i] = (u64)out_base + ex;
+                    a.child_count[i] = cnt;
+                }
             }
         }
 
@@ -730,6 +736,7 @@ struct HorizonShared {
     u32 ex[HP + 1]; // exclusive prefix of the parents' commit counts
     u32 n_rec[HP];
     int acc[HP];
+    u32 claim; // CHAIN: the tile this block pulled
 };
 struct SharedRecordOut {
     HorizonShared &sh;
@@ -743,12 +750,24 @@ struct SharedRecordOut {
         n_moves += (u32)__popcll(mask);
     }
 };
-template <bool STUNS> __global__ void __launch_bounds__(BLOCK, 6) k_horizon(const ExpandArgs a) {
+// CHAIN: the level's size is resident on the device (a.n_in) and persistent blocks pull tiles from a.tile_counter -- the
+// launch needs no host round trip (the small-batch path of ll_horizon_batch)
+template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOCK, 6) k_horizon(const ExpandArgs a) {
     __shared__ HorizonShared sh;
     const int tid = threadIdx.x;
-    const size_t tile = blockIdx.x;
+    if (CHAIN && *(volatile u32 *)a.overflow) return; // see expand_tiles
+    const size_t n = CHAIN ? (size_t)*(volatile const u64 *)a.n_in : a.n;
+#pragma unroll 1
+    for (;;) {
+    size_t tile = blockIdx.x;
+    if (CHAIN) {
+        if (tid == 0) sh.claim = atomicAdd(a.tile_counter, 1u);
+        __syncthreads();
+        tile = (size_t)sh.claim;
+        if (tile * HP >= n) break;
+    }
     const size_t i = tile * HP + tid;
-    const bool mine = tid < HP && i < a.n;
+    const bool mine = tid < HP && i < n;
     u32 cnt = 0;
     if (mine) {
         const Pos p = soa_load(a.in, i);
@@ -816,6 +835,9 @@ template <bool STUNS> __global__ void __launch_bounds__(BLOCK, 6) k_horizon(cons
     }
     scored = __reduce_add_sync(0xffffffffu, scored);
     if ((tid & 31) == 0 && scored && a.scored) atomicAdd((unsigned long long *)a.scored, (unsigned long long)scored);
+    if (!CHAIN) break;
+    __syncthreads(); // the tile and the claim slot are reused by the next round
+    }
 }
 
 // keep the units u with u % world == rank (frontier sharding by subtree).  n_in / n_out
@@ -905,6 +927,28 @@ __global__ void __launch_bounds__(BLOCK) k_backup(Soa parents, size_t n, const u
         for (u32 k = 0; k < c; k++) v = fmaxf(v, -child_values[first + k]);
     }
     values[i] = v;
+}
+
+// the same back-up where the children were placed order-free (the horizon chain): every parent knows its own range,
+// the level's size stays on the device
+__global__ void __launch_bounds__(BLOCK) k_backup_ranges(Soa parents, size_t n_host, const u64 *__restrict__ n_in, const u32 *__restrict__ overflow,
+                                                         const u64 *__restrict__ child_first, const u32 *__restrict__ child_count,
+                                                         const float *__restrict__ child_values, float *__restrict__ values) {
+    if (*(volatile const u32 *)overflow) return;
+    const size_t n = n_in ? (size_t)*(volatile const u64 *)n_in : n_host;
+    for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (size_t)gridDim.x * BLOCK) {
+        const u32 c = child_count[i];
+        float v = -INFINITY;
+        if (c == 0) {
+            const Pos p = soa_load(parents, i);
+            const float s = score(p);
+            v = meta_stm(p.meta) ? -s : s;
+        } else {
+            const size_t first = (size_t)child_first[i];
+            for (u32 k = 0; k < c; k++) v = fmaxf(v, -child_values[first + k]);
+        }
+        values[i] = v;
+    }
 }
 
 // ---- principal variation (the `Variation` memory of mind.rs:208-224) -------------------------------------

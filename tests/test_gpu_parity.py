@@ -335,6 +335,32 @@ def test_horizon_matches_exact_negamax(eng, playouts, reckless_worlds, plies):
         assert np.array_equal(got, want), np.nonzero(got != want)
 
 
+def test_horizon_launch_chain_equals_level_by_level(eng, playouts, reckless_worlds):
+    # small batches run as ONE launch chain (device-resident level sizes, order-free placement, back-up by recorded
+    # ranges); a level that outgrows its scratch capacity (4096 x ~35^2 nodes here) sends the call down the
+    # level-by-level path: the values are the same every way
+    big = np.concatenate([playouts] * 4)
+    assert len(big) == 4096
+    for worlds, plies in ((playouts[:300], 2), (reckless_worlds[:64], 3), (named_worlds(), 3), (big, 2), (big, 3),
+                          (named_worlds()[:6], 4), (playouts[:1], 4), (playouts[7:8], 2)):
+        eng.force_synced(False)
+        chained = eng.horizon(worlds, plies)
+        again = eng.horizon(worlds, plies)
+        eng.force_synced(True)
+        try:
+            synced = eng.horizon(worlds, plies)
+        finally:
+            eng.force_synced(False)
+        assert chained.tobytes() == synced.tobytes() == again.tobytes(), (len(worlds), plies)
+    import leafline_b200 as ll
+
+    bad = np.array([playouts[0], playouts[1]], dtype=ll.WORLD_DTYPE)
+    bad[1]["plane"][0] |= np.uint64(1)  # overlapping planes
+    bad[1]["plane"][7] |= np.uint64(1)
+    with pytest.raises(ll.LeaflineError, match="position 1 is not well-formed"):
+        eng.horizon(bad, 2)
+
+
 def test_horizon_depth_3_on_a_few(eng, playouts):
     worlds = playouts[:4]
     got = eng.horizon(worlds, 3)
@@ -440,6 +466,23 @@ def test_host_alpha_beta_driver_equals_full_width_search(eng, fen, depth, device
         for _ in range(depth - device_plies - 1):
             frontier = np.ascontiguousarray(eng.reckless_lookahead(frontier)[1]["tree"])
         assert handed_off < len(frontier)
+
+
+def test_host_alpha_beta_memory_bank_is_sound(eng):
+    # mind.rs:312-344 made sound (whole-position keys, exact/lower/upper kinds): transpositions are answered from the
+    # bank and the root scores are still those of the full-width search, bit for bit; a root nearer than the hand-off
+    # depth is searched to ITS depth
+    import leafline_b200 as ll
+
+    for fen, depth, device_plies in ((OPENING, 6, 2), (OPENING, 6, 3), (KIWIPETE, 5, 2), ("8/2p5/3p4/KP5r/1R3p1k/8/4P1P1/8 w - -", 7, 2),
+                                     (OPENING, 3, 4), (KIWIPETE, 2, 4)):
+        w = ll.reconstruct(fen)
+        pruned, expanded, handed_off = eng.alpha_beta_forecast(w, depth, device_plies=device_plies)
+        full = eng.forecast(w, depth)
+        assert pruned["score"].tobytes() == full["score"].tobytes(), (fen, depth, device_plies)
+        assert pruned["commit"].tobytes() == full["commit"].tobytes()
+        if depth - device_plies >= 4:
+            assert eng.last_search_stats["values_remembered"] > 0
 
 
 def test_kickoff_family(eng):
