@@ -327,14 +327,14 @@ int horizon_levels(ll_ctx *ctx, size_t l, int plies, int quiet_ext, uint64_t *sc
 // level by level (which also grows the buffers).  plies >= 2, no quiescence extension.
 constexpr size_t HORIZON_CHAIN_MAX_BATCH = 4096;
 constexpr size_t HORIZON_CHAIN_MIN_CAP = 1u << 20; // positions per scratch level (100 MB), so that small batches fit from the start
-int horizon_chain(ll_ctx *ctx, int plies, bool *launched) {
+int horizon_chain(ll_ctx *ctx, size_t l0, int plies, bool *launched) {
     *launched = false;
-    const size_t bottom = (size_t)plies - 1;
+    const size_t bottom = l0 + (size_t)plies - 1;
     if (bottom + 2 > 60) return LL_OK;
-    const size_t n = ctx->levels[0].n;
-    for (size_t j = 1; j <= bottom; j++) LL_TRY(reserve_level(ctx, j, HORIZON_CHAIN_MIN_CAP, false, true));
-    LL_TRY(reserve_level(ctx, 0, n, false, true));
-    for (size_t j = 0; j < bottom; j++) LL_TRY(ensure(ctx, ctx->levels[j].child_first, ctx->levels[j].cap * sizeof(u64)));
+    const size_t n = ctx->levels[l0].n;
+    for (size_t j = l0 + 1; j <= bottom; j++) LL_TRY(reserve_level(ctx, j, HORIZON_CHAIN_MIN_CAP, false, true));
+    LL_TRY(reserve_level(ctx, l0, n, false, true));
+    for (size_t j = l0; j < bottom; j++) LL_TRY(ensure(ctx, ctx->levels[j].child_first, ctx->levels[j].cap * sizeof(u64)));
     u64 *sc = (u64 *)ctx->scalars.ptr;
     u64 *N = sc + SC_N;
     u32 *tileq = (u32 *)(sc + SC_TILEQ);
@@ -342,13 +342,13 @@ int horizon_chain(ll_ctx *ctx, int plies, bool *launched) {
     const unsigned resident = (unsigned)ctx->sm_count * LL_EXPAND_MIN_BLOCKS;
     CUDA_TRY(cudaMemsetAsync(sc + SC_LEAVES, 0, (SC_SLOTS - SC_LEAVES) * sizeof(u64), ctx->stream));
     int q = 0;
-    for (size_t j = 0; j < bottom; j++) {
+    for (size_t j = l0; j < bottom; j++) {
         Frontier &f = ctx->levels[j];
         Frontier &g = ctx->levels[j + 1];
         ExpandArgs a{};
         a.in = f.soa();
         a.n = n;
-        a.n_in = j == 0 ? nullptr : N + j;
+        a.n_in = j == l0 ? nullptr : N + j;
         a.tile_counter = tileq + q++;
         a.out = g.soa();
         a.n_out = N + j + 1;
@@ -356,10 +356,12 @@ int horizon_chain(ll_ctx *ctx, int plies, bool *launched) {
         a.overflow = overflow;
         a.child_first = (u64 *)f.child_first.ptr;
         a.child_count = (u32 *)f.counts.ptr;
-        const unsigned grid = (unsigned)std::min<size_t>(nblocks(j == 0 ? n : f.cap, 32), resident);
+        const bool narrow = j < l0 + 2; // the first levels below a small batch: 32-parent tiles reach more SMs
+        const unsigned grid = (unsigned)std::min<size_t>(nblocks(j == l0 ? n : f.cap, narrow ? 32 : BLOCK), resident);
         Timed t(ctx, "emit_reckless");
-        k_expand<true, MODE_EMIT, 32><<<grid, BLOCK, 0, ctx->stream>>>(a);
-        LL_TRY(check_launch("k_expand<EMIT, 32>"));
+        if (narrow) k_expand<true, MODE_EMIT, 32><<<grid, BLOCK, 0, ctx->stream>>>(a);
+        else k_expand<true, MODE_EMIT><<<grid, BLOCK, 0, ctx->stream>>>(a);
+        LL_TRY(check_launch("k_expand<EMIT> (chain)"));
         g.n = 0; // its size lives on the device
     }
     {
@@ -375,12 +377,12 @@ int horizon_chain(ll_ctx *ctx, int plies, bool *launched) {
         k_horizon<false, true><<<(unsigned)std::min<size_t>(nblocks(fb.cap, HP), resident), BLOCK, 0, ctx->stream>>>(a);
         LL_TRY(check_launch("k_horizon<CHAIN>"));
     }
-    for (size_t lev = bottom; lev > 0; lev--) {
+    for (size_t lev = bottom; lev > l0; lev--) {
         Frontier &par = ctx->levels[lev - 1];
         Frontier &chi = ctx->levels[lev];
         Timed t(ctx, "backup");
-        k_backup_ranges<<<(unsigned)std::min<size_t>(nblocks(lev == 1 ? n : par.cap), resident), BLOCK, 0, ctx->stream>>>(
-            par.soa(), n, lev == 1 ? nullptr : N + lev - 1, overflow, (const u64 *)par.child_first.ptr, (const u32 *)par.counts.ptr,
+        k_backup_ranges<<<(unsigned)std::min<size_t>(nblocks(lev == l0 + 1 ? n : par.cap), resident), BLOCK, 0, ctx->stream>>>(
+            par.soa(), n, lev == l0 + 1 ? nullptr : N + lev - 1, overflow, (const u64 *)par.child_first.ptr, (const u32 *)par.counts.ptr,
             (const float *)chi.values.ptr, (float *)par.values.ptr);
         LL_TRY(check_launch("k_backup_ranges"));
     }
@@ -1035,7 +1037,7 @@ extern "C" int ll_horizon_batch(ll_ctx *ctx, const ll_world_t *frontier, size_t 
     LL_TRY(upload_worlds(ctx, frontier, n, 0));
     if (small) {
         bool launched = false;
-        LL_TRY(horizon_chain(ctx, plies, &launched));
+        LL_TRY(horizon_chain(ctx, 0, plies, &launched));
         if (launched) {
             u32 outgrown = 0;
             CUDA_TRY(cudaMemcpyAsync(values, ctx->levels[0].values.ptr, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1129,7 +1131,26 @@ static int kickoff_core(ll_ctx *ctx, const ll_world_t *root, int depth, int quie
     }
     uint64_t scored = 0;
     size_t bottom = search_level;
-    LL_TRY(horizon_levels(ctx, search_level, depth - 1, quiet_extension, &scored, variations != nullptr, &bottom)); // mind.rs:406-411: full window per root
+    std::vector<float> vals(kept);
+    bool chained = false;
+    if (!variations && quiet_extension <= 0 && depth - 1 >= 2 && kept && kept <= HORIZON_CHAIN_MAX_BATCH && !ctx->force_synced) {
+        // scores only: the levels below the root moves as one launch chain, no host round trip per ply (see horizon_chain)
+        bool launched = false;
+        LL_TRY(horizon_chain(ctx, search_level, depth - 1, &launched));
+        if (launched) {
+            u64 *sc = (u64 *)ctx->scalars.ptr;
+            u64 flags[2] = {0, 0};
+            CUDA_TRY(cudaMemcpyAsync(vals.data(), ctx->levels[search_level].values.ptr, kept * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(&flags[0], sc + SC_OVERFLOW, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(&flags[1], sc + SC_SCORED, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            if (!(u32)flags[0]) {
+                chained = true;
+                scored = flags[1];
+            }
+        }
+    }
+    if (!chained) LL_TRY(horizon_levels(ctx, search_level, depth - 1, quiet_extension, &scored, variations != nullptr, &bottom)); // mind.rs:406-411: full window per root
     if (leaves_scored) *leaves_scored = scored;
     std::vector<u32> pv;
     const int expanding = (depth - 1) + (quiet_extension > 0 ? quiet_extension : 0);
@@ -1153,8 +1174,7 @@ static int kickoff_core(ll_ctx *ctx, const ll_world_t *root, int depth, int quie
         pv.resize(kept * (PV_MAX + 1));
         CUDA_TRY(cudaMemcpyAsync(pv.data(), ctx->flags.ptr, pv.size() * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
     }
-    std::vector<float> vals(kept);
-    if (kept) CUDA_TRY(cudaMemcpyAsync(vals.data(), ctx->levels[search_level].values.ptr, kept * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (kept && !chained) CUDA_TRY(cudaMemcpyAsync(vals.data(), ctx->levels[search_level].values.ptr, kept * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     for (u64 i = 0; i < total; i++) scores[i] = -INFINITY;
     for (size_t o = 0; o < kept; o++) scores[(size_t)shard_rank + o * (size_t)shard_world] = -vals[o]; // mind.rs:425

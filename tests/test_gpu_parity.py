@@ -532,6 +532,29 @@ def test_kickoff_depth_5_and_6_match_the_oracle(eng):
         assert sorted(pruned["score"]) == sorted(want_scores)
 
 
+def test_kickoff_launch_chain_equals_level_by_level(eng):
+    # ll_kickoff (scores only, no quiet extension) searches the levels below the root moves as one launch chain; the first
+    # call at a new size may outgrow a scratch level and fall back, the second one stays on the chain: same scores, same
+    # number of leaves scored, sharded or not
+    import leafline_b200 as ll
+
+    for fen, depth in ((OPENING, 3), (OPENING, 4), (OPENING, 5), (OPENING, 6), (KIWIPETE, 4), (KIWIPETE, 5), (POSITION_5, 4)):
+        w = ll.reconstruct(fen)
+        for shard in (None, (1, 3)):
+            kw = {} if shard is None else {"shard": shard}
+            first = eng.kickoff(w, depth, **kw)
+            second = eng.kickoff(w, depth, **kw)
+            eng.force_synced(True)
+            try:
+                synced = eng.kickoff(w, depth, **kw)
+            finally:
+                eng.force_synced(False)
+            for got in (first, second):
+                assert got[0].tobytes() == synced[0].tobytes()
+                assert got[1].tobytes() == synced[1].tobytes(), (fen, depth, shard)
+                assert got[2] == synced[2]
+
+
 @pytest.mark.parametrize("world_size", [2, 4])
 def test_kickoff_shards_gather_to_the_whole(eng, world_size):
     import leafline_b200 as ll
