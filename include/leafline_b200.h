@@ -159,7 +159,9 @@ int ll_alpha_beta_forecast(ll_ctx *ctx, const ll_world_t *root, int depth, int d
 /* replaces `fixed_depth_sequence_kickoff` (src/mind.rs:473-490) */
 int ll_fixed_depth_sequence_forecast(ll_ctx *ctx, const ll_world_t *root, const uint8_t *depths, uint32_t n_depths, int nihilistically,
                                      ll_forecast_t *forecasts, uint32_t cap, uint32_t *n_forecasts);
-/* replaces `iterative_deepening_kickoff` (src/mind.rs:451-469): the deepest iteration that finished inside the timeout */
+/* replaces `iterative_deepening_kickoff` (src/mind.rs:451-469): the deepest iteration that finished inside the timeout.
+ * Iterations are full-width on the device (ll_forecast) while the tree fits HBM and depth < 8, then the host alpha-beta
+ * driver (ll_alpha_beta_forecast's search, abandoned in mid-iteration at the deadline): same scores either way. */
 int ll_iterative_deepening_forecast(ll_ctx *ctx, const ll_world_t *root, double timeout_seconds, int nihilistically, ll_forecast_t *forecasts,
                                     uint32_t cap, uint32_t *n_forecasts, uint32_t *depth_reached);
 

@@ -1250,6 +1250,8 @@ struct AlphaBeta {
     std::unordered_map<uint32_t, uint32_t> intuition; // the "intuition bank": Patch -> credit (mind.rs:353-359)
     uint64_t expanded = 0, handed_off = 0, remembered = 0;
     int rc = LL_OK;
+    bool timebound = false, out_of_time = false; // mind.rs:416-420: a search that overruns its deadline is abandoned
+    std::chrono::steady_clock::time_point deadline;
 
     struct Key { // the position and the plies left
         u64 w[13];
@@ -1342,6 +1344,11 @@ struct AlphaBeta {
     // value of `node` for its side to move with `depth` plies left, window (alpha, beta); fail-soft
     float search(const ll_world_t &node, int depth, float alpha, float beta) {
         if (rc != LL_OK) return 0.0f;
+        if (timebound && std::chrono::steady_clock::now() > deadline) {
+            out_of_time = true;
+            rc = LL_ERR_CAPACITY; // unwinds the recursion; the caller reports the time-out, not this code
+            return 0.0f;
+        }
         if (depth <= device_plies) {
             float v = 0.0f;
             device_values(&node, 1, depth < 0 ? 0 : depth, &v);
@@ -1406,25 +1413,34 @@ struct AlphaBeta {
 
 } // namespace
 
-extern "C" int ll_alpha_beta_forecast(ll_ctx *ctx, const ll_world_t *root, int depth, int device_plies, int quiet_extension, int nihilistically,
-                                      ll_forecast_t *forecasts, uint32_t cap, uint32_t *n_forecasts, uint64_t *stats3) {
-    LL_TRY(check_ctx(ctx));
-    if (!root || !forecasts || !n_forecasts) return fail(LL_ERR_INVALID_ARG, "null argument");
-    if (depth < 1 || depth > 32) return fail(LL_ERR_INVALID_ARG, "depth %d out of range (1..32)", depth);
-    if (device_plies < 0 || device_plies > 8) return fail(LL_ERR_INVALID_ARG, "device_plies %d out of range (0..8)", device_plies);
-    if (quiet_extension > 8) return fail(LL_ERR_INVALID_ARG, "quiet extension %d out of range", quiet_extension);
+// `deadline` (nullable): give up once it has passed -> *timed_out = true, forecasts untouched
+static int alpha_beta_core(ll_ctx *ctx, const ll_world_t *root, int depth, int device_plies, int quiet_extension, int nihilistically,
+                           ll_forecast_t *forecasts, uint32_t cap, uint32_t *n_forecasts, uint64_t *stats3,
+                           const std::chrono::steady_clock::time_point *deadline, bool *timed_out) {
+    if (timed_out) *timed_out = false;
     uint32_t offsets[2] = {0, 0};
     std::vector<ll_commit_t> roots(1024);
     LL_TRY(ll_lookahead_batch(ctx, root, 1, nihilistically, offsets, roots.data(), roots.size())); // mind.rs:388-392
     roots.resize(offsets[1]);
-    *n_forecasts = offsets[1];
-    if (offsets[1] > cap) return fail(LL_ERR_CAPACITY, "%u forecasts do not fit the capacity of %u", offsets[1], cap);
+    if (offsets[1] > cap) {
+        *n_forecasts = offsets[1];
+        return fail(LL_ERR_CAPACITY, "%u forecasts do not fit the capacity of %u", offsets[1], cap);
+    }
     AlphaBeta ab{ctx, device_plies, quiet_extension};
+    if (deadline) {
+        ab.timebound = true;
+        ab.deadline = *deadline;
+    }
     std::vector<float> scores(roots.size());
     for (size_t i = 0; i < roots.size(); i++) { // every root move gets the full window (mind.rs:406-411)
         scores[i] = -ab.search(roots[i].tree, depth - 1, -INFINITY, INFINITY);
+        if (ab.out_of_time) {
+            if (timed_out) *timed_out = true;
+            return LL_OK;
+        }
         if (ab.rc != LL_OK) return ab.rc;
     }
+    *n_forecasts = offsets[1];
     std::vector<uint32_t> order(roots.size());
     for (uint32_t i = 0; i < roots.size(); i++) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return scores[x] > scores[y]; }); // mind.rs:436
@@ -1445,6 +1461,16 @@ extern "C" int ll_alpha_beta_forecast(ll_ctx *ctx, const ll_world_t *root, int d
     return LL_OK;
 }
 
+extern "C" int ll_alpha_beta_forecast(ll_ctx *ctx, const ll_world_t *root, int depth, int device_plies, int quiet_extension, int nihilistically,
+                                      ll_forecast_t *forecasts, uint32_t cap, uint32_t *n_forecasts, uint64_t *stats3) {
+    LL_TRY(check_ctx(ctx));
+    if (!root || !forecasts || !n_forecasts) return fail(LL_ERR_INVALID_ARG, "null argument");
+    if (depth < 1 || depth > 32) return fail(LL_ERR_INVALID_ARG, "depth %d out of range (1..32)", depth);
+    if (device_plies < 0 || device_plies > 8) return fail(LL_ERR_INVALID_ARG, "device_plies %d out of range (0..8)", device_plies);
+    if (quiet_extension > 8) return fail(LL_ERR_INVALID_ARG, "quiet extension %d out of range", quiet_extension);
+    return alpha_beta_core(ctx, root, depth, device_plies, quiet_extension, nihilistically, forecasts, cap, n_forecasts, stats3, nullptr, nullptr);
+}
+
 extern "C" int ll_fixed_depth_sequence_forecast(ll_ctx *ctx, const ll_world_t *root, const uint8_t *depths, uint32_t n_depths, int nihilistically,
                                                 ll_forecast_t *forecasts, uint32_t cap, uint32_t *n_forecasts) {
     if (!depths || !n_depths) return fail(LL_ERR_INVALID_ARG, "`depth_sequence` should be nonempty"); // mind.rs:480
@@ -1457,23 +1483,39 @@ extern "C" int ll_iterative_deepening_forecast(ll_ctx *ctx, const ll_world_t *ro
     if (!forecasts || !n_forecasts || !depth_reached) return fail(LL_ERR_INVALID_ARG, "null argument");
     const auto t0 = std::chrono::steady_clock::now();
     auto elapsed = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
-    // mind.rs:451-469: depth 1 always completes; then deepen while an iteration finishes before the deadline
+    const auto deadline = t0 + std::chrono::duration_cast<std::chrono::steady_clock::duration>(std::chrono::duration<double>(timeout_seconds > 0 ? timeout_seconds : 0));
+    // mind.rs:451-469: depth 1 always completes; then deepen while an iteration finishes before the deadline.  The
+    // shallow iterations are full-width searches resident in HBM (ll_forecast: milliseconds, with variations); once the
+    // tree no longer fits -- depth 8 from the opening -- the host alpha-beta driver takes over (same scores, root move
+    // as the variation) and is abandoned in mid-search if it overruns, like the reference's time-bound search.
     LL_TRY(ll_forecast(ctx, root, 1, -1, nihilistically, forecasts, cap, n_forecasts, nullptr));
     *depth_reached = 1;
     std::vector<ll_forecast_t> next(cap);
-    for (int depth = 2; depth <= 9; depth++) {
+    bool full_width = true;
+    for (int depth = 2; depth <= 32; depth++) {
         const double before = elapsed();
         if (before >= timeout_seconds) break;
         uint32_t n = 0;
-        const int rc = ll_forecast(ctx, root, depth, -1, nihilistically, next.data(), cap, &n, nullptr);
-        if (rc == LL_ERR_OOM) break; // the full-width tree no longer fits HBM: keep the previous iteration
-        LL_TRY(rc);
+        if (full_width && depth >= 8) full_width = false;
+        if (full_width) {
+            const int rc = ll_forecast(ctx, root, depth, -1, nihilistically, next.data(), cap, &n, nullptr);
+            if (rc == LL_ERR_OOM) full_width = false; // the full-width tree no longer fits HBM
+            else LL_TRY(rc);
+        }
+        if (!full_width) {
+            bool timed_out = false;
+            LL_TRY(alpha_beta_core(ctx, root, depth, depth >= 9 ? 5 : 4, -1, nihilistically, next.data(), cap, &n, nullptr, &deadline, &timed_out));
+            if (timed_out) break;
+        }
         if (elapsed() > timeout_seconds) break; // finished late: discarded, like the reference's `None` (mind.rs:416-420)
         memcpy(forecasts, next.data(), n * sizeof(ll_forecast_t));
         *n_forecasts = n;
         *depth_reached = (uint32_t)depth;
+        if (!n) break; // nothing to play
         const double took = elapsed() - before;
-        if (elapsed() + took * 20.0 > timeout_seconds) break; // the next ply is ~30x wider: it cannot finish in time
+        // a full-width ply is ~30x wider than the last; the pruned search grows ~9x per ply (and ~6x over the last full-width one)
+        const double growth = full_width && depth + 1 < 8 ? 20.0 : full_width ? 8.0 : 9.5;
+        if (elapsed() + took * growth > timeout_seconds) break; // the next iteration cannot finish in time
     }
     return LL_OK;
 }
