@@ -233,6 +233,17 @@ class Engine:
                                          _ptr(out), 1024, C.byref(n), C.byref(scored)))
         return out[: n.value].copy()
 
+    def deep_forecast(self, world, depth, nihilistically=False, quiet=None):
+        """kickoff to any depth: full-width on the device (with variations) while the tree fits HBM, the host alpha-beta
+        driver over device frontier batches beyond that (same scores; the variation is the root move)."""
+        if depth < 8:
+            try:
+                return self.forecast(world, depth, nihilistically=nihilistically, quiet=quiet)
+            except LeaflineError as e:
+                if e.code != _abi.ERR_OOM:
+                    raise
+        return self.alpha_beta_forecast(world, depth, device_plies=5 if depth >= 9 else 4, nihilistically=nihilistically, quiet=quiet)[0]
+
     def alpha_beta_forecast(self, world, depth, device_plies=4, nihilistically=False, quiet=None):
         """The reference's search structure: alpha-beta with MVV-LVA + history ordering on the host, frontier nodes with
         `device_plies` plies left valued exactly on the device -> (forecasts, host nodes expanded, frontier nodes handed off);

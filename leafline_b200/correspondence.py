@@ -58,7 +58,7 @@ def forecast(engine, world, bound):
     """main.rs:152-180 -> (forecasts, depth, thinking time in ms)"""
     start = time.perf_counter()
     if isinstance(bound, Depth):
-        forecasts, depth = engine.forecast(world, bound.depth, quiet=bound.extension), bound.depth
+        forecasts, depth = engine.deep_forecast(world, bound.depth, quiet=bound.extension), bound.depth
     elif isinstance(bound, DepthSequence):
         forecasts, depth = engine.fixed_depth_sequence_kickoff(world, bound.depths), bound.depths[-1]
     else:

@@ -56,7 +56,7 @@ def dæmon(engine=None, stdin=None, stdout=None):
                 for key in it:
                     options[key] = int(next(it))  # "expected option value" / "expected an integer literal"
                 if "depth" in options:
-                    forecasts = engine.forecast(world, options["depth"])
+                    forecasts = engine.deep_forecast(world, options["depth"])
                 else:
                     time_key, increment_key = ("wtime", "winc") if int(world["initiative"]) == 0 else ("btime", "binc")
                     deadline = (options[time_key] // options["movestogo"] + options.get(increment_key, 0)) // 1000

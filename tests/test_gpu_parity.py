@@ -679,6 +679,9 @@ def test_correspondence_wire_format(eng):
     assert d["hospitalization"] == {"team": "Blue", "job_description": "Pony"} and d["rosetta_stone"] == "Ba1"
     d = json.loads(co.correspondence(eng, "rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq -", co.Seconds(1)))
     assert d["depth"] >= 3 and len(d["counterreplies"]) == 20
+    # a depth whose full-width tree does not fit HBM goes to the host alpha-beta driver: same card
+    d = json.loads(co.correspondence(eng, "rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq -", co.Depth(8)))
+    assert d["depth"] == 8 and len(d["counterreplies"]) == 20 and d["patch"]["star"]["team"] == "Orange"
 
 
 def test_uci_daemon_and_command_line(eng):
