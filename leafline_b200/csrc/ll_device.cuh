@@ -166,13 +166,23 @@ template <int S> LL_HD u64 ks_up(u64 g, u64 e, u64 keep) {
     g |= e & (g << (4 * S));
     return (g << S) & keep;
 }
+// East is special: along a rank "up" is plain binary carry, so all sliders of all ranks move at once by one per-byte
+// (SWAR) subtraction -- occupied - 2*sliders flips exactly the squares from each slider to its first blocker (or the
+// edge: the borrow dies at the byte boundary).  14 instructions instead of the fill's 26.  Sliders must be occupied
+// squares (they are: `empty` excludes them).
+LL_HD u64 east_attacks(u64 sliders, u64 empty) {
+    const u64 H = 0x8080808080808080ull;
+    const u64 x = ~empty, y = (sliders << 1) & ~FILE_A;
+    const u64 z = ((x | H) - (y & ~H)) ^ ((x ^ ~y) & H); // x - y in every byte
+    return x ^ z;
+}
 // attacks of the orthogonal sliders `orth` and the diagonal sliders `diag` in the four up directions (north, east,
 // ne, nw); called with bit-reversed arguments it yields the bit-reversed attacks in the four down directions
 LL_HD u64 ks_up_attacks(u64 orth, u64 diag, u64 empty) {
-    return ks_up<8>(orth, empty, ~0ull) | ks_up<1>(orth, empty, ~FILE_A) | ks_up<9>(diag, empty, ~FILE_A) | ks_up<7>(diag, empty, ~FILE_H);
+    return ks_up<8>(orth, empty, ~0ull) | east_attacks(orth, empty) | ks_up<9>(diag, empty, ~FILE_A) | ks_up<7>(diag, empty, ~FILE_H);
 }
 LL_HD u32 ks_up_count(u64 orth, u64 diag, u64 empty, u64 ok) {
-    return (u32)(popc64(ks_up<8>(orth, empty, ~0ull) & ok) + popc64(ks_up<1>(orth, empty, ~FILE_A) & ok) +
+    return (u32)(popc64(ks_up<8>(orth, empty, ~0ull) & ok) + popc64(east_attacks(orth, empty) & ok) +
                  popc64(ks_up<9>(diag, empty, ~FILE_A) & ok) + popc64(ks_up<7>(diag, empty, ~FILE_H) & ok));
 }
 

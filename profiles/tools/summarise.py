@@ -99,7 +99,7 @@ with open(os.path.join(OUT, f"{tag}_kernels.csv"), "w", newline="") as f:
 
         dram = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
         tinst = float(r[hdr.index("smsp__inst_executed.sum")]) * float(r[hdr.index("smsp__thread_inst_executed_per_inst_executed.ratio")])
-        key = {"k_expand<legal, PERFT>": "perft6_tail", "k_expand_records<PERFT>": "perft6_tail", "k_horizon<0>": "horizon_2p20", "k_horizon<false>": "horizon_2p20", "k_score": "score"}.get(name)
+        key = {"k_expand<legal, PERFT>": "perft6_tail", "k_expand_records<PERFT>": "perft6_tail", "k_horizon<0>": "horizon_2p20", "k_horizon<false>": "horizon_2p20", "k_horizon<0, 0>": "horizon_2p20", "k_horizon<false, false>": "horizon_2p20", "k_score": "score"}.get(name)
         if key:  # the last launch of each kind wins (steady state)
             consts[f"{key}_dram_bytes"] = dram
             consts[f"{key}_thread_inst"] = tinst
