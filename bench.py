@@ -348,7 +348,7 @@ def main():
         for _ in range(reps):
             eng.perft(root, depth)
         kernels = {}
-        for name in ("perft_tail", "count_leaves", "count_legal", "emit_legal", "scan_block_sums", "aos_to_soa", "validate", "shard_filter"):
+        for name in ("perft_tail", "count_leaves", "count_legal", "emit_legal", "scan_block_sums", "store_world", "aos_to_soa", "validate", "shard_filter"):
             ms, n = eng.timing_query(name)
             if n:
                 kernels[name] = {"ms_per_step": ms / reps, "launches_per_step": n / reps}

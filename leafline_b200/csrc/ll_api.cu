@@ -183,6 +183,21 @@ int upload_worlds(ll_ctx *ctx, const ll_world_t *worlds, size_t n, size_t level)
     return check_launch("k_aos_to_soa");
 }
 
+// level 0 := one root position, passed as a kernel argument
+int upload_root(ll_ctx *ctx, const ll_world_t *root) {
+    static_assert(sizeof(WorldWords) == sizeof(ll_world_t), "ll_world_t is 13 words");
+    LL_TRY(reserve_level(ctx, 0, 1, false, false));
+    Frontier &f = ctx->levels[0];
+    f.n = 1;
+    WorldWords words;
+    memcpy(&words, root, sizeof words);
+    {
+        Timed t(ctx, "store_world");
+        k_store_world<<<1, 32, 0, ctx->stream>>>(words, f.soa(), 0);
+    }
+    return check_launch("k_store_world");
+}
+
 int validate_level(ll_ctx *ctx, const Soa &soa, size_t n) {
     if (!n) return LL_OK;
     u64 *sc = (u64 *)ctx->scalars.ptr;
@@ -638,14 +653,21 @@ extern "C" int ll_score_soa(ll_ctx *ctx, const ll_soa_t *soa, float *d_scores) {
 
 // ---- movegen -----------------------------------------------------------------------------------------
 
+static bool host_well_formed(const ll_world_t *w);
+
 extern "C" int ll_lookahead_batch(ll_ctx *ctx, const ll_world_t *worlds, size_t n, int nihilistically, uint32_t *offsets,
                                   ll_commit_t *commits, size_t commits_cap) {
     LL_TRY(check_ctx(ctx));
     if (!offsets || (n && !worlds)) return fail(LL_ERR_INVALID_ARG, "null buffer");
     offsets[0] = 0;
     if (!n) return LL_OK;
-    LL_TRY(upload_worlds(ctx, worlds, n, 0));
-    LL_TRY(validate_level(ctx, ctx->levels[0].soa(), n));
+    if (n == 1) { // a search driver asking for one node's commits: checked on the host, handed over as a kernel argument
+        if (!host_well_formed(worlds)) return fail(LL_ERR_DOMAIN, "position 0 is not well-formed (see include/leafline_b200.h, domain W)");
+        LL_TRY(upload_root(ctx, worlds));
+    } else {
+        LL_TRY(upload_worlds(ctx, worlds, n, 0));
+        LL_TRY(validate_level(ctx, ctx->levels[0].soa(), n));
+    }
     u64 total = 0;
     LL_TRY(count_level(ctx, 0, nihilistically != 0, &total));
     if (total > 0xFFFFFFFFull) return fail(LL_ERR_CAPACITY, "more than 2^32 commits in one batch");
@@ -986,7 +1008,7 @@ extern "C" int ll_perft(ll_ctx *ctx, const ll_world_t *root, int depth, int shar
     *leaves = 0;
     if (n_roots) *n_roots = 0;
     if (!host_well_formed(root)) return fail(LL_ERR_DOMAIN, "position 0 is not well-formed (see include/leafline_b200.h, domain W)");
-    LL_TRY(upload_worlds(ctx, root, 1, 0));
+    LL_TRY(upload_root(ctx, root));
     if (depth == 0) {
         *leaves = shard_rank == 0 ? 1 : 0;
         return LL_OK;
@@ -997,7 +1019,7 @@ extern "C" int ll_perft(ll_ctx *ctx, const ll_world_t *root, int depth, int shar
         if (done) return LL_OK;
         *leaves = 0;
         if (n_roots) *n_roots = 0;
-        LL_TRY(upload_worlds(ctx, root, 1, 0)); // level 0 again: a failed chain may have left the scratch levels half-written
+        LL_TRY(upload_root(ctx, root)); // level 0 again: a failed chain may have left the scratch levels half-written
     }
     return perft_synced(ctx, depth, shard_rank, shard_world, leaves, per_root, root_cap, n_roots);
 }
@@ -1008,7 +1030,7 @@ extern "C" int ll_perft_device(ll_ctx *ctx, const ll_world_t *root, int depth, i
     if (depth < 3 || depth > 32) return fail(LL_ERR_INVALID_ARG, "depth %d out of range (3..32)", depth);
     if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) return fail(LL_ERR_INVALID_ARG, "bad shard %d/%d", shard_rank, shard_world);
     if (!host_well_formed(root)) return fail(LL_ERR_DOMAIN, "position 0 is not well-formed (see include/leafline_b200.h, domain W)");
-    LL_TRY(upload_worlds(ctx, root, 1, 0));
+    LL_TRY(upload_root(ctx, root));
     bool launched = false;
     LL_TRY(perft_chain_launch(ctx, depth, shard_rank, shard_world, &launched));
     if (!launched) return fail(LL_ERR_CAPACITY, "level buffers are not sized yet: call ll_perft once for this depth first");
@@ -1034,7 +1056,8 @@ extern "C" int ll_horizon_batch(ll_ctx *ctx, const ll_world_t *frontier, size_t 
             if (!host_well_formed(&frontier[i]))
                 return fail(LL_ERR_DOMAIN, "position %llu is not well-formed (see include/leafline_b200.h, domain W)", (unsigned long long)i);
     }
-    LL_TRY(upload_worlds(ctx, frontier, n, 0));
+    if (small && n == 1) LL_TRY(upload_root(ctx, frontier));
+    else LL_TRY(upload_worlds(ctx, frontier, n, 0));
     if (small) {
         bool launched = false;
         LL_TRY(horizon_chain(ctx, 0, plies, &launched));
@@ -1096,8 +1119,8 @@ static int kickoff_core(ll_ctx *ctx, const ll_world_t *root, int depth, int quie
     if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) return fail(LL_ERR_INVALID_ARG, "bad shard %d/%d", shard_rank, shard_world);
     *n_roots = 0;
     if (leaves_scored) *leaves_scored = 0;
-    LL_TRY(upload_worlds(ctx, root, 1, 0));
-    LL_TRY(validate_level(ctx, ctx->levels[0].soa(), 1));
+    if (!host_well_formed(root)) return fail(LL_ERR_DOMAIN, "position 0 is not well-formed (see include/leafline_b200.h, domain W)");
+    LL_TRY(upload_root(ctx, root));
     u64 total = 0;
     LL_TRY(count_level(ctx, 0, nihilistically != 0, &total)); // mind.rs:388-392
     if (total > root_cap) return fail(LL_ERR_CAPACITY, "%llu root moves do not fit root_cap %u", (unsigned long long)total, root_cap);

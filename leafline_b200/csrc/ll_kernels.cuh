@@ -75,6 +75,16 @@ __global__ void __launch_bounds__(BLOCK) k_aos_to_soa(const u64 *__restrict__ ao
         out.meta[i] = make_meta((u32)(m & 1u), (u32)((m >> 8) & 0xFu), (u32)((m >> 16) & 0xFFu));
     }
 }
+// one position handed over as a kernel ARGUMENT (the root of ll_perft / ll_kickoff): no staging copy, no separate
+// host-to-device transfer in front of the launch chain
+struct WorldWords {
+    u64 w[13];
+};
+__global__ void __launch_bounds__(32) k_store_world(const WorldWords world, Soa out, size_t at) {
+    const int j = threadIdx.x;
+    if (j < 12) out.pl[(size_t)j * out.stride + at] = world.w[j];
+    else if (j == 12) out.meta[at] = make_meta((u32)(world.w[12] & 1u), (u32)((world.w[12] >> 8) & 0xFu), (u32)((world.w[12] >> 16) & 0xFFu));
+}
 __device__ __forceinline__ u64 meta_to_word(u32 meta) {
     return (u64)meta_stm(meta) | ((u64)meta_elig(meta) << 8) | ((u64)meta_pb(meta) << 16);
 }
