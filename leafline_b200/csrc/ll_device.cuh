@@ -884,4 +884,139 @@ LL_HD float score(const Pos &p) {
     return v;
 }
 
+// ---- the same evaluation from FEATURES ---------------------------------------------------------------------------
+// score() reads a position only through small integers -- twelve head counts, two centre counts, the cops and
+// servants on a few ranks, the servants per file -- and turns them into floats in a fixed order.  A child differs
+// from its parent in at most three squares, so its integers follow from the parent's by a few +-1: the horizon kernel
+// (one child per thread, never stored) keeps the parent's features in shared memory and evaluates
+// score_features(child_features(...)) instead of building twelve planes and counting them again.  Same integers, same
+// float sequence: bit-identical to score(make_child(...)) (tests/hostcheck checks every commit of every test position).
+struct Feat {
+    u32 w[7]; // w0-w2: head counts, a byte per plane (plane j in byte j&3 of word j>>2)
+              // w3: bytes oc, bc (servants and ponies in the centre), orange cops on rank 6, blue cops on rank 1
+              // w4: bytes orange servants on rank 6, on rank 5, blue servants on rank 1, on rank 2
+              // w5, w6: orange / blue servants per file, a nibble per file
+};
+LL_HD Feat features_of(const Pos &p) {
+    Feat f;
+#pragma unroll
+    for (int w = 0; w < 3; w++)
+        f.w[w] = (u32)popc64(p.pl[4 * w]) | ((u32)popc64(p.pl[4 * w + 1]) << 8) | ((u32)popc64(p.pl[4 * w + 2]) << 16) | ((u32)popc64(p.pl[4 * w + 3]) << 24);
+    const u64 center = 0x00003C3C3C3C0000ull, high_seventh = 0xFFull << 48, low_seventh = 0xFFull << 8;
+    const u64 os = p.pl[SERVANT], bs = p.pl[6 + SERVANT];
+    f.w[3] = (u32)popc64((os | p.pl[PONY]) & center) | ((u32)popc64((bs | p.pl[6 + PONY]) & center) << 8) |
+             ((u32)popc64(p.pl[COP] & high_seventh) << 16) | ((u32)popc64(p.pl[6 + COP] & low_seventh) << 24);
+    f.w[4] = (u32)popc64(os & high_seventh) | ((u32)popc64(os & (0xFFull << 40)) << 8) | ((u32)popc64(bs & low_seventh) << 16) |
+             ((u32)popc64(bs & (0xFFull << 16)) << 24);
+    u32 of = 0, bf = 0;
+#pragma unroll
+    for (int file = 0; file < 8; file++) {
+        of |= (u32)popc64(os & (FILE_A << file)) << (4 * file);
+        bf |= (u32)popc64(bs & (FILE_A << file)) << (4 * file);
+    }
+    f.w[5] = of;
+    f.w[6] = bf;
+    return f;
+}
+LL_HD float score_features(const Feat &f, u32 stm, u32 elig) {
+    const float values[6] = {1.0f, 3.2f, 3.3f, 5.1f, 8.8f, 20000.0f}; // mind.rs:36-48
+    float v = 0.0f;
+    v = fadd(v, fmul(0.5f, stm ? -1.0f : 1.0f)); // mind.rs:53
+#pragma unroll
+    for (int team = 0; team < 2; team++) { // mind.rs:55-68
+        const float orient = team ? -1.0f : 1.0f;
+#pragma unroll
+        for (int job = 0; job < 6; job++) {
+            const int j = 6 * team + job;
+            v = fadd(v, fmul((float)((f.w[j >> 2] >> (8 * (j & 3))) & 0xFFu), fmul(orient, values[job])));
+        }
+        const int j = 6 * team + SCHOLAR;
+        if (((f.w[j >> 2] >> (8 * (j & 3))) & 0xFFu) >= 2) v = fadd(v, fmul(orient, 0.5f));
+    }
+    const int oc = (int)(f.w[3] & 0xFFu), bc = (int)((f.w[3] >> 8) & 0xFFu); // mind.rs:70-81
+    v = fadd(v, fmul(0.1f, (float)(oc - bc)));
+    v = fadd(v, fmul(0.5f, (float)((f.w[3] >> 16) & 0xFFu))); // mind.rs:83-89
+    v = fadd(v, -fmul(0.5f, (float)(f.w[3] >> 24)));
+    { // mind.rs:91-111: only files with a second servant add anything; ascending, Orange before Blue
+        u32 files = (f.w[5] | f.w[6]) & 0xEEEEEEEEu; // a nibble >= 2 has one of its upper three bits set
+        while (files) {
+            const int sh = lsb32(files) & ~3;
+            files &= ~(0xFu << sh);
+            const int o = (int)((f.w[5] >> sh) & 0xFu), b = (int)((f.w[6] >> sh) & 0xFu);
+            if (o > 1) v = fadd(v, -fmul(0.5f, (float)(o - 1)));
+            if (b > 1) v = fadd(v, fmul(0.5f, (float)(b - 1)));
+        }
+    }
+    v = fadd(v, fmul(1.8f, (float)(f.w[4] & 0xFFu))); // mind.rs:113-131
+    v = fadd(v, fmul(0.6f, (float)((f.w[4] >> 8) & 0xFFu)));
+    v = fadd(v, -fmul(1.8f, (float)((f.w[4] >> 16) & 0xFFu)));
+    v = fadd(v, -fmul(0.6f, (float)(f.w[4] >> 24)));
+    if (elig & 0x3u) v = fadd(v, 0.1f); // mind.rs:133-140
+    if (elig & 0xCu) v = fadd(v, -0.1f);
+    return v;
+}
+LL_HD void feat_count(Feat &f, u32 plane, u32 delta) { // head count of `plane` += delta (two's complement for -1)
+    const u32 d = delta << (8 * (plane & 3u));
+    f.w[0] += (plane >> 2) == 0 ? d : 0u;
+    f.w[1] += (plane >> 2) == 1 ? d : 0u;
+    f.w[2] += (plane >> 2) == 2 ? d : 0u;
+}
+// Features, eligibility and hospitalized job of the child that commit `m` (mover T) makes of a parent with features
+// `f` and eligibility `elig`.  Planes: u64 operator()(int plane) gives the PARENT's planes (only the opposition's six
+// are always read; the mover's cop and figurehead planes only by a secret service) -- life.rs:569-676 through the
+// integers score() reads, see make_child_as for the same steps on the planes.
+template <int T, class Planes> LL_HD u32 child_features(Feat &f, u32 &elig, const Planes &planes, u32 m) {
+    constexpr int E = 1 - T;
+    const int from = mv_from(m), to = mv_to(m);
+    const u32 job = mv_job(m), asc = mv_asc(m);
+    const u64 center = 0x00003C3C3C3C0000ull;
+    const u64 tb = 1ull << to;
+    const u64 victim = (m & MV_PASSING_BY) ? (T == 0 ? tb >> 8 : tb << 8) : tb;
+    const int vs = (m & MV_PASSING_BY) ? (T == 0 ? to - 8 : to + 8) : to;
+    u32 hosp = JOB_NONE;
+#pragma unroll
+    for (int j = 5; j >= 0; j--)
+        if (planes(6 * E + j) & victim) hosp = (u32)j; // first in dramatis_personae order wins (life.rs:550-557)
+    // ---- eligibility (life.rs:577-605)
+    if (job == FIGUREHEAD) elig &= T == 0 ? ~0x3u : ~0xCu;
+    if (job == COP) {
+        const int file = from & 7;
+        if (file == 0) elig &= T == 0 ? ~0x1u : ~0x4u;
+        if (file == 7) elig &= T == 0 ? ~0x2u : ~0x8u;
+    }
+    // ---- head counts
+    if (hosp != JOB_NONE) feat_count(f, 6u * E + hosp, 0xFFFFFFFFu);
+    if (asc != ASC_NONE) { // the servant alights as its new job (life.rs:701-726)
+        feat_count(f, 6u * T + SERVANT, 0xFFFFFFFFu);
+        feat_count(f, 6u * T + asc, 1u);
+    }
+    if (m & MV_SERVICE) { // the transits happen whether or not somebody is there (life.rs:573-575, 610-629)
+        const int rank8 = to & 56;
+        const u64 corner = 1ull << (rank8 + ((to & 7) == 6 ? 7 : 0));
+        if (!(planes(6 * T + COP) & corner)) feat_count(f, 6u * T + COP, 1u);          // a cop out of thin air
+        if (!(planes(6 * T + FIGUREHEAD) & (1ull << from))) feat_count(f, 6u * T + FIGUREHEAD, 1u); // and a figurehead
+    }
+    // ---- servants and ponies in the centre (never on a first or last rank: ascensions need no special case)
+    const u32 in_from = (u32)(center >> from) & 1u, in_to = (u32)(center >> to) & 1u, in_vs = (u32)(center >> vs) & 1u;
+    if (job <= PONY) f.w[3] += (in_to - in_from) << (8 * T);
+    if (hosp <= PONY) f.w[3] -= in_vs << (8 * E);
+    // ---- cops on the opposition's servant rank
+    const int rf = from >> 3, rt = to >> 3, rv = vs >> 3;
+    const int cop_rank_t = T == 0 ? 6 : 1, cop_rank_e = E == 0 ? 6 : 1;
+    if (job == COP) f.w[3] += ((u32)(rt == cop_rank_t) - (u32)(rf == cop_rank_t)) << (16 + 8 * T);
+    if (hosp == COP) f.w[3] -= (u32)(rv == cop_rank_e) << (16 + 8 * E);
+    // ---- servants by rank and by file (an ascending servant leaves the board: rank 7 / 0 is not counted, its file is not re-entered)
+    const int near_t = T == 0 ? 6 : 1, far_t = T == 0 ? 5 : 2, near_e = E == 0 ? 6 : 1, far_e = E == 0 ? 5 : 2;
+    if (job == SERVANT) {
+        f.w[4] += (((u32)(rt == near_t) - (u32)(rf == near_t)) << (16 * T)) + (((u32)(rt == far_t) - (u32)(rf == far_t)) << (16 * T + 8));
+        f.w[5 + T] -= 1u << (4 * (from & 7));
+        if (asc == ASC_NONE) f.w[5 + T] += 1u << (4 * (to & 7));
+    }
+    if (hosp == SERVANT) {
+        f.w[4] -= ((u32)(rv == near_e) << (16 * E)) + ((u32)(rv == far_e) << (16 * E + 8));
+        f.w[5 + E] -= 1u << (4 * (vs & 7));
+    }
+    return hosp;
+}
+
 } // namespace ll

@@ -736,7 +736,8 @@ __global__ void __launch_bounds__(BLOCK, LL_EXPAND_MIN_BLOCKS) k_expand_coop(con
 // ---- horizon by records (mind.rs:279-301): children decoded from (piece, target mask) records ---------------
 // Phase 1 costs per PIECE, not per move: a parent thread writes at most REC_MAX records (ll_device.cuh) into shared
 // memory.  Phase 2 runs one CHILD per thread: binary-search the parent by the prefix sums, the record by its base,
-// select the t-th set bit, rebuild the child from the parent tile, score it, max-reduce per parent.
+// select the t-th set bit, derive the child's evaluation features from the parent's by the move's +-1 (the child's planes
+// are never built: child_features / score_features, bit-identical to score(make_child(...))), max-reduce per parent.
 constexpr int HP = 64; // parents per horizon tile
 struct HorizonShared {
     u64 tile_pl[12][HP];
@@ -746,7 +747,13 @@ struct HorizonShared {
     u32 ex[HP + 1]; // exclusive prefix of the parents' commit counts
     u32 n_rec[HP];
     int acc[HP];
+    u32 feat[7][HP]; // the parents' evaluation features (ll_device.cuh: Feat), transposed like the records
     u32 claim; // CHAIN: the tile this block pulled
+};
+struct TilePlanes { // the planes of one parent of the tile, read where child_features asks for them
+    const HorizonShared &sh;
+    u32 slot;
+    __device__ __forceinline__ u64 operator()(int j) const { return sh.tile_pl[j][slot]; }
 };
 struct SharedRecordOut {
     HorizonShared &sh;
@@ -789,6 +796,9 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
         cnt = out.n_moves;
         sh.n_rec[tid] = out.n_rec;
         sh.acc[tid] = float_key(-INFINITY);
+        const Feat f = features_of(p);
+#pragma unroll
+        for (int w = 0; w < 7; w++) sh.feat[w][tid] = f.w[w];
     }
     u32 total;
     const u32 ex = block_exclusive_scan(cnt, &total);
@@ -816,13 +826,18 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
                 else rhi = mid;
             }
             const u32 info = sh.rec_info[r][slot];
-            Pos par, c;
+            const u32 meta = sh.tile_meta[slot];
+            const u32 team = meta_stm(meta);
+            const u32 m = rec_move(sh.rec_mask[r][slot], info, j - rec_base(info), team);
+            Feat f;
 #pragma unroll
-            for (int q = 0; q < 12; q++) par.pl[q] = sh.tile_pl[q][slot];
-            par.meta = sh.tile_meta[slot];
-            make_child(par, rec_move(sh.rec_mask[r][slot], info, j - rec_base(info), meta_stm(par.meta)), c);
-            const float s = score(c);
-            v = float_key(meta_stm(c.meta) ? s : -s); // -(orientation(child) * score(child)), mind.rs:283, 331-336
+            for (int w = 0; w < 7; w++) f.w[w] = sh.feat[w][slot];
+            u32 elig = meta_elig(meta);
+            const TilePlanes planes{sh, slot};
+            if (team == 0) child_features<0>(f, elig, planes, m);
+            else child_features<1>(f, elig, planes, m);
+            const float s = score_features(f, team ^ 1u, elig);
+            v = float_key(team ? -s : s); // -(orientation(child) * score(child)), the child's initiative being the other team's (mind.rs:283, 331-336)
         }
         const unsigned peers = __match_any_sync(0xffffffffu, live ? slot : 0xFFFFFFFFu);
         const int best = __reduce_max_sync(peers, v);
@@ -833,12 +848,12 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
     if (mine) {
         float v = cnt ? key_float(sh.acc[tid]) : -INFINITY;
         if (cnt == 0 || (STUNS && a.stand_pat)) { // nothing to play: the node is itself a leaf (mind.rs:281-283, 295-299)
-            Pos p;
+            Feat f;
 #pragma unroll
-            for (int q = 0; q < 12; q++) p.pl[q] = sh.tile_pl[q][tid];
-            p.meta = sh.tile_meta[tid];
-            const float s = score(p);
-            v = fmaxf(v, meta_stm(p.meta) ? -s : s);
+            for (int w = 0; w < 7; w++) f.w[w] = sh.feat[w][tid];
+            const u32 meta = sh.tile_meta[tid];
+            const float s = score_features(f, meta_stm(meta), meta_elig(meta));
+            v = fmaxf(v, meta_stm(meta) ? -s : s);
         }
         a.values[i] = v;
         scored = cnt ? cnt : 1u;

@@ -3,6 +3,7 @@
 // box, over far more positions than a GPU call affords.  Nothing in the product links or loads this.
 #include "../../include/leafline_b200.h"
 #include "../../leafline_b200/csrc/ll_device.cuh"
+#include <cstring>
 
 using namespace ll;
 
@@ -157,3 +158,41 @@ extern "C" int hc_legal_generator_moves(const ll_world_t *w, uint32_t *moves, in
 }
 
 extern "C" uint32_t hc_canonical_key(uint32_t move) { return canonical_key(move); }
+
+// the horizon kernel's evaluation by features: score_features(features_of(p)) must be score(p), and for every reckless
+// commit score_features(child_features(...)) must be score(make_child(...)), bit for bit, with the same eligibility and
+// hospitalization.  Returns the number of disagreements (0 = fine); *checked = commits compared.
+struct PosPlanes {
+    const Pos &p;
+    u64 operator()(int j) const { return p.pl[j]; }
+};
+static u32 bits_of(float x) {
+    u32 b;
+    memcpy(&b, &x, sizeof b);
+    return b;
+}
+extern "C" int hc_feature_check(const ll_world_t *w, int *checked) {
+    const Pos p = to_pos(w);
+    int bad = 0;
+    const Feat f0 = features_of(p);
+    if (bits_of(score_features(f0, meta_stm(p.meta), meta_elig(p.meta))) != bits_of(score(p))) bad++;
+    static thread_local ListSink sink;
+    sink.n = 0;
+    lookahead<true>(p, sink);
+    *checked = (int)sink.n;
+    const PosPlanes planes{p};
+    for (u32 i = 0; i < sink.n && i < 1024; i++) {
+        const u32 m = sink.moves[i];
+        Pos c;
+        const u32 hosp = make_child(p, m, c);
+        Feat f = f0;
+        u32 elig = meta_elig(p.meta);
+        const u32 got_hosp = meta_stm(p.meta) == 0 ? child_features<0>(f, elig, planes, m) : child_features<1>(f, elig, planes, m);
+        const Feat want = features_of(c);
+        bool same = got_hosp == hosp && elig == meta_elig(c.meta);
+        for (int k = 0; k < 7; k++) same = same && f.w[k] == want.w[k];
+        if (bits_of(score_features(f, meta_stm(c.meta), elig)) != bits_of(score(c))) same = false;
+        if (!same) bad++;
+    }
+    return bad;
+}

@@ -35,6 +35,7 @@ def hc():
     lib.hc_generator_moves.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.hc_legal_record_moves.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     lib.hc_legal_generator_moves.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.hc_feature_check.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     lib.hc_canonical_key.argtypes = [C.c_uint32]
     lib.hc_canonical_key.restype = C.c_uint32
     lib.hc_init()
@@ -54,6 +55,10 @@ def check(hc, worlds):
             assert buf[:n].tobytes() == want.tobytes(), (O.preserve(w), nihil)
             assert hc.hc_count(ptr, nihil) == n, (O.preserve(w), nihil)
         assert np.float32(hc.hc_score(ptr)).tobytes() == np.float32(O.score(w)).tobytes()
+        # the horizon kernel's evaluation by features (+-1 updates of the parent's integers) equals score(make_child(...))
+        checked = C.c_int(0)
+        assert hc.hc_feature_check(ptr, C.byref(checked)) == 0, O.preserve(w)
+        assert checked.value == len(want)
         # the record form of the reckless commits (horizon kernel) holds exactly the generator's commits, in another order
         a, b, nrec = np.zeros(1024, dtype=np.uint32), np.zeros(1024, dtype=np.uint32), C.c_int(0)
         for stuns in (0, 1):
