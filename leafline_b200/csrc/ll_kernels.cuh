@@ -711,25 +711,20 @@ template <int T> __device__ __forceinline__ void coop_expand_parent(const Expand
 }
 __global__ void __launch_bounds__(BLOCK, LL_EXPAND_MIN_BLOCKS) k_expand_coop(const ExpandArgs a) {
     __shared__ CoopShared sh;
-    if (a.n_in && a.overflow && *(volatile u32 *)a.overflow) return; // see expand_tiles
-    const size_t n = a.n_in ? (size_t)*(volatile const u64 *)a.n_in : a.n;
+    u32 outgrown = 0; // see expand_tiles; the two loads are issued together (one round trip, not two)
+    size_t n = a.n;
+    if (a.n_in) {
+        outgrown = *(volatile u32 *)a.overflow;
+        n = (size_t)*(volatile const u64 *)a.n_in;
+    }
+    if (outgrown) return;
     const int warp = threadIdx.x >> 5;
-    for (;;) {
-        size_t tile = blockIdx.x;
-        if (a.tile_counter) {
-            if (threadIdx.x == 0) sh.claim = atomicAdd(a.tile_counter, 1u);
-            __syncthreads();
-            tile = (size_t)sh.claim;
-            __syncthreads(); // everybody has read the claim before the next round overwrites it
-        }
-        if (tile * COOP_WARPS >= n) break;
-        const size_t parent = tile * COOP_WARPS + warp;
-        if (parent < n) {
-            const Pos p = soa_load(a.in, parent); // every lane holds the whole parent
-            if (meta_stm(p.meta) == 0) coop_expand_parent<0>(a, p, parent, sh.descs[warp], sh.keys[warp]);
-            else coop_expand_parent<1>(a, p, parent, sh.descs[warp], sh.keys[warp]);
-        }
-        if (!a.tile_counter) break;
+    // parents are dealt to the warps by a grid-stride loop, not from the tile queue: these levels are a dependent chain
+    // per warp, and a claim is a ~1 us atomic round trip in front of it (and another one to learn that nothing is left)
+    for (size_t parent = (size_t)blockIdx.x * COOP_WARPS + warp; parent < n; parent += (size_t)gridDim.x * COOP_WARPS) {
+        const Pos p = soa_load(a.in, parent); // every lane holds the whole parent
+        if (meta_stm(p.meta) == 0) coop_expand_parent<0>(a, p, parent, sh.descs[warp], sh.keys[warp]);
+        else coop_expand_parent<1>(a, p, parent, sh.descs[warp], sh.keys[warp]);
     }
 }
 
