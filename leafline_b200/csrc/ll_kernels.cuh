@@ -530,7 +530,6 @@ constexpr int COOP_CAP = 256; // commits of one position (the reference's genera
 struct CoopShared {
     u32 descs[COOP_WARPS][COOP_CAP];
     u32 keys[COOP_WARPS][COOP_CAP];
-    u64 claim;
 };
 __device__ __forceinline__ u64 warp_or64(u64 v) {
     const u32 lo = __reduce_or_sync(0xffffffffu, (u32)v), hi = __reduce_or_sync(0xffffffffu, (u32)(v >> 32));
