@@ -733,8 +733,10 @@ __global__ void __launch_bounds__(BLOCK, LL_EXPAND_MIN_BLOCKS) k_expand_coop(con
 // select the t-th set bit, derive the child's evaluation features from the parent's by the move's +-1 (the child's planes
 // are never built: child_features / score_features, bit-identical to score(make_child(...))), max-reduce per parent.
 constexpr int HP = 64; // parents per horizon tile
+constexpr u32 OWNER_CAP = 3072; // children of a tile whose parent is looked up, not searched for (the space of six planes)
 struct HorizonShared {
-    u64 tile_pl[12][HP];
+    u64 tile_op[6][HP]; // the OPPOSITION's planes of every parent: all that the children's evaluation reads of the board
+    unsigned char owner[OWNER_CAP]; // child k of the tile -> its parent's slot
     u32 tile_meta[HP];
     u64 rec_mask[REC_MAX][HP]; // transposed: neighbouring parents write neighbouring words
     u32 rec_info[REC_MAX][HP];
@@ -744,10 +746,15 @@ struct HorizonShared {
     u32 feat[7][HP]; // the parents' evaluation features (ll_device.cuh: Feat), transposed like the records
     u32 claim; // CHAIN: the tile this block pulled
 };
-struct TilePlanes { // the planes of one parent of the tile, read where child_features asks for them
+template <int T> struct TilePlanes { // the planes of one parent (mover T), read where child_features asks for them
     const HorizonShared &sh;
     u32 slot;
-    __device__ __forceinline__ u64 operator()(int j) const { return sh.tile_pl[j][slot]; }
+    const Soa &in; // the mover's own planes are read by a secret service only: from global memory
+    size_t at;
+    __device__ __forceinline__ u64 operator()(int j) const {
+        if (j / 6 == 1 - T) return sh.tile_op[j % 6][slot];
+        return ldg(in.pl + (size_t)j * in.stride + at);
+    }
 };
 struct SharedRecordOut {
     HorizonShared &sh;
@@ -782,8 +789,9 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
     u32 cnt = 0;
     if (mine) {
         const Pos p = soa_load(a.in, i);
+        const bool blue = meta_stm(p.meta) != 0;
 #pragma unroll
-        for (int j = 0; j < 12; j++) sh.tile_pl[j][tid] = p.pl[j];
+        for (int j = 0; j < 6; j++) sh.tile_op[j][tid] = blue ? p.pl[j] : p.pl[6 + j];
         sh.tile_meta[tid] = p.meta;
         SharedRecordOut out{sh, tid};
         reckless_records<STUNS>(p, out);
@@ -798,6 +806,9 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
     const u32 ex = block_exclusive_scan(cnt, &total);
     if (tid < HP) sh.ex[tid] = ex;
     if (tid == 0) sh.ex[HP] = total;
+    const bool mapped = total <= OWNER_CAP; // block-uniform
+    if (mapped && mine)
+        for (u32 c = 0; c < cnt; c++) sh.owner[ex + c] = (unsigned char)tid;
     __syncthreads();
     for (u32 k0 = 0; k0 < total; k0 += BLOCK) {
         const u32 k = k0 + tid;
@@ -805,12 +816,16 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
         u32 slot = 0;
         int v = float_key(-INFINITY);
         if (live) {
-            u32 hi = HP;
+            if (mapped) {
+                slot = sh.owner[k];
+            } else {
+                u32 hi = HP;
 #pragma unroll
-            for (int step = 0; step < 6; step++) { // HP = 2^6: the last parent whose prefix is <= k
-                const u32 mid = (slot + hi) >> 1;
-                if (sh.ex[mid] <= k) slot = mid;
-                else hi = mid;
+                for (int step = 0; step < 6; step++) { // HP = 2^6: the last parent whose prefix is <= k
+                    const u32 mid = (slot + hi) >> 1;
+                    if (sh.ex[mid] <= k) slot = mid;
+                    else hi = mid;
+                }
             }
             const u32 j = k - sh.ex[slot];
             u32 r = 0, rhi = sh.n_rec[slot];
@@ -827,9 +842,8 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
 #pragma unroll
             for (int w = 0; w < 7; w++) f.w[w] = sh.feat[w][slot];
             u32 elig = meta_elig(meta);
-            const TilePlanes planes{sh, slot};
-            if (team == 0) child_features<0>(f, elig, planes, m);
-            else child_features<1>(f, elig, planes, m);
+            if (team == 0) child_features<0>(f, elig, TilePlanes<0>{sh, slot, a.in, tile * HP + slot}, m);
+            else child_features<1>(f, elig, TilePlanes<1>{sh, slot, a.in, tile * HP + slot}, m);
             const float s = score_features(f, team ^ 1u, elig);
             v = float_key(team ? -s : s); // -(orientation(child) * score(child)), the child's initiative being the other team's (mind.rs:283, 331-336)
         }
