@@ -91,6 +91,41 @@ def test_reckless_walk_positions(hc):
     check(hc, reckless_walk_worlds(seed=23, games=60, plies=70))
 
 
+def random_domain_worlds(seed, n):
+    """Arbitrary members of the ABI's domain W (include/leafline_b200.h): up to 16 figurines a team anywhere on the board --
+    servants on first and last ranks, a dozen princesses, no figurehead at all -- with a consistent eligibility."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        w = np.zeros((), dtype=O.WORLD_DTYPE)
+        squares = rng.permutation(64)
+        k = 0
+        for team in range(2):
+            count = int(rng.integers(1, 17))
+            has_figurehead = rng.random() < 0.85
+            for i in range(count):
+                sq = int(squares[k])
+                k += 1
+                job = 5 if (i == 0 and has_figurehead) else int(rng.choice([0, 0, 0, 1, 2, 3, 4]))
+                w["plane"][6 * team + job] |= np.uint64(1) << np.uint64(sq)
+        w["initiative"] = int(rng.integers(0, 2))
+        elig = 0
+        if int(w["plane"][5]) in (0, 1 << 4):
+            elig |= int(rng.integers(0, 4))
+        if int(w["plane"][11]) in (0, 1 << 60):
+            elig |= int(rng.integers(0, 4)) << 2
+        w["service_eligibility"] = elig
+        w["passing_by"] = 0xFF
+        out.append(w)
+    return np.array(out, dtype=O.WORLD_DTYPE)
+
+
+def test_arbitrary_positions_of_the_domain(hc):
+    # the ABI accepts every well-formed position, not only reachable ones: generator, counts, records, features and
+    # score must follow the reference's rules there too
+    check(hc, random_domain_worlds(20261019, 1500))
+
+
 def test_checks_pins_and_passing_by_corners(hc):
     fens = [
         "4k3/8/8/8/8/8/4r3/4K3 w - -",          # adjacent checker, capture by the figurehead only
