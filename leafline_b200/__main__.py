@@ -1,16 +1,16 @@
-"""`python -m leafline_b200` -- the reference binary's non-interactive entry points (src/main.rs:253-345):
+"""`python -m leafline_b200` -- the reference binary's entry points (src/main.rs:253-456):
 
     python -m leafline_b200 --correspond --depth 4 --from "<preservation runes>"     # what the web client shells out to
     python -m leafline_b200 --correspond --seconds 5 --from "<runes>"
     python -m leafline_b200 --uci
+    python -m leafline_b200 [--depth 4 | --seconds 5 | --depth-sequence 2,4] [--from "<runes>"]   # the console game
 
-`--déjà-vu-bound` and `--debug` are accepted and ignored (no transposition table on the device, no log file);
-the console game of the reference (main.rs:377-455) is not provided.
+`--déjà-vu-bound` and `--debug` are accepted and ignored (the search's memory bank sizes itself, there is no log file).
 """
 import argparse
 import sys
 
-from . import Engine, correspondence as co, uci
+from . import Engine, console, correspondence as co, uci
 
 
 def main(argv=None):
@@ -47,7 +47,13 @@ def main(argv=None):
     if args.uci:
         uci.dæmon()
         return 0
-    sys.exit("the console game is not part of the leaf layer: use --correspond or --uci")
+    try:
+        bound = console.bound_from_args(args.depth, args.quiet, args.depth_sequence, args.seconds)
+    except ValueError as error:
+        sys.exit(str(error))
+    with Engine(args.device) as engine:
+        console.game(engine, args.from_runes, bound, colour=sys.stdout.isatty())
+    return 0
 
 
 if __name__ == "__main__":
