@@ -1,12 +1,13 @@
-"""The console game (leafline_b200/console.py) against a stand-in engine made of the oracle: depiction, the movement
-runes of the reference's own tests, the prompt loop.  No GPU: the front end computes nothing itself."""
+"""The front ends either side of the leaf layer -- console game, UCI dæmon, `--correspond` wire format -- against a
+stand-in engine made of the oracle.  No GPU: the front ends compute nothing themselves (the same dialogues run against
+the real engine in tests/test_gpu_parity.py)."""
 import io
 
 import numpy as np
 import pytest
 
 import oracle as O
-from leafline_b200 import console, correspondence as co
+from leafline_b200 import console, correspondence as co, uci
 from leafline_b200._abi import FORECAST_DTYPE
 
 
@@ -18,6 +19,7 @@ class OracleEngine:
         return np.array([0, len(commits)], dtype=np.uint32), commits
 
     def in_critical_endangerment(self, worlds, teams):
+        teams = np.broadcast_to(np.asarray(teams), (len(worlds),))  # a scalar team applies to every world, like Engine's
         return np.array([bool(O.in_critical_endangerment(np.ascontiguousarray(w), int(t))) for w, t in zip(worlds, teams)])
 
     def deep_forecast(self, world, depth, nihilistically=False, quiet=None):
@@ -31,6 +33,14 @@ class OracleEngine:
             for field in ("team", "job", "whence", "whither"):
                 out[k]["variation"][0][field] = roots[i][field]
         return out
+
+    forecast = deep_forecast
+
+    def fixed_depth_sequence_kickoff(self, world, depths, nihilistically=False):
+        return self.deep_forecast(world, depths[-1], nihilistically)
+
+    def iterative_deepening_kickoff(self, world, seconds, nihilistically=False):
+        return self.deep_forecast(world, 2, nihilistically), 2
 
 
 def test_world_depiction():
@@ -99,3 +109,37 @@ def test_bounds_from_arguments():
     assert console.bound_from_args(None, None, None, 5).seconds == 5
     with pytest.raises(ValueError):
         console.bound_from_args(4, None, None, 5)
+
+
+def test_uci_dialogue():
+    # uci.rs:13-104
+    script = "uci\nisready\nucinewgame\nposition startpos moves e2e4\ngo depth 2\nposition startpos moves e2e4 x g1f3\ngo wtime 4000 btime 4000 movestogo 2\nquit\n"
+    out = io.StringIO()
+    uci.dæmon(engine=OracleEngine(), stdin=io.StringIO(script), stdout=out)
+    lines = out.getvalue().splitlines()
+    assert lines[0].startswith("id name Leafline") and lines[1].startswith("id author") and lines[2] == "uciok" and lines[3] == "readyok"
+    best = [l for l in lines if l.startswith("bestmove ")]
+    assert len(best) == 2 and all(len(b.split()[1]) == 4 for b in best)
+    assert any(l.startswith("info depth 2 score cp ") for l in lines)
+    # the reply to 1.e4 at depth 2 is the move exact negamax ranks first (stable order)
+    after_e4 = [c for c in O.lookahead(O.new_world()) if O.to_algebraic(c["whence"]) + O.to_algebraic(c["whither"]) == "e2e4"][0]["tree"]
+    roots, scores = O.kickoff(np.ascontiguousarray(after_e4), 2, False)
+    top = roots[int(np.argmax(scores))]
+    assert best[0] == "bestmove " + O.to_algebraic(top["whence"]) + O.to_algebraic(top["whither"])
+    with pytest.raises(ValueError):
+        uci.dæmon(engine=OracleEngine(), stdin=io.StringIO("frobnicate\n"), stdout=io.StringIO())
+
+
+def test_correspondence_cards():
+    import json
+
+    eng = OracleEngine()
+    # main.rs:461-469: the reference's own end-to-end test
+    assert co.correspondence(eng, "R6k/6pp/8/8/8/8/8/8 b - -", co.Depth(2, None)) == '{"the_triumphant":"Orange"}'
+    assert co.correspondence(eng, "7k/5Q2/6K1/8/8/8/8/8 b - -", co.Depth(1, None)) == '{"the_triumphant":null}'
+    card = co.correspondence(eng, "8/q1P1k/8/8/8/8/6PP/7K w - -", co.DepthSequence.from_depiction("1,2,3"))
+    d = json.loads(card)
+    assert list(d) == ["world", "patch", "hospitalization", "thinking_time", "depth", "counterreplies", "rosetta_stone"]
+    assert d["world"] == "2N5/q3k3/8/8/8/8/6PP/7K b - -" and d["depth"] == 3 and d["hospitalization"] is None and d["rosetta_stone"] == "c8"
+    assert d["patch"] == {"star": {"team": "Orange", "job_description": "Servant"}, "whence": {"rank": 6, "file": 2}, "whither": {"rank": 7, "file": 2}}
+    assert len(d["counterreplies"]) == len(O.lookahead(O.reconstruct(d["world"]))) and ", " not in card and "\": " not in card
