@@ -729,8 +729,8 @@ __global__ void __launch_bounds__(BLOCK, LL_EXPAND_MIN_BLOCKS) k_expand_coop(con
 
 // ---- horizon by records (mind.rs:279-301): children decoded from (piece, target mask) records ---------------
 // Phase 1 costs per PIECE, not per move: a parent thread writes at most REC_MAX records (ll_device.cuh) into shared
-// memory.  Phase 2 runs one CHILD per thread: binary-search the parent by the prefix sums, the record by its base,
-// select the t-th set bit, derive the child's evaluation features from the parent's by the move's +-1 (the child's planes
+// memory.  Phase 2 runs one CHILD per thread: look its parent up in the owner map the parents wrote after the scan (binary
+// search by the prefix sums only for a tile too big for the map), binary-search the record by its base, select the t-th set bit, derive the child's evaluation features from the parent's by the move's +-1 (the child's planes
 // are never built: child_features / score_features, bit-identical to score(make_child(...))), max-reduce per parent.
 constexpr int HP = 64; // parents per horizon tile
 constexpr u32 OWNER_CAP = 3072; // children of a tile whose parent is looked up, not searched for (the space of six planes)
