@@ -350,7 +350,21 @@ template <int T> LL_HD Legal legal_context(const Pos &p, u64 own, u64 opp) {
     const u64 e_diag = p.pl[6 * E + SCHOLAR] | p.pl[6 * E + PRINCESS], e_orth = p.pl[6 * E + COP] | p.pl[6 * E + PRINCESS];
     // danger map: the opposition's attacks with our figurehead lifted (it cannot hide behind itself).  Only the
     // figurehead's own steps consult it, so a boxed-in figurehead (siblings in a perft frontier share that) skips it.
-    if (figurehead_moves(ksq) & ~own) {
+    const u64 escapes = figurehead_moves(ksq) & ~own;
+#ifdef LL_SINGLE_ESCAPE_TEST
+    // EXPERIMENT, off by default (tests/test_hostcheck.py keeps it equal to the oracle): 44 % of the perft(6)
+    // tail's children have exactly ONE escape square -- ask whether that square is attacked (four lines from it, the
+    // figurehead lifted) instead of filling the whole map.  Not timed on the GPU yet.
+    if (escapes && !(escapes & (escapes - 1))) {
+        const int sq = lsb64(escapes);
+        const u64 occ_wo_k = occ ^ k;
+        const u64 attackers = (servant_attackers_of<E>(escapes) & p.pl[6 * E + SERVANT]) | (pony_moves(sq) & p.pl[6 * E + PONY]) |
+                              (figurehead_moves(sq) & p.pl[6 * E + FIGUREHEAD]) | (diag_attacks(sq, occ_wo_k) & e_diag) |
+                              (orth_attacks(sq, occ_wo_k) & e_orth);
+        L.danger = attackers ? escapes : 0ull;
+    } else
+#endif
+    if (escapes) {
         const u64 empty_wo_k = ~(occ ^ k);
         u64 danger = servant_attacks<E>(p.pl[6 * E + SERVANT]) | pony_attacks(p.pl[6 * E + PONY]);
         if (p.pl[6 * E + FIGUREHEAD]) danger |= figurehead_moves(lsb64(p.pl[6 * E + FIGUREHEAD]));

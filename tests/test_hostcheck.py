@@ -126,6 +126,25 @@ def test_arbitrary_positions_of_the_domain(hc):
     check(hc, random_domain_worlds(20261019, 1500))
 
 
+def test_single_escape_square_experiment_keeps_parity(hc):
+    # ll_device.cuh carries one experiment that is off in the product build (LL_SINGLE_ESCAPE_TEST: a figurehead with one
+    # escape square asks whether that square is attacked instead of filling the danger map).  Built here with the switch
+    # on, it must still equal the oracle everywhere, so that it can be timed on the GPU at any moment.
+    so = SO.replace("_hostcheck.so", "_hostcheck_single_escape.so")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-DLL_SINGLE_ESCAPE_TEST", "-o", so, SRC], check=True)
+    lib = C.CDLL(so)
+    for name in ("hc_count", "hc_lookahead", "hc_score", "hc_well_formed", "hc_record_moves", "hc_generator_moves", "hc_legal_record_moves",
+                 "hc_legal_generator_moves", "hc_feature_check", "hc_canonical_key"):
+        getattr(lib, name).argtypes = getattr(hc, name).argtypes
+        getattr(lib, name).restype = getattr(hc, name).restype
+    lib.hc_init()
+    check(lib, named_worlds())
+    check(lib, O.playout_batch(0x1EAF11E, 5000, 1200))
+    check(lib, reckless_walk_worlds(seed=41, games=25, plies=60))
+    check(lib, random_domain_worlds(7, 600))
+
+
 def test_checks_pins_and_passing_by_corners(hc):
     fens = [
         "4k3/8/8/8/8/8/4r3/4K3 w - -",          # adjacent checker, capture by the figurehead only
