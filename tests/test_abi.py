@@ -35,6 +35,31 @@ def test_header_and_binding_agree(lib):
         assert hasattr(lib, name), f"{name} is declared in include/leafline_b200.h but not exported"
 
 
+def c_parameter_counts():
+    text = open(os.path.join(ROOT, "include", "leafline_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return {name: (0 if args.strip() in ("", "void") else args.count(",") + 1)
+            for name, args in re.findall(r"\b(ll_[a-z_0-9]+)\s*\(([^)]*)\)\s*;", text)}
+
+
+def test_rust_shim_declares_the_header(lib):
+    # host/rust/b200.rs is shipped as source (no Rust toolchain here): every extern it declares must be an entry point
+    # of the header with the same number of parameters, and the repr(C) structs must have the header's sizes
+    text = open(os.path.join(ROOT, "host", "rust", "b200.rs")).read()
+    block = text[text.index('extern "C" {'):]
+    block = block[:block.index("\n}\n")]
+    declared = re.findall(r"fn (ll_[a-z_0-9]+)\(([^)]*)\)", block)
+    counts = c_parameter_counts()
+    assert len(declared) >= 12
+    for name, args in declared:
+        assert name in counts, f"{name} is not in include/leafline_b200.h"
+        n = 0 if not args.strip() else args.count(",") + 1
+        assert n == counts[name], (name, n, counts[name])
+        assert hasattr(lib, name)
+    assert "plane: [u64; 12]" in text and "pad: [u8; 5]" in text and "variation: [LlPatch; LL_MAX_VARIATION]" in text
+    assert "const LL_MAX_VARIATION: usize = 16;" in text
+
+
 def test_struct_sizes_match_header():
     from leafline_b200 import _abi
 
