@@ -206,6 +206,9 @@ int ll_debug_force_synced(ll_ctx *ctx, int on);
  * made, kept iff the mover's figurehead is not endangered afterwards, src/life.rs:692-699) must agree.
  * result4 = { disagreeing positions, first disagreeing index (~0 if none), legal commits, reckless commits }. */
 int ll_debug_selfcheck_soa(ll_ctx *ctx, const ll_soa_t *soa, uint64_t *result4);
+/* testing aid: the two generated movement tables as they are resident on the device (64 entries each), to be compared
+ * with the output of the reference's generator (furniture/tablemaker.py:41-62; tests/golden/reference_tables.json). */
+int ll_debug_tables(ll_ctx *ctx, uint64_t *pony64, uint64_t *figurehead64);
 /* measurement utility for the integer roofline: sustained thread-level integer instructions per second
  * of a dependency-free stream; kind 0 = LOP3 only (ALU pipe), 1 = LOP3 + IMAD (ALU + FMA pipes) */
 int ll_measure_int_peak(ll_ctx *ctx, int kind, double *thread_ops_per_sec);

@@ -135,6 +135,12 @@ class Engine:
         _abi.check(self._lib.ll_debug_selfcheck_soa(self._ctx, C.byref(soa), _ptr(out)))
         return int(out[0]), (None if out[1] == np.uint64(0xFFFFFFFFFFFFFFFF) else int(out[1])), int(out[2]), int(out[3])
 
+    def debug_tables(self):
+        """(pony, figurehead) movement tables as resident on the device, 64 u64 each"""
+        pony, fig = np.zeros(64, dtype=np.uint64), np.zeros(64, dtype=np.uint64)
+        _abi.check(self._lib.ll_debug_tables(self._ctx, _ptr(pony), _ptr(fig)))
+        return pony, fig
+
     def measure_int_peak(self, kind=0):
         """Sustained thread-level integer instructions/s (0: LOP3 stream, 1: LOP3+IMAD) for the integer roofline."""
         v = C.c_double(0)

@@ -9,6 +9,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <tuple>
 #include <type_traits>
@@ -44,6 +46,16 @@ static int fail(int code, const char *fmt, ...) {
         if (rc_ != LL_OK) return rc_; \
     } while (0)
 
+// Nothing unwinds across the C boundary (include/leafline_b200.h): every entry point that can allocate on the host runs
+// its body inside this guard.
+#define LL_ABI_BEGIN try {
+#define LL_ABI_END                                                                                   \
+    }                                                                                                \
+    catch (const std::bad_alloc &) { return fail(LL_ERR_OOM, "host allocation failed"); }            \
+    catch (const std::length_error &e) { return fail(LL_ERR_INVALID_ARG, "%s", e.what()); }          \
+    catch (const std::exception &e) { return fail(LL_ERR_CUDA, "unexpected exception: %s", e.what()); } \
+    catch (...) { return fail(LL_ERR_CUDA, "unexpected exception"); }
+
 namespace {
 
 struct DevBuf { // grow-only device allocation
@@ -55,6 +67,7 @@ struct Frontier { // one BFS level resident in HBM
     DevBuf planes, meta, root, counts, block_sums, block_base, cmeta, values, child_first;
     size_t cap = 0; // positions
     size_t n = 0;
+    bool borrowed = false; // planes / meta belong to the caller (ll_horizon_soa): never grown or freed here
     Soa soa() const { return Soa{(u64 *)planes.ptr, (u32 *)meta.ptr, cap}; }
 };
 
@@ -88,46 +101,81 @@ struct ll_ctx {
 
 namespace {
 
+size_t nblocks(size_t n, size_t per = BLOCK) { return (n + per - 1) / per; }
+
+// Grow-only: on failure the buffer is EMPTY (ptr == nullptr, cap == 0), never stale.  The new block is allocated before the
+// old one is released when both fit; a level that needs most of HBM falls back to release-then-allocate.
 int ensure(ll_ctx *ctx, DevBuf &b, size_t bytes) {
     if (bytes <= b.cap) return LL_OK;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    if (b.ptr) CUDA_TRY(cudaFree(b.ptr));
-    b.ptr = nullptr;
-    b.cap = 0;
+    if (ctx->chain_exec) { // the captured perft chain holds the old addresses
+        cudaGraphExecDestroy(ctx->chain_exec);
+        ctx->chain_exec = nullptr;
+    }
+    void *fresh = nullptr;
     size_t want = bytes + bytes / 4 + 256;
-    cudaError_t e = cudaMalloc(&b.ptr, want);
+    cudaError_t e = cudaMalloc(&fresh, want);
     if (e != cudaSuccess) {
         cudaGetLastError();
-        want = bytes;
-        e = cudaMalloc(&b.ptr, want);
+        if (b.ptr) cudaFree(b.ptr);
+        b.ptr = nullptr;
+        b.cap = 0;
+        e = cudaMalloc(&fresh, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            want = bytes;
+            e = cudaMalloc(&fresh, want);
+        }
     }
     if (e != cudaSuccess) {
         cudaGetLastError();
         return fail(LL_ERR_OOM, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
     }
+    if (b.ptr) cudaFree(b.ptr);
+    b.ptr = fresh;
     b.cap = want;
     return LL_OK;
 }
 
-size_t nblocks(size_t n, size_t per = BLOCK) { return (n + per - 1) / per; }
+void drop_buf(DevBuf &b) {
+    if (b.ptr) cudaFree(b.ptr);
+    b.ptr = nullptr;
+    b.cap = 0;
+}
+// a level whose growth failed half-way is emptied entirely: the next call re-reserves it from scratch (LL_ERR_OOM is
+// recoverable: the context stays usable)
+void drop_level(Frontier &f) {
+    drop_buf(f.planes); drop_buf(f.meta); drop_buf(f.root); drop_buf(f.counts); drop_buf(f.block_sums); drop_buf(f.block_base);
+    drop_buf(f.cmeta); drop_buf(f.values); drop_buf(f.child_first);
+    f.cap = 0;
+    f.n = 0;
+}
 
 // make level `l` able to hold `n` positions (contents are NOT preserved when it grows)
 int reserve_level(ll_ctx *ctx, size_t l, size_t n, bool with_cmeta, bool with_values) {
     if (ctx->levels.size() <= l) ctx->levels.resize(l + 1);
     Frontier &f = ctx->levels[l];
-    if (n > f.cap) {
-        size_t cap = ((n + n / 8 + 63) / 64) * 64; // even stride, 16-byte aligned planes
-        LL_TRY(ensure(ctx, f.planes, cap * 12 * sizeof(u64)));
-        LL_TRY(ensure(ctx, f.meta, cap * sizeof(u32)));
-        LL_TRY(ensure(ctx, f.root, cap * sizeof(u32)));
-        LL_TRY(ensure(ctx, f.counts, cap * sizeof(u32)));
-        LL_TRY(ensure(ctx, f.block_sums, (nblocks(cap) + 1) * sizeof(u32)));
-        LL_TRY(ensure(ctx, f.block_base, (nblocks(cap) + 1) * sizeof(u64)));
+    if (f.borrowed) { // level 0 aliasing caller-owned planes (ll_horizon_soa): never reallocated
+        if (n > f.cap) return fail(LL_ERR_INVALID_ARG, "%zu positions do not fit the caller's stride %zu", n, f.cap);
+    } else if (n > f.cap) {
+        const size_t cap = ((n + n / 8 + 63) / 64) * 64; // even stride, 16-byte aligned planes
+        int rc = ensure(ctx, f.planes, cap * 12 * sizeof(u64));
+        if (rc == LL_OK) rc = ensure(ctx, f.meta, cap * sizeof(u32));
+        if (rc == LL_OK) rc = ensure(ctx, f.root, cap * sizeof(u32));
+        if (rc == LL_OK) rc = ensure(ctx, f.counts, cap * sizeof(u32));
+        if (rc == LL_OK) rc = ensure(ctx, f.block_sums, (nblocks(cap) + 1) * sizeof(u32));
+        if (rc == LL_OK) rc = ensure(ctx, f.block_base, (nblocks(cap) + 1) * sizeof(u64));
+        if (rc != LL_OK) {
+            drop_level(f);
+            return rc;
+        }
         f.cap = cap;
     }
-    if (with_cmeta) LL_TRY(ensure(ctx, f.cmeta, f.cap * sizeof(u32)));
-    if (with_values) LL_TRY(ensure(ctx, f.values, f.cap * sizeof(float)));
-    return LL_OK;
+    int rc = LL_OK;
+    if (with_cmeta) rc = ensure(ctx, f.cmeta, f.cap * sizeof(u32));
+    if (rc == LL_OK && with_values) rc = ensure(ctx, f.values, f.cap * sizeof(float));
+    if (rc != LL_OK && !f.borrowed) drop_level(f);
+    return rc;
 }
 
 struct Timed { // scope guard: counts the launch and, when timing is on, brackets it with CUDA events on the launching stream
@@ -271,6 +319,14 @@ int check_ctx(ll_ctx *ctx) {
     CUDA_TRY(cudaSetDevice(ctx->device));
     return LL_OK;
 }
+// a caller-owned ll_soa_t: device pointers present, n inside the stride, planes 16-byte aligned
+int check_soa(const ll_soa_t *soa) {
+    if (!soa) return fail(LL_ERR_INVALID_ARG, "null soa");
+    if (soa->n > soa->stride) return fail(LL_ERR_INVALID_ARG, "soa->n %zu exceeds its stride %zu", soa->n, soa->stride);
+    if (soa->n && (!soa->planes || !soa->meta)) return fail(LL_ERR_INVALID_ARG, "null planes / meta");
+    if (soa->stride & 1) return fail(LL_ERR_INVALID_ARG, "stride must be even");
+    return LL_OK;
+}
 
 // horizon values of level `l` nodes (n of them) into levels[l].values; uses levels l+1.. as scratch.
 // The node at level l has `plies` plies of full-width reckless search left; with quiet_ext > 0 the search
@@ -411,23 +467,10 @@ int horizon_chain(ll_ctx *ctx, size_t l0, int plies, bool *launched) {
 
 extern "C" const char *ll_last_error(void) { return g_error; }
 
-extern "C" int ll_init(int device, ll_ctx **out) {
-    if (!out) return fail(LL_ERR_INVALID_ARG, "null out pointer");
-    *out = nullptr;
-    int count = 0;
-    cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count == 0) {
-        cudaGetLastError();
-        return fail(LL_ERR_NO_DEVICE, "no CUDA device available (%s); leafline_b200 has no CPU fallback",
-                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
-    }
-    if (device < 0 || device >= count) return fail(LL_ERR_INVALID_ARG, "device %d out of range (0..%d)", device, count - 1);
-    CUDA_TRY(cudaSetDevice(device));
-    ll_ctx *ctx = new ll_ctx();
-    ctx->device = device;
+static int init_ctx(ll_ctx *ctx) {
     ctx->levels.reserve(64); // references to levels stay valid while deeper levels are added
     cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    CUDA_TRY(cudaGetDeviceProperties(&prop, ctx->device));
     ctx->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -457,28 +500,47 @@ extern "C" int ll_init(int device, ll_ctx **out) {
         }
     CUDA_TRY(cudaMemcpyToSymbol(d_pony_table, pony, sizeof pony));
     CUDA_TRY(cudaMemcpyToSymbol(d_figurehead_table, fig, sizeof fig));
-    int rc = ensure(ctx, ctx->scalars, SC_SLOTS * sizeof(u64));
-    if (rc != LL_OK) {
-        delete ctx;
+    LL_TRY(ensure(ctx, ctx->scalars, SC_SLOTS * sizeof(u64)));
+    return LL_OK;
+}
+
+extern "C" int ll_init(int device, ll_ctx **out) {
+    LL_ABI_BEGIN
+    if (!out) return fail(LL_ERR_INVALID_ARG, "null out pointer");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(LL_ERR_NO_DEVICE, "no CUDA device available (%s); leafline_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= count) return fail(LL_ERR_INVALID_ARG, "device %d out of range (0..%d)", device, count - 1);
+    CUDA_TRY(cudaSetDevice(device));
+    ll_ctx *ctx = new ll_ctx();
+    ctx->device = device;
+    const int rc = init_ctx(ctx);
+    if (rc != LL_OK) { // release whatever was created (streams, events, buffers); g_error keeps the cause
+        char keep[sizeof g_error];
+        memcpy(keep, g_error, sizeof keep);
+        ll_shutdown(ctx);
+        memcpy(g_error, keep, sizeof keep);
         return rc;
     }
     *out = ctx;
     return LL_OK;
+    LL_ABI_END
 }
 
 extern "C" int ll_shutdown(ll_ctx *ctx) {
+    LL_ABI_BEGIN
     if (!ctx) return LL_OK;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    auto drop = [](DevBuf &b) {
-        if (b.ptr) cudaFree(b.ptr);
-        b.ptr = nullptr;
-        b.cap = 0;
-    };
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    auto drop = [](DevBuf &b) { drop_buf(b); };
     drop(ctx->ext.counts); drop(ctx->ext.block_sums); drop(ctx->ext.block_base); drop(ctx->ext.values);
-    for (Frontier &f : ctx->levels) {
-        drop(f.planes); drop(f.meta); drop(f.root); drop(f.counts); drop(f.block_sums); drop(f.block_base); drop(f.cmeta); drop(f.values); drop(f.child_first);
-    }
+    for (Frontier &f : ctx->levels)
+        if (!f.borrowed) drop_level(f);
     drop(ctx->aos_in); drop(ctx->aos_out); drop(ctx->scalars); drop(ctx->scores); drop(ctx->teams); drop(ctx->flags);
     for (TimedLaunch &t : ctx->timed) {
         cudaEventDestroy(t.start);
@@ -494,29 +556,37 @@ extern "C" int ll_shutdown(ll_ctx *ctx) {
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return LL_OK;
+    LL_ABI_END
 }
 
 extern "C" int ll_set_stream(ll_ctx *ctx, void *cuda_stream) {
+    LL_ABI_BEGIN
     LL_TRY(check_ctx(ctx));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     return LL_OK;
+    LL_ABI_END
 }
 
 extern "C" int ll_synchronize(ll_ctx *ctx) {
+    LL_ABI_BEGIN
     LL_TRY(check_ctx(ctx));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return LL_OK;
+    LL_ABI_END
 }
 
 extern "C" int ll_device_sm_count(ll_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 
 extern "C" int ll_timing_enable(ll_ctx *ctx, int on) {
+    LL_ABI_BEGIN
     LL_TRY(check_ctx(ctx));
     ctx->timing = on != 0;
     return LL_OK;
+    LL_ABI_END
 }
 extern "C" int ll_timing_reset(ll_ctx *ctx) {
+    LL_ABI_BEGIN
     LL_TRY(check_ctx(ctx));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     for (TimedLaunch &t : ctx->timed) {
@@ -525,8 +595,10 @@ extern "C" int ll_timing_reset(ll_ctx *ctx) {
     }
     ctx->timed.clear();
     return LL_OK;
+    LL_ABI_END
 }
 extern "C" int ll_timing_query(ll_ctx *ctx, const char *kernel, double *ms, uint64_t *launches) {
+    LL_ABI_BEGIN
     LL_TRY(check_ctx(ctx));
     if (!kernel) return fail(LL_ERR_INVALID_ARG, "null kernel name");
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -542,18 +614,23 @@ extern "C" int ll_timing_query(ll_ctx *ctx, const char *kernel, double *ms, uint
     if (ms) *ms = total;
     if (launches) *launches = count;
     return LL_OK;
+    LL_ABI_END
 }
 extern "C" uint64_t ll_launch_count(ll_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int ll_debug_force_synced(ll_ctx *ctx, int on) {
+    LL_ABI_BEGIN
     LL_TRY(check_ctx(ctx));
     ctx->force_synced = on == 1;
     ctx->no_graph = on == 2;
     return LL_OK;
+    LL_ABI_END
 }
 
 extern "C" int ll_debug_selfcheck_soa(ll_ctx *ctx, const ll_soa_t *soa, uint64_t *result4) {
+    LL_ABI_BEGIN
     LL_TRY(check_ctx(ctx));
     if (!soa || !result4) return fail(LL_ERR_INVALID_ARG, "null argument");
+    LL_TRY(check_soa(soa));
     u64 *sc = (u64 *)ctx->scalars.ptr + SC_SPARE;
     const u64 init[4] = {0, ~0ull, 0, 0};
     CUDA_TRY(cudaMemcpyAsync(sc, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
@@ -565,9 +642,20 @@ extern "C" int ll_debug_selfcheck_soa(ll_ctx *ctx, const ll_soa_t *soa, uint64_t
     CUDA_TRY(cudaMemcpyAsync(result4, sc, 4 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return LL_OK;
+    LL_ABI_END
+}
+
+extern "C" int ll_debug_tables(ll_ctx *ctx, uint64_t *pony64, uint64_t *figurehead64) {
+    LL_TRY(check_ctx(ctx));
+    if (!pony64 || !figurehead64) return fail(LL_ERR_INVALID_ARG, "null argument");
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaMemcpyFromSymbol(pony64, d_pony_table, 64 * sizeof(u64)));
+    CUDA_TRY(cudaMemcpyFromSymbol(figurehead64, d_figurehead_table, 64 * sizeof(u64)));
+    return LL_OK;
 }
 
 extern "C" int ll_measure_int_peak(ll_ctx *ctx, int kind, double *thread_ops_per_sec) {
+    LL_ABI_BEGIN
     LL_TRY(check_ctx(ctx));
     if (!thread_ops_per_sec || kind < 0 || kind > 1) return fail(LL_ERR_INVALID_ARG, "bad argument");
     const int iters = 4096, blocks = ctx->sm_count * 8, threads = 256;
@@ -591,6 +679,7 @@ extern "C" int ll_measure_int_peak(ll_ctx *ctx, int kind, double *thread_ops_per
     cudaEventDestroy(b);
     *thread_ops_per_sec = (double)blocks * threads * iters * 16.0 / (best * 1e-3);
     return LL_OK;
+    LL_ABI_END
 }
 
 // ---- scoring -----------------------------------------------------------------------------------------
@@ -603,6 +692,7 @@ static int launch_score(ll_ctx *ctx, const Soa &soa, size_t n, float *d_out) {
 }
 
 extern "C" int ll_score_batch(ll_ctx *ctx, const ll_world_t *worlds, size_t n, float *scores) {
+    LL_ABI_BEGIN
     LL_TRY(check_ctx(ctx));
     if (n && (!worlds || !scores)) return fail(LL_ERR_INVALID_ARG, "null buffer");
     if (!n) return LL_OK;
@@ -642,13 +732,16 @@ extern "C" int ll_score_batch(ll_ctx *ctx, const ll_world_t *worlds, size_t n, f
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
     return LL_OK;
+    LL_ABI_END
 }
 
 extern "C" int ll_score_soa(ll_ctx *ctx, const ll_soa_t *soa, float *d_scores) {
+    LL_ABI_BEGIN
     LL_TRY(check_ctx(ctx));
     if (!soa || !d_scores) return fail(LL_ERR_INVALID_ARG, "null argument");
-    if (soa->stride & 1) return fail(LL_ERR_INVALID_ARG, "stride must be even");
+    LL_TRY(check_soa(soa));
     return launch_score(ctx, Soa{(u64 *)soa->planes, soa->meta, soa->stride}, soa->n, d_scores);
+    LL_ABI_END
 }
 
 // ---- movegen -----------------------------------------------------------------------------------------
@@ -657,6 +750,7 @@ static bool host_well_formed(const ll_world_t *w);
 
 extern "C" int ll_lookahead_batch(ll_ctx *ctx, const ll_world_t *worlds, size_t n, int nihilistically, uint32_t *offsets,
                                   ll_commit_t *commits, size_t commits_cap) {
+    LL_ABI_BEGIN
     LL_TRY(check_ctx(ctx));
     if (!offsets || (n && !worlds)) return fail(LL_ERR_INVALID_ARG, "null buffer");
     offsets[0] = 0;
@@ -700,9 +794,11 @@ extern "C" int ll_lookahead_batch(ll_ctx *ctx, const ll_world_t *worlds, size_t 
     }
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return LL_OK;
+    LL_ABI_END
 }
 
 extern "C" int ll_in_critical_endangerment_batch(ll_ctx *ctx, const ll_world_t *worlds, const uint8_t *teams, size_t n, uint8_t *endangered) {
+    LL_ABI_BEGIN
     LL_TRY(check_ctx(ctx));
     if (n && (!worlds || !teams || !endangered)) return fail(LL_ERR_INVALID_ARG, "null buffer");
     if (!n) return LL_OK;
@@ -721,6 +817,7 @@ extern "C" int ll_in_critical_endangerment_batch(ll_ctx *ctx, const ll_world_t *
     CUDA_TRY(cudaMemcpyAsync(endangered, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return LL_OK;
+    LL_ABI_END
 }
 
 // ---- perft -------------------------------------------------------------------------------------------
@@ -764,8 +861,10 @@ static int perft_chain_launch(ll_ctx *ctx, int depth, int shard_rank, int shard_
     const int shard_ply = tail_ply < 2 ? tail_ply : 2;
     const size_t need = (size_t)tail_ply + (shard_world > 1 ? 2 : 1);
     if (ctx->levels.size() < need) return LL_OK;
-    for (size_t l = 0; l < need; l++)
-        if (!ctx->levels[l].cap) return LL_OK;
+    for (size_t l = 0; l < need; l++) {
+        const Frontier &f = ctx->levels[l];
+        if (!f.cap || !f.planes.ptr || !f.meta.ptr || !f.root.ptr) return LL_OK; // not sized yet (or emptied by a failed growth)
+    }
     u64 *sc = (u64 *)ctx->scalars.ptr;
     u64 *N = sc + SC_N;
     u32 *tileq = (u32 *)(sc + SC_TILEQ);
@@ -1001,6 +1100,7 @@ static int perft_synced(ll_ctx *ctx, int depth, int shard_rank, int shard_world,
 
 extern "C" int ll_perft(ll_ctx *ctx, const ll_world_t *root, int depth, int shard_rank, int shard_world, uint64_t *leaves,
                         uint64_t *per_root, uint32_t root_cap, uint32_t *n_roots) {
+    LL_ABI_BEGIN
     LL_TRY(check_ctx(ctx));
     if (!root || !leaves) return fail(LL_ERR_INVALID_ARG, "null argument");
     if (depth < 0 || depth > 32) return fail(LL_ERR_INVALID_ARG, "depth %d out of range", depth);
@@ -1022,9 +1122,11 @@ extern "C" int ll_perft(ll_ctx *ctx, const ll_world_t *root, int depth, int shar
         LL_TRY(upload_root(ctx, root)); // level 0 again: a failed chain may have left the scratch levels half-written
     }
     return perft_synced(ctx, depth, shard_rank, shard_world, leaves, per_root, root_cap, n_roots);
+    LL_ABI_END
 }
 
 extern "C" int ll_perft_device(ll_ctx *ctx, const ll_world_t *root, int depth, int shard_rank, int shard_world, uint64_t *d_out) {
+    LL_ABI_BEGIN
     LL_TRY(check_ctx(ctx));
     if (!root || !d_out) return fail(LL_ERR_INVALID_ARG, "null argument");
     if (depth < 3 || depth > 32) return fail(LL_ERR_INVALID_ARG, "depth %d out of range (3..32)", depth);
@@ -1040,11 +1142,13 @@ extern "C" int ll_perft_device(ll_ctx *ctx, const ll_world_t *root, int depth, i
         k_pack_perft_result<<<1, 1024, 0, ctx->stream>>>(sc + SC_LEAVES, sc + SC_N + 1, (const u32 *)(sc + SC_OVERFLOW), sc + SC_PER_ROOT, (u64 *)d_out);
     }
     return check_launch("k_pack_perft_result");
+    LL_ABI_END
 }
 
 // ---- horizon / kickoff -------------------------------------------------------------------------------
 
 extern "C" int ll_horizon_batch(ll_ctx *ctx, const ll_world_t *frontier, size_t n, int plies, int quiet_extension, float *values) {
+    LL_ABI_BEGIN
     LL_TRY(check_ctx(ctx));
     if (n && (!frontier || !values)) return fail(LL_ERR_INVALID_ARG, "null buffer");
     if (plies < 0 || plies > 8) return fail(LL_ERR_INVALID_ARG, "plies %d out of range", plies);
@@ -1075,15 +1179,17 @@ extern "C" int ll_horizon_batch(ll_ctx *ctx, const ll_world_t *frontier, size_t 
     CUDA_TRY(cudaMemcpyAsync(values, ctx->levels[0].values.ptr, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return LL_OK;
+    LL_ABI_END
 }
 
 extern "C" int ll_horizon_soa(ll_ctx *ctx, const ll_soa_t *soa, int plies, int quiet_extension, float *d_values, uint64_t *leaves_scored) {
+    LL_ABI_BEGIN
     LL_TRY(check_ctx(ctx));
     if (!soa || !d_values) return fail(LL_ERR_INVALID_ARG, "null argument");
     if (plies < 0 || plies > 8) return fail(LL_ERR_INVALID_ARG, "plies %d out of range", plies);
     if (leaves_scored) *leaves_scored = 0;
     if (!soa->n) return LL_OK;
-    if (soa->stride & 1) return fail(LL_ERR_INVALID_ARG, "stride must be even");
+    LL_TRY(check_soa(soa));
     LL_TRY(validate_level(ctx, Soa{(u64 *)soa->planes, soa->meta, soa->stride}, soa->n));
     // level 0 aliases the caller's planes for the duration of the call; its scratch arrays persist in ctx->ext
     if (ctx->levels.empty()) ctx->levels.resize(1);
@@ -1100,6 +1206,7 @@ extern "C" int ll_horizon_soa(ll_ctx *ctx, const ll_soa_t *soa, int plies, int q
     view.meta.cap = soa->stride * sizeof(u32);
     view.cap = soa->stride;
     view.n = soa->n;
+    view.borrowed = true; // reserve_level never reallocates (or frees) the caller's planes
     ctx->levels[0] = view;
     int rc = horizon_levels(ctx, 0, plies, quiet_extension, leaves_scored);
     if (rc == LL_OK && cudaMemcpyAsync(d_values, ctx->levels[0].values.ptr, soa->n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess)
@@ -1107,6 +1214,7 @@ extern "C" int ll_horizon_soa(ll_ctx *ctx, const ll_soa_t *soa, int plies, int q
     if (rc == LL_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(LL_ERR_CUDA, "synchronize failed");
     ctx->levels[0] = saved;
     return rc;
+    LL_ABI_END
 }
 
 // variations (nullable): [root_cap][PV_MAX + 1] u32 -- length, then the packed commits of the line BELOW each root move
@@ -1212,7 +1320,9 @@ static int kickoff_core(ll_ctx *ctx, const ll_world_t *root, int depth, int quie
 
 extern "C" int ll_kickoff(ll_ctx *ctx, const ll_world_t *root, int depth, int quiet_extension, int nihilistically, int shard_rank, int shard_world,
                           ll_commit_t *roots, float *scores, uint32_t root_cap, uint32_t *n_roots, uint64_t *leaves_scored) {
+    LL_ABI_BEGIN
     return kickoff_core(ctx, root, depth, quiet_extension, nihilistically, shard_rank, shard_world, roots, scores, root_cap, n_roots, leaves_scored, nullptr);
+    LL_ABI_END
 }
 
 // ---- the kickoff family as the reference's callers see it (mind.rs:441-490): forecasts sorted by score ------
@@ -1226,6 +1336,7 @@ static void unpack_patch(u32 m, ll_patch_t *p) {
 
 extern "C" int ll_forecast(ll_ctx *ctx, const ll_world_t *root, int depth, int quiet_extension, int nihilistically, ll_forecast_t *forecasts,
                            uint32_t cap, uint32_t *n_forecasts, uint64_t *leaves_scored) {
+    LL_ABI_BEGIN
     if (!forecasts || !n_forecasts) return fail(LL_ERR_INVALID_ARG, "null argument");
     static_assert(PV_MAX == LL_MAX_VARIATION, "variation capacity");
     std::vector<ll_commit_t> roots(1024);
@@ -1251,6 +1362,7 @@ extern "C" int ll_forecast(ll_ctx *ctx, const ll_world_t *root, int depth, int q
         f.variation_len = len;
     }
     return LL_OK;
+    LL_ABI_END
 }
 
 // ---- the host alpha-beta driver (mind.rs:145-169, 271-364) over device frontier batches -----------------------
@@ -1486,23 +1598,28 @@ static int alpha_beta_core(ll_ctx *ctx, const ll_world_t *root, int depth, int d
 
 extern "C" int ll_alpha_beta_forecast(ll_ctx *ctx, const ll_world_t *root, int depth, int device_plies, int quiet_extension, int nihilistically,
                                       ll_forecast_t *forecasts, uint32_t cap, uint32_t *n_forecasts, uint64_t *stats3) {
+    LL_ABI_BEGIN
     LL_TRY(check_ctx(ctx));
     if (!root || !forecasts || !n_forecasts) return fail(LL_ERR_INVALID_ARG, "null argument");
     if (depth < 1 || depth > 32) return fail(LL_ERR_INVALID_ARG, "depth %d out of range (1..32)", depth);
     if (device_plies < 0 || device_plies > 8) return fail(LL_ERR_INVALID_ARG, "device_plies %d out of range (0..8)", device_plies);
     if (quiet_extension > 8) return fail(LL_ERR_INVALID_ARG, "quiet extension %d out of range", quiet_extension);
     return alpha_beta_core(ctx, root, depth, device_plies, quiet_extension, nihilistically, forecasts, cap, n_forecasts, stats3, nullptr, nullptr);
+    LL_ABI_END
 }
 
 extern "C" int ll_fixed_depth_sequence_forecast(ll_ctx *ctx, const ll_world_t *root, const uint8_t *depths, uint32_t n_depths, int nihilistically,
                                                 ll_forecast_t *forecasts, uint32_t cap, uint32_t *n_forecasts) {
+    LL_ABI_BEGIN
     if (!depths || !n_depths) return fail(LL_ERR_INVALID_ARG, "`depth_sequence` should be nonempty"); // mind.rs:480
     for (uint32_t k = 0; k < n_depths; k++) LL_TRY(ll_forecast(ctx, root, depths[k], -1, nihilistically, forecasts, cap, n_forecasts, nullptr));
     return LL_OK;
+    LL_ABI_END
 }
 
 extern "C" int ll_iterative_deepening_forecast(ll_ctx *ctx, const ll_world_t *root, double timeout_seconds, int nihilistically, ll_forecast_t *forecasts,
                                                uint32_t cap, uint32_t *n_forecasts, uint32_t *depth_reached) {
+    LL_ABI_BEGIN
     if (!forecasts || !n_forecasts || !depth_reached) return fail(LL_ERR_INVALID_ARG, "null argument");
     const auto t0 = std::chrono::steady_clock::now();
     auto elapsed = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
@@ -1541,11 +1658,13 @@ extern "C" int ll_iterative_deepening_forecast(ll_ctx *ctx, const ll_world_t *ro
         if (elapsed() + took * growth > timeout_seconds) break; // the next iteration cannot finish in time
     }
     return LL_OK;
+    LL_ABI_END
 }
 
 // ---- device-resident positions -----------------------------------------------------------------------
 
 extern "C" int ll_soa_alloc(ll_ctx *ctx, size_t n, ll_soa_t *soa) {
+    LL_ABI_BEGIN
     LL_TRY(check_ctx(ctx));
     if (!soa) return fail(LL_ERR_INVALID_ARG, "null soa");
     memset(soa, 0, sizeof *soa);
@@ -1568,9 +1687,11 @@ extern "C" int ll_soa_alloc(ll_ctx *ctx, size_t n, ll_soa_t *soa) {
     soa->stride = stride;
     soa->n = n;
     return LL_OK;
+    LL_ABI_END
 }
 
 extern "C" int ll_soa_free(ll_ctx *ctx, ll_soa_t *soa) {
+    LL_ABI_BEGIN
     LL_TRY(check_ctx(ctx));
     if (!soa) return LL_OK;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1578,9 +1699,11 @@ extern "C" int ll_soa_free(ll_ctx *ctx, ll_soa_t *soa) {
     if (soa->meta) cudaFree(soa->meta);
     memset(soa, 0, sizeof *soa);
     return LL_OK;
+    LL_ABI_END
 }
 
 extern "C" int ll_soa_upload(ll_ctx *ctx, const ll_world_t *worlds, size_t n, ll_soa_t *dst) {
+    LL_ABI_BEGIN
     LL_TRY(check_ctx(ctx));
     if (!dst || (n && !worlds)) return fail(LL_ERR_INVALID_ARG, "null argument");
     if (n > dst->stride) return fail(LL_ERR_CAPACITY, "%zu positions do not fit stride %zu", n, dst->stride);
@@ -1595,9 +1718,11 @@ extern "C" int ll_soa_upload(ll_ctx *ctx, const ll_world_t *worlds, size_t n, ll
     LL_TRY(check_launch("k_aos_to_soa"));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return LL_OK;
+    LL_ABI_END
 }
 
 extern "C" int ll_soa_download(ll_ctx *ctx, const ll_soa_t *src, size_t first, size_t n, ll_world_t *worlds) {
+    LL_ABI_BEGIN
     LL_TRY(check_ctx(ctx));
     if (!src || (n && !worlds)) return fail(LL_ERR_INVALID_ARG, "null argument");
     if (first + n > src->n) return fail(LL_ERR_INVALID_ARG, "range %zu+%zu exceeds %zu positions", first, n, src->n);
@@ -1611,9 +1736,11 @@ extern "C" int ll_soa_download(ll_ctx *ctx, const ll_soa_t *src, size_t first, s
     CUDA_TRY(cudaMemcpyAsync(worlds, ctx->aos_out.ptr, n * sizeof(ll_world_t), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return LL_OK;
+    LL_ABI_END
 }
 
 extern "C" int ll_playout_soa(ll_ctx *ctx, uint64_t seed, uint64_t first_index, size_t n, ll_soa_t *dst) {
+    LL_ABI_BEGIN
     LL_TRY(check_ctx(ctx));
     if (!dst) return fail(LL_ERR_INVALID_ARG, "null soa");
     if (n > dst->stride) return fail(LL_ERR_CAPACITY, "%zu positions do not fit stride %zu", n, dst->stride);
@@ -1624,4 +1751,5 @@ extern "C" int ll_playout_soa(ll_ctx *ctx, uint64_t seed, uint64_t first_index, 
         k_playout<<<(unsigned)nblocks(n), BLOCK, 0, ctx->stream>>>(seed, first_index, n, Soa{(u64 *)dst->planes, dst->meta, dst->stride});
     }
     return check_launch("k_playout");
+    LL_ABI_END
 }

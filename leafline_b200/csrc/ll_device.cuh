@@ -81,6 +81,15 @@ LL_HD u32 meta_stm(u32 m) { return m & 1u; }
 LL_HD u32 meta_elig(u32 m) { return (m >> 1) & 0xFu; }
 LL_HD u32 meta_pb(u32 m) { return (m >> 8) & 0xFFu; }
 LL_HD u32 make_meta(u32 stm, u32 elig, u32 pb) { return stm | (elig << 1) | (pb << 8); }
+// bit 16: the ABI bytes this position came from were out of range (initiative > 1 or eligibility > 0xF).  Set only by
+// the repacking kernels, read only by well_formed(): a malformed ll_world_t is rejected on every path alike instead of
+// being silently answered as the position its masked fields spell.
+constexpr u32 META_MALFORMED = 1u << 16;
+// word 12 of an ll_world_t (initiative | eligibility << 8 | passing_by << 16 | padding) -> meta
+LL_HD u32 meta_of_abi_word(u64 m) {
+    const u32 stm = (u32)(m & 0xFFu), elig = (u32)((m >> 8) & 0xFFu);
+    return make_meta(stm & 1u, elig & 0xFu, (u32)((m >> 16) & 0xFFu)) | ((stm > 1u || elig > 0xFu) ? META_MALFORMED : 0u);
+}
 LL_HD int loc_to_sq(u32 loc) { return (int)(((loc >> 4) << 3) | (loc & 7u)); }
 LL_HD u32 sq_to_loc(int sq) { return (u32)(((sq >> 3) << 4) | (sq & 7)); }
 LL_HD u64 passing_by_bit(u32 meta) { // the square a servant may stun "in passing", 0 if none
@@ -817,6 +826,7 @@ LL_HD u32 canonical_key(u32 m) {
 
 // ---- well-formedness (domain W, include/leafline_b200.h) ----------------------------------------
 LL_HD bool well_formed(const Pos &p) {
+    if (p.meta & META_MALFORMED) return false;
     u64 acc = 0, overlap = 0;
 #pragma unroll
     for (int j = 0; j < 12; j++) {

@@ -71,8 +71,7 @@ __global__ void __launch_bounds__(BLOCK) k_aos_to_soa(const u64 *__restrict__ ao
         const size_t i = out_first + base + threadIdx.x;
 #pragma unroll
         for (int j = 0; j < 12; j++) out.pl[(size_t)j * out.stride + i] = s[j];
-        const u64 m = s[12];
-        out.meta[i] = make_meta((u32)(m & 1u), (u32)((m >> 8) & 0xFu), (u32)((m >> 16) & 0xFFu));
+        out.meta[i] = meta_of_abi_word(s[12]);
     }
 }
 // one position handed over as a kernel ARGUMENT (the root of ll_perft / ll_kickoff): no staging copy, no separate
@@ -83,7 +82,7 @@ struct WorldWords {
 __global__ void __launch_bounds__(32) k_store_world(const WorldWords world, Soa out, size_t at) {
     const int j = threadIdx.x;
     if (j < 12) out.pl[(size_t)j * out.stride + at] = world.w[j];
-    else if (j == 12) out.meta[at] = make_meta((u32)(world.w[12] & 1u), (u32)((world.w[12] >> 8) & 0xFu), (u32)((world.w[12] >> 16) & 0xFFu));
+    else if (j == 12) out.meta[at] = meta_of_abi_word(world.w[12]);
 }
 __device__ __forceinline__ u64 meta_to_word(u32 meta) {
     return (u64)meta_stm(meta) | ((u64)meta_elig(meta) << 8) | ((u64)meta_pb(meta) << 16);

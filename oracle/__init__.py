@@ -30,12 +30,38 @@ COMMIT_DTYPE = np.dtype(
 assert WORLD_DTYPE.itemsize == 104 and COMMIT_DTYPE.itemsize == 112
 
 
+def _host_signature():
+    """what `-march=native` means on this machine: the library is rebuilt when it was compiled for another CPU
+    (the built .so travels to the GPU box with the snapshot; its host cores are not this container's)"""
+    flags = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    flags = line.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    import hashlib
+
+    return hashlib.sha256(flags.encode()).hexdigest()[:16]
+
+
 def build(force=False):
-    """Compile the oracle with gcc (oracle/Makefile)."""
+    """Compile the oracle with gcc (oracle/Makefile: -O3 -march=native -ffp-contract=off)."""
     src = [os.path.join(_HERE, f) for f in ("leafline_oracle.c", "leafline_oracle.h", "Makefile")]
-    stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src)
+    stamp = os.path.join(_HERE, "_build", "host_signature.txt")
+    sig = _host_signature()
+    built_for = open(stamp).read().strip() if os.path.exists(stamp) else ""
+    stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src) or built_for != sig
     if force or stale:
-        subprocess.run(["make", "-C", _HERE], check=True, stdout=subprocess.DEVNULL)
+        import shutil
+
+        if shutil.which(os.environ.get("CC", "gcc")) is None and os.path.exists(_SO):
+            return _SO  # no compiler on this box: keep the library that travelled (x86-64-v2 build is the fallback target)
+        subprocess.run(["make", "-B", "-C", _HERE], check=True, stdout=subprocess.DEVNULL)
+        with open(stamp, "w") as f:
+            f.write(sig + "\n")
     return _SO
 
 

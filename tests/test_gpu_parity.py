@@ -41,6 +41,20 @@ def assert_scores(got, want):
     assert got.tobytes() == want.tobytes(), "scores are within tolerance but not bit-exact"
 
 
+# ---------------------------------------------------------------- generated tables (furniture/tablemaker.py:41-62)
+def test_device_tables_equal_the_reference_generator(eng):
+    """The movement tables resident on the device, entry by entry, against the output of the reference's own generator
+    (tests/golden/reference_tables.json, written by tests/golden/make_tables.py from furniture/tablemaker.py)."""
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_tables.json")) as f:
+        ref = json.load(f)
+    pony, fig = eng.debug_tables()
+    assert [int(x) for x in pony] == ref["pony_movement_table"]
+    assert [int(x) for x in fig] == ref["figurehead_movement_table"]
+
+
 # ---------------------------------------------------------------- score (mind.rs:50-143)
 def test_score_golden_bit_patterns(eng):
     import leafline_b200 as ll

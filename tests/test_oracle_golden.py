@@ -45,6 +45,36 @@ def test_generated_tables():
         assert m == 0x0101010101010101 << f and bin(m).count("1") == 8
 
 
+def test_tables_equal_the_reference_generator_entry_by_entry():
+    """All 2 x 64 movement-table entries and every landmark mask of the oracle against the OUTPUT of the reference's own
+    generator (furniture/tablemaker.py, run unmodified by tests/golden/make_tables.py).  Where the reference tree is
+    present (this container) the committed fixture is first re-derived from it."""
+    import json
+    import os
+    import sys
+
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    with open(os.path.join(golden, "reference_tables.json")) as f:
+        ref = json.load(f)
+    sys.path.insert(0, golden)
+    import make_tables
+
+    if os.path.exists(os.path.join(make_tables.REFERENCE, "furniture", "tablemaker.py")):
+        assert make_tables.reference_tables() == ref, "tests/golden/reference_tables.json is stale: rerun make_tables.py"
+    L = O.lib()
+    pony = (O.C.c_uint64 * 64).in_dll(L, "LO_PONY_MOVEMENT_TABLE")
+    fig = (O.C.c_uint64 * 64).in_dll(L, "LO_FIGUREHEAD_MOVEMENT_TABLE")
+    assert list(pony) == ref["pony_movement_table"]
+    assert list(fig) == ref["figurehead_movement_table"]
+    L.lo_center_of_the_world.restype = O.C.c_uint64
+    L.lo_forward_contour.restype = O.C.c_uint64
+    L.lo_sideways_contour.restype = O.C.c_uint64
+    assert L.lo_center_of_the_world() == ref["center_of_the_world"]
+    assert L.lo_forward_contour(1) == ref["low_seventh_heaven"] and L.lo_forward_contour(2) == ref["low_colonelcy"]
+    assert L.lo_forward_contour(6) == ref["high_seventh_heaven"] and L.lo_forward_contour(5) == ref["high_colonelcy"]
+    assert [L.lo_sideways_contour(f) for f in range(8)] == ref["files"]
+
+
 # ---------------------------------------------------------------- life.rs tests
 def test_basic_leering_test():
     # life.rs:1262-1266
