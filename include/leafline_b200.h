@@ -39,6 +39,7 @@ extern "C" {
 #define LL_ERR_DOMAIN (-4)   /* a position is outside the well-formed domain W */
 #define LL_ERR_NO_DEVICE (-5)
 #define LL_ERR_OOM (-6)
+#define LL_ERR_NCCL (-7)     /* NCCL is missing (it is loaded at run time, by the multi-GPU calls only) or reported an error */
 
 /* src/identity.rs:8-11, 36-43 */
 enum { LL_ORANGE = 0, LL_BLUE = 1 };
@@ -97,11 +98,11 @@ int ll_in_critical_endangerment_batch(ll_ctx *ctx, const ll_world_t *worlds, con
 
 /* perft = number of leaves of the legal-move tree (recursive `lookahead()`);
  * depth 0 -> 1.  per_root (nullable, root_cap entries) receives the leaf count below each root
- * move in canonical order and *n_roots their number ("divide").  With shard_world > 1 only the
- * work units u with u % shard_world == shard_rank are counted, the units being the nodes of ply
- * min(2, depth - 2) in canonical order (2-ply prefixes for depth >= 4; ply 1 for depth 2 and 3; the
- * whole tree is rank 0's for depth 1): summing the results of all ranks (a u64 allreduce) gives the
- * full answer.  The frontier is materialised in HBM up to ply depth - 2 (100 B per node + 12 B of ids and
+ * move in canonical order and *n_roots their number ("divide").  With shard_world > 1 (<= 32) only this rank's
+ * work units are counted: the units are the nodes of ply min(3, depth - 2), each named by its parent and its index c
+ * among the parent's commits in canonical order, owner = (hash(parent) + c) mod shard_world -- a pure function of the
+ * tree, so no rank needs to hear from another (trees of depth <= 3 are not dealt: rank 0 counts them whole).  Summing
+ * the results of all ranks (a u64 allreduce; ll_perft_multi does it on the devices) gives the full answer.  The frontier is materialised in HBM up to ply depth - 2 (100 B per node + 12 B of ids and
  * counts); the last two plies are generated and counted on chip.  LL_ERR_OOM if a level does not fit. */
 int ll_perft(ll_ctx *ctx, const ll_world_t *root, int depth, int shard_rank, int shard_world, uint64_t *leaves,
              uint64_t *per_root, uint32_t root_cap, uint32_t *n_roots);
@@ -128,6 +129,43 @@ int ll_horizon_batch(ll_ctx *ctx, const ll_world_t *frontier, size_t n, int plie
  * the others get -INFINITY (gather with a max). */
 int ll_kickoff(ll_ctx *ctx, const ll_world_t *root, int depth, int quiet_extension, int nihilistically, int shard_rank, int shard_world,
                ll_commit_t *roots, float *scores, uint32_t root_cap, uint32_t *n_roots, uint64_t *leaves_scored);
+
+/* ---- several GPUs sharing ONE tree (replaces the reference's fan-out inside the engine: a thread per root move and an
+ * mpsc gather, src/mind.rs:399-437).  A group owns one ll_ctx per GPU, the NCCL communicator between them and the
+ * device-resident reduction of their results.  Subtrees are dealt to the ranks, no position ever crosses NVLink; the only
+ * exchange is a u64 sum of leaf counts or an element-wise max of per-parent f32 keys, done on the devices -- by NCCL, or by
+ * this library's own kernel over NVLink peer memory where every rank can map every other's (ll_multi_reduce_path).
+ *   one process, n GPUs:  ll_init_multi -- ncclCommInitAll, one persistent host thread and one stream per device; one call
+ *                         of ll_*_multi drives them all.
+ *   one process per GPU:  ll_multi_unique_id on one rank, the 128 bytes carried to every process by the caller (torchrun,
+ *                         MPI, a pipe), ll_init_multi_rank everywhere; ll_*_multi is then COLLECTIVE: every rank calls it with
+ *                         the same arguments and every rank gets the whole answer.
+ * A group is used from one host thread at a time.  Errors on one rank are voted on inside the collective: every rank returns
+ * an error, none hangs. */
+typedef struct ll_mctx ll_mctx;
+#define LL_NCCL_UNIQUE_ID_BYTES 128
+int ll_multi_unique_id(void *id128);
+int ll_init_multi(const int *devices, int n, ll_mctx **group);
+int ll_init_multi_rank(int device, int rank, int world, const void *unique_id128, ll_mctx **group);
+int ll_shutdown_multi(ll_mctx *group);
+int ll_multi_world(ll_mctx *group);        /* ranks sharing a tree */
+int ll_multi_local_count(ll_mctx *group);  /* members living in this process */
+ll_ctx *ll_multi_ctx(ll_mctx *group, int local_index); /* a member's context, e.g. for ll_set_stream / ll_timing_* */
+int ll_multi_reduce_path(ll_mctx *group);  /* 0 = NCCL, 1 = the library's reduction over NVLink peer memory */
+/* trees shallower than these are not dealt: every rank answers them whole and no collective is paid for (defaults 5 and 6;
+ * 0 keeps a value).  Collective: set the same values on every rank. */
+int ll_multi_set_shard_min_depth(ll_mctx *group, int perft_depth, int kickoff_depth);
+
+/* ll_perft over the group: ONE tree, its ply-min(3, depth - 2) nodes dealt to the ranks (the rule of ll_perft's
+ * shard_rank / shard_world), counts summed on the devices.  per_root / n_roots as in ll_perft. */
+int ll_perft_multi(ll_mctx *group, const ll_world_t *root, int depth, uint64_t *leaves, uint64_t *per_root, uint32_t root_cap, uint32_t *n_roots);
+/* perft of n independent roots (<= 1024), root i counted by rank i % world: leaves[i] for every i on every rank. */
+int ll_perft_batch_multi(ll_mctx *group, const ll_world_t *roots, uint32_t n, int depth, uint64_t *leaves);
+/* ll_kickoff over the group (src/mind.rs:399-437 on n GPUs): the levels down to ply min(3, depth - 1) are expanded in canonical
+ * order on every rank, the nodes of that ply dealt round-robin, searched, their values folded into their parents' keys,
+ * max-reduced on the devices and backed up: scores[i] are the exact per-root scores of ll_kickoff, on every rank. */
+int ll_kickoff_multi(ll_mctx *group, const ll_world_t *root, int depth, int quiet_extension, int nihilistically, ll_commit_t *roots, float *scores,
+                     uint32_t root_cap, uint32_t *n_roots, uint64_t *leaves_scored);
 
 /* ---- the kickoff family as the reference's callers see it (src/mind.rs:441-490) ----------------------- */
 #define LL_MAX_VARIATION 16

@@ -14,6 +14,7 @@ include/leafline_b200.h (hand-written sm_100a CUDA, leafline_b200/csrc/):
     mind::score(world)             mind.rs:50         Engine.score(worlds)
     α_β_negamax_search leaf rule   mind.rs:279-287    Engine.horizon(worlds, plies)
     mind::kickoff(world, depth..)  mind.rs:441        Engine.kickoff(world, depth, nihilistically)
+    kickoff's thread-per-root-move fan-out mind.rs:399-437  MultiEngine.kickoff / .perft (several GPUs, one tree)
 
 Positions are numpy records of WORLD_DTYPE (= ll_world_t, 104 bytes), commits of COMMIT_DTYPE
 (= ll_commit_t).  Everything is batch-first.  There is no CPU path: constructing an Engine
@@ -76,16 +77,20 @@ def _ptr(a):
 class Engine:
     """One ll_ctx: a CUDA device, a stream and the HBM scratch of the leaf layer.  Not thread-safe."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, _borrowed_ctx=None):
         self._lib = _abi.load()
         self._ctx = C.c_void_p()
-        _abi.check(self._lib.ll_init(device, C.byref(self._ctx)))
+        self._owned = _borrowed_ctx is None
+        if self._owned:
+            _abi.check(self._lib.ll_init(device, C.byref(self._ctx)))
+        else:
+            self._ctx = C.c_void_p(_borrowed_ctx)  # a member of an ll_mctx: the group shuts it down
         self.device = device
 
     def close(self):
-        if self._ctx:
+        if self._ctx and self._owned:
             self._lib.ll_shutdown(self._ctx)
-            self._ctx = C.c_void_p()
+        self._ctx = C.c_void_p()
 
     def __enter__(self):
         return self
@@ -320,3 +325,101 @@ class Engine:
             soa = self.soa_alloc(n)
         _abi.check(self._lib.ll_playout_soa(self._ctx, seed, first_index, n, C.byref(soa)))
         return soa
+
+
+class MultiEngine:
+    """One ll_mctx: several GPUs sharing ONE tree behind the C ABI (the reference's fan-out inside the engine,
+    mind.rs:399-437).  The group owns a context per GPU, the NCCL communicator and the device-resident reduction.
+
+        MultiEngine(devices=[0, 1, ...])                      one process, one host thread + stream per device
+        MultiEngine.for_rank(device, rank, world, unique_id)  one process per GPU (torchrun): every call is collective
+    """
+
+    def __init__(self, devices=None, _handle=None):
+        self._lib = _abi.load()
+        self._g = C.c_void_p()
+        if _handle is not None:
+            self._g = _handle
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            _abi.check(self._lib.ll_init_multi(arr, len(devices), C.byref(self._g)))
+
+    @staticmethod
+    def unique_id():
+        """128 bytes naming a new communicator; carry them to every process (ncclGetUniqueId)."""
+        buf = (C.c_ubyte * 128)()
+        _abi.check(_abi.load().ll_multi_unique_id(C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    @classmethod
+    def for_rank(cls, device, rank, world, unique_id):
+        lib = _abi.load()
+        g = C.c_void_p()
+        buf = (C.c_ubyte * 128)(*unique_id) if unique_id is not None else None
+        _abi.check(lib.ll_init_multi_rank(device, rank, world, C.cast(buf, C.c_void_p) if buf is not None else None, C.byref(g)))
+        return cls(_handle=g)
+
+    def close(self):
+        if self._g:
+            self._lib.ll_shutdown_multi(self._g)
+            self._g = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def world(self):
+        return self._lib.ll_multi_world(self._g)
+
+    @property
+    def local_count(self):
+        return self._lib.ll_multi_local_count(self._g)
+
+    @property
+    def reduce_path(self):
+        return "peer-memory" if self._lib.ll_multi_reduce_path(self._g) else "nccl"
+
+    def member(self, local_index=0):
+        """The member's ll_ctx as an Engine (borrowed: set_stream, timing, launch_count ...)."""
+        ctx = self._lib.ll_multi_ctx(self._g, local_index)
+        if not ctx:
+            raise IndexError(local_index)
+        return Engine(_borrowed_ctx=ctx)
+
+    def set_shard_min_depth(self, perft_depth=0, kickoff_depth=0):
+        _abi.check(self._lib.ll_multi_set_shard_min_depth(self._g, perft_depth, kickoff_depth))
+
+    def perft(self, world, depth):
+        """ll_perft_multi -> (leaves, per_root[n_roots]) of the whole tree."""
+        w = _worlds(world)
+        leaves, n_roots = C.c_uint64(0), C.c_uint32(0)
+        per_root = np.zeros(1024, dtype=np.uint64)
+        _abi.check(self._lib.ll_perft_multi(self._g, _ptr(w), depth, C.byref(leaves), _ptr(per_root), 1024, C.byref(n_roots)))
+        return int(leaves.value), per_root[: n_roots.value].copy()
+
+    def perft_batch(self, worlds, depth, out=None):
+        """ll_perft_batch_multi: leaf counts of independent roots, root i counted by rank i % world -> uint64[n]."""
+        w = _worlds(worlds)
+        if out is None:
+            out = np.zeros(len(w), dtype=np.uint64)
+        _abi.check(self._lib.ll_perft_batch_multi(self._g, _ptr(w), len(w), depth, _ptr(out)))
+        return out
+
+    def kickoff(self, world, depth, nihilistically=False, quiet=None):
+        """ll_kickoff_multi -> (root commits, root scores, leaves scored), canonical order, on every rank."""
+        w = _worlds(world)
+        roots = np.zeros(1024, dtype=COMMIT_DTYPE)
+        scores = np.zeros(1024, dtype=np.float32)
+        n_roots, scored = C.c_uint32(0), C.c_uint64(0)
+        _abi.check(self._lib.ll_kickoff_multi(self._g, _ptr(w), depth, -1 if quiet is None else int(quiet), int(nihilistically),
+                                              _ptr(roots), _ptr(scores), 1024, C.byref(n_roots), C.byref(scored)))
+        return roots[: n_roots.value].copy(), scores[: n_roots.value].copy(), int(scored.value)

@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LEAFLINE_B200_LIB") or os.path.join(_HERE, "libleafline_b200.so")  # the env override is for A/B builds
 
-OK, ERR_INVALID_ARG, ERR_CUDA, ERR_CAPACITY, ERR_DOMAIN, ERR_NO_DEVICE, ERR_OOM = 0, -1, -2, -3, -4, -5, -6
+OK, ERR_INVALID_ARG, ERR_CUDA, ERR_CAPACITY, ERR_DOMAIN, ERR_NO_DEVICE, ERR_OOM, ERR_NCCL = 0, -1, -2, -3, -4, -5, -6, -7
 
 WORLD_DTYPE = np.dtype(
     [("plane", "<u8", (12,)), ("initiative", "u1"), ("service_eligibility", "u1"), ("passing_by", "u1"),
@@ -55,6 +55,18 @@ SIGNATURES = {
     "ll_perft_device": ([_vp, _vp, _i, _i, _i, _vp], _i),
     "ll_horizon_batch": ([_vp, _vp, _sz, _i, _i, _vp], _i),
     "ll_kickoff": ([_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(_u64)], _i),
+    "ll_multi_unique_id": ([_vp], _i),
+    "ll_init_multi": ([C.POINTER(_i), _i, C.POINTER(_vp)], _i),
+    "ll_init_multi_rank": ([_i, _i, _i, _vp, C.POINTER(_vp)], _i),
+    "ll_shutdown_multi": ([_vp], _i),
+    "ll_multi_world": ([_vp], _i),
+    "ll_multi_local_count": ([_vp], _i),
+    "ll_multi_ctx": ([_vp, _i], _vp),
+    "ll_multi_reduce_path": ([_vp], _i),
+    "ll_multi_set_shard_min_depth": ([_vp, _i, _i], _i),
+    "ll_perft_multi": ([_vp, _vp, _i, C.POINTER(_u64), _vp, C.c_uint32, C.POINTER(C.c_uint32)], _i),
+    "ll_perft_batch_multi": ([_vp, _vp, C.c_uint32, _i, _vp], _i),
+    "ll_kickoff_multi": ([_vp, _vp, _i, _i, _i, _vp, _vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(_u64)], _i),
     "ll_forecast": ([_vp, _vp, _i, _i, _i, _vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(_u64)], _i),
     "ll_alpha_beta_forecast": ([_vp, _vp, _i, _i, _i, _i, _vp, C.c_uint32, C.POINTER(C.c_uint32), _vp], _i),
     "ll_fixed_depth_sequence_forecast": ([_vp, _vp, _vp, C.c_uint32, _i, _vp, C.c_uint32, C.POINTER(C.c_uint32)], _i),

@@ -64,7 +64,7 @@ struct DevBuf { // grow-only device allocation
 };
 
 struct Frontier { // one BFS level resident in HBM
-    DevBuf planes, meta, root, counts, block_sums, block_base, cmeta, values, child_first;
+    DevBuf planes, meta, root, counts, block_sums, block_base, cmeta, values, child_first, tag;
     size_t cap = 0; // positions
     size_t n = 0;
     bool borrowed = false; // planes / meta belong to the caller (ll_horizon_soa): never grown or freed here
@@ -86,6 +86,7 @@ struct ll_ctx {
     cudaEvent_t slot_uploaded[2] = {nullptr, nullptr}, slot_consumed[2] = {nullptr, nullptr};
     std::vector<Frontier> levels;
     Frontier ext; // scratch (counts / scan / values) used when level 0 aliases caller-owned planes
+    Frontier unit_scratch; // the whole shard level before this rank's units are picked out of it (level-by-level paths)
     DevBuf aos_in, aos_out, scalars, scores, teams, flags;
     void *pinned = nullptr; // small host staging
     size_t pinned_cap = 0;
@@ -146,7 +147,7 @@ void drop_buf(DevBuf &b) {
 // recoverable: the context stays usable)
 void drop_level(Frontier &f) {
     drop_buf(f.planes); drop_buf(f.meta); drop_buf(f.root); drop_buf(f.counts); drop_buf(f.block_sums); drop_buf(f.block_base);
-    drop_buf(f.cmeta); drop_buf(f.values); drop_buf(f.child_first);
+    drop_buf(f.cmeta); drop_buf(f.values); drop_buf(f.child_first); drop_buf(f.tag);
     f.cap = 0;
     f.n = 0;
 }
@@ -287,11 +288,27 @@ int count_level(ll_ctx *ctx, size_t l, bool nihil, u64 *total_out, bool stuns_on
     return LL_OK;
 }
 
-// expand level l into level l+1 (count_level(l) must have run).  root_mode: 0 none, 1 inherit, 2 own index
-int emit_level(ll_ctx *ctx, size_t l, bool nihil, u64 total, bool with_cmeta, int root_mode, bool stuns_only = false) {
-    LL_TRY(reserve_level(ctx, l + 1, (size_t)total, with_cmeta, false));
+// expand level l into `g` (count_level(l) must have run).  root_mode: 0 none, 1 inherit, 2 own index, 3 parent's index.
+// shard_world > 1: every child is tagged with the rank that owns it (g.tag; see unit_hash)
+int emit_level_into(ll_ctx *ctx, size_t l, Frontier &g, bool nihil, u64 total, bool with_cmeta, int root_mode, bool stuns_only, int shard_world) {
     Frontier &f = ctx->levels[l];
-    Frontier &g = ctx->levels[l + 1];
+    if ((size_t)total > g.cap || (with_cmeta && g.cmeta.cap < g.cap * sizeof(u32))) {
+        // (g may be a scratch frontier outside ctx->levels: the same growth rule as reserve_level)
+        const size_t cap = std::max<size_t>(g.cap, (((size_t)total + (size_t)total / 8 + 63) / 64) * 64);
+        int rc = ensure(ctx, g.planes, cap * 12 * sizeof(u64));
+        if (rc == LL_OK) rc = ensure(ctx, g.meta, cap * sizeof(u32));
+        if (rc == LL_OK) rc = ensure(ctx, g.root, cap * sizeof(u32));
+        if (rc == LL_OK) rc = ensure(ctx, g.counts, cap * sizeof(u32));
+        if (rc == LL_OK) rc = ensure(ctx, g.block_sums, (nblocks(cap) + 1) * sizeof(u32));
+        if (rc == LL_OK) rc = ensure(ctx, g.block_base, (nblocks(cap) + 1) * sizeof(u64));
+        if (rc == LL_OK && with_cmeta) rc = ensure(ctx, g.cmeta, cap * sizeof(u32));
+        if (rc != LL_OK) {
+            drop_level(g);
+            return rc;
+        }
+        g.cap = cap;
+    }
+    if (shard_world > 1) LL_TRY(ensure(ctx, g.tag, g.cap * sizeof(u32)));
     g.n = (size_t)total;
     if (!f.n || !total) return LL_OK;
     ExpandArgs a{};
@@ -302,8 +319,14 @@ int emit_level(ll_ctx *ctx, size_t l, bool nihil, u64 total, bool with_cmeta, in
     a.root_in = root_mode == 1 ? (const u32 *)f.root.ptr : nullptr;
     a.out = g.soa();
     a.cmeta = with_cmeta ? (u32 *)g.cmeta.ptr : nullptr;
-    a.root_out = root_mode ? (u32 *)g.root.ptr : nullptr;
+    a.root_out = root_mode == 1 || root_mode == 2 ? (u32 *)g.root.ptr : nullptr;
+    a.parent_out = root_mode == 3 ? (u32 *)g.root.ptr : nullptr;
     a.root_is_index = root_mode == 2;
+    if (shard_world > 1) {
+        if (shard_world > 32) return fail(LL_ERR_INVALID_ARG, "at most 32 ranks share a tree");
+        a.shard_world = shard_world;
+        a.unit_owner = (u32 *)g.tag.ptr;
+    }
     {
         Timed t(ctx, nihil ? "emit_reckless" : "emit_legal");
         if (stuns_only && !nihil) return fail(LL_ERR_INVALID_ARG, "quiescence levels are reckless");
@@ -312,6 +335,11 @@ int emit_level(ll_ctx *ctx, size_t l, bool nihil, u64 total, bool with_cmeta, in
         else k_expand<false, MODE_EMIT><<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(a);
     }
     return check_launch("k_expand<EMIT>");
+}
+// expand level l into level l+1
+int emit_level(ll_ctx *ctx, size_t l, bool nihil, u64 total, bool with_cmeta, int root_mode, bool stuns_only = false) {
+    LL_TRY(reserve_level(ctx, l + 1, (size_t)total, with_cmeta, false));
+    return emit_level_into(ctx, l, ctx->levels[l + 1], nihil, total, with_cmeta, root_mode, stuns_only, 1);
 }
 
 int check_ctx(ll_ctx *ctx) {
@@ -541,6 +569,7 @@ extern "C" int ll_shutdown(ll_ctx *ctx) {
     drop(ctx->ext.counts); drop(ctx->ext.block_sums); drop(ctx->ext.block_base); drop(ctx->ext.values);
     for (Frontier &f : ctx->levels)
         if (!f.borrowed) drop_level(f);
+    drop_level(ctx->unit_scratch);
     drop(ctx->aos_in); drop(ctx->aos_out); drop(ctx->scalars); drop(ctx->scores); drop(ctx->teams); drop(ctx->flags);
     for (TimedLaunch &t : ctx->timed) {
         cudaEventDestroy(t.start);
@@ -851,6 +880,15 @@ static bool host_well_formed(const ll_world_t *w) {
     return true;
 }
 
+// Frontier sharding: with shard_world > 1 the work units are the nodes of ply `unit_ply`, dealt to the
+// ranks by unit_hash (ll_device.cuh) in the expansion that creates them; 0 = the tree is too shallow to deal (rank 0
+// counts all of it).  Both perft paths and every rank apply the same rule, so the ranks' counts always add up.
+static int perft_unit_ply(int depth) {
+    const int tail_ply = depth >= 3 ? depth - 2 : depth - 1;
+    const int s = tail_ply < 3 ? tail_ply : 3;
+    return s >= 2 ? s : 0;
+}
+
 // The chained path: the same levels, but every level's size stays on the device (ExpandArgs::n_in / n_out),
 // the kernels are persistent tile loops and children are placed by an atomic claim per tile (perft needs no
 // order) -- one launch chain, one synchronisation.  It runs inside the capacities the synced path has grown;
@@ -858,8 +896,9 @@ static bool host_well_formed(const ll_world_t *w) {
 static int perft_chain_launch(ll_ctx *ctx, int depth, int shard_rank, int shard_world, bool *launched) {
     *launched = false;
     const int tail_ply = depth - 2;
-    const int shard_ply = tail_ply < 2 ? tail_ply : 2;
-    const size_t need = (size_t)tail_ply + (shard_world > 1 ? 2 : 1);
+    const int unit_ply = shard_world > 1 ? perft_unit_ply(depth) : 0;
+    if (shard_world > 1 && unit_ply == 0) return LL_OK; // shallow trees are not dealt: the level-by-level path answers
+    const size_t need = (size_t)tail_ply + 1;
     if (ctx->levels.size() < need) return LL_OK;
     for (size_t l = 0; l < need; l++) {
         const Frontier &f = ctx->levels[l];
@@ -870,13 +909,11 @@ static int perft_chain_launch(ll_ctx *ctx, int depth, int shard_rank, int shard_
     u32 *tileq = (u32 *)(sc + SC_TILEQ);
     u32 *overflow = (u32 *)(sc + SC_OVERFLOW);
     const unsigned resident = (unsigned)ctx->sm_count * LL_EXPAND_MIN_BLOCKS;
-    // the plan: one step per ply (+ the shard filter); each step reads its level's size from the device
+    // the plan: one step per ply; each step reads its level's size from the device
     struct Plan { // zero-filled (padding included): its bytes are the signature of the captured graph
         ExpandArgs steps[CHAIN_MAX_STEPS];
-        ShardArgs shard;
         int kinds[CHAIN_MAX_STEPS];
         unsigned grids[CHAIN_MAX_STEPS];
-        bool canonical[CHAIN_MAX_STEPS]; // expanded by the canonical generator: the plies between the root and the shard ply (unit numbering)
         int n_steps;
     };
     static_assert(std::is_trivially_copyable<Plan>::value, "the plan is hashed byte-wise");
@@ -884,73 +921,52 @@ static int perft_chain_launch(ll_ctx *ctx, int depth, int shard_rank, int shard_
     memset(&plan, 0, sizeof plan);
     ExpandArgs *steps = plan.steps;
     int *kinds = plan.kinds;
-    bool *canonical = plan.canonical;
     unsigned *grids = plan.grids;
-    ShardArgs &shard = plan.shard;
-    size_t l = 0;
     int q = 0, n_steps = 0;
-    bool sharded = shard_world == 1, too_deep = false;
-    for (int ply = 0; ply <= tail_ply; ply++) {
-        if (n_steps + 2 > CHAIN_MAX_STEPS) {
-            too_deep = true;
-            break;
-        }
-        if (!sharded && ply == shard_ply) { // keep this rank's units (ply >= 1 here)
-            Frontier &f = ctx->levels[l];
-            Frontier &g = ctx->levels[l + 1];
-            shard = ShardArgs{f.soa(), (const u32 *)f.root.ptr, 0, N + l, g.soa(), (u32 *)g.root.ptr, N + l + 1, g.cap, overflow, shard_rank, shard_world,
-                              shard_ply == 2 ? N + 1 : nullptr};
-            grids[n_steps] = (unsigned)std::min<size_t>(nblocks(f.cap), resident);
-            kinds[n_steps++] = STEP_SHARD;
-            l++;
-            sharded = true;
-        }
-        Frontier &f = ctx->levels[l];
+    if (tail_ply + 1 > CHAIN_MAX_STEPS) return LL_OK; // deeper than the plan holds: the level-by-level path takes it
+    for (int ply = 0; ply <= tail_ply; ply++) { // level index == ply
+        Frontier &f = ctx->levels[ply];
         ExpandArgs &a = steps[n_steps];
         a.in = f.soa();
         a.n = 1;
-        a.n_in = l == 0 ? nullptr : N + l;
+        a.n_in = ply == 0 ? nullptr : N + ply;
         a.tile_counter = tileq + q++;
         a.root_in = ply == 0 ? nullptr : (const u32 *)f.root.ptr;
         a.overflow = overflow;
-        grids[n_steps] = l == 0 ? 1u : (unsigned)std::min<size_t>(nblocks(f.cap), resident);
+        grids[n_steps] = ply == 0 ? 1u : (unsigned)std::min<size_t>(nblocks(f.cap), resident);
         if (ply == tail_ply) {
             a.per_root = sc + SC_PER_ROOT;
             a.total = sc + SC_LEAVES;
             kinds[n_steps++] = STEP_TAIL;
             break;
         }
-        Frontier &g = ctx->levels[l + 1];
+        Frontier &g = ctx->levels[ply + 1];
         a.out = g.soa();
         a.root_out = (u32 *)g.root.ptr;
         a.root_is_index = ply == 0;
-        a.n_out = N + l + 1;
+        a.n_out = N + ply + 1;
         a.out_cap = g.cap;
-        // the first plies are narrow (1, ~30, ~900, ~27 000 nodes): 32-parent tiles reach more SMs and finish sooner
-        // (not above the shard ply: the units dealt to the ranks must be in canonical order, which a level keeps only
-        // while its parents fit ONE tile -- the shard filter checks that)
-        const bool small = ply < LL_SMALL_TILE_PLIES && (shard_world == 1 || ply >= shard_ply);
-        canonical[n_steps] = ply != 0 && shard_world > 1 && ply < shard_ply; // (the root ply sorts its records by canonical key)
-        if (small && l != 0) grids[n_steps] = (unsigned)std::min<size_t>(nblocks(f.cap, canonical[n_steps] ? 32 : COOP_WARPS), resident);
+        if (ply + 1 == unit_ply) { // this expansion creates the work units: every rank expands all parents, keeps its own units
+            a.shard_rank = shard_rank;
+            a.shard_world = shard_world;
+        }
+        // the first plies are narrow (1, ~30, ~900, ~27 000 nodes): one warp per parent reaches more SMs and finishes sooner
+        const bool small = ply < LL_SMALL_TILE_PLIES;
+        if (small && ply != 0) grids[n_steps] = (unsigned)std::min<size_t>(nblocks(f.cap, COOP_WARPS), resident);
         kinds[n_steps++] = small ? STEP_EMIT_SMALL : STEP_EMIT;
-        l++;
     }
-    if (too_deep) return LL_OK; // deeper than the plan holds: the level-by-level path takes it
     plan.n_steps = n_steps;
     // (a single cooperative launch with grid-wide barriers between the plies was measured: no faster -- DESIGN.md)
     auto issue = [&]() -> int {
         CUDA_TRY(cudaMemsetAsync(sc + SC_LEAVES, 0, (SC_SLOTS - SC_LEAVES) * sizeof(u64), ctx->stream));
         for (int s = 0; s < n_steps; s++) {
             const int kind = kinds[s];
-            Timed t(ctx, kind == STEP_TAIL ? "perft_tail" : kind == STEP_SHARD ? "shard_filter" : "emit_legal");
-            if (kind == STEP_SHARD) k_shard_filter<<<grids[s], BLOCK, 0, ctx->stream>>>(shard);
+            Timed t(ctx, kind == STEP_TAIL ? "perft_tail" : "emit_legal");
             // order-free steps expand from legal RECORDS (small code: these launches are bound by instruction fetch and by one
-            // thread's serial latency); the plies whose order matters keep the canonical generator
-            else if (kind == STEP_TAIL) k_expand_records<MODE_PERFT><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
-            else if (kind == STEP_EMIT_SMALL && !canonical[s]) k_expand_coop<<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]); // narrow level: one warp per parent
-            else if (kind == STEP_EMIT && !canonical[s]) k_expand_records<MODE_EMIT><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
-            else if (kind == STEP_EMIT_SMALL) k_expand<false, MODE_EMIT, 32><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
-            else k_expand<false, MODE_EMIT><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
+            // thread's serial latency); narrow levels by one warp per parent
+            if (kind == STEP_TAIL) k_expand_records<MODE_PERFT><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
+            else if (kind == STEP_EMIT_SMALL) k_expand_coop<<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
+            else k_expand_records<MODE_EMIT><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
             LL_TRY(check_launch("perft chain step"));
         }
         return LL_OK;
@@ -1031,29 +1047,13 @@ static int perft_synced(ll_ctx *ctx, int depth, int shard_rank, int shard_world,
     // legal moves are bulk-counted, so the widest materialised level is ply depth-2 (depth >= 3).
     const bool fused = depth >= 3;
     const int tail_ply = fused ? depth - 2 : depth - 1;
-    const int shard_ply = tail_ply < 2 ? tail_ply : 2; // units = frontier nodes at this ply
+    const int unit_ply = shard_world > 1 ? perft_unit_ply(depth) : 0;
+    const bool idle = shard_world > 1 && unit_ply == 0 && shard_rank != 0; // a tree too shallow to deal is rank 0's
     u64 root_count = 0;
-    size_t l = 0;
-    bool sharded = shard_world == 1;
-    for (int ply = 0;; ply++) {
-        if (!sharded && ply == shard_ply) { // keep this rank's units
-            Frontier &f = ctx->levels[l];
-            const size_t kept = f.n > (size_t)shard_rank ? (f.n - shard_rank + shard_world - 1) / shard_world : 0;
-            LL_TRY(reserve_level(ctx, l + 1, kept, false, false));
-            Frontier &g = ctx->levels[l + 1];
-            if (kept) {
-                Timed t(ctx, "shard_filter");
-                k_shard_filter<<<(unsigned)nblocks(kept), BLOCK, 0, ctx->stream>>>(ShardArgs{ctx->levels[l].soa(), (const u32 *)ctx->levels[l].root.ptr, ctx->levels[l].n,
-                                                                                            nullptr, g.soa(), (u32 *)g.root.ptr, nullptr, 0, nullptr, shard_rank, shard_world, nullptr});
-                LL_TRY(check_launch("k_shard_filter"));
-            }
-            g.n = kept;
-            l++;
-            sharded = true;
-        }
-        Frontier &f = ctx->levels[l];
+    for (int ply = 0;; ply++) { // level index == ply
+        Frontier &f = ctx->levels[ply];
         if (ply == tail_ply) { // frontier reached: bulk-count the leaves
-            if (f.n && fused) {
+            if (f.n && fused && !idle) {
                 ExpandArgs a{};
                 a.in = f.soa();
                 a.n = f.n;
@@ -1063,7 +1063,7 @@ static int perft_synced(ll_ctx *ctx, int depth, int shard_rank, int shard_world,
                 Timed t(ctx, "perft_tail");
                 k_expand_records<MODE_PERFT><<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(a);
                 LL_TRY(check_launch("k_expand_records<PERFT>"));
-            } else if (f.n) {
+            } else if (f.n && !idle) {
                 Timed t(ctx, "count_leaves");
                 k_count_leaves<<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(f.soa(), f.n, ply == 0 ? nullptr : (const u32 *)f.root.ptr,
                                                                                  ply == 0 ? nullptr : sc + SC_PER_ROOT, sc + SC_LEAVES);
@@ -1072,13 +1072,33 @@ static int perft_synced(ll_ctx *ctx, int depth, int shard_rank, int shard_world,
             break;
         }
         u64 total = 0;
-        LL_TRY(count_level(ctx, l, false, &total));
+        LL_TRY(count_level(ctx, ply, false, &total));
         if (ply == 0) {
             root_count = total;
             if (root_count > 1024) return fail(LL_ERR_CAPACITY, "more than 1024 root moves");
         }
-        LL_TRY(emit_level(ctx, l, false, total, false, ply == 0 ? 2 : 1));
-        l++;
+        if (ply + 1 == unit_ply) { // this expansion creates the work units: expand canonically with owner tags, keep this rank's
+            Frontier &all = ctx->unit_scratch;
+            LL_TRY(emit_level_into(ctx, ply, all, false, total, false, ply == 0 ? 2 : 1, false, shard_world));
+            LL_TRY(reserve_level(ctx, ply + 1, (size_t)total, false, false)); // at most all of them
+            Frontier &g = ctx->levels[ply + 1];
+            u64 kept = 0;
+            if (total) {
+                CUDA_TRY(cudaMemsetAsync(sc + SC_TOTAL, 0, sizeof(u64), ctx->stream));
+                {
+                    Timed t(ctx, "shard_filter");
+                    k_shard_filter<<<(unsigned)nblocks((size_t)total), BLOCK, 0, ctx->stream>>>(
+                        ShardArgs{all.soa(), (const u32 *)all.root.ptr, (const u32 *)all.tag.ptr, (size_t)total, g.soa(), (u32 *)g.root.ptr, sc + SC_TOTAL, shard_rank});
+                }
+                LL_TRY(check_launch("k_shard_filter"));
+                CUDA_TRY(cudaMemcpyAsync(&kept, sc + SC_TOTAL, sizeof kept, cudaMemcpyDeviceToHost, ctx->stream));
+                CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            }
+            g.n = (size_t)kept;
+            if (!kept) break;
+            continue;
+        }
+        LL_TRY(emit_level(ctx, ply, false, total, false, ply == 0 ? 2 : 1));
         if (!total) break;
     }
     u64 host[1 + 1024];
@@ -1086,10 +1106,7 @@ static int perft_synced(ll_ctx *ctx, int depth, int shard_rank, int shard_world,
     CUDA_TRY(cudaMemcpyAsync(&host[1], sc + SC_PER_ROOT, 1024 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     *leaves = host[0];
-    if (depth == 1) { // the root's own move count: every root move is one leaf
-        root_count = host[0];
-        if (shard_world > 1 && shard_rank != 0) root_count = 0;
-    }
+    if (depth == 1) root_count = idle ? 0 : host[0]; // the root's own move count: every root move is one leaf
     if (n_roots) *n_roots = (uint32_t)root_count;
     if (per_root) {
         if (root_count > root_cap) return fail(LL_ERR_CAPACITY, "%llu root moves do not fit root_cap %u", (unsigned long long)root_count, root_cap);
@@ -1253,8 +1270,8 @@ static int kickoff_core(ll_ctx *ctx, const ll_world_t *root, int depth, int quie
         Frontier &h = ctx->levels[2];
         if (kept) {
             Timed t(ctx, "shard_filter");
-            k_shard_filter<<<(unsigned)nblocks(kept), BLOCK, 0, ctx->stream>>>(ShardArgs{ctx->levels[1].soa(), (const u32 *)ctx->levels[1].root.ptr, ctx->levels[1].n,
-                                                                                        nullptr, h.soa(), (u32 *)h.root.ptr, nullptr, 0, nullptr, shard_rank, shard_world, nullptr});
+            k_deal_units<<<(unsigned)nblocks(kept), BLOCK, 0, ctx->stream>>>(ctx->levels[1].soa(), (const u32 *)ctx->levels[1].root.ptr, ctx->levels[1].n, shard_rank,
+                                                                            shard_world, h.soa(), (u32 *)h.root.ptr);
             LL_TRY(check_launch("k_shard_filter"));
         }
         h.n = kept;
@@ -1753,3 +1770,4 @@ extern "C" int ll_playout_soa(ll_ctx *ctx, uint64_t seed, uint64_t first_index, 
     return check_launch("k_playout");
     LL_ABI_END
 }
+#include "ll_multi.inl"

@@ -257,7 +257,20 @@ LL_HD int mv_from(u32 m) { return (int)(m & 63u); }
 LL_HD int mv_to(u32 m) { return (int)((m >> 6) & 63u); }
 LL_HD u32 mv_job(u32 m) { return (m >> 12) & 7u; }
 LL_HD u32 mv_asc(u32 m) { return (m >> 15) & 7u; }
-LL_HD u32 mv_slot(u32 m) { return m >> 20; }
+LL_HD u32 mv_slot(u32 m) { return (m >> 20) & 0x7Fu; }
+LL_HD u32 mv_owner(u32 m) { return m >> 27; } // canonical expansion of a sharded level: the rank that owns this child
+
+// ---- which rank owns which work unit (frontier sharding by subtree) ---------------------------------
+// A unit is a node of the shard ply, named by its PARENT and its index c among the parent's commits in the reference's
+// order (lookahead(), life.rs:1052-1084): owner = (hash(parent) + c) mod world.  A pure function of the tree -- every
+// rank, every kernel flavour (warp-per-parent, canonical, level-by-level) and every run deals the same units to the same
+// ranks without exchanging anything; a parent's commits go round the ranks, the hash only rotates where the round starts.
+LL_HD u32 unit_hash(const Pos &p) {
+    u64 h = (u64)(p.meta & 0xFFFFu) * 0x9E3779B97F4A7C15ull;
+#pragma unroll
+    for (int j = 0; j < 12; j++) h = (h ^ p.pl[j]) * 0xD6E8FEB86659FD93ull + (h >> 29);
+    return (u32)(h >> 32);
+}
 
 // ---- make-move (life.rs:569-676 + ascension life.rs:701-726) ----------------------------------------
 // T = mover (== initiative).  Returns the hospitalized job (JOB_NONE if nobody was stunned).

@@ -227,10 +227,12 @@ template <bool STUNS> struct DescSink {
     u32 *buf;
     u32 idx, lo, hi, slot_bits;
     u64 onto; // STUNS: the opposition's squares -- keep only the commits that hospitalize somebody (quiescence, mind.rs:292-294)
+    u32 owner = 0, world = 0; // sharded level: owner of the NEXT commit (unit_hash(parent) mod world for the first), see unit_hash
     LL_HDM void move(u32 job, int from, int to, u32 asc, u32 flags) {
         if (STUNS && !((1ull << to) & onto) && !(flags & MV_PASSING_BY)) return;
-        if (idx >= lo && idx < hi) buf[idx - lo] = mv_pack(job, from, to, asc, flags) | slot_bits;
+        if (idx >= lo && idx < hi) buf[idx - lo] = mv_pack(job, from, to, asc, flags) | slot_bits | (owner << 27);
         idx++;
+        if (world && ++owner == world) owner = 0;
     }
 };
 struct ExpandArgs {
@@ -252,6 +254,9 @@ struct ExpandArgs {
     u32 *overflow;
     u64 *child_first;       // EMIT, order-free (nullable): where each parent's children went ...
     u32 *child_count;       // ... and how many there are (the negamax back-up of the horizon chain reads these)
+    int shard_rank, shard_world; // shard_world > 1: this expansion creates the work units (see unit_hash):
+    u32 *unit_owner;        //   canonical k_expand tags every child with its owner; k_expand_coop keeps only shard_rank's
+    u32 *parent_out;        // EMIT, canonical (nullable): index of each child's parent in the input level
     // MODE_PERFT
     u64 *per_root, *total;
     // k_horizon
@@ -329,6 +334,10 @@ template <bool NIHIL, int MODE, int P, bool STUNS> __device__ __forceinline__ vo
             if (cnt && ex < w0 + DESC_CAP && ex + cnt > w0) { // phase 1: this parent's commits into the window
                 const Pos p = tile_load(sh, tid);
                 DescSink<STUNS> sink{sh.descs, ex, w0, w0 + DESC_CAP, (u32)tid << 20, STUNS ? opposition_squares(p) : 0ull};
+                if (a.shard_world > 1) {
+                    sink.world = (u32)a.shard_world;
+                    sink.owner = unit_hash(p) % (u32)a.shard_world;
+                }
                 lookahead<NIHIL>(p, sink);
             }
             __syncthreads();
@@ -350,6 +359,8 @@ template <bool NIHIL, int MODE, int P, bool STUNS> __device__ __forceinline__ vo
                         soa_store(a.out, o, c);
                         if (a.cmeta) a.cmeta[o] = pack_commit(meta_stm(c.meta) ^ 1u, m, hosp);
                         if (a.root_out) a.root_out[o] = a.root_is_index ? (u32)o : a.root_in[tile * P + slot];
+                        if (a.unit_owner) a.unit_owner[o] = mv_owner(m);
+                        if (a.parent_out) a.parent_out[o] = (u32)(tile * P + slot);
                     }
                 } else {
                     const int v = live ? (int)count_moves<false>(c) : 0;
@@ -664,19 +675,28 @@ template <int T> __device__ __forceinline__ void coop_expand_parent(const Expand
     u32 at = warp_inclusive_scan(mine);
     const u32 total = __shfl_sync(0xffffffffu, at, 31);
     at -= mine;
-    size_t base = 0;
-    if (lane == 0 && total) base = (size_t)atomicAdd((unsigned long long *)a.n_out, (unsigned long long)total);
-    base = (size_t)__shfl_sync(0xffffffffu, (unsigned long long)base, 0);
     if (total == 0) return;
-    if (total > (u32)COOP_CAP || base + total > a.out_cap) { // cannot happen / the level outgrew its buffer
+    // a sharded level (this expansion creates the work units): of the commits in the reference's order this rank keeps
+    // number first, first + world, ... -- see unit_hash
+    u32 first = 0, stride = 1, kept = total;
+    if (a.shard_world > 1) {
+        stride = (u32)a.shard_world;
+        first = ((u32)a.shard_rank + stride - unit_hash(p) % stride) % stride;
+        kept = first < total ? (total - first + stride - 1) / stride : 0u;
+    }
+    size_t base = 0;
+    if (lane == 0 && kept) base = (size_t)atomicAdd((unsigned long long *)a.n_out, (unsigned long long)kept);
+    base = (size_t)__shfl_sync(0xffffffffu, (unsigned long long)base, 0);
+    if (total > (u32)COOP_CAP || base + kept > a.out_cap) { // cannot happen / the level outgrew its buffer
         if (lane == 0) atomicExch(a.overflow, 1u);
         return;
     }
+    if (kept == 0) return;
     for (u64 m = plain; m; m &= m - 1) descs[at++] = rec_move_to(info, lsb64(m), T);
     for (u64 m = ascending; m; m &= m - 1)
         for (u32 asc = PONY; asc <= PRINCESS; asc++) descs[at++] = rec_move_to((info & ~(7u << 12)) | (asc << 12), lsb64(m), T);
     __syncwarp();
-    if (a.root_is_index) { // the root's children become the divide table's rows: the reference's order
+    if (a.root_is_index || a.shard_world > 1) { // the reference's order: the root's children are the divide table's rows, a sharded level's the units
         for (u32 i = lane; i < total; i += 32) keys[i] = canonical_key(descs[i]);
         __syncwarp();
         u32 moved[COOP_CAP / 32], rank[COOP_CAP / 32];
@@ -698,12 +718,13 @@ template <int T> __device__ __forceinline__ void coop_expand_parent(const Expand
         __syncwarp();
     }
     const u32 root = a.root_is_index ? 0u : a.root_in[parent];
-    for (u32 i = lane; i < total; i += 32) { // 32 children at a time: coalesced plane stores
+    for (u32 k = lane; k < kept; k += 32) { // 32 children at a time: coalesced plane stores
+        const u32 i = first + k * stride;
         Pos c;
         make_child_as<T>(p, descs[i], c);
-        const size_t o = base + i;
+        const size_t o = base + k;
         soa_store(a.out, o, c);
-        if (a.root_out) a.root_out[o] = a.root_is_index ? (u32)o : root;
+        if (a.root_out) a.root_out[o] = a.root_is_index ? i : root;
     }
     __syncwarp();
 }
@@ -872,41 +893,45 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
     }
 }
 
-// keep the units u with u % world == rank (frontier sharding by subtree).  n_in / n_out
-// (nullable) are device-resident counts for the launch chain that never returns to the host.
+// keep the units this rank owns: the children whose owner tag (written by the canonical expansion of the shard level,
+// see unit_hash) equals `rank`.  Order-free compaction (perft and the search's fold need no order: ids travel with the nodes).
 struct ShardArgs {
     Soa in;
-    const u32 *root_in;
+    const u32 *root_in;   // per-node id carried along (root move / parent index), nullable
+    const u32 *owner;     // per-node owner tag
     size_t n;
-    const u64 *n_in;
     Soa out;
     u32 *root_out;
-    u64 *n_out;
-    size_t out_cap;
-    u32 *overflow;
-    int rank, world;
-    const u64 *single_tile_guard;
+    u64 *n_out;           // device counter, zeroed by the caller
+    int rank;
 };
 __global__ void __launch_bounds__(BLOCK) k_shard_filter(const ShardArgs a) {
-    if (a.n_in && a.overflow && *(volatile u32 *)a.overflow) return;
-    const size_t n = a.n_in ? (size_t)*(volatile const u64 *)a.n_in : a.n;
-    size_t kept = n > (size_t)a.rank ? (n - a.rank + a.world - 1) / a.world : 0;
-    // order-free placement keeps the canonical order only below a level that fitted one tile; with more root moves
-    // than that the unit numbering is not reproducible across ranks -- hand the call to the level-by-level path
-    if (a.overflow && ((a.single_tile_guard && *(volatile const u64 *)a.single_tile_guard > BLOCK) || kept > a.out_cap)) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(a.overflow, 1u);
-        kept = 0;
-    }
-    if (a.n_out && blockIdx.x == 0 && threadIdx.x == 0) *a.n_out = kept;
-    for (size_t o = (size_t)blockIdx.x * BLOCK + threadIdx.x; o < kept; o += (size_t)gridDim.x * BLOCK) { // o-th kept unit = unit rank + o*world
-        const size_t i = (size_t)a.rank + o * (size_t)a.world;
-        soa_store(a.out, o, soa_load(a.in, i));
-        a.root_out[o] = a.root_in ? a.root_in[i] : 0u;
+    const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    const bool keep = i < a.n && a.owner[i] == (u32)a.rank;
+    const unsigned votes = __ballot_sync(0xffffffffu, keep);
+    if (!votes) return;
+    const int lane = threadIdx.x & 31, leader = __ffs((int)votes) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd((unsigned long long *)a.n_out, (unsigned long long)__popc(votes));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (!keep) return;
+    const size_t o = (size_t)base + (size_t)__popc(votes & ((1u << lane) - 1u));
+    soa_store(a.out, o, soa_load(a.in, i));
+    if (a.root_out) a.root_out[o] = a.root_in ? a.root_in[i] : 0u;
+}
+// index-based dealing of a level whose order is the same on every rank (the search's canonical levels): unit u -> rank u % world
+__global__ void __launch_bounds__(BLOCK) k_deal_units(Soa in, const u32 *__restrict__ tag_in, size_t n, int rank, int world, Soa out, u32 *__restrict__ tag_out) {
+    const size_t kept = n > (size_t)rank ? (n - rank + world - 1) / world : 0;
+    for (size_t o = (size_t)blockIdx.x * BLOCK + threadIdx.x; o < kept; o += (size_t)gridDim.x * BLOCK) {
+        const size_t i = (size_t)rank + o * (size_t)world;
+        soa_store(out, o, soa_load(in, i));
+        tag_out[o] = tag_in ? tag_in[i] : (u32)i;
     }
 }
+
 // ---- the perft launch chain: one step per ply (+ the shard filter), every size resident on the device --------
 constexpr int CHAIN_MAX_STEPS = 12;
-enum { STEP_EMIT_SMALL = 0, STEP_EMIT = 1, STEP_TAIL = 2, STEP_SHARD = 3 };
+enum { STEP_EMIT_SMALL = 0, STEP_EMIT = 1, STEP_TAIL = 2 };
 
 // ll_perft_device: gather the chain's results into the caller's device buffer (see the header for the layout)
 __global__ void __launch_bounds__(1024) k_pack_perft_result(const u64 *leaves, const u64 *n_roots, const u32 *overflow, const u64 *per_root, u64 *out) {

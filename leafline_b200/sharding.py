@@ -10,13 +10,33 @@ import numpy as np
 ROOT_SLOTS = 1024  # ll_perft / ll_kickoff root capacity
 
 
-def unit_owner(unit, world_size):
-    """Rank that owns work unit `unit` (units in canonical order, dealt round-robin) -- the rule
-    ll_perft(shard_rank, shard_world) and ll_kickoff apply on the device."""
-    return unit % world_size
+_M64 = (1 << 64) - 1
+
+
+def unit_hash(parent):
+    """`unit_hash` of csrc/ll_device.cuh restated on a WORLD_DTYPE record (host-side mirror, used by the CPU tests)."""
+    meta = int(parent["initiative"]) | (int(parent["service_eligibility"]) << 1) | (int(parent["passing_by"]) << 8)
+    h = ((meta & 0xFFFF) * 0x9E3779B97F4A7C15) & _M64
+    for plane in parent["plane"]:
+        h = (((h ^ int(plane)) * 0xD6E8FEB86659FD93) + (h >> 29)) & _M64
+    return h >> 32
+
+
+def perft_unit_ply(depth):
+    """The ply whose nodes are the work units of a sharded ll_perft (0: the tree is too shallow to deal, rank 0 counts it)."""
+    tail_ply = depth - 2 if depth >= 3 else depth - 1
+    s = min(3, tail_ply)
+    return s if s >= 2 else 0
+
+
+def unit_owner(parent, c, world_size):
+    """Rank that owns the unit made by the c-th commit (canonical order) of `parent` -- the rule ll_perft(shard_rank,
+    shard_world) and ll_perft_multi apply on the device: a pure function of the tree, nothing is exchanged."""
+    return (unit_hash(parent) + c) % world_size
 
 
 def units_of(rank, world_size, n_units):
+    """Units dealt by index (the root-move sharding of ll_kickoff; the canonical levels of ll_kickoff_multi)."""
     return range(rank, n_units, world_size)
 
 

@@ -167,6 +167,32 @@ def test_lookahead_empty_batch_and_capacity_error(eng):
     assert not small.tobytes().strip(b"\0"), "nothing may be written past / into a too-small buffer"
 
 
+def test_out_of_memory_is_recoverable():
+    """LL_ERR_OOM leaves the context usable: a level whose growth failed is emptied, not left with a stale capacity
+    (perft(9) of the opening needs a 3.2 G-node level, ~370 GB)."""
+    import leafline_b200 as ll
+    from leafline_b200 import _abi
+
+    root = ll.new_world()
+    with ll.Engine(0) as e:
+        assert e.perft(root, 6)[0] == 119060324
+        assert e.perft(root, 7)[0] == 3195901860  # sizes level 5 (4.9 M nodes)
+        with pytest.raises(ll.LeaflineError) as err:
+            e.perft(root, 9)
+        assert err.value.code == _abi.ERR_OOM
+        assert e.perft(root, 6)[0] == 119060324  # smaller trees again, on the same context
+        assert e.perft(root, 7)[0] == 3195901860
+        w = O.playout_batch(0x1EAF11E, 0, 64)
+        assert e.horizon(w, 2).tobytes() == np.array([O.negamax(x, 2) for x in w], dtype=np.float32).tobytes()
+        # a malformed ABI byte is rejected alike by the single-position and the batch paths
+        bad = np.array([root, root], dtype=ll.WORLD_DTYPE)
+        bad["service_eligibility"][1] = 0x1F
+        for batch in (bad[1:], bad):
+            with pytest.raises(ll.LeaflineError) as err:
+                e.lookahead(batch)
+            assert err.value.code == _abi.ERR_DOMAIN
+
+
 def test_domain_errors_are_reported_not_guessed(eng):
     import leafline_b200 as ll
 

@@ -12,6 +12,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 KIWIPETE = "r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq -"
+POSITION_3 = "8/2p5/3p4/KP5r/1R3p1k/8/4P1P1/8 w - -"
+POSITION_4 = "r3k2r/Pppp1ppp/1b3nbN/nP6/BBP1P3/q4N2/Pp1P2PP/R2Q1RK1 w kq -"
 
 
 def free_port():
@@ -29,14 +31,21 @@ def worker(rank, world, port, fen, depth, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     root = O.reconstruct(fen)
     roots = O.lookahead(root)
-    # units = 2-ply prefixes in canonical order, dealt round-robin (the rule of ll_perft)
+    # units = the nodes of ply perft_unit_ply(depth), each owned by (hash(parent) + index among the parent's commits) mod world
+    # (the rule of ll_perft / ll_perft_multi; tests/test_gpu_parity.py checks the device against this restatement)
+    unit_ply = sharding.perft_unit_ply(depth)
+    assert unit_ply in (2, 3)
     per_root = np.zeros(len(roots), dtype=np.uint64)
-    unit = 0
+
+    def descend(node, ply, root_index):
+        for k, d in enumerate(O.lookahead(node)):
+            if ply + 1 < unit_ply:
+                descend(d["tree"], ply + 1, root_index)
+            elif sharding.unit_owner(node, k, world) == rank:
+                per_root[root_index] += np.uint64(O.perft(d["tree"], depth - unit_ply))
+
     for i, c in enumerate(roots):
-        for d in O.lookahead(c["tree"]):
-            if sharding.unit_owner(unit, world) == rank:
-                per_root[i] += np.uint64(O.perft(d["tree"], depth - 2))
-            unit += 1
+        descend(c["tree"], 1, i)
     # make the sums cross 2^63 once to prove the u64-as-i64 transport is exact
     bias = np.uint64(0x7FFFFFFFFFFFFFFF) if rank == 0 else np.uint64(1)
     biased = per_root.copy()
@@ -57,17 +66,16 @@ def worker(rank, world, port, fen, depth, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_perft_and_kickoff_reduce_to_the_whole(world, tmp_path):
+@pytest.mark.parametrize("world,fen,depth", [(2, POSITION_4, 4), (3, POSITION_3, 5)])
+def test_sharded_perft_and_kickoff_reduce_to_the_whole(world, fen, depth, tmp_path):
     import oracle as O
 
     O.build()
-    depth = 3
-    mp.spawn(worker, args=(world, free_port(), KIWIPETE, depth, str(tmp_path)), nprocs=world, join=True)
-    root = O.reconstruct(KIWIPETE)
+    mp.spawn(worker, args=(world, free_port(), fen, depth, str(tmp_path)), nprocs=world, join=True)
+    root = O.reconstruct(fen)
     want = O.perft_divide(root, depth, threads=4)
     summed = np.load(tmp_path / "summed.npy")
-    assert list(summed) == list(want) and int(np.load(tmp_path / "total.npy")[0]) == 97814
+    assert list(summed) == list(want) and int(np.load(tmp_path / "total.npy")[0]) == int(want.sum())
     biased = np.load(tmp_path / "biased.npy")
     expect0 = (int(want[0]) + 0x7FFFFFFFFFFFFFFF + (world - 1)) % (1 << 64)
     assert int(biased[0]) == expect0 and list(biased[1:]) == list(want[1:])
