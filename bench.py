@@ -4,19 +4,22 @@
 Workload (BASELINE.json configs[1]): perft depth 6 from the opening WorldState -- 119 060 324 leaves
 of the legal-move tree, i.e. legal move generation over the whole frontier.  One "step" is one full
 perft(6) per GPU.  `value` is leaf positions per second timed on the device (CUDA events on the
-launching stream); `e2e` is the same metric by the host's clock around the C-ABI call ll_perft with
-HOST buffers (host root in, host counts out, copies inside the timed region).
+launching stream); `e2e` is the same metric by the host's clock around the C-ABI call with HOST buffers
+(host roots in, host counts out, copies inside the timed region).
 
-With --gpus N > 1 (launched under torchrun) the path shards by independent root positions (weak
-scaling): the batch holds one root per GPU -- every root is the opening WorldState, so that each
-rank's count stays pinned to 119 060 324 -- and the only collective is a u64 all-reduce of the
-per-root leaf counts over NCCL.  The strong-scaling figure (one perft(7) tree dealt by 2-ply prefixes)
-is reported beside it as `perft7_strong`.
+With --gpus N > 1 (launched under torchrun, one process per GPU) every rank joins ONE library-owned group
+(ll_init_multi_rank: NCCL communicator + the device-resident reduction live behind the C ABI) and a step is
+one call of ll_perft_batch_multi on a batch of N roots -- root i counted by rank i, counts reduced on the
+devices (weak scaling; every root is the opening WorldState so each count stays pinned to 119 060 324).
+The partition of ONE tree is reported beside it: perft(7) (`perft7_strong`, ll_perft_multi), the depth-7
+search (`kickoff7`, ll_kickoff_multi) and configs[4], perft(7) of Kiwipete (`config5`), each with the same
+tree timed on one GPU in the same run (`strong_efficiency` = t1 / (N * tN)).
 
 --impl reference times the CPU oracle (the reference algorithm restated in C; the Rust reference
 cannot be built in this image) on the host cores instead.
 """
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -29,6 +32,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 PERFT_OPENING = {1: 20, 2: 400, 3: 8902, 4: 197281, 5: 4865609, 6: 119060324, 7: 3195901860}
+KIWIPETE = "r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq -"
+KIWIPETE_PERFT7 = 373424113829  # the reference's rules (orthodox chess: 374 190 009 323), profiles/r01_config5_kiwipete_perft7_8gpu.json
 METRIC = "perft_leaf_positions_per_sec"
 UNIT = "leaf positions/s"
 WORKLOAD = "perft(6) from the opening WorldState (BASELINE.json configs[1]); 119060324 leaves"
@@ -42,13 +47,28 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+def device_code_hash():
+    """sha256 over the device code the kernels are built from (what an ncu instruction count is a property of)"""
+    h = hashlib.sha256()
+    for name in ("ll_device.cuh", "ll_kernels.cuh"):
+        with open(os.path.join(ROOT, "leafline_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def profile_constants():
-    """Per-launch instruction / DRAM byte counts taken from the committed ncu captures (profiles/constants.json)."""
+    """Per-launch instruction / DRAM byte counts taken from the committed ncu captures (profiles/constants.json).  They are
+    properties of the device code: when the sources no longer hash to what the capture was taken from, the instruction-count
+    rooflines are withheld instead of being computed from stale counts."""
     path = os.path.join(ROOT, "profiles", "constants.json")
-    if os.path.exists(path):
-        with open(path) as f:
-            return json.load(f)
-    return {}
+    if not os.path.exists(path):
+        return {}, "profiles/constants.json missing"
+    with open(path) as f:
+        consts = json.load(f)
+    if consts.get("device_code_sha256") != device_code_hash():
+        return {}, ("profiles/constants.json was captured from other device code (device_code_sha256 differs): "
+                    "instruction-count rooflines withheld until the kernels are re-profiled")
+    return consts, None
 
 
 class ClockSampler(threading.Thread):
@@ -100,39 +120,61 @@ class ClockSampler(threading.Thread):
 
 
 def reference_arm(args, rank, world):
-    """The reference's own algorithm on the host cores (oracle port; see module docstring)."""
+    """The reference's own algorithm on the host cores (oracle port; see module docstring): perft(6) of the opening,
+    every step the subtrees of the first m of its 20 root moves -- m = 20 (the whole tree) when the run fits the time
+    budget, fewer otherwise (a bounded sample of the same workload, said in `config`).  Threads: below every root move
+    one thread per reply (the reference's own model one ply down, mind.rs:399-414), all host threads busy."""
     if rank != 0:
         return
     import oracle as O
 
     O.build()
     cores = os.cpu_count() or 1
-    w = O.new_world()
-    depth, leaves = 5, PERFT_OPENING[5]  # bounded sample of the workload: one ply shallower
+    root = O.new_world()
+    children = [c["tree"].copy() for c in O.lookahead(root)]
+
+    def subtree(i):
+        return int(O.perft_divide(children[i], 5, threads=cores).sum())
+
+    t0 = time.perf_counter()
+    first = subtree(0)
+    per_move = time.perf_counter() - t0  # calibration, untimed: one root move's subtree
+    budget_s = 200.0
+    m = int(max(1, min(len(children), budget_s / ((args.steps + args.warmup) * per_move))))
+    want = None
     for _ in range(args.warmup):
-        O.perft_divide(w, depth, threads=cores)
+        got = sum(subtree(i) for i in range(m))
+        assert want is None or got == want
+        want = got
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        got = int(O.perft_divide(w, depth, threads=cores).sum())
-        assert got == leaves
+        got = sum(subtree(i) for i in range(m))
+        assert want is None or got == want
+        want = got
     dt = time.perf_counter() - t0
-    value = leaves * args.steps / dt
-    sample = (f"perft(5) from the opening ({leaves} leaves) per step, one thread per root move "
-              f"(the reference's own model, mind.rs:399-414) over {cores} host threads")
+    if m == len(children):
+        assert want == PERFT_OPENING[6], want
+    assert first > 0
+    value = want * args.steps / dt
+    sample = (f"perft(6) from the opening: the depth-5 subtrees of the first {m} of its {len(children)} root moves per step "
+              f"({want} of {PERFT_OPENING[6]} leaves), one thread per reply below each root move over {cores} host threads; "
+              f"oracle built -O3 -march=native -ffp-contract=off")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reference_sample": sample},
+        "config": {"workload": WORKLOAD, "reference_sample": sample, "root_moves_per_step": m, "leaves_per_step": want},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def timed(stream, fn, reps, torch):
-    """median CUDA-event time (ms) of fn() on `stream`"""
+def timed(stream, fn, reps, torch, flush=None):
+    """median CUDA-event time (ms) of fn() on `stream` (L2 flushed before every repetition when `flush` is given)"""
     times = []
     for _ in range(reps):
+        if flush is not None:
+            flush.fill_(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
         fn()
@@ -145,17 +187,17 @@ def timed(stream, fn, reps, torch):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 2000, about 1.2 s; 40 for --impl reference)")
-    ap.add_argument("--warmup", type=int, default=None, help="warm-up steps (default 50; 3 for --impl reference)")
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 2000, about 1.2 s; 5 for --impl reference)")
+    ap.add_argument("--warmup", type=int, default=None, help="warm-up steps (default 50; 1 for --impl reference)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--depth", type=int, default=6)
     ap.add_argument("--no-extras", action="store_true", help="skip the cpu baseline and the secondary kernels")
     args = ap.parse_args()
-    # a reference step is ~0.5 s of all-core CPU work, a B200 step ~0.5 ms: different defaults, explicit values are honoured
+    # a reference step is ~15 s of all-core CPU work, a B200 step ~0.4 ms: different defaults, explicit values are honoured
     if args.steps is None:
-        args.steps = 2000 if args.impl == "b200" else 40
+        args.steps = 2000 if args.impl == "b200" else 5
     if args.warmup is None:
-        args.warmup = 50 if args.impl == "b200" else 3
+        args.warmup = 50 if args.impl == "b200" else 1
     if args.impl == "b200":
         args.warmup = max(args.warmup, 3)
 
@@ -182,41 +224,40 @@ def main():
     if world > 1:
         dist.barrier()
     import leafline_b200 as ll
-    from leafline_b200 import sharding
 
-    eng = ll.Engine(local_rank)
+    group = None
+    if world > 1:
+        # the library owns the communicator: the id is made on rank 0 and carried to the other processes by torch.distributed
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(ll.MultiEngine.unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        group = ll.MultiEngine.for_rank(local_rank, rank, world, bytes(uid.cpu().numpy()))
+        eng = group.member(0)
+    else:
+        eng = ll.Engine(local_rank)
+    solo = ll.Engine(local_rank) if world > 1 else eng  # the same trees on ONE GPU, timed in the same run
     # a real (non-default) stream: the engine launches on it, so the CUDA events below see its kernels
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
+    if solo is not eng:
+        solo.set_stream(stream.cuda_stream)
 
     root = ll.new_world()
     depth = args.depth
     expected = PERFT_OPENING.get(depth)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    counts = torch.zeros(1024, dtype=torch.int64, device="cuda")
-
-    def reduce_counts(per_root):
-        """u64 all-reduce (sum) of the per-root leaf counts over NCCL (leafline_b200/sharding.py)"""
-        return sharding.reduce_leaf_counts(per_root, dist, torch, device="cuda", scratch=counts)[0]
-
-    d_out = torch.zeros(ll.PERFT_DEVICE_WORDS, dtype=torch.int64, device="cuda")
-    h_out = torch.zeros(ll.PERFT_DEVICE_WORDS, dtype=torch.int64).pin_memory()
+    batch = np.array([root] * world, dtype=ll.WORLD_DTYPE)
+    counts = np.zeros(world, dtype=np.uint64)
 
     def step():
-        """one perft per GPU (this rank's root of the batch) + the count all-reduce"""
+        """one perft per GPU: ll_perft on one GPU; ll_perft_batch_multi (root i -> rank i, counts reduced on the devices) on N"""
         if world == 1:
             return eng.perft(root, depth)[0]
-        # counts stay on the device: launch chain -> NCCL u64 sum -> one D2H read of the reduced table
-        eng.perft_device(root, depth, d_out.data_ptr())
-        dist.all_reduce(d_out)
-        h_out.copy_(d_out, non_blocking=True)
-        stream.synchronize()
-        if int(h_out[2]) != 0:  # some rank's level outgrew its buffer: redo through the re-sizing host path
-            return reduce_counts(eng.perft(root, depth)[1])
-        return int(h_out[0])
+        return int(group.perft_batch(batch, depth, out=counts).sum())
 
-    eng.perft(root, depth)  # the first call sizes the level buffers (level-by-level path); the steps run the launch chain
+    step()  # the first call sizes the level buffers (level-by-level path); the steps run the launch chain
     sampler = ClockSampler(local_rank)
     if rank == 0:  # one nvidia-smi poller per job: the clocks reported are rank 0's GPU
         sampler.start()
@@ -256,6 +297,7 @@ def main():
     ms_per_step = device_ms / args.steps
     value = leaves_total / (ms_per_step * 1e-3)
     e2e_value = leaves_total / (host_ms / args.steps * 1e-3)
+    expanded_per_tree = sum(PERFT_OPENING[d] for d in range(1, depth)) + 1 if depth <= 7 else None  # nodes of plies 0 .. depth-1
 
     result = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -263,84 +305,88 @@ def main():
         "dtype": "u64", "data": "synthetic",
         "config": {"workload": WORKLOAD if depth == 6 else f"perft({depth}) from the opening WorldState",
                    "depth": depth, "leaves_per_step": leaves_total, "roots_per_step": world,
-                   "sharding": (f"one root position per GPU ({world} ranks), no position ever crosses NVLink; "
-                                "u64 all-reduce of per-root leaf counts") if world > 1 else "single GPU",
+                   "sharding": (f"ll_perft_batch_multi: one root position per GPU ({world} ranks, one process each, library-owned group), no position "
+                                f"ever crosses NVLink; u64 sum of the {world} leaf counts on the devices by {group.reduce_path}") if world > 1 else "single GPU (ll_perft)",
                    "l2": "flushed between timed steps (256 MiB write, untimed)"},
         "clocks": clocks, "gpu_launches": launches,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 104, "d2h_bytes_per_step": 8 + 8 * 1024,
+        "expanded_nodes_per_sec": None if expanded_per_tree is None else expanded_per_tree * world / (ms_per_step * 1e-3),
+        "expanded_nodes_note": ("SURVEY.md 8(d) work unit: a node whose legal children are generated (plies 0 .. depth-1; the last ply's children are "
+                                "bulk-counted, never built) -- leaf positions/s counts those bulk-counted leaves"),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 104 * world, "d2h_bytes_per_step": (8 + 8 * 1024) if world == 1 else 8 * world,
                 "ms_per_step": host_ms / args.steps,
                 "note": ("host clock around the C-ABI call ll_perft (host root in, host leaf counts out, both copies inside)" if world == 1 else
-                         "host clock around ll_perft_device (host root in) + NCCL u64 all-reduce of the count table + its D2H read")},
+                         "host clock around the C-ABI call ll_perft_batch_multi (host roots in, device-side reduction, host counts out)")},
     }
+    if world > 1:
+        result["reduce_path"] = group.reduce_path
 
-    # strong-scaling companion: ONE perft(7) tree dealt to the ranks by 2-ply prefixes + u64 all-reduce
+    def strong(name, fn_multi, fn_solo, reps, units, unit_name):
+        """ONE tree on the whole group and, in the same run, on one GPU: ms (max over ranks), rate, efficiency t1 / (N * tN)"""
+        want = fn_solo()
+        got = fn_multi()
+        if world > 1:
+            dist.barrier()
+        ms_n = timed(stream, fn_multi, reps, torch, flush)
+        ms_1 = timed(stream, fn_solo, reps, torch, flush) if world > 1 else ms_n
+        tt = torch.tensor([ms_n, ms_1], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_n, ms_1 = float(tt[0].item()), float(tt[1].item())
+        out = {"ms": ms_n, unit_name: units / (ms_n * 1e-3), "scaling": "strong", "single_gpu_ms_same_run": ms_1,
+               "strong_efficiency": ms_1 / (world * ms_n)}
+        return want, got, out
+
     if not args.no_extras:
-        def perft7():
-            leaves, per_root = eng.perft(root, 7, shard=(rank, world))
-            return reduce_counts(per_root) if world > 1 else leaves
+        # strong scaling, perft: ONE perft(7) tree; its ply-3 nodes dealt to the ranks (ll_perft_multi)
+        want, got, out = strong("perft7", (lambda: group.perft(root, 7)[0]) if world > 1 else (lambda: eng.perft(root, 7)[0]),
+                                lambda: solo.perft(root, 7)[0], 5, PERFT_OPENING[7], "leaf_positions_per_sec")
+        assert want == got == PERFT_OPENING[7], (want, got)
+        out.update({"leaves": PERFT_OPENING[7], "sharding": f"ply-3 nodes dealt over {world} rank(s) by (hash(parent) + canonical index) mod world; u64 sum on the devices"})
+        result["perft7_strong"] = out
 
-        assert perft7() == PERFT_OPENING[7]
-        if world > 1:
-            dist.barrier()
-        ms7 = timed(stream, perft7, 3, torch)
-        t7 = torch.tensor([ms7], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t7, op=dist.ReduceOp.MAX)
-        ms7 = float(t7.item())
-        result["perft7_strong"] = {"leaves": PERFT_OPENING[7], "ms": ms7, "leaf_positions_per_sec": PERFT_OPENING[7] / (ms7 * 1e-3),
-                                   "scaling": "strong", "sharding": f"2-ply prefixes round-robin over {world} rank(s)"}
+        # configs[3]: depth-5 search of the opening (TT-free exact negamax below every root move).  4.9 M leaves are ~0.3 ms of
+        # work: the library answers such a tree whole on every rank instead of dealing it (ll_multi_set_shard_min_depth)
+        def kick(e_or_g, d):
+            roots, scores, scored = e_or_g.kickoff(root, d)
+            return scores.tobytes(), scored
 
-    # configs[3]: depth-5 search from the opening (TT-free exact negamax below every root move), root moves
-    # dealt to the ranks, per-root scores gathered with a max over NCCL
-    if not args.no_extras:
-        def kickoff5():
-            roots, scores, scored = eng.kickoff(root, 5, shard=(rank, world))
-            if world > 1:
-                scores = sharding.gather_root_scores(scores, dist, torch, device="cuda")
-            return scores, scored
+        for d, reps in ((5, 5), (7, 3)):
+            want, got, out = strong(f"kickoff{d}", (lambda: kick(group, d)) if world > 1 else (lambda: kick(eng, d)), lambda: kick(solo, d), reps, 1, "x")
+            assert want == got, f"kickoff{d}: group scores differ from one GPU's"
+            scored = want[1]
+            out.pop("x")
+            out.update({"depth": d, "root_moves": len(want[0]) // 4, "best_score": float(np.frombuffer(want[0], dtype=np.float32).max()), "leaves_scored": scored,
+                        "leaf_positions_per_sec": scored / (out["ms"] * 1e-3),
+                        "sharding": ("answered whole by every rank (below the dealing threshold)" if d < 6 or world == 1 else
+                                     f"ll_kickoff_multi: ply-3 nodes dealt round-robin over {world} rank(s); per-parent f32 keys max-reduced on the devices")})
+            result[f"kickoff{d}"] = out
 
-        scores5, scored5 = kickoff5()
-        if world > 1:
-            dist.barrier()
-        ms5 = timed(stream, kickoff5, 3, torch)
-        t5 = torch.tensor([ms5, float(scored5)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            tmax = t5.clone()
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            dist.all_reduce(t5, op=dist.ReduceOp.SUM)
-            ms5, scored_all = float(tmax[0].item()), int(t5[1].item())
-        else:
-            scored_all = scored5
-        result["kickoff5"] = {"depth": 5, "root_moves": len(scores5), "best_score": float(np.max(scores5)), "leaves_scored": scored_all,
-                              "ms": ms5, "leaf_positions_per_sec": scored_all / (ms5 * 1e-3), "scaling": "strong",
-                              "sharding": f"root moves round-robin over {world} rank(s); max-gather of per-root f32 scores"}
-
-        # the same search two plies deeper (3.3 G leaves): large enough for the root-subtree sharding to show
-        def kickoff7():
-            roots, scores, scored = eng.kickoff(root, 7, shard=(rank, world))
-            if world > 1:
-                scores = sharding.gather_root_scores(scores, dist, torch, device="cuda")
-            return scores, scored
-
-        scores7, scored7 = kickoff7()
-        if world > 1:
-            dist.barrier()
-        ms7k = timed(stream, kickoff7, 3, torch)
-        t7k = torch.tensor([ms7k, float(scored7)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            tmax = t7k.clone()
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            dist.all_reduce(t7k, op=dist.ReduceOp.SUM)
-            ms7k, scored7_all = float(tmax[0].item()), int(t7k[1].item())
-        else:
-            scored7_all = scored7
-        result["kickoff7"] = {"depth": 7, "root_moves": len(scores7), "best_score": float(np.max(scores7)), "leaves_scored": scored7_all,
-                              "ms": ms7k, "leaf_positions_per_sec": scored7_all / (ms7k * 1e-3), "scaling": "strong",
-                              "sharding": f"root moves round-robin over {world} rank(s); max-gather of per-root f32 scores"}
+        # configs[4]: perft(7) of Kiwipete (ascension, secret service, passing by all live) on the whole group
+        kiwi = ll.reconstruct(KIWIPETE)
+        want, got, out = strong("config5", (lambda: group.perft(kiwi, 7)) if world > 1 else (lambda: eng.perft(kiwi, 7)), lambda: solo.perft(kiwi, 7), 2,
+                                KIWIPETE_PERFT7, "leaf_positions_per_sec")
+        assert got[0] == want[0] == KIWIPETE_PERFT7 and list(got[1]) == list(want[1]), (got[0], want[0])
+        checks = {"single_gpu_recount": True, "divide_table_equal": True}
+        children_sum = 0
+        if rank == 0:  # sum of the 48 root children's perft(6), each counted separately on one GPU
+            _, kids = solo.lookahead(kiwi)
+            children_sum = sum(solo.perft(c["tree"], 6)[0] for c in kids)
+            assert children_sum == KIWIPETE_PERFT7
+            checks["sum_of_root_children_perft6"] = children_sum
+            fixture = os.path.join(ROOT, "tests", "golden", "kiwipete_prefix_perft5.json")
+            if os.path.exists(fixture):  # oracle recounts of sampled 2-ply prefixes at sub-depth 5 (committed fixture)
+                with open(fixture) as f:
+                    fx = json.load(f)
+                for s in fx["samples"]:
+                    assert solo.perft(ll.reconstruct(s["runes"]), 5)[0] == s["perft5"], s
+                checks["oracle_prefix_samples_at_sub_depth_5"] = len(fx["samples"])
+        out.update({"position": KIWIPETE, "depth": 7, "leaves": KIWIPETE_PERFT7, "verified": checks,
+                    "note": "the reference's rules (orthodox chess counts 374190009323: SURVEY.md 8(a) quirks 1-2)"})
+        result["config5"] = out
 
     if rank == 0 and world == 1 and not args.no_extras:
         peaks, peak_src = measured_peaks()
-        consts = profile_constants()
+        consts, consts_problem = profile_constants()
         # per-kernel device time inside one step, measured live (CUDA events on the launching stream)
         eng.timing(True)
         eng.timing_reset()
@@ -363,28 +409,31 @@ def main():
             k_ms = kernels["perft_tail"]["ms_per_step"]
             nodes = PERFT_OPENING[4]
             alg_bytes = nodes * 104.0 + 21 * 8  # 100 B position + 4 B root id per expanded node, per-root counts out
-            achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-            result["roofline"] = {
-                "kernel": "k_expand_records<PERFT>", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": consts.get("perft6_tail_dram_bytes"), "peak_source": peak_src,
-                "ms": k_ms,
-                "note": "the perft tail reads only the ply-4 frontier (197281 positions x 104 B) and builds the 4.87 M ply-5 "
-                        "positions and their 119 M leaves on-chip: it is integer-issue bound, see int_roofline",
-            }
+            hbm = {"achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "peak_source": peak_src,
+                   "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": alg_bytes,
+                   "note": "the tail reads only the ply-4 frontier (197281 positions x 104 B): HBM is nowhere near the bound"}
             inst = consts.get("perft6_tail_thread_inst")
+            roof = {"kernel": "k_expand_records<PERFT>", "bound": "int-issue", "unit": "T thread-inst/s", "ms": k_ms,
+                    "traffic": consts.get("perft6_tail_dram_bytes"), "hbm": hbm, "leaves_per_launch": expected,
+                    "expanded_nodes_per_launch": PERFT_OPENING[4] + PERFT_OPENING[5]}
             if inst:
                 rate = inst / (k_ms * 1e-3)
-                result["int_roofline"] = {
-                    "kernel": "k_expand_records<PERFT>", "bound": "int-issue", "achieved": rate / 1e12,
-                    "peak": int_peak["lop3_imad_thread_inst_per_sec"] / 1e12,
-                    "unit": "T thread-inst/s", "frac": rate / int_peak["lop3_imad_thread_inst_per_sec"],
-                    "frac_of_alu_pipe": rate / int_peak["lop3_thread_inst_per_sec"],
-                    "thread_inst_per_launch": inst, "leaves_per_launch": expected,
+                alu_warp_inst = consts.get("perft6_tail_alu_pipe_warp_inst")
+                roof.update({
+                    "achieved": rate / 1e12, "peak": int_peak["lop3_imad_thread_inst_per_sec"] / 1e12,
+                    "frac": rate / int_peak["lop3_imad_thread_inst_per_sec"],
+                    "thread_inst_per_launch": inst, "thread_inst_per_expanded_child": inst / PERFT_OPENING[5],
+                    # the binding pipe: warp instructions the ALU pipe executed, each occupying it for a full 32-lane warp, against the
+                    # measured LOP3-only stream (the ALU pipe's peak)
+                    "alu_pipe_frac": None if not alu_warp_inst else alu_warp_inst * 32.0 / (k_ms * 1e-3) / int_peak["lop3_thread_inst_per_sec"],
                     "ncu": {"alu_pipe_busy_pct": consts.get("perft6_tail_alu_pipe_pct"), "issue_slots_busy_pct": consts.get("perft6_tail_issue_active_pct"),
                             "lanes_active_of_32": consts.get("perft6_tail_lanes_active_of_32")},
-                    "note": "thread-level instructions per launch from the committed ncu capture (profiles/constants.json); "
-                            "peak = dependency-free LOP3+IMAD stream measured in this run (issue port), frac_of_alu_pipe = vs LOP3 only",
-                }
+                    "note": "achieved = thread-level instructions per launch (committed ncu capture of this device code, profiles/constants.json) / the "
+                            "kernel's live CUDA-event time; peak = dependency-free LOP3+IMAD stream measured in this run (the issue port)",
+                })
+            else:
+                roof.update({"achieved": None, "peak": int_peak["lop3_imad_thread_inst_per_sec"] / 1e12, "frac": None, "withheld": consts_problem})
+            result["roofline"] = roof
         # movegen+eval half of the metric: horizon over seeded playout positions resident in HBM (configs[2]/[3] shape)
         n_h = 1 << 22
         soa = eng.playout_soa(n_h)
@@ -395,7 +444,7 @@ def main():
         result["horizon"] = {
             "frontier_positions": n_h, "plies": 1, "leaf_positions": scored, "ms": h_ms,
             "leaf_positions_per_sec": scored / (h_ms * 1e-3),
-            "int_roofline": None if not h_inst else {
+            "int_roofline": {"withheld": consts_problem} if not h_inst else {
                 "kernel": "k_horizon", "bound": "int-issue", "achieved": h_inst * (n_h / (1 << 20)) / (h_ms * 1e-3) / 1e12,
                 "peak": int_peak["lop3_imad_thread_inst_per_sec"] / 1e12, "unit": "T thread-inst/s",
                 "frac": h_inst * (n_h / (1 << 20)) / (h_ms * 1e-3) / int_peak["lop3_imad_thread_inst_per_sec"],
@@ -442,23 +491,23 @@ def main():
             "l2": "input 1.7 GB > 126 MB L2",
         }
         del pinned_in, pinned_out, w_np
-        # CPU baseline: the reference algorithm (oracle port) on this box's host cores
+        # CPU baseline: the reference algorithm (oracle port) on this box's host cores, the SAME workload: perft(6) of the
+        # opening once (about 15 s), below every root move one thread per reply
         import oracle as O
 
         cores = os.cpu_count() or 1
         w = O.new_world()
+        kids = [c["tree"].copy() for c in O.lookahead(w)]
         t0 = time.perf_counter()
-        reps_cpu = 0
-        while time.perf_counter() - t0 < 10.0:
-            got = int(O.perft_divide(w, 5, threads=cores).sum())
-            assert got == PERFT_OPENING[5]
-            reps_cpu += 1
-        dt = (time.perf_counter() - t0) / reps_cpu
+        got = sum(int(O.perft_divide(k, 5, threads=cores).sum()) for k in kids)
+        dt = time.perf_counter() - t0
+        assert got == PERFT_OPENING[6]
         result["cpu_baseline"] = {
-            "value": PERFT_OPENING[5] / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"perft(5) from the opening ({PERFT_OPENING[5]} leaves) x{reps_cpu}, one thread per root move over {cores} host threads, {dt:.2f} s each",
+            "value": PERFT_OPENING[6] / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"perft(6) from the opening once ({PERFT_OPENING[6]} leaves, {dt:.1f} s), one thread per reply below each root move over {cores} host threads; "
+                      "oracle built -O3 -march=native -ffp-contract=off",
         }
-        # beside it: the same on ONE host thread, and the CPU scorer on a 2^20-position prefix
+        # beside it: perft(5) on ONE host thread, and the CPU scorer on a 2^20-position prefix
         t0 = time.perf_counter()
         assert int(O.perft_divide(w, 5, threads=1).sum()) == PERFT_OPENING[5]
         dt1 = time.perf_counter() - t0
@@ -474,7 +523,12 @@ def main():
 
     if rank == 0:
         print(json.dumps(result))
-    eng.close()
+    if solo is not eng:
+        solo.close()
+    if group is not None:
+        group.close()
+    else:
+        eng.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

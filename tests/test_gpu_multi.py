@@ -139,7 +139,7 @@ def test_group_of_one_rank(ll, eng):
 
 WORKER = r"""
 import os, sys
-sys.path.insert(0, %r)
+sys.path.insert(0, REPO_ROOT)
 import numpy as np, torch, torch.distributed as dist
 import leafline_b200 as ll
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -177,7 +177,7 @@ try:
 except ll.LeaflineError:
     pass
 assert g.perft(ll.new_world(), 5)[0] == 4865609
-print("rank", rank, "ok", g.reduce_path, flush=True)
+print("rank %d ok %s\n" % (rank, g.reduce_path), end="", flush=True)
 g.close(); e.close()
 dist.barrier(); dist.destroy_process_group()
 """
@@ -191,9 +191,9 @@ def test_one_process_per_gpu(ll, reduce_path, tmp_path):
         pytest.skip("needs two GPUs")
     world = min(n, 8)
     script = tmp_path / "worker.py"
-    script.write_text(WORKER % ROOT)
+    script.write_text(WORKER.replace("REPO_ROOT", repr(ROOT)))
     env = dict(os.environ, LEAFLINE_B200_REDUCE=reduce_path)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                           "--master-port", "29561", str(script)], env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
-    assert out.stdout.count(" ok ") == world
+    assert out.stdout.count("ok") == world, out.stdout  # (the ranks' lines may interleave)
