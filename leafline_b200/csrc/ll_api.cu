@@ -528,6 +528,24 @@ static int init_ctx(ll_ctx *ctx) {
         }
     CUDA_TRY(cudaMemcpyToSymbol(d_pony_table, pony, sizeof pony));
     CUDA_TRY(cudaMemcpyToSymbol(d_figurehead_table, fig, sizeof fig));
+    u64 lines[64 * 4]; // StagedLines: diagonal, anti-diagonal, file and rank through every square, the square excluded
+    for (int sq = 0; sq < 64; sq++) {
+        const int r = sq >> 3, f = sq & 7;
+        u64 d = 0, a = 0, fl = 0, rk = 0;
+        for (int t = 0; t < 64; t++) {
+            const int tr = t >> 3, tf = t & 7;
+            if (t == sq) continue;
+            if (tf - tr == f - r) d |= 1ull << t;
+            if (tf + tr == f + r) a |= 1ull << t;
+            if (tf == f) fl |= 1ull << t;
+            if (tr == r) rk |= 1ull << t;
+        }
+        lines[4 * sq] = d;
+        lines[4 * sq + 1] = a;
+        lines[4 * sq + 2] = fl;
+        lines[4 * sq + 3] = rk;
+    }
+    CUDA_TRY(cudaMemcpyToSymbol(d_line_table, lines, sizeof lines));
     LL_TRY(ensure(ctx, ctx->scalars, SC_SLOTS * sizeof(u64)));
     return LL_OK;
 }

@@ -123,9 +123,11 @@ LL_HD void soa_store(const Soa &s, size_t i, const Pos &p) {
 #ifdef __CUDACC__
 __device__ u64 d_pony_table[64];
 __device__ u64 d_figurehead_table[64];
+__device__ u64 d_line_table[64 * 4]; // StagedLines
 #else
 static u64 d_pony_table[64];
 static u64 d_figurehead_table[64];
+static u64 d_line_table[64 * 4];
 #endif
 LL_HD u64 pony_moves(int sq) { return ldg(&d_pony_table[sq]); }
 LL_HD u64 figurehead_moves(int sq) { return ldg(&d_figurehead_table[sq]); }
@@ -358,7 +360,35 @@ LL_HD bool lands_legally(const Legal &L, u64 fb, u64 tb) {
 }
 LL_HD u64 between_on(u64 line, u64 a, u64 b) { return ((a - 1) ^ (b - 1)) & line & ~(a | b); } // a, b on `line`
 
-template <int T> LL_HD Legal legal_context(const Pos &p, u64 own, u64 opp) {
+// The four lines through a square, the square itself excluded -- computed (shifts of the two main diagonals: ALU pipe) or
+// read from a 2 KiB table staged in shared memory (two 128-bit loads: LSU pipe).  BASELINE.json's north_star names the
+// choice ("Kogge-Stone fills or shared-memory-staged ... tables"); both are built and A/B-timed with ncu counters on the
+// perft tail, whose bound is the ALU pipe.  The set-wise fills have no table form: a table answers one
+// slider at a time, the fills answer all sliders of a direction at once at a cost independent of their number.
+struct ComputedLines {
+    LL_HDM void operator()(int sq, u64 bit, u64 &kd, u64 &ka, u64 &kf, u64 &kr) const {
+        kd = diag_mask(sq) & ~bit;
+        ka = anti_mask(sq) & ~bit;
+        kf = file_mask(sq) & ~bit;
+        kr = rank_mask(sq) & ~bit;
+    }
+};
+struct StagedLines {
+    const u64 *table; // [64][4]: diagonal, anti-diagonal, file, rank through the square, the square excluded; 32-byte rows
+    LL_HDM void operator()(int sq, u64, u64 &kd, u64 &ka, u64 &kf, u64 &kr) const {
+#ifdef __CUDACC__
+        const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(table + 4 * sq), b = *reinterpret_cast<const ulonglong2 *>(table + 4 * sq + 2);
+        kd = a.x;
+        ka = a.y;
+        kf = b.x;
+        kr = b.y;
+#else
+        kd = table[4 * sq]; ka = table[4 * sq + 1]; kf = table[4 * sq + 2]; kr = table[4 * sq + 3];
+#endif
+    }
+};
+
+template <int T, class Lines = ComputedLines> LL_HD Legal legal_context(const Pos &p, u64 own, u64 opp, const Lines &lines = Lines()) {
     constexpr int E = 1 - T;
     Legal L;
     L.check = ~0ull;
@@ -394,10 +424,7 @@ template <int T> LL_HD Legal legal_context(const Pos &p, u64 own, u64 opp) {
         L.danger = danger;
     }
     // checkers and pins along the four lines through the figurehead
-    L.kd = diag_mask(ksq) & ~k;
-    L.ka = anti_mask(ksq) & ~k;
-    L.kf = file_mask(ksq) & ~k;
-    L.kr = rank_mask(ksq) & ~k;
+    lines(ksq, k, L.kd, L.ka, L.kf, L.kr);
     u64 checkers = (servant_attackers_of<E>(k) & p.pl[6 * E + SERVANT]) | (pony_moves(ksq) & p.pl[6 * E + PONY]) |
                    (figurehead_moves(ksq) & p.pl[6 * E + FIGUREHEAD]);
     u64 pinned = 0;
@@ -574,10 +601,10 @@ struct CountSink {
     LL_HDM void move(u32, int, int, u32, u32) { n++; }
 };
 
-template <int T, bool NIHIL> LL_HD u32 count_moves_as(const Pos &p) {
+template <int T, bool NIHIL, class Lines = ComputedLines> LL_HD u32 count_moves_as(const Pos &p, const Lines &lines = Lines()) {
     const u64 own = occupied_by<T>(p), opp = occupied_by<1 - T>(p), occ = own | opp, empty = ~occ;
     Legal L;
-    if (!NIHIL) L = legal_context<T>(p, own, opp);
+    if (!NIHIL) L = legal_context<T>(p, own, opp, lines);
     else { L.check = ~0ull; L.pinned = 0; L.danger = 0; L.kd = L.ka = L.kf = L.kr = 0; }
     u32 n = 0;
     if (p.pl[6 * T + FIGUREHEAD]) n += popc64(figurehead_moves(lsb64(p.pl[6 * T + FIGUREHEAD])) & ~own & ~L.danger);
@@ -628,6 +655,9 @@ template <int T, bool NIHIL> LL_HD u32 count_moves_as(const Pos &p) {
 }
 template <bool NIHIL> LL_HD u32 count_moves(const Pos &p) {
     return meta_stm(p.meta) == 0 ? count_moves_as<0, NIHIL>(p) : count_moves_as<1, NIHIL>(p);
+}
+template <bool NIHIL, class Lines> LL_HD u32 count_moves(const Pos &p, const Lines &lines) {
+    return meta_stm(p.meta) == 0 ? count_moves_as<0, NIHIL>(p, lines) : count_moves_as<1, NIHIL>(p, lines);
 }
 
 // ---- reckless commits as (piece or servant-set, target mask) records ------------------------------------
@@ -955,7 +985,10 @@ LL_HD Feat features_of(const Pos &p) {
     f.w[6] = bf;
     return f;
 }
-LL_HD float score_features(const Feat &f, u32 stm, u32 elig) {
+// score_features in two halves, the float sequence unchanged: the material terms (mind.rs:53-68) read the twelve head
+// counts only -- a child that stuns nobody, ascends nothing and conjures nothing has its parent's, so the horizon kernel
+// computes this half once per PARENT for all such children -- and the positional terms (mind.rs:70-140) continue from it.
+LL_HD float score_material(const Feat &f, u32 stm) {
     const float values[6] = {1.0f, 3.2f, 3.3f, 5.1f, 8.8f, 20000.0f}; // mind.rs:36-48
     float v = 0.0f;
     v = fadd(v, fmul(0.5f, stm ? -1.0f : 1.0f)); // mind.rs:53
@@ -970,27 +1003,72 @@ LL_HD float score_features(const Feat &f, u32 stm, u32 elig) {
         const int j = 6 * team + SCHOLAR;
         if (((f.w[j >> 2] >> (8 * (j & 3))) & 0xFFu) >= 2) v = fadd(v, fmul(orient, 0.5f));
     }
-    const int oc = (int)(f.w[3] & 0xFFu), bc = (int)((f.w[3] >> 8) & 0xFFu); // mind.rs:70-81
+    return v;
+}
+LL_HD float score_positional(float v, u32 w3, u32 w4, u32 w5, u32 w6, u32 elig) {
+    const int oc = (int)(w3 & 0xFFu), bc = (int)((w3 >> 8) & 0xFFu); // mind.rs:70-81
     v = fadd(v, fmul(0.1f, (float)(oc - bc)));
-    v = fadd(v, fmul(0.5f, (float)((f.w[3] >> 16) & 0xFFu))); // mind.rs:83-89
-    v = fadd(v, -fmul(0.5f, (float)(f.w[3] >> 24)));
+    v = fadd(v, fmul(0.5f, (float)((w3 >> 16) & 0xFFu))); // mind.rs:83-89
+    v = fadd(v, -fmul(0.5f, (float)(w3 >> 24)));
     { // mind.rs:91-111: only files with a second servant add anything; ascending, Orange before Blue
-        u32 files = (f.w[5] | f.w[6]) & 0xEEEEEEEEu; // a nibble >= 2 has one of its upper three bits set
+        u32 files = (w5 | w6) & 0xEEEEEEEEu; // a nibble >= 2 has one of its upper three bits set
         while (files) {
             const int sh = lsb32(files) & ~3;
             files &= ~(0xFu << sh);
-            const int o = (int)((f.w[5] >> sh) & 0xFu), b = (int)((f.w[6] >> sh) & 0xFu);
+            const int o = (int)((w5 >> sh) & 0xFu), b = (int)((w6 >> sh) & 0xFu);
             if (o > 1) v = fadd(v, -fmul(0.5f, (float)(o - 1)));
             if (b > 1) v = fadd(v, fmul(0.5f, (float)(b - 1)));
         }
     }
-    v = fadd(v, fmul(1.8f, (float)(f.w[4] & 0xFFu))); // mind.rs:113-131
-    v = fadd(v, fmul(0.6f, (float)((f.w[4] >> 8) & 0xFFu)));
-    v = fadd(v, -fmul(1.8f, (float)((f.w[4] >> 16) & 0xFFu)));
-    v = fadd(v, -fmul(0.6f, (float)(f.w[4] >> 24)));
+    v = fadd(v, fmul(1.8f, (float)(w4 & 0xFFu))); // mind.rs:113-131
+    v = fadd(v, fmul(0.6f, (float)((w4 >> 8) & 0xFFu)));
+    v = fadd(v, -fmul(1.8f, (float)((w4 >> 16) & 0xFFu)));
+    v = fadd(v, -fmul(0.6f, (float)(w4 >> 24)));
     if (elig & 0x3u) v = fadd(v, 0.1f); // mind.rs:133-140
     if (elig & 0xCu) v = fadd(v, -0.1f);
     return v;
+}
+LL_HD float score_features(const Feat &f, u32 stm, u32 elig) {
+    return score_positional(score_material(f, stm), f.w[3], f.w[4], f.w[5], f.w[6], elig);
+}
+// The score of the child that a QUIET commit makes (nobody stunned, nothing ascended, no secret service, no passing by:
+// the head counts and the servants' files are the parent's): `material` = score_material(parent's features, child's
+// initiative), w3 / w4 / elig the parent's, updated here by the move alone.  Same integers, same float sequence as
+// score_features(child_features(...)) -- tests/hostcheck compares the two on every quiet commit of every test position.
+template <int T> LL_HD float quiet_child_score(float material, u32 w3, u32 w4, u32 w5, u32 w6, u32 elig, u32 job, int from, int to) {
+    const u64 center = 0x00003C3C3C3C0000ull;
+    if (job == FIGUREHEAD) elig &= T == 0 ? ~0x3u : ~0xCu; // life.rs:577-605
+    if (job == COP) {
+        const int file = from & 7;
+        if (file == 0) elig &= T == 0 ? ~0x1u : ~0x4u;
+        if (file == 7) elig &= T == 0 ? ~0x2u : ~0x8u;
+        const int cop_rank = T == 0 ? 6 : 1;
+        w3 += ((u32)((to >> 3) == cop_rank) - (u32)((from >> 3) == cop_rank)) << (16 + 8 * T);
+    }
+    if (job <= PONY) w3 += ((u32)((center >> to) & 1u) - (u32)((center >> from) & 1u)) << (8 * T);
+    if (job == SERVANT) { // a push: the file stays, the rank counts move
+        const int rf = from >> 3, rt = to >> 3, near_t = T == 0 ? 6 : 1, far_t = T == 0 ? 5 : 2;
+        w4 += (((u32)(rt == near_t) - (u32)(rf == near_t)) << (16 * T)) + (((u32)(rt == far_t) - (u32)(rf == far_t)) << (16 * T + 8));
+    }
+    return score_positional(material, w3, w4, w5, w6, elig);
+}
+// the same with the mover as a run-time value: ONE copy of the code in the horizon kernel (its tile loop is bound by instruction fetch)
+LL_HD float quiet_child_score_rt(const int T, float material, u32 w3, u32 w4, u32 w5, u32 w6, u32 elig, u32 job, int from, int to) {
+    const u64 center = 0x00003C3C3C3C0000ull;
+    if (job == FIGUREHEAD) elig &= T == 0 ? ~0x3u : ~0xCu; // life.rs:577-605
+    if (job == COP) {
+        const int file = from & 7;
+        if (file == 0) elig &= T == 0 ? ~0x1u : ~0x4u;
+        if (file == 7) elig &= T == 0 ? ~0x2u : ~0x8u;
+        const int cop_rank = T == 0 ? 6 : 1;
+        w3 += ((u32)((to >> 3) == cop_rank) - (u32)((from >> 3) == cop_rank)) << (16 + 8 * T);
+    }
+    if (job <= PONY) w3 += ((u32)((center >> to) & 1u) - (u32)((center >> from) & 1u)) << (8 * T);
+    if (job == SERVANT) { // a push: the file stays, the rank counts move
+        const int rf = from >> 3, rt = to >> 3, near_t = T == 0 ? 6 : 1, far_t = T == 0 ? 5 : 2;
+        w4 += (((u32)(rt == near_t) - (u32)(rf == near_t)) << (16 * T)) + (((u32)(rt == far_t) - (u32)(rf == far_t)) << (16 * T + 8));
+    }
+    return score_positional(material, w3, w4, w5, w6, elig);
 }
 LL_HD void feat_count(Feat &f, u32 plane, u32 delta) { // head count of `plane` += delta (two's complement for -1)
     const u32 d = delta << (8 * (plane & 3u));
@@ -1052,6 +1130,63 @@ template <int T, class Planes> LL_HD u32 child_features(Feat &f, u32 &elig, cons
     if (hosp == SERVANT) {
         f.w[4] -= ((u32)(rv == near_e) << (16 * E)) + ((u32)(rv == far_e) << (16 * E + 8));
         f.w[5 + E] -= 1u << (4 * (vs & 7));
+    }
+    return hosp;
+}
+
+// the same with the mover as a run-time value (see quiet_child_score_rt)
+template <class Planes> LL_HD u32 child_features_rt(const int T, Feat &f, u32 &elig, const Planes &planes, u32 m) {
+    const int E = 1 - T;
+    const int from = mv_from(m), to = mv_to(m);
+    const u32 job = mv_job(m), asc = mv_asc(m);
+    const u64 center = 0x00003C3C3C3C0000ull;
+    const u64 tb = 1ull << to;
+    const u64 victim = (m & MV_PASSING_BY) ? (T == 0 ? tb >> 8 : tb << 8) : tb;
+    const int vs = (m & MV_PASSING_BY) ? (T == 0 ? to - 8 : to + 8) : to;
+    u32 hosp = JOB_NONE;
+#pragma unroll
+    for (int j = 5; j >= 0; j--)
+        if (planes(6 * E + j) & victim) hosp = (u32)j; // first in dramatis_personae order wins (life.rs:550-557)
+    // ---- eligibility (life.rs:577-605)
+    if (job == FIGUREHEAD) elig &= T == 0 ? ~0x3u : ~0xCu;
+    if (job == COP) {
+        const int file = from & 7;
+        if (file == 0) elig &= T == 0 ? ~0x1u : ~0x4u;
+        if (file == 7) elig &= T == 0 ? ~0x2u : ~0x8u;
+    }
+    // ---- head counts
+    if (hosp != JOB_NONE) feat_count(f, 6u * E + hosp, 0xFFFFFFFFu);
+    if (asc != ASC_NONE) { // the servant alights as its new job (life.rs:701-726)
+        feat_count(f, 6u * T + SERVANT, 0xFFFFFFFFu);
+        feat_count(f, 6u * T + asc, 1u);
+    }
+    if (m & MV_SERVICE) { // the transits happen whether or not somebody is there (life.rs:573-575, 610-629)
+        const int rank8 = to & 56;
+        const u64 corner = 1ull << (rank8 + ((to & 7) == 6 ? 7 : 0));
+        if (!(planes(6 * T + COP) & corner)) feat_count(f, 6u * T + COP, 1u);          // a cop out of thin air
+        if (!(planes(6 * T + FIGUREHEAD) & (1ull << from))) feat_count(f, 6u * T + FIGUREHEAD, 1u); // and a figurehead
+    }
+    // ---- servants and ponies in the centre (never on a first or last rank: ascensions need no special case)
+    const u32 in_from = (u32)(center >> from) & 1u, in_to = (u32)(center >> to) & 1u, in_vs = (u32)(center >> vs) & 1u;
+    if (job <= PONY) f.w[3] += (in_to - in_from) << (8 * T);
+    if (hosp <= PONY) f.w[3] -= in_vs << (8 * E);
+    // ---- cops on the opposition's servant rank
+    const int rf = from >> 3, rt = to >> 3, rv = vs >> 3;
+    const int cop_rank_t = T == 0 ? 6 : 1, cop_rank_e = E == 0 ? 6 : 1;
+    if (job == COP) f.w[3] += ((u32)(rt == cop_rank_t) - (u32)(rf == cop_rank_t)) << (16 + 8 * T);
+    if (hosp == COP) f.w[3] -= (u32)(rv == cop_rank_e) << (16 + 8 * E);
+    // ---- servants by rank and by file (an ascending servant leaves the board: rank 7 / 0 is not counted, its file is not re-entered)
+    const int near_t = T == 0 ? 6 : 1, far_t = T == 0 ? 5 : 2, near_e = E == 0 ? 6 : 1, far_e = E == 0 ? 5 : 2;
+    if (job == SERVANT) {
+        f.w[4] += (((u32)(rt == near_t) - (u32)(rf == near_t)) << (16 * T)) + (((u32)(rt == far_t) - (u32)(rf == far_t)) << (16 * T + 8));
+        const u32 d = (asc == ASC_NONE ? 1u << (4 * (to & 7)) : 0u) - (1u << (4 * (from & 7))); // (no run-time index into f.w: it would live in local memory)
+        f.w[5] += T == 0 ? d : 0u;
+        f.w[6] += T == 0 ? 0u : d;
+    }
+    if (hosp == SERVANT) {
+        f.w[4] -= ((u32)(rv == near_e) << (16 * E)) + ((u32)(rv == far_e) << (16 * E + 8));
+        f.w[5] -= E == 0 ? 1u << (4 * (vs & 7)) : 0u;
+        f.w[6] -= E == 0 ? 0u : 1u << (4 * (vs & 7));
     }
     return hosp;
 }

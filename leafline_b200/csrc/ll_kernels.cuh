@@ -23,6 +23,12 @@ constexpr int BLOCK = 128;
 constexpr int DESC_CAP = LL_DESC_CAP; // move descriptors per window (24 KiB); a tile with more moves takes several windows
 
 enum { MODE_EMIT = 0, MODE_PERFT = 1 };
+// The perft tail reads the four lines through the figurehead from a table staged in shared memory (StagedLines, ll_device.cuh);
+// -DLL_TAIL_COMPUTED_LINES builds the variant that computes them (the A/B of DESIGN.md 7b: 171.5 M -> 165.5 M warp
+// instructions per perft(6) tail, perft(7) 6.65 -> 6.25 ms).
+#if !defined(LL_TAIL_COMPUTED_LINES) && !defined(LL_TAIL_STAGED_LINES)
+#define LL_TAIL_STAGED_LINES
+#endif
 
 // ---- block-level helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ u32 warp_inclusive_scan(u32 v) {
@@ -274,6 +280,9 @@ struct ExpandShared {
     u32 descs[DESC_CAP];
     int acc[BLOCK]; // PERFT: leaves below each parent
     u64 claim;      // next tile / claimed output base
+#ifdef LL_TAIL_STAGED_LINES
+    alignas(16) u64 lines[64 * 4]; // PERFT tail: the lines through every square (StagedLines), 2 KiB, read 128 bits at a time
+#endif
 };
 LL_HD Pos tile_load(const ExpandShared &sh, u32 slot) {
     Pos p;
@@ -414,6 +423,10 @@ struct RecordSink {
 };
 template <int MODE, int P> __device__ __forceinline__ void expand_tiles_records(const ExpandArgs &a, ExpandShared &sh) {
     const int tid = threadIdx.x;
+#ifdef LL_TAIL_STAGED_LINES
+    if (MODE == MODE_PERFT) // (the first barrier of the tile loop orders these stores before the children's loads)
+        for (int i = tid; i < 64 * 4; i += BLOCK) sh.lines[i] = d_line_table[i];
+#endif
     if (a.n_in && a.overflow && *(volatile u32 *)a.overflow) return; // see expand_tiles
     const size_t n = a.n_in ? (size_t)*(volatile const u64 *)a.n_in : a.n;
     for (;;) {
@@ -498,7 +511,11 @@ template <int MODE, int P> __device__ __forceinline__ void expand_tiles_records(
                         if (a.root_out) a.root_out[o] = a.root_is_index ? (u32)o : a.root_in[tile * P + slot];
                     }
                 } else {
+#ifdef LL_TAIL_STAGED_LINES
+                    const int v = live ? (int)count_moves<false>(c, StagedLines{sh.lines}) : 0;
+#else
                     const int v = live ? (int)count_moves<false>(c) : 0;
+#endif
                     // children of one parent are neighbours in the list: reduce per parent inside the warp first
                     const unsigned peers = __match_any_sync(0xffffffffu, live ? slot : 0xFFFFFFFFu);
                     const int r = __reduce_add_sync(peers, v);
@@ -749,21 +766,40 @@ __global__ void __launch_bounds__(BLOCK, LL_EXPAND_MIN_BLOCKS) k_expand_coop(con
 
 // ---- horizon by records (mind.rs:279-301): children decoded from (piece, target mask) records ---------------
 // Phase 1 costs per PIECE, not per move: a parent thread writes at most REC_MAX records (ll_device.cuh) into shared
-// memory.  Phase 2 runs one CHILD per thread: look its parent up in the owner map the parents wrote after the scan (binary
-// search by the prefix sums only for a tile too big for the map), binary-search the record by its base, select the t-th set bit, derive the child's evaluation features from the parent's by the move's +-1 (the child's planes
-// are never built: child_features / score_features, bit-identical to score(make_child(...))), max-reduce per parent.
-constexpr int HP = 64; // parents per horizon tile
-constexpr u32 OWNER_CAP = 3072; // children of a tile whose parent is looked up, not searched for (the space of six planes)
+// memory, together with its evaluation features, the union of the opposition's planes and the material half of the
+// evaluation as all its QUIET children will share it (score_material: their head counts are the parent's).
+// Phase 2 runs one CHILD per thread, in two passes over the tile so that the lanes of a warp run the same code:
+//   quiet commits (nobody stunned, nothing ascended, no secret service, no passing by: ~85 % of all) -- decode, update
+//     three feature words by the move alone, run the positional half of the evaluation from the parent's material value
+//     (quiet_child_score);
+//   loud commits -- the opposition's planes searched for the victim, the features updated by its loss / the ascension / the
+//     conjured cop, the whole evaluation (child_features + score_features).
+// A record's targets split into the two kinds by the opposition's squares; each kind numbers its commits by its own prefix
+// sums (per parent and per record), each has its own owner map (child -> parent slot; binary search over the prefix sums
+// only when a tile has more children than the map holds).  The child's planes are never built; both evaluations are
+// bit-identical to score(make_child(...)) (tests/hostcheck).  Per parent: max over its children, shared-memory atomicMax
+// after a warp-level segmented max.
+#ifndef LL_HP
+#define LL_HP 64
+#endif
+constexpr int HP = LL_HP; // parents per horizon tile
+constexpr u32 OWNER_CAP = 3072; // children of a tile whose parent is looked up, not searched for
+#ifndef LL_HORIZON_MIN_BLOCKS
+#define LL_HORIZON_MIN_BLOCKS 5
+#endif
 struct HorizonShared {
-    u64 tile_op[6][HP]; // the OPPOSITION's planes of every parent: all that the children's evaluation reads of the board
-    unsigned char owner[OWNER_CAP]; // child k of the tile -> its parent's slot
+    u64 tile_op[6][HP]; // the OPPOSITION's planes of every parent: all that the loud children's evaluation reads of the board
+    unsigned char owner[OWNER_CAP]; // quiet child k -> owner[k], loud child k -> owner[OWNER_CAP - 1 - k]
     u32 tile_meta[HP];
+    u64 tile_opp[HP]; // the union of the six
     u64 rec_mask[REC_MAX][HP]; // transposed: neighbouring parents write neighbouring words
-    u32 rec_info[REC_MAX][HP];
-    u32 ex[HP + 1]; // exclusive prefix of the parents' commit counts
+    u32 rec_info[REC_MAX][HP]; // kind, job, from, ascension, passing-by (16 bits) | number of the record's first QUIET commit << 16
+    unsigned char rec_loud[REC_MAX][HP]; // number of the record's first LOUD commit (<= 8 stuns a piece, <= 12 loud commits a servant: < 256)
+    u32 exq[HP + 1], exl[HP + 1]; // exclusive prefixes of the parents' quiet / loud commit counts
     u32 n_rec[HP];
     int acc[HP];
     u32 feat[7][HP]; // the parents' evaluation features (ll_device.cuh: Feat), transposed like the records
+    float material[HP]; // score_material(parent's features, the CHILD's initiative)
     u32 claim; // CHAIN: the tile this block pulled
 };
 template <int T> struct TilePlanes { // the planes of one parent (mover T), read where child_features asks for them
@@ -776,21 +812,52 @@ template <int T> struct TilePlanes { // the planes of one parent (mover T), read
         return ldg(in.pl + (size_t)j * in.stride + at);
     }
 };
+struct TilePlanesRt { // the same, the mover a run-time value
+    const HorizonShared &sh;
+    u32 slot;
+    const Soa &in;
+    size_t at;
+    int team;
+    __device__ __forceinline__ u64 operator()(int j) const {
+        if (j / 6 == 1 - team) return sh.tile_op[j % 6][slot];
+        return ldg(in.pl + (size_t)j * in.stride + at);
+    }
+};
+LL_HD bool rec_splits(u32 info) { return (info & 7u) == REC_PIECE && !((info >> 15) & 1u); } // a piece's targets: quiet where empty, loud where the opposition stands
 struct SharedRecordOut {
     HorizonShared &sh;
     int slot;
-    u32 n_rec = 0, n_moves = 0;
+    u64 opp;
+    u32 n_rec = 0, n_quiet = 0, n_loud = 0;
     LL_HDM void put(u64 mask, u32 info) {
         if (n_rec >= REC_MAX) return; // cannot happen on a well-formed position (<= 16 figurines a team); never write past the tile
+        const u32 kind = info & 7u, asc = (info >> 12) & 7u;
+        const u32 all = (u32)__popcll(mask);
+        const u32 quiet = rec_splits(info) ? (u32)__popcll(mask & ~opp) : ((kind == REC_PUSH || kind == REC_DOUBLE) && asc == ASC_NONE) ? all : 0u;
         sh.rec_mask[n_rec][slot] = mask;
-        sh.rec_info[n_rec][slot] = info | (n_moves << 16);
+        sh.rec_info[n_rec][slot] = (info & 0xFFFFu) | (n_quiet << 16);
+        sh.rec_loud[n_rec][slot] = (unsigned char)n_loud;
         n_rec++;
-        n_moves += (u32)__popcll(mask);
+        n_quiet += quiet;
+        n_loud += all - quiet;
     }
 };
+// the parent slot of child k of one kind: looked up, or -- a tile with more children than the map holds -- the last parent
+// whose prefix is <= k
+__device__ __forceinline__ u32 horizon_owner(const HorizonShared &sh, const u32 *ex, bool mapped, u32 at, u32 k) {
+    if (mapped) return sh.owner[at];
+    u32 slot = 0, hi = HP;
+#pragma unroll
+    for (int step = 0; step < 7; step++) { // HP <= 2^7
+        const u32 mid = (slot + hi) >> 1;
+        if (ex[mid] <= k) slot = mid;
+        else hi = mid;
+    }
+    return slot;
+}
 // CHAIN: the level's size is resident on the device (a.n_in) and persistent blocks pull tiles from a.tile_counter -- the
 // launch needs no host round trip (the small-batch path of ll_horizon_batch)
-template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOCK, 6) k_horizon(const ExpandArgs a) {
+template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOCK, LL_HORIZON_MIN_BLOCKS) k_horizon(const ExpandArgs a) {
     __shared__ HorizonShared sh;
     const int tid = threadIdx.x;
     if (CHAIN && *(volatile u32 *)a.overflow) return; // see expand_tiles
@@ -806,74 +873,139 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
     }
     const size_t i = tile * HP + tid;
     const bool mine = tid < HP && i < n;
-    u32 cnt = 0;
+    u32 cnt_q = 0, cnt_l = 0;
     if (mine) {
         const Pos p = soa_load(a.in, i);
         const bool blue = meta_stm(p.meta) != 0;
+        u64 opp = 0;
 #pragma unroll
-        for (int j = 0; j < 6; j++) sh.tile_op[j][tid] = blue ? p.pl[j] : p.pl[6 + j];
+        for (int j = 0; j < 6; j++) {
+            const u64 pl = blue ? p.pl[j] : p.pl[6 + j];
+            sh.tile_op[j][tid] = pl;
+            opp |= pl;
+        }
+        sh.tile_opp[tid] = opp;
         sh.tile_meta[tid] = p.meta;
-        SharedRecordOut out{sh, tid};
+        SharedRecordOut out{sh, tid, opp};
         reckless_records<STUNS>(p, out);
-        cnt = out.n_moves;
+        cnt_q = out.n_quiet;
+        cnt_l = out.n_loud;
         sh.n_rec[tid] = out.n_rec;
         sh.acc[tid] = float_key(-INFINITY);
         const Feat f = features_of(p);
 #pragma unroll
         for (int w = 0; w < 7; w++) sh.feat[w][tid] = f.w[w];
+        sh.material[tid] = score_material(f, meta_stm(p.meta) ^ 1u);
     }
     u32 total;
-    const u32 ex = block_exclusive_scan(cnt, &total);
-    if (tid < HP) sh.ex[tid] = ex;
-    if (tid == 0) sh.ex[HP] = total;
-    const bool mapped = total <= OWNER_CAP; // block-uniform
-    if (mapped && mine)
-        for (u32 c = 0; c < cnt; c++) sh.owner[ex + c] = (unsigned char)tid;
+    const u32 ex = block_exclusive_scan(cnt_q | (cnt_l << 16), &total); // both prefixes in one scan (a tile's quiet commits stay far below 2^16)
+    const u32 ex_q = ex & 0xFFFFu, ex_l = ex >> 16, total_q = total & 0xFFFFu, total_l = total >> 16;
+    if (tid < HP) {
+        sh.exq[tid] = ex_q;
+        sh.exl[tid] = ex_l;
+    }
+    if (tid == 0) {
+        sh.exq[HP] = total_q;
+        sh.exl[HP] = total_l;
+    }
+    const bool mapped = total_q + total_l <= OWNER_CAP; // block-uniform
+    if (mapped && mine) {
+        for (u32 c = 0; c < cnt_q; c++) sh.owner[ex_q + c] = (unsigned char)tid;
+        for (u32 c = 0; c < cnt_l; c++) sh.owner[OWNER_CAP - 1u - (ex_l + c)] = (unsigned char)tid;
+    }
     __syncthreads();
-    for (u32 k0 = 0; k0 < total; k0 += BLOCK) {
-        const u32 k = k0 + tid;
-        const bool live = k < total;
-        u32 slot = 0;
-        int v = float_key(-INFINITY);
-        if (live) {
-            if (mapped) {
-                slot = sh.owner[k];
-            } else {
-                u32 hi = HP;
+    // (LL_HZ_ILP children per thread and pass: measured at 2, 3 and 4 -- 3.9-4.2 ms against 3.24 ms at one, the unrolled loop
+    // bodies cost more in instruction fetch than the second chain hides in latency: DESIGN.md 7b)
+    auto quiet_child = [&](u32 k, u32 &slot) -> int {
+        slot = horizon_owner(sh, sh.exq, mapped, k, k);
+        const u32 j = k - sh.exq[slot];
+        u32 r = 0, rhi = sh.n_rec[slot];
 #pragma unroll
-                for (int step = 0; step < 6; step++) { // HP = 2^6: the last parent whose prefix is <= k
-                    const u32 mid = (slot + hi) >> 1;
-                    if (sh.ex[mid] <= k) slot = mid;
-                    else hi = mid;
-                }
-            }
-            const u32 j = k - sh.ex[slot];
-            u32 r = 0, rhi = sh.n_rec[slot];
-            while (rhi - r > 1) { // the last record whose base is <= j
-                const u32 mid = (r + rhi) >> 1;
-                if (rec_base(sh.rec_info[mid][slot]) <= j) r = mid;
-                else rhi = mid;
-            }
-            const u32 info = sh.rec_info[r][slot];
-            const u32 meta = sh.tile_meta[slot];
-            const u32 team = meta_stm(meta);
-            const u32 m = rec_move(sh.rec_mask[r][slot], info, j - rec_base(info), team);
-            Feat f;
-#pragma unroll
-            for (int w = 0; w < 7; w++) f.w[w] = sh.feat[w][slot];
-            u32 elig = meta_elig(meta);
-            if (team == 0) child_features<0>(f, elig, TilePlanes<0>{sh, slot, a.in, tile * HP + slot}, m);
-            else child_features<1>(f, elig, TilePlanes<1>{sh, slot, a.in, tile * HP + slot}, m);
-            const float s = score_features(f, team ^ 1u, elig);
-            v = float_key(team ? -s : s); // -(orientation(child) * score(child)), the child's initiative being the other team's (mind.rs:283, 331-336)
+        for (int step = 0; step < 6; step++) { // REC_MAX <= 2^6: the last record whose first quiet commit is <= j (it has one: empty
+            const u32 mid = (r + rhi) >> 1;    // records share their successor's number); branch-free, a converged search re-reads r
+            const bool le = (sh.rec_info[mid][slot] >> 16) <= j;
+            r = le ? mid : r;
+            rhi = le ? rhi : mid;
         }
+        const u32 info = sh.rec_info[r][slot];
+        const u64 mask = sh.rec_mask[r][slot];
+        const u32 meta = sh.tile_meta[slot];
+        const u32 team = meta_stm(meta);
+        const int to = select_bit(rec_splits(info) ? mask & ~sh.tile_opp[slot] : mask, j - (info >> 16));
+        const u32 m = rec_move_to(info & 0xFFFFu, to, team);
+        const float s = quiet_child_score_rt((int)team, sh.material[slot], sh.feat[3][slot], sh.feat[4][slot], sh.feat[5][slot], sh.feat[6][slot],
+                                             meta_elig(meta), mv_job(m), mv_from(m), to);
+        return float_key(team ? -s : s); // -(orientation(child) * score(child)), the child's initiative being the other team's (mind.rs:283, 331-336)
+    };
+    auto loud_child = [&](u32 k, u32 &slot) -> int {
+        slot = horizon_owner(sh, sh.exl, mapped, OWNER_CAP - 1u - k, k);
+        const u32 j = k - sh.exl[slot];
+        u32 r = 0, rhi = sh.n_rec[slot];
+#pragma unroll
+        for (int step = 0; step < 6; step++) {
+            const u32 mid = (r + rhi) >> 1;
+            const bool le = sh.rec_loud[mid][slot] <= j;
+            r = le ? mid : r;
+            rhi = le ? rhi : mid;
+        }
+        const u32 info = sh.rec_info[r][slot];
+        const u64 mask = sh.rec_mask[r][slot];
+        const u32 meta = sh.tile_meta[slot];
+        const u32 team = meta_stm(meta);
+        const int to = select_bit(rec_splits(info) ? mask & sh.tile_opp[slot] : mask, j - sh.rec_loud[r][slot]);
+        const u32 m = rec_move_to(info & 0xFFFFu, to, team);
+        Feat f;
+#pragma unroll
+        for (int w = 0; w < 7; w++) f.w[w] = sh.feat[w][slot];
+        u32 elig = meta_elig(meta);
+        child_features_rt((int)team, f, elig, TilePlanesRt{sh, slot, a.in, tile * HP + slot, (int)team}, m);
+        const float s = score_features(f, team ^ 1u, elig);
+        return float_key(team ? -s : s);
+    };
+    auto fold = [&](bool live, u32 slot, int v) { // per parent: max inside the warp first, then one shared atomic per (warp, parent)
         const unsigned peers = __match_any_sync(0xffffffffu, live ? slot : 0xFFFFFFFFu);
         const int best = __reduce_max_sync(peers, v);
         if (live && (tid & 31) == __ffs((int)peers) - 1) atomicMax(&sh.acc[slot], best);
+    };
+#ifndef LL_HZ_ILP
+#define LL_HZ_ILP 1
+#endif
+    // ---- quiet commits
+    for (u32 k0 = 0; k0 < total_q; k0 += LL_HZ_ILP * BLOCK) {
+        u32 slot[LL_HZ_ILP];
+        int v[LL_HZ_ILP];
+        bool live[LL_HZ_ILP];
+#pragma unroll
+        for (int u = 0; u < LL_HZ_ILP; u++) {
+            const u32 k = k0 + u * BLOCK + tid;
+            live[u] = k < total_q;
+            slot[u] = 0;
+            v[u] = quiet_child(live[u] ? k : 0u, slot[u]); // (no branch around the chain: a dead lane evaluates child 0 and is masked out)
+            if (!live[u]) v[u] = float_key(-INFINITY);
+        }
+#pragma unroll
+        for (int u = 0; u < LL_HZ_ILP; u++) fold(live[u], slot[u], v[u]);
+    }
+    // ---- loud commits
+    for (u32 k0 = 0; k0 < total_l; k0 += LL_HZ_ILP * BLOCK) {
+        u32 slot[LL_HZ_ILP];
+        int v[LL_HZ_ILP];
+        bool live[LL_HZ_ILP];
+#pragma unroll
+        for (int u = 0; u < LL_HZ_ILP; u++) {
+            const u32 k = k0 + u * BLOCK + tid;
+            live[u] = k < total_l;
+            slot[u] = 0;
+            v[u] = loud_child(live[u] ? k : 0u, slot[u]);
+            if (!live[u]) v[u] = float_key(-INFINITY);
+        }
+#pragma unroll
+        for (int u = 0; u < LL_HZ_ILP; u++) fold(live[u], slot[u], v[u]);
     }
     __syncthreads();
     u32 scored = 0;
     if (mine) {
+        const u32 cnt = cnt_q + cnt_l;
         float v = cnt ? key_float(sh.acc[tid]) : -INFINITY;
         if (cnt == 0 || (STUNS && a.stand_pat)) { // nothing to play: the node is itself a leaf (mind.rs:281-283, 295-299)
             Feat f;

@@ -192,6 +192,15 @@ extern "C" int hc_feature_check(const ll_world_t *w, int *checked) {
         bool same = got_hosp == hosp && elig == meta_elig(c.meta);
         for (int k = 0; k < 7; k++) same = same && f.w[k] == want.w[k];
         if (bits_of(score_features(f, meta_stm(c.meta), elig)) != bits_of(score(c))) same = false;
+        // the horizon kernel's quiet path: nobody stunned, nothing ascended, no secret service, no passing by
+        if (hosp == JOB_NONE && mv_asc(m) == ASC_NONE && !(m & (MV_SERVICE | MV_PASSING_BY))) {
+            const u32 stm_child = meta_stm(p.meta) ^ 1u;
+            const float material = score_material(f0, stm_child);
+            const float quiet = meta_stm(p.meta) == 0
+                                    ? quiet_child_score<0>(material, f0.w[3], f0.w[4], f0.w[5], f0.w[6], meta_elig(p.meta), mv_job(m), mv_from(m), mv_to(m))
+                                    : quiet_child_score<1>(material, f0.w[3], f0.w[4], f0.w[5], f0.w[6], meta_elig(p.meta), mv_job(m), mv_from(m), mv_to(m));
+            if (bits_of(quiet) != bits_of(score(c))) same = false;
+        }
         if (!same) bad++;
     }
     return bad;
