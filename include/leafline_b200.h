@@ -15,12 +15,21 @@
  *  - there is NO CPU fallback: without a CUDA device ll_init() fails with LL_ERR_NO_DEVICE.
  *  - an ll_ctx is NOT thread-safe; use one ll_ctx per host thread (the reference calls the leaf
  *    layer from one thread per root move, src/mind.rs:405).
- *  - positions must be "well-formed" (domain W: no two planes overlap; at most one
- *    figurehead and at most 16 figurines per team; a set service-eligibility bit implies that team's figurehead, if any,
- *    stands on its home e-square; passing_by is None or an empty square directly behind an enemy
- *    servant on its double-step rank).  Every state reachable from a well-formed state by the
- *    reference's own move generator is well-formed.  Other inputs are rejected with
- *    LL_ERR_DOMAIN rather than answered differently from the reference.
+ *  - DOMAINS.  Every position the reference answers and this ABI can spell is answered identically:
+ *      domain W (the fast path: set-wise kernels, legality by check / pin / danger masks): no two planes overlap; at most one
+ *        figurehead and at most 16 figurines per team; a set service-eligibility bit implies that team's figurehead, if any,
+ *        stands on its home e-square, and that the cop stands on that corner or the team has at most 15 figurines (secret
+ *        service conjures a cop where none stands, src/life.rs:621-628); passing_by is None or an empty square directly behind
+ *        an enemy servant on its double-step rank.  Every state reachable from a state of W by the reference's own move
+ *        generator is in W (tests/test_domain.py), so a tree rooted in W never leaves the fast path.
+ *      the literal domain (any number of figureheads and figurines, any eligibility -- the reference loops over every
+ *        figurehead, src/life.rs:678-690, and `--from` takes any runes, src/main.rs:199): answered by the literal path, the
+ *        canonical generator with the reference's own legality (every commit made, kept iff no figurehead of the mover is
+ *        endangered afterwards, src/life.rs:692-699), level by level.  Same results as the reference, at a fraction of the
+ *        fast path's speed; a call takes it as soon as one of its positions is outside W.
+ *      rejected with LL_ERR_DOMAIN: overlapping planes, initiative / eligibility bytes out of range, a passing_by square that
+ *        is off the board, occupied or not behind an enemy servant (the reference would panic or answer nonsense).
+ *    ll_score_batch / ll_score_soa / ll_soa_upload do not classify their input: mind::score is defined on any twelve planes.
  */
 #ifndef LEAFLINE_B200_H
 #define LEAFLINE_B200_H
@@ -36,7 +45,7 @@ extern "C" {
 #define LL_ERR_INVALID_ARG (-1)
 #define LL_ERR_CUDA (-2)
 #define LL_ERR_CAPACITY (-3) /* an output buffer is too small; nothing is written past its capacity */
-#define LL_ERR_DOMAIN (-4)   /* a position is outside the well-formed domain W */
+#define LL_ERR_DOMAIN (-4)   /* a position cannot be answered at all (see DOMAINS above) */
 #define LL_ERR_NO_DEVICE (-5)
 #define LL_ERR_OOM (-6)
 #define LL_ERR_NCCL (-7)     /* NCCL is missing (it is loaded at run time, by the multi-GPU calls only) or reported an error */

@@ -91,6 +91,7 @@ struct ll_ctx {
     void *pinned = nullptr; // small host staging
     size_t pinned_cap = 0;
     bool timing = false;
+    bool literal = false;      // this call holds a position outside domain W: the literal path answers it (ll_device.cuh: DOMAIN_LITERAL)
     bool force_synced = false; // tests: always take the level-by-level path
     bool no_graph = false;     // tests: issue the perft launch chain launch by launch instead of replaying its CUDA graph
     uint64_t chain_sig = 0;    // the captured perft chain (same plan, same buffers, same stream -> replay)
@@ -214,9 +215,9 @@ int pinned(ll_ctx *ctx, size_t bytes) {
     return LL_OK;
 }
 
-// scalars buffer layout (u64 slots): 0 = first bad index, 1 = scan total, 2 = leaf total, 3 = leaves scored,
+// scalars buffer layout (u64 slots): 4, 5 = first bad index and literal-path flag, 1 = scan total, 2 = leaf total, 3 = leaves scored,
 // 8.. = per-root counts
-constexpr size_t SC_BAD = 0, SC_TOTAL = 1, SC_LEAVES = 2, SC_SCORED = 3, SC_PER_ROOT = 8, SC_SPARE = 8 + 1024,
+constexpr size_t SC_BAD = 4 /* and 5: needs-the-literal-path flag, see validate_level */, SC_TOTAL = 1, SC_LEAVES = 2, SC_SCORED = 3, SC_PER_ROOT = 8, SC_SPARE = 8 + 1024,
                  SC_N = 1040 /* 64 device-resident level sizes */, SC_TILEQ = 1104 /* 64 u32 tile queues */, SC_OVERFLOW = 1136, SC_SLOTS = 1152;
 
 int upload_worlds(ll_ctx *ctx, const ll_world_t *worlds, size_t n, size_t level) {
@@ -247,21 +248,24 @@ int upload_root(ll_ctx *ctx, const ll_world_t *root) {
     return check_launch("k_store_world");
 }
 
+// classify n resident positions: LL_ERR_DOMAIN for one outside every domain; ctx->literal if one needs the literal path
 int validate_level(ll_ctx *ctx, const Soa &soa, size_t n) {
     if (!n) return LL_OK;
     u64 *sc = (u64 *)ctx->scalars.ptr;
-    CUDA_TRY(cudaMemsetAsync(sc + SC_BAD, 0xFF, sizeof(u64), ctx->stream));
+    const u64 init[2] = {~0ull, 0ull};
+    CUDA_TRY(cudaMemcpyAsync(sc + SC_BAD, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
     {
         Timed t(ctx, "validate");
         k_validate<<<(unsigned)nblocks(n), BLOCK, 0, ctx->stream>>>(soa, n, (unsigned long long *)(sc + SC_BAD));
     }
     LL_TRY(check_launch("k_validate"));
-    u64 bad = 0;
-    CUDA_TRY(cudaMemcpyAsync(&bad, sc + SC_BAD, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+    u64 got[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(got, sc + SC_BAD, sizeof got, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    if (bad != ~0ull)
-        return fail(LL_ERR_DOMAIN, "position %llu is not well-formed (see include/leafline_b200.h, domain W)",
-                    (unsigned long long)bad);
+    if (got[0] != ~0ull)
+        return fail(LL_ERR_DOMAIN, "position %llu cannot be answered: overlapping planes, bytes out of range or an inconsistent passing-by square (see include/leafline_b200.h)",
+                    (unsigned long long)got[0]);
+    if (got[1]) ctx->literal = true;
     return LL_OK;
 }
 
@@ -274,8 +278,8 @@ int count_level(ll_ctx *ctx, size_t l, bool nihil, u64 *total_out, bool stuns_on
     u64 *sc = (u64 *)ctx->scalars.ptr;
     {
         Timed t(ctx, nihil ? "count_reckless" : "count_legal");
-        if (nihil) k_count<true><<<(unsigned)nb, BLOCK, 0, ctx->stream>>>(f.soa(), f.n, (u32 *)f.counts.ptr, (u32 *)f.block_sums.ptr, stuns_only);
-        else k_count<false><<<(unsigned)nb, BLOCK, 0, ctx->stream>>>(f.soa(), f.n, (u32 *)f.counts.ptr, (u32 *)f.block_sums.ptr, stuns_only);
+        if (nihil) k_count<true><<<(unsigned)nb, BLOCK, 0, ctx->stream>>>(f.soa(), f.n, (u32 *)f.counts.ptr, (u32 *)f.block_sums.ptr, stuns_only, ctx->literal);
+        else k_count<false><<<(unsigned)nb, BLOCK, 0, ctx->stream>>>(f.soa(), f.n, (u32 *)f.counts.ptr, (u32 *)f.block_sums.ptr, stuns_only, ctx->literal);
     }
     LL_TRY(check_launch("k_count"));
     {
@@ -330,7 +334,8 @@ int emit_level_into(ll_ctx *ctx, size_t l, Frontier &g, bool nihil, u64 total, b
     {
         Timed t(ctx, nihil ? "emit_reckless" : "emit_legal");
         if (stuns_only && !nihil) return fail(LL_ERR_INVALID_ARG, "quiescence levels are reckless");
-        if (stuns_only) k_expand<true, MODE_EMIT, BLOCK, true><<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(a);
+        if (ctx->literal && !nihil) k_expand<false, MODE_EMIT, BLOCK, false, true><<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(a); // (the reckless generator is literal as it is)
+        else if (stuns_only) k_expand<true, MODE_EMIT, BLOCK, true><<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(a);
         else if (nihil) k_expand<true, MODE_EMIT><<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(a);
         else k_expand<false, MODE_EMIT><<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(a);
     }
@@ -345,6 +350,7 @@ int emit_level(ll_ctx *ctx, size_t l, bool nihil, u64 total, bool with_cmeta, in
 int check_ctx(ll_ctx *ctx) {
     if (!ctx) return fail(LL_ERR_INVALID_ARG, "null context");
     CUDA_TRY(cudaSetDevice(ctx->device));
+    ctx->literal = false; // every entry point classifies its own positions
     return LL_OK;
 }
 // a caller-owned ll_soa_t: device pointers present, n inside the stride, planes 16-byte aligned
@@ -374,9 +380,11 @@ int horizon_levels(ll_ctx *ctx, size_t l, int plies, int quiet_ext, uint64_t *sc
         if (scored_total) *scored_total += f0.n;
         return check_launch("k_leaf_values");
     }
-    // level l + j has plies - j plies left; at <= 0 it is a quiescence level
+    // level l + j has plies - j plies left; at <= 0 it is a quiescence level.  The last expansion happens on chip
+    // (k_horizon: children scored in registers) -- except on the literal path (a position outside domain W: more figurines than
+    // the record lists hold), which materialises that level too and scores it like any other
     size_t bottom = l;
-    for (int j = 0; j < expanding - 1; j++) {
+    for (int j = 0; j < (ctx->literal ? expanding : expanding - 1); j++) {
         const bool quiet = plies - j <= 0;
         u64 total = 0;
         LL_TRY(count_level(ctx, bottom, true, &total, quiet));
@@ -384,10 +392,17 @@ int horizon_levels(ll_ctx *ctx, size_t l, int plies, int quiet_ext, uint64_t *sc
         bottom++;
     }
     Frontier &fb = ctx->levels[bottom];
-    if (bottom_out) *bottom_out = bottom;
+    if (bottom_out) *bottom_out = ctx->literal ? bottom - 1 : bottom;
     LL_TRY(reserve_level(ctx, bottom, fb.n, false, true));
     CUDA_TRY(cudaMemsetAsync(sc + SC_SCORED, 0, sizeof(u64), ctx->stream));
-    if (fb.n) {
+    if (ctx->literal) {
+        if (fb.n) {
+            Timed t(ctx, "leaf_values");
+            k_leaf_values<<<(unsigned)nblocks(fb.n), BLOCK, 0, ctx->stream>>>(fb.soa(), fb.n, (float *)fb.values.ptr);
+            LL_TRY(check_launch("k_leaf_values"));
+        }
+        if (scored_total) *scored_total += fb.n;
+    } else if (fb.n) {
         const bool quiet = plies - (expanding - 1) <= 0;
         ExpandArgs a{};
         a.in = fb.soa();
@@ -405,6 +420,7 @@ int horizon_levels(ll_ctx *ctx, size_t l, int plies, int quiet_ext, uint64_t *sc
         Frontier &chi = ctx->levels[lev];
         LL_TRY(reserve_level(ctx, lev - 1, par.n, false, true));
         const bool quiet = plies - (int)(lev - 1 - l) <= 0;
+        if (!par.n) continue; // the tree died out above this level
         Timed t(ctx, "backup");
         k_backup<<<(unsigned)nblocks(par.n), BLOCK, 0, ctx->stream>>>(par.soa(), par.n, (const u32 *)par.counts.ptr, (const u64 *)par.block_base.ptr,
                                                                      (const float *)chi.values.ptr, (float *)par.values.ptr, quiet);
@@ -794,6 +810,7 @@ extern "C" int ll_score_soa(ll_ctx *ctx, const ll_soa_t *soa, float *d_scores) {
 // ---- movegen -----------------------------------------------------------------------------------------
 
 static bool host_well_formed(const ll_world_t *w);
+static int classify_root(ll_ctx *ctx, const ll_world_t *w, size_t index);
 
 extern "C" int ll_lookahead_batch(ll_ctx *ctx, const ll_world_t *worlds, size_t n, int nihilistically, uint32_t *offsets,
                                   ll_commit_t *commits, size_t commits_cap) {
@@ -803,7 +820,7 @@ extern "C" int ll_lookahead_batch(ll_ctx *ctx, const ll_world_t *worlds, size_t 
     offsets[0] = 0;
     if (!n) return LL_OK;
     if (n == 1) { // a search driver asking for one node's commits: checked on the host, handed over as a kernel argument
-        if (!host_well_formed(worlds)) return fail(LL_ERR_DOMAIN, "position 0 is not well-formed (see include/leafline_b200.h, domain W)");
+        LL_TRY(classify_root(ctx, worlds, 0));
         LL_TRY(upload_root(ctx, worlds));
     } else {
         LL_TRY(upload_worlds(ctx, worlds, n, 0));
@@ -870,33 +887,48 @@ extern "C" int ll_in_critical_endangerment_batch(ll_ctx *ctx, const ll_world_t *
 // ---- perft -------------------------------------------------------------------------------------------
 
 
-// host-side argument check of a single root (domain W of the header); the batch entry points validate on the device
-static bool host_well_formed(const ll_world_t *w) {
+// host-side classification of a single position -- the mirror of domain_class (ll_device.cuh); the batch entry points
+// classify on the device
+enum { HOST_FAST = 0, HOST_LITERAL = 1, HOST_REJECT = 2 };
+static int host_domain_class(const ll_world_t *w) {
     uint64_t acc = 0;
     for (int j = 0; j < 12; j++) {
-        if (acc & w->plane[j]) return false;
+        if (acc & w->plane[j]) return HOST_REJECT;
         acc |= w->plane[j];
     }
-    if (__builtin_popcountll(w->plane[5]) > 1 || __builtin_popcountll(w->plane[11]) > 1) return false;
-    uint64_t orange = 0, blue = 0;
-    for (int j = 0; j < 6; j++) orange |= w->plane[j], blue |= w->plane[6 + j];
-    if (__builtin_popcountll(orange) > 16 || __builtin_popcountll(blue) > 16) return false;
-    if (w->initiative > 1 || w->service_eligibility > 0xF) return false;
-    if ((w->service_eligibility & 0x3) && (w->plane[5] & ~(1ull << 4))) return false;
-    if ((w->service_eligibility & 0xC) && (w->plane[11] & ~(1ull << 60))) return false;
+    if (w->initiative > 1 || w->service_eligibility > 0xF) return HOST_REJECT;
     if (w->passing_by != 0xFF) {
         const unsigned r = w->passing_by >> 4, f = w->passing_by & 0xF;
-        if (r > 7 || f > 7) return false;
+        if (r > 7 || f > 7) return HOST_REJECT;
         const uint64_t bit = 1ull << (8 * r + f);
-        if (acc & bit) return false;
+        if (acc & bit) return HOST_REJECT;
         if (w->initiative == 0) {
-            if (r != 5 || !(w->plane[6] & (bit >> 8)) || (acc & (bit << 8))) return false;
+            if (r != 5 || !(w->plane[6] & (bit >> 8)) || (acc & (bit << 8))) return HOST_REJECT;
         } else {
-            if (r != 2 || !(w->plane[0] & (bit << 8)) || (acc & (bit >> 8))) return false;
+            if (r != 2 || !(w->plane[0] & (bit << 8)) || (acc & (bit >> 8))) return HOST_REJECT;
         }
     }
-    return true;
+    if (__builtin_popcountll(w->plane[5]) > 1 || __builtin_popcountll(w->plane[11]) > 1) return HOST_LITERAL;
+    uint64_t orange = 0, blue = 0;
+    for (int j = 0; j < 6; j++) orange |= w->plane[j], blue |= w->plane[6 + j];
+    const int n_orange = __builtin_popcountll(orange), n_blue = __builtin_popcountll(blue);
+    if (n_orange > 16 || n_blue > 16) return HOST_LITERAL;
+    const unsigned elig = w->service_eligibility;
+    if ((elig & 0x3) && (w->plane[5] & ~(1ull << 4))) return HOST_LITERAL;
+    if ((elig & 0xC) && (w->plane[11] & ~(1ull << 60))) return HOST_LITERAL;
+    if (n_orange == 16 && (((elig & 0x1) && !(w->plane[3] & (1ull << 0))) || ((elig & 0x2) && !(w->plane[3] & (1ull << 7))))) return HOST_LITERAL;
+    if (n_blue == 16 && (((elig & 0x4) && !(w->plane[9] & (1ull << 56))) || ((elig & 0x8) && !(w->plane[9] & (1ull << 63))))) return HOST_LITERAL;
+    return HOST_FAST;
 }
+// classify one position handed over by the caller: LL_ERR_DOMAIN, or ctx->literal set when the literal path must answer
+static int classify_root(ll_ctx *ctx, const ll_world_t *w, size_t index) {
+    const int cls = host_domain_class(w);
+    if (cls == HOST_REJECT)
+        return fail(LL_ERR_DOMAIN, "position %zu cannot be answered: overlapping planes, bytes out of range or an inconsistent passing-by square (see include/leafline_b200.h)", index);
+    if (cls == HOST_LITERAL) ctx->literal = true;
+    return LL_OK;
+}
+static bool host_well_formed(const ll_world_t *w) { return host_domain_class(w) == HOST_FAST; } // (the multi-GPU layer deals only domain-W trees)
 
 // Frontier sharding: with shard_world > 1 the work units are the nodes of ply `unit_ply`, dealt to the
 // ranks by unit_hash (ll_device.cuh) in the expansion that creates them; 0 = the tree is too shallow to deal (rank 0
@@ -1063,9 +1095,11 @@ static int perft_synced(ll_ctx *ctx, int depth, int shard_rank, int shard_world,
     CUDA_TRY(cudaMemsetAsync(sc + SC_PER_ROOT, 0, 1024 * sizeof(u64), ctx->stream));
     // The last two plies are fused: the nodes at ply depth-2 are expanded in registers and every child's
     // legal moves are bulk-counted, so the widest materialised level is ply depth-2 (depth >= 3).
-    const bool fused = depth >= 3;
+    // (the literal path -- a root outside domain W -- materialises every level down to ply depth-1 and counts the legal moves of
+    // its nodes with the reference's own legality; such trees are not dealt: rank 0 counts them whole)
+    const bool fused = depth >= 3 && !ctx->literal;
     const int tail_ply = fused ? depth - 2 : depth - 1;
-    const int unit_ply = shard_world > 1 ? perft_unit_ply(depth) : 0;
+    const int unit_ply = shard_world > 1 && !ctx->literal ? perft_unit_ply(depth) : 0;
     const bool idle = shard_world > 1 && unit_ply == 0 && shard_rank != 0; // a tree too shallow to deal is rank 0's
     u64 root_count = 0;
     for (int ply = 0;; ply++) { // level index == ply
@@ -1084,7 +1118,7 @@ static int perft_synced(ll_ctx *ctx, int depth, int shard_rank, int shard_world,
             } else if (f.n && !idle) {
                 Timed t(ctx, "count_leaves");
                 k_count_leaves<<<(unsigned)nblocks(f.n), BLOCK, 0, ctx->stream>>>(f.soa(), f.n, ply == 0 ? nullptr : (const u32 *)f.root.ptr,
-                                                                                 ply == 0 ? nullptr : sc + SC_PER_ROOT, sc + SC_LEAVES);
+                                                                                 ply == 0 ? nullptr : sc + SC_PER_ROOT, sc + SC_LEAVES, ctx->literal);
                 LL_TRY(check_launch("k_count_leaves"));
             }
             break;
@@ -1142,13 +1176,13 @@ extern "C" int ll_perft(ll_ctx *ctx, const ll_world_t *root, int depth, int shar
     if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) return fail(LL_ERR_INVALID_ARG, "bad shard %d/%d", shard_rank, shard_world);
     *leaves = 0;
     if (n_roots) *n_roots = 0;
-    if (!host_well_formed(root)) return fail(LL_ERR_DOMAIN, "position 0 is not well-formed (see include/leafline_b200.h, domain W)");
+    LL_TRY(classify_root(ctx, root, 0));
     LL_TRY(upload_root(ctx, root));
     if (depth == 0) {
         *leaves = shard_rank == 0 ? 1 : 0;
         return LL_OK;
     }
-    if (depth >= 3 && !ctx->force_synced) {
+    if (depth >= 3 && !ctx->force_synced && !ctx->literal) {
         bool done = false;
         LL_TRY(perft_chained(ctx, depth, shard_rank, shard_world, leaves, per_root, root_cap, n_roots, &done));
         if (done) return LL_OK;
@@ -1166,7 +1200,7 @@ extern "C" int ll_perft_device(ll_ctx *ctx, const ll_world_t *root, int depth, i
     if (!root || !d_out) return fail(LL_ERR_INVALID_ARG, "null argument");
     if (depth < 3 || depth > 32) return fail(LL_ERR_INVALID_ARG, "depth %d out of range (3..32)", depth);
     if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) return fail(LL_ERR_INVALID_ARG, "bad shard %d/%d", shard_rank, shard_world);
-    if (!host_well_formed(root)) return fail(LL_ERR_DOMAIN, "position 0 is not well-formed (see include/leafline_b200.h, domain W)");
+    if (!host_well_formed(root)) return fail(LL_ERR_DOMAIN, "position 0 is outside domain W (ll_perft answers the literal domain too; see include/leafline_b200.h)");
     LL_TRY(upload_root(ctx, root));
     bool launched = false;
     LL_TRY(perft_chain_launch(ctx, depth, shard_rank, shard_world, &launched));
@@ -1189,14 +1223,18 @@ extern "C" int ll_horizon_batch(ll_ctx *ctx, const ll_world_t *frontier, size_t 
     if (plies < 0 || plies > 8) return fail(LL_ERR_INVALID_ARG, "plies %d out of range", plies);
     if (!n) return LL_OK;
     if (quiet_extension > 8) return fail(LL_ERR_INVALID_ARG, "quiet extension %d out of range", quiet_extension);
-    const bool small = n <= HORIZON_CHAIN_MAX_BATCH && plies >= 2 && quiet_extension <= 0 && !ctx->force_synced;
+    bool small = n <= HORIZON_CHAIN_MAX_BATCH && plies >= 2 && quiet_extension <= 0 && !ctx->force_synced;
     if (small) { // the alpha-beta driver's hand-offs: check on the host, then one launch chain and ONE synchronisation
-        for (size_t i = 0; i < n; i++)
-            if (!host_well_formed(&frontier[i]))
-                return fail(LL_ERR_DOMAIN, "position %llu is not well-formed (see include/leafline_b200.h, domain W)", (unsigned long long)i);
+        for (size_t i = 0; i < n; i++) LL_TRY(classify_root(ctx, &frontier[i], i));
+        const bool literal = ctx->literal;
+        if (literal) small = false; // the literal path goes level by level
+        if (n == 1) LL_TRY(upload_root(ctx, frontier));
+        else LL_TRY(upload_worlds(ctx, frontier, n, 0));
+        ctx->literal = literal;
+    } else {
+        LL_TRY(upload_worlds(ctx, frontier, n, 0));
+        LL_TRY(validate_level(ctx, ctx->levels[0].soa(), n));
     }
-    if (small && n == 1) LL_TRY(upload_root(ctx, frontier));
-    else LL_TRY(upload_worlds(ctx, frontier, n, 0));
     if (small) {
         bool launched = false;
         LL_TRY(horizon_chain(ctx, 0, plies, &launched));
@@ -1207,8 +1245,6 @@ extern "C" int ll_horizon_batch(ll_ctx *ctx, const ll_world_t *frontier, size_t 
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
             if (!outgrown) return LL_OK;
         }
-    } else {
-        LL_TRY(validate_level(ctx, ctx->levels[0].soa(), n));
     }
     LL_TRY(horizon_levels(ctx, 0, plies, quiet_extension, nullptr));
     CUDA_TRY(cudaMemcpyAsync(values, ctx->levels[0].values.ptr, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1262,7 +1298,7 @@ static int kickoff_core(ll_ctx *ctx, const ll_world_t *root, int depth, int quie
     if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) return fail(LL_ERR_INVALID_ARG, "bad shard %d/%d", shard_rank, shard_world);
     *n_roots = 0;
     if (leaves_scored) *leaves_scored = 0;
-    if (!host_well_formed(root)) return fail(LL_ERR_DOMAIN, "position 0 is not well-formed (see include/leafline_b200.h, domain W)");
+    LL_TRY(classify_root(ctx, root, 0));
     LL_TRY(upload_root(ctx, root));
     u64 total = 0;
     LL_TRY(count_level(ctx, 0, nihilistically != 0, &total)); // mind.rs:388-392
@@ -1299,7 +1335,7 @@ static int kickoff_core(ll_ctx *ctx, const ll_world_t *root, int depth, int quie
     size_t bottom = search_level;
     std::vector<float> vals(kept);
     bool chained = false;
-    if (!variations && quiet_extension <= 0 && depth - 1 >= 2 && kept && kept <= HORIZON_CHAIN_MAX_BATCH && !ctx->force_synced) {
+    if (!variations && quiet_extension <= 0 && depth - 1 >= 2 && kept && kept <= HORIZON_CHAIN_MAX_BATCH && !ctx->force_synced && !ctx->literal) {
         // scores only: the levels below the root moves as one launch chain, no host round trip per ply (see horizon_chain)
         bool launched = false;
         LL_TRY(horizon_chain(ctx, search_level, depth - 1, &launched));

@@ -867,34 +867,83 @@ LL_HD u32 canonical_key(u32 m) {
     return (cls << 16) | ((u32)from << 8) | sub;
 }
 
-// ---- well-formedness (domain W, include/leafline_b200.h) ----------------------------------------
-LL_HD bool well_formed(const Pos &p) {
-    if (p.meta & META_MALFORMED) return false;
+// ---- domains (include/leafline_b200.h) -----------------------------------------------------------------------------------
+// FAST     domain W: what the set-wise kernels assume -- disjoint planes, at most one figurehead and at most 16 figurines a
+//          team, a set eligibility bit means that team's figurehead (if any) stands on its home square and either the cop
+//          stands on that corner or the team has at most 15 figurines (secret service conjures a cop where none stands,
+//          life.rs:621-628: the sixteenth figurine must not become a seventeenth), passing-by square consistent.  Closed
+//          under the reference's own generator.
+// LITERAL  everything else the reference answers and this library can represent: disjoint planes and a consistent
+//          passing-by square, any number of figureheads and figurines, any eligibility.  Answered by the literal path:
+//          the canonical generator with the reference's own legality (every commit made, kept iff no figurehead of the
+//          mover is endangered afterwards, life.rs:678-699), one thread per position, level by level.
+// REJECT   overlapping planes, ABI bytes out of range, a passing-by square that is off the board, occupied or not directly
+//          behind an enemy servant on its double-step rank (LL_ERR_DOMAIN).
+enum { DOMAIN_FAST = 0, DOMAIN_LITERAL = 1, DOMAIN_REJECT = 2 };
+LL_HD int domain_class(const Pos &p) {
+    if (p.meta & META_MALFORMED) return DOMAIN_REJECT;
     u64 acc = 0, overlap = 0;
 #pragma unroll
     for (int j = 0; j < 12; j++) {
         overlap |= acc & p.pl[j];
         acc |= p.pl[j];
     }
-    if (overlap) return false;
-    if (popc64(p.pl[FIGUREHEAD]) > 1 || popc64(p.pl[6 + FIGUREHEAD]) > 1) return false;
-    if (popc64(occupied_by<0>(p)) > 16 || popc64(occupied_by<1>(p)) > 16) return false; // bounds the record lists (REC_MAX)
-    const u32 elig = meta_elig(p.meta);
-    if ((elig & 0x3u) && (p.pl[FIGUREHEAD] & ~(1ull << 4))) return false;
-    if ((elig & 0xCu) && (p.pl[6 + FIGUREHEAD] & ~(1ull << 60))) return false;
+    if (overlap) return DOMAIN_REJECT;
     const u32 pb = meta_pb(p.meta);
     if (pb != 0xFFu) {
-        if ((pb >> 4) > 7 || (pb & 0xFu) > 7) return false;
+        if ((pb >> 4) > 7 || (pb & 0xFu) > 7) return DOMAIN_REJECT;
         const int sq = loc_to_sq(pb);
         const u64 bit = 1ull << sq;
-        if (acc & bit) return false;
+        if (acc & bit) return DOMAIN_REJECT;
         if (meta_stm(p.meta) == 0) { // Orange to move: a Blue servant just double-stepped over rank 5
-            if ((sq >> 3) != 5 || !(p.pl[6 + SERVANT] & (bit >> 8)) || (acc & (bit << 8))) return false;
+            if ((sq >> 3) != 5 || !(p.pl[6 + SERVANT] & (bit >> 8)) || (acc & (bit << 8))) return DOMAIN_REJECT;
         } else {
-            if ((sq >> 3) != 2 || !(p.pl[SERVANT] & (bit << 8)) || (acc & (bit >> 8))) return false;
+            if ((sq >> 3) != 2 || !(p.pl[SERVANT] & (bit << 8)) || (acc & (bit >> 8))) return DOMAIN_REJECT;
         }
     }
-    return true;
+    if (popc64(p.pl[FIGUREHEAD]) > 1 || popc64(p.pl[6 + FIGUREHEAD]) > 1) return DOMAIN_LITERAL;
+    const int n_orange = popc64(occupied_by<0>(p)), n_blue = popc64(occupied_by<1>(p));
+    if (n_orange > 16 || n_blue > 16) return DOMAIN_LITERAL; // bounds the record lists (REC_MAX) and the warp-per-parent lanes
+    const u32 elig = meta_elig(p.meta);
+    if ((elig & 0x3u) && (p.pl[FIGUREHEAD] & ~(1ull << 4))) return DOMAIN_LITERAL;
+    if ((elig & 0xCu) && (p.pl[6 + FIGUREHEAD] & ~(1ull << 60))) return DOMAIN_LITERAL;
+    if (n_orange == 16 && (((elig & 0x1u) && !(p.pl[COP] & (1ull << 0))) || ((elig & 0x2u) && !(p.pl[COP] & (1ull << 7))))) return DOMAIN_LITERAL;
+    if (n_blue == 16 && (((elig & 0x4u) && !(p.pl[6 + COP] & (1ull << 56))) || ((elig & 0x8u) && !(p.pl[6 + COP] & (1ull << 63))))) return DOMAIN_LITERAL;
+    return DOMAIN_FAST;
+}
+LL_HD bool well_formed(const Pos &p) { return domain_class(p) == DOMAIN_FAST; }
+
+// ---- the literal path: lookahead() exactly as the reference defines it (life.rs:692-699, 728-739, 1052-1084) ---------------
+// The reckless generator above is already literal on any position of disjoint planes (it loops over every figurehead, asks
+// no question about the number of figurines, reproduces the secret-service rules square by square); what domain W buys is
+// only the legality by masks.  Here every reckless commit is made and kept iff none of the mover's figureheads is endangered
+// afterwards; in_critical_endangerment / attacked_by are the opponent's whole reckless_lookahead boiled down to "is this
+// square the destination of a capture-capable move", which holds on any disjoint position (the child's passing-by square, the
+// only way to stun something that is not on the destination, always lies behind the servant that just stepped).
+template <int T, class Sink> struct CarefulSink {
+    const Pos &par;
+    Sink &inner;
+    LL_HDM void move(u32 job, int from, int to, u32 asc, u32 flags) {
+        Pos c;
+        make_child_as<T>(par, mv_pack(job, from, to, asc, flags), c);
+        if (!in_critical_endangerment<T>(c)) inner.move(job, from, to, asc, flags);
+    }
+};
+template <bool NIHIL, class Sink> LL_HD void lookahead_literal(const Pos &p, Sink &sink) {
+    if (NIHIL) {
+        lookahead<true>(p, sink);
+    } else if (meta_stm(p.meta) == 0) {
+        CarefulSink<0, Sink> careful{p, sink};
+        lookahead_as<0, true>(p, careful);
+    } else {
+        CarefulSink<1, Sink> careful{p, sink};
+        lookahead_as<1, true>(p, careful);
+    }
+}
+template <bool NIHIL> LL_HD u32 count_moves_literal(const Pos &p) {
+    CountSink sink;
+    lookahead_literal<NIHIL>(p, sink);
+    return sink.n;
 }
 
 // ---- static evaluation (mind.rs:50-143): strict f32, one rounded multiply and one rounded add per

@@ -131,10 +131,13 @@ __global__ void __launch_bounds__(BLOCK) k_commits_to_aos(Soa in, const u32 *__r
 }
 
 // ---- validation -------------------------------------------------------------------------------------
+// first_bad[0] = first position outside every domain (atomicMin), first_bad[1] != 0 if some position needs the literal path
 __global__ void __launch_bounds__(BLOCK) k_validate(Soa in, size_t n, unsigned long long *first_bad) {
     const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
     if (i >= n) return;
-    if (!well_formed(soa_load(in, i))) atomicMin(first_bad, (unsigned long long)i);
+    const int cls = domain_class(soa_load(in, i));
+    if (cls == DOMAIN_REJECT) atomicMin(first_bad, (unsigned long long)i);
+    else if (cls == DOMAIN_LITERAL) first_bad[1] = 1ull;
 }
 
 // ---- static scoring: HBM-bound streaming kernel, 2 positions per thread, 128-bit loads ---------------
@@ -174,14 +177,21 @@ template <bool NIHIL> LL_HD u32 count_stuns(const Pos &p) {
     lookahead<NIHIL>(p, sink);
     return sink.n;
 }
+template <bool NIHIL> LL_HD u32 count_stuns_literal(const Pos &p) {
+    StunCountSink sink{opposition_squares(p)};
+    lookahead_literal<NIHIL>(p, sink);
+    return sink.n;
+}
 
 // ---- movegen: set-wise count -> scan -> expand ---------------------------------------------------------
-template <bool NIHIL> __global__ void __launch_bounds__(BLOCK) k_count(Soa in, size_t n, u32 *__restrict__ counts, u32 *__restrict__ block_sums, int stuns_only) {
+// literal: positions outside domain W (ll_device.cuh: DOMAIN_LITERAL) -- counted by the generator with the reference's legality
+template <bool NIHIL> __global__ void __launch_bounds__(BLOCK) k_count(Soa in, size_t n, u32 *__restrict__ counts, u32 *__restrict__ block_sums, int stuns_only, int literal) {
     const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
     u32 c = 0;
     if (i < n) {
         const Pos p = soa_load(in, i);
-        c = stuns_only ? count_stuns<NIHIL>(p) : count_moves<NIHIL>(p);
+        if (literal) c = stuns_only ? count_stuns_literal<NIHIL>(p) : count_moves_literal<NIHIL>(p);
+        else c = stuns_only ? count_stuns<NIHIL>(p) : count_moves<NIHIL>(p);
         counts[i] = c;
     }
     u32 total;
@@ -294,7 +304,7 @@ LL_HD Pos tile_load(const ExpandShared &sh, u32 slot) {
 // P = parents per tile (BLOCK, or fewer for narrow levels: shorter tiles spread over more SMs; canonical-order
 // emission needs P == BLOCK because the scan works on BLOCK-sized groups)
 // STUNS = quiescence level: only stunning commits are expanded
-template <bool NIHIL, int MODE, int P, bool STUNS> __device__ __forceinline__ void expand_tiles(const ExpandArgs &a, ExpandShared &sh) {
+template <bool NIHIL, int MODE, int P, bool STUNS, bool LITERAL = false> __device__ __forceinline__ void expand_tiles(const ExpandArgs &a, ExpandShared &sh) {
     const int tid = threadIdx.x;
     // chained launches: once a level has outgrown its buffer, its recorded size says nothing about what was
     // written -- everything downstream stands down and the host redoes the call level by level
@@ -347,7 +357,8 @@ template <bool NIHIL, int MODE, int P, bool STUNS> __device__ __forceinline__ vo
                     sink.world = (u32)a.shard_world;
                     sink.owner = unit_hash(p) % (u32)a.shard_world;
                 }
-                lookahead<NIHIL>(p, sink);
+                if (LITERAL) lookahead_literal<NIHIL>(p, sink);
+                else lookahead<NIHIL>(p, sink);
             }
             __syncthreads();
             const u32 wn = min((u32)DESC_CAP, total - w0);
@@ -397,9 +408,9 @@ template <bool NIHIL, int MODE, int P, bool STUNS> __device__ __forceinline__ vo
         __syncthreads(); // the tile and the claim slot are reused by the next round
     }
 }
-template <bool NIHIL, int MODE, int P = BLOCK, bool STUNS = false> __global__ void __launch_bounds__(BLOCK, LL_EXPAND_MIN_BLOCKS) k_expand(const ExpandArgs a) {
+template <bool NIHIL, int MODE, int P = BLOCK, bool STUNS = false, bool LITERAL = false> __global__ void __launch_bounds__(BLOCK, LL_EXPAND_MIN_BLOCKS) k_expand(const ExpandArgs a) {
     __shared__ ExpandShared sh;
-    expand_tiles<NIHIL, MODE, P, STUNS>(a, sh);
+    expand_tiles<NIHIL, MODE, P, STUNS, LITERAL>(a, sh);
 }
 
 // ---- the order-free legal expansion (perft launch chain and tail): phase 1 by records ------------------------
@@ -1073,11 +1084,11 @@ __global__ void __launch_bounds__(1024) k_pack_perft_result(const u64 *leaves, c
 }
 
 // ---- perft tail on an already materialised frontier: count the legal moves of every node ---------------
-__global__ void __launch_bounds__(BLOCK) k_count_leaves(Soa in, size_t n, const u32 *__restrict__ root_in, u64 *__restrict__ per_root, u64 *__restrict__ total) {
+__global__ void __launch_bounds__(BLOCK) k_count_leaves(Soa in, size_t n, const u32 *__restrict__ root_in, u64 *__restrict__ per_root, u64 *__restrict__ total, int literal) {
     const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
     u32 c = 0, root = 0xFFFFFFFFu;
     if (i < n) {
-        c = count_moves<false>(soa_load(in, i));
+        c = literal ? count_moves_literal<false>(soa_load(in, i)) : count_moves<false>(soa_load(in, i));
         root = root_in ? root_in[i] : 0u;
     }
     const unsigned peers = __match_any_sync(0xffffffffu, root);

@@ -653,7 +653,7 @@ int member_perft_tree(Member &m, const ll_world_t *root, int depth) {
     ll_ctx *ctx = m.ctx;
     const int W = m.group->world;
     u64 *host = m.host_words;
-    if (W == 1 || depth < m.group->perft_shard_min_depth) { // every rank counts the whole (small) tree: no collective
+    if (W == 1 || depth < m.group->perft_shard_min_depth || host_domain_class(root) == HOST_LITERAL) { // every rank counts the whole (small, or literal-path) tree: no collective
         uint32_t n = 0;
         LL_TRY(ll_perft(ctx, root, depth, 0, 1, (uint64_t *)&host[MW_LEAVES], (uint64_t *)(host + MW_TABLE), 1024, &n));
         host[MW_ROOTS] = n;
@@ -664,7 +664,7 @@ int member_perft_tree(Member &m, const ll_world_t *root, int depth) {
     // buffer, or was never sized): every rank redoes its share through ll_perft, which re-sizes, and the counts are reduced again
     int own = LL_OK;
     bool launched = false;
-    if (!host_well_formed(root)) own = fail(LL_ERR_DOMAIN, "position 0 is not well-formed (see include/leafline_b200.h, domain W)");
+    if (!host_well_formed(root)) own = classify_root(ctx, root, 0); // (a literal-path root never gets here)
     if (own == LL_OK) own = upload_root(ctx, root);
     if (own == LL_OK && !ctx->force_synced) own = perft_chain_launch(ctx, depth, m.rank, W, &launched);
     if (own == LL_OK && launched) {
@@ -714,7 +714,12 @@ int member_perft_batch(Member &m, const ll_world_t *roots, uint32_t n, int depth
         u64 *sc = (u64 *)ctx->scalars.ptr;
         for (uint32_t i = (uint32_t)m.rank; i < n && own == LL_OK && !unsized; i += (uint32_t)W) {
             bool launched = false;
-            if (!host_well_formed(&roots[i])) own = fail(LL_ERR_DOMAIN, "position %u is not well-formed (see include/leafline_b200.h, domain W)", i);
+            const int cls = host_domain_class(&roots[i]);
+            if (cls == HOST_REJECT) own = classify_root(ctx, &roots[i], i);
+            if (cls == HOST_LITERAL) { // answered by ll_perft's literal path in the redo below
+                unsized = true;
+                break;
+            }
             if (own == LL_OK) own = upload_root(ctx, &roots[i]);
             if (own == LL_OK) own = perft_chain_launch(ctx, depth, 0, 1, &launched);
             if (own != LL_OK) break;
@@ -766,7 +771,7 @@ int member_kickoff(Member &m, const ll_world_t *root, int depth, int quiet_exten
     const int W = m.group->world;
     out.n_roots = 0;
     out.leaves_scored = 0;
-    if (W == 1 || depth < 3 || depth < m.group->kickoff_shard_min_depth) // small trees: every rank searches the whole, no collective
+    if (W == 1 || depth < 3 || depth < m.group->kickoff_shard_min_depth || (root && host_domain_class(root) == HOST_LITERAL)) // small or literal-path trees: every rank searches the whole, no collective
         return ll_kickoff(ctx, root, depth, quiet_extension, nihilistically, 0, 1, out.roots, out.scores, out.root_cap, &out.n_roots, &out.leaves_scored);
     if (depth > 9) return fail(LL_ERR_INVALID_ARG, "depth %d out of range (1..9)", depth);
     if (quiet_extension > 8) return fail(LL_ERR_INVALID_ARG, "quiet extension %d out of range", quiet_extension);
@@ -778,7 +783,7 @@ int member_kickoff(Member &m, const ll_world_t *root, int depth, int quiet_exten
     uint64_t scored = 0;
     auto local = [&]() -> int {
         if (!root || !out.scores) return fail(LL_ERR_INVALID_ARG, "null argument");
-        if (!host_well_formed(root)) return fail(LL_ERR_DOMAIN, "position 0 is not well-formed (see include/leafline_b200.h, domain W)");
+        LL_TRY(classify_root(ctx, root, 0));
         LL_TRY(upload_root(ctx, root));
         LL_TRY(count_level(ctx, 0, nihilistically != 0, &n_roots)); // mind.rs:388-392
         if (n_roots > out.root_cap) return fail(LL_ERR_CAPACITY, "%llu root moves do not fit root_cap %u", (unsigned long long)n_roots, out.root_cap);

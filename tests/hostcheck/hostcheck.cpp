@@ -78,6 +78,32 @@ extern "C" int hc_lookahead(const ll_world_t *w, int nihil, ll_commit_t *out, in
     return (int)sink.n;
 }
 
+// the literal path (positions outside domain W): lookahead() / reckless_lookahead() by the reference's own legality
+extern "C" int hc_lookahead_literal(const ll_world_t *w, int nihil, ll_commit_t *out, int cap) {
+    const Pos p = to_pos(w);
+    static thread_local ListSink sink;
+    sink.n = 0;
+    if (nihil) lookahead_literal<true>(p, sink);
+    else lookahead_literal<false>(p, sink);
+    const u32 team = meta_stm(p.meta);
+    for (u32 i = 0; i < sink.n && (int)i < cap; i++) {
+        const u32 m = sink.moves[i];
+        Pos c;
+        const u32 hosp = make_child(p, m, c);
+        ll_commit_t *o = out + i;
+        o->team = (uint8_t)team;
+        o->job = (uint8_t)mv_job(m);
+        o->whence = (uint8_t)sq_to_loc(mv_from(m));
+        o->whither = (uint8_t)sq_to_loc(mv_to(m));
+        o->hospitalization = hosp == JOB_NONE ? 0xFF : (uint8_t)(((team ^ 1u) << 3) | hosp);
+        o->ascension = mv_asc(m) == ASC_NONE ? 0xFF : (uint8_t)((team << 3) | mv_asc(m));
+        o->pad[0] = o->pad[1] = 0;
+        from_pos(c, &o->tree);
+    }
+    return (int)sink.n;
+}
+extern "C" int hc_domain_class(const ll_world_t *w) { return domain_class(to_pos(w)); }
+
 extern "C" float hc_score(const ll_world_t *w) { return score(to_pos(w)); }
 extern "C" int hc_well_formed(const ll_world_t *w) { return well_formed(to_pos(w)) ? 1 : 0; }
 

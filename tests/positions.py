@@ -57,6 +57,25 @@ def reckless_walk_worlds(seed, games, plies):
     return np.array(out, dtype=O.WORLD_DTYPE)
 
 
+# positions OUTSIDE domain W that the reference answers all the same (`--from` takes any runes, main.rs:199; lookahead loops over
+# every figurehead, life.rs:678-690): the literal path's test set
+OUTSIDE_W = [
+    "4k3/8/8/8/8/8/3K4/4K2R w K -",            # two Orange figureheads, one of them on its home square: secret service live
+    "4k2k/8/8/8/8/8/r7/K3K3 w - -",            # two figureheads either side; the a1 one is boxed in
+    "k3k3/8/8/3Q4/8/8/8/4K3 b - -",            # the mover has two figureheads, both endangered by one princess
+    "kk6/8/8/8/8/8/PPPPPPPP/RNBQKBNR w KQ -",  # two Blue figureheads
+    "4k3/pppppppp/8/8/8/N7/PPPPPPPP/RNBQKBNR w KQ -",  # seventeen Orange figurines
+    "rnbqkbnr/pppppppp/n6n/8/8/8/8/4K3 b kq -",        # eighteen Blue figurines
+    "4k3/8/8/8/8/8/8/R2K3R w KQ -",            # eligibility with the figurehead off its home square (a figurehead is conjured on c1 / g1)
+    "4k3/8/8/8/8/NNN5/PPPPPPPP/RNBQK3 w K -",  # sixteen figurines, east eligibility, no cop on h1: secret service makes a seventeenth
+    "r3k3/pppppppp/nnnnnn2/8/8/8/8/4K3 b kq -",  # the same for Blue (sixteen, the h8 corner empty)
+]
+
+
+def outside_w_worlds():
+    return np.array([O.reconstruct(f) for f in OUTSIDE_W], dtype=O.WORLD_DTYPE)
+
+
 def is_well_formed(w):
     """Domain W of include/leafline_b200.h, restated on the host for the closure test."""
     planes = [int(x) for x in w["plane"]]
@@ -76,6 +95,11 @@ def is_well_formed(w):
     if e & 3 and planes[5] & ~(1 << 4):
         return False
     if e & 12 and planes[11] & ~(1 << 60):
+        return False
+    # a set eligibility bit wants the cop on its corner or a spare seat among the sixteen (secret service conjures a cop)
+    if bin(orange).count("1") == 16 and ((e & 1 and not planes[3] & 1) or (e & 2 and not planes[3] & (1 << 7))):
+        return False
+    if bin(blue).count("1") == 16 and ((e & 4 and not planes[9] & (1 << 56)) or (e & 8 and not planes[9] & (1 << 63))):
         return False
     pb = int(w["passing_by"])
     if pb != 0xFF:

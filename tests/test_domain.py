@@ -25,3 +25,23 @@ def test_playout_positions_are_well_formed():
     assert all(is_well_formed(w) for w in worlds)
     lens = [len(O.lookahead(w)) for w in worlds[:50]]
     assert 15 < np.mean(lens) < 50
+
+
+def test_the_tightened_domain_is_closed_under_secret_service_with_a_phantom_cop():
+    """A team of sixteen with an eligibility bit and no cop on that corner would grow a seventeenth figurine by secret service
+    (life.rs:621-628): such positions belong to the literal domain, and nothing inside W can reach one."""
+    from positions import OUTSIDE_W
+
+    for fen in OUTSIDE_W:
+        assert not is_well_formed(O.reconstruct(fen)), fen
+    # sixteen figurines, the cop standing on its corner: inside W, and so are all its children
+    w = O.reconstruct("4k3/8/8/8/8/NN6/PPPPPPPP/RNBQK2R w K -")
+    assert is_well_formed(w)
+    for c in O.reckless_lookahead(w):
+        assert is_well_formed(c["tree"])
+    # a phantom cop appears only where a seat is free: fifteen figurines, east eligibility, h1 empty
+    w = O.reconstruct("4k3/8/8/8/8/NN6/PPPPPPPP/RNBQK3 w K -")
+    assert is_well_formed(w)
+    kids = O.reckless_lookahead(w)
+    assert any(bin(int(np.bitwise_or.reduce(c["tree"]["plane"][:6]))).count("1") == 16 for c in kids)
+    assert all(is_well_formed(c["tree"]) for c in kids)

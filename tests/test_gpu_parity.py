@@ -201,12 +201,56 @@ def test_domain_errors_are_reported_not_guessed(eng):
     with pytest.raises(ll.LeaflineError) as e:
         eng.lookahead(np.array([ll.new_world(), bad], dtype=ll.WORLD_DTYPE))
     assert e.value.code == -4 and "position 1" in str(e.value)
-    crowd = ll.reconstruct("4k3/8/8/8/NNNNNNNN/NNNNNNNN/8/4K3 w - -")  # 17 orange figurines: beyond the record bound
-    with pytest.raises(ll.LeaflineError):
-        eng.horizon(crowd, 1)
-    two_kings = ll.reconstruct("4k3/8/8/8/8/8/8/K3K3 w - -")
-    with pytest.raises(ll.LeaflineError):
-        eng.perft(two_kings, 2)
+    ghost = ll.new_world().copy()
+    ghost["passing_by"] = ll.algebraic("e6")  # no Blue servant on e5: not a passing-by square
+    with pytest.raises(ll.LeaflineError) as e:
+        eng.perft(ghost, 2)
+    assert e.value.code == -4
+    assert eng.perft(ll.new_world(), 2)[0] == 400  # the context carries on
+
+
+def test_literal_path_answers_positions_outside_domain_w(eng):
+    """The reference answers any runes (`--from`, main.rs:199; lookahead loops over every figurehead, life.rs:678-690): two
+    figureheads a team, seventeen figurines, eligibility with nothing in place.  Such positions take the literal path (the
+    canonical generator with the reference's own make-the-move-and-test legality): lookahead, reckless_lookahead, perft,
+    horizon values and kickoff scores must equal the oracle's, byte for byte."""
+    import leafline_b200 as ll
+    from positions import outside_w_worlds
+    from test_hostcheck import walk
+
+    roots = outside_w_worlds()
+    worlds = np.array(walk(roots, 6, seed=4), dtype=ll.WORLD_DTYPE)
+    assert len(worlds) > 60
+    for nihil, ref in ((False, O.lookahead), (True, O.reckless_lookahead)):
+        offsets, commits = eng.lookahead(worlds, nihilistically=nihil)  # one batch: some members inside W, some outside
+        for i, w in enumerate(worlds):
+            assert commits[offsets[i]:offsets[i + 1]].tobytes() == ref(w).tobytes(), (O.preserve(w), nihil)
+        one = eng.lookahead(worlds[:1], nihilistically=nihil)[1]  # the single-position hand-over
+        assert one.tobytes() == ref(worlds[0]).tobytes()
+    for w in roots:
+        for depth in (1, 2, 3):
+            leaves, per_root = eng.perft(w, depth)
+            want = O.perft_divide(w, depth, threads=4)
+            assert leaves == int(want.sum()) and list(per_root) == list(want), (O.preserve(w), depth)
+        parts = [eng.perft(w, 3, shard=(r, 3))[0] for r in range(3)]
+        assert sum(parts) == eng.perft(w, 3)[0]
+    for plies in (0, 1, 2):
+        got = eng.horizon(worlds[:40], plies)
+        want = np.array([O.negamax(w, plies) for w in worlds[:40]], dtype=np.float32)
+        assert got.tobytes() == want.tobytes(), plies
+    got = eng.horizon(worlds[:20], 1, quiet=2)
+    assert got.tobytes() == np.array([O.negamax(w, 1, quiet=2) for w in worlds[:20]], dtype=np.float32).tobytes()
+    for w in roots[:5]:
+        r_got, s_got, _ = eng.kickoff(w, 3)
+        r_want, s_want = O.kickoff(w, 3, False, threads=4)
+        assert r_got.tobytes() == r_want.tobytes() and s_got.tobytes() == s_want.tobytes(), O.preserve(w)
+        fc = eng.forecast(w, 2)
+        assert sorted(float(x) for x in fc["score"]) == sorted(float(x) for x in O.kickoff(w, 2, False, threads=4)[1])
+    with ll.MultiEngine([0, 0]) as g:  # a group answers such a tree whole on every rank
+        g.set_shard_min_depth(perft_depth=2, kickoff_depth=3)
+        assert g.perft(roots[0], 3)[0] == int(O.perft_divide(roots[0], 3, threads=4).sum())
+        assert g.kickoff(roots[0], 3)[1].tobytes() == O.kickoff(roots[0], 3, False, threads=4)[1].tobytes()
+    assert eng.perft(ll.new_world(), 5)[0] == 4865609  # and the fast path is back for the next call
 
 
 def test_in_critical_endangerment(eng, playouts, reckless_worlds):
@@ -397,7 +441,7 @@ def test_horizon_launch_chain_equals_level_by_level(eng, playouts, reckless_worl
     bad = np.array([playouts[0], playouts[1]], dtype=ll.WORLD_DTYPE)
     bad[1]["plane"][0] |= np.uint64(1)  # overlapping planes
     bad[1]["plane"][7] |= np.uint64(1)
-    with pytest.raises(ll.LeaflineError, match="position 1 is not well-formed"):
+    with pytest.raises(ll.LeaflineError, match="position 1 cannot be answered"):
         eng.horizon(bad, 2)
 
 

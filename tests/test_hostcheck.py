@@ -31,6 +31,8 @@ def hc():
     lib.hc_score.argtypes = [C.c_void_p]
     lib.hc_score.restype = C.c_float
     lib.hc_well_formed.argtypes = [C.c_void_p]
+    lib.hc_lookahead_literal.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.hc_domain_class.argtypes = [C.c_void_p]
     lib.hc_record_moves.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     lib.hc_generator_moves.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.hc_legal_record_moves.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
@@ -94,9 +96,11 @@ def test_reckless_walk_positions(hc):
 def random_domain_worlds(seed, n):
     """Arbitrary members of the ABI's domain W (include/leafline_b200.h): up to 16 figurines a team anywhere on the board --
     servants on first and last ranks, a dozen princesses, no figurehead at all -- with a consistent eligibility."""
+    from positions import is_well_formed
+
     rng = np.random.default_rng(seed)
     out = []
-    for _ in range(n):
+    while len(out) < n:
         w = np.zeros((), dtype=O.WORLD_DTYPE)
         squares = rng.permutation(64)
         k = 0
@@ -116,7 +120,8 @@ def random_domain_worlds(seed, n):
             elig |= int(rng.integers(0, 4)) << 2
         w["service_eligibility"] = elig
         w["passing_by"] = 0xFF
-        out.append(w)
+        if is_well_formed(w):  # (a full team with an eligibility bit and no cop on that corner belongs to the literal domain)
+            out.append(w)
     return np.array(out, dtype=O.WORLD_DTYPE)
 
 
@@ -176,3 +181,45 @@ def test_checks_pins_and_passing_by_corners(hc):
             for d in O.reckless_lookahead(c["tree"])[:12]:
                 deeper.append(d["tree"].copy())
     check(hc, deeper)
+
+
+def walk(worlds, plies, seed):
+    """the given positions and seeded reckless / legal descendants of them"""
+    import random
+
+    rng = random.Random(seed)
+    out = []
+    for w in worlds:
+        for reckless in (False, True):
+            cur = w.copy()
+            for _ in range(plies):
+                out.append(cur.copy())
+                kids = O.reckless_lookahead(cur) if reckless else O.lookahead(cur)
+                if not len(kids):
+                    break
+                cur = kids[rng.randrange(len(kids))]["tree"].copy()
+    return out
+
+
+def test_literal_path_answers_positions_outside_domain_w(hc):
+    """Two figureheads a team, seventeen figurines, eligibility without figurehead or cop in place (life.rs:678-699 loops over any
+    number of figureheads): the literal generator's commits equal the oracle's, byte for byte and in order, on such positions and
+    on seeded descendants of them; on positions inside W it equals the fast generator."""
+    from positions import is_well_formed, outside_w_worlds
+
+    roots = outside_w_worlds()
+    assert all(hc.hc_domain_class(np.ascontiguousarray(w).ctypes.data_as(C.c_void_p)) == 1 for w in roots)
+    worlds = walk(roots, 12, seed=3) + list(named_worlds()) + list(reckless_walk_worlds(seed=9, games=6, plies=40))
+    buf = np.zeros(1024, dtype=O.COMMIT_DTYPE)
+    outside = 0
+    for w in worlds:
+        w = np.ascontiguousarray(w).reshape(())
+        ptr = w.ctypes.data_as(C.c_void_p)
+        cls = hc.hc_domain_class(ptr)
+        assert cls in (0, 1) and (cls == 0) == is_well_formed(w), O.preserve(w)
+        outside += cls
+        for nihil, ref in ((0, O.lookahead), (1, O.reckless_lookahead)):
+            want = ref(w)
+            n = hc.hc_lookahead_literal(ptr, nihil, buf.ctypes.data_as(C.c_void_p), 1024)
+            assert n == len(want) and buf[:n].tobytes() == want.tobytes(), (O.preserve(w), nihil, n, len(want))
+    assert outside > 100
