@@ -197,18 +197,29 @@ int ll_forecast(ll_ctx *ctx, const ll_world_t *root, int depth, int quiet_extens
  * cut-offs, MVV-LVA + history ordering and a full window below every root move run on the HOST; a node with
  * `device_plies` plies left is handed to the device, which returns its exact full-width value (quiet_extension as in
  * ll_horizon_batch).  Scores equal ll_forecast's (alpha-beta is exact at the root); only the work is pruned, so
- * depths beyond ll_forecast's HBM limit are reachable.  variation holds the root move only.  The memory bank
- * (mind.rs:312-344) is sound here: entries are keyed by the whole position and the plies left and say whether their
- * value is exact or a bound, so remembering changes the work, never a root score.
+ * depths beyond ll_forecast's HBM limit are reachable.  The memory bank (mind.rs:312-344) is sound here: entries are keyed
+ * by the whole position and the plies left and say whether their value is exact or a bound, so remembering changes the
+ * work, never a root score; it forgets the least recently used entry under a byte budget (mind.rs:367-372;
+ * ll_set_deja_vu_bound).  variation is the principal variation (mind.rs:208-224): the bank's best commits through the plies
+ * the host searched, the device's variation below the frontier node.
  * stats3 (nullable): { nodes expanded on the host, frontier nodes handed to the device, values taken from the bank }. */
 int ll_alpha_beta_forecast(ll_ctx *ctx, const ll_world_t *root, int depth, int device_plies, int quiet_extension, int nihilistically,
                            ll_forecast_t *forecasts, uint32_t cap, uint32_t *n_forecasts, uint64_t *stats3);
+/* ll_alpha_beta_forecast over the group: the root moves are searched concurrently, root move i on rank i % world (the
+ * reference searches every root move on a thread of its own, src/mind.rs:399-414); scores and variations are gathered in
+ * one max-reduction on the devices.  stats3 are summed over the ranks. */
+int ll_alpha_beta_forecast_multi(ll_mctx *group, const ll_world_t *root, int depth, int device_plies, int quiet_extension, int nihilistically,
+                                 ll_forecast_t *forecasts, uint32_t cap, uint32_t *n_forecasts, uint64_t *stats3);
+/* the `déjà_vu_bound` argument of the reference's kickoff functions (GiB of memory bank, src/mind.rs:367-372, 441-448) for the
+ * searches of this context; default 0.25 */
+int ll_set_deja_vu_bound(ll_ctx *ctx, double gib);
 /* replaces `fixed_depth_sequence_kickoff` (src/mind.rs:473-490) */
 int ll_fixed_depth_sequence_forecast(ll_ctx *ctx, const ll_world_t *root, const uint8_t *depths, uint32_t n_depths, int nihilistically,
                                      ll_forecast_t *forecasts, uint32_t cap, uint32_t *n_forecasts);
 /* replaces `iterative_deepening_kickoff` (src/mind.rs:451-469): the deepest iteration that finished inside the timeout.
  * Iterations are full-width on the device (ll_forecast) while the tree fits HBM and depth < 8, then the host alpha-beta
- * driver (ll_alpha_beta_forecast's search, abandoned in mid-iteration at the deadline): same scores either way. */
+ * driver (ll_alpha_beta_forecast's search, abandoned in mid-iteration at the deadline): same scores either way.  One
+ * intuition bank serves all the iterations (mind.rs:456-464) and, like the reference, the call uses its whole budget. */
 int ll_iterative_deepening_forecast(ll_ctx *ctx, const ll_world_t *root, double timeout_seconds, int nihilistically, ll_forecast_t *forecasts,
                                     uint32_t cap, uint32_t *n_forecasts, uint32_t *depth_reached);
 

@@ -269,6 +269,10 @@ class Engine:
                                   "values_remembered": int(stats[2])}
         return out[: n.value].copy(), int(stats[0]), int(stats[1])
 
+    def set_deja_vu_bound(self, gib):
+        """The `déjà_vu_bound` of the reference's kickoff functions: GiB of memory bank for this engine's searches."""
+        _abi.check(self._lib.ll_set_deja_vu_bound(self._ctx, float(gib)))
+
     def fixed_depth_sequence_kickoff(self, world, depth_sequence, nihilistically=False):
         """mind.rs:473-490."""
         w = _worlds(world)
@@ -423,3 +427,16 @@ class MultiEngine:
         _abi.check(self._lib.ll_kickoff_multi(self._g, _ptr(w), depth, -1 if quiet is None else int(quiet), int(nihilistically),
                                               _ptr(roots), _ptr(scores), 1024, C.byref(n_roots), C.byref(scored)))
         return roots[: n_roots.value].copy(), scores[: n_roots.value].copy(), int(scored.value)
+
+    def alpha_beta_forecast(self, world, depth, device_plies=4, nihilistically=False, quiet=None):
+        """ll_alpha_beta_forecast_multi: root moves searched concurrently, one subset per GPU -> (forecasts, host nodes
+        expanded, frontier nodes handed off), summed over the ranks."""
+        w = _worlds(world)
+        out = np.zeros(1024, dtype=FORECAST_DTYPE)
+        n = C.c_uint32(0)
+        stats = np.zeros(3, dtype=np.uint64)
+        _abi.check(self._lib.ll_alpha_beta_forecast_multi(self._g, _ptr(w), depth, device_plies, -1 if quiet is None else int(quiet),
+                                                          int(nihilistically), _ptr(out), 1024, C.byref(n), _ptr(stats)))
+        self.last_search_stats = {"host_nodes_expanded": int(stats[0]), "frontier_nodes_handed_to_device": int(stats[1]),
+                                  "values_remembered": int(stats[2])}
+        return out[: n.value].copy(), int(stats[0]), int(stats[1])

@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <list>
 #include <new>
 #include <stdexcept>
 #include <string>
@@ -91,6 +92,7 @@ struct ll_ctx {
     void *pinned = nullptr; // small host staging
     size_t pinned_cap = 0;
     bool timing = false;
+    double deja_vu_gib = 0.25; // byte budget of the search drivers' memory bank (mind.rs:367-372; ll_set_deja_vu_bound)
     bool literal = false;      // this call holds a position outside domain W: the literal path answers it (ll_device.cuh: DOMAIN_LITERAL)
     bool force_synced = false; // tests: always take the level-by-level path
     bool no_graph = false;     // tests: issue the perft launch chain launch by launch instead of replaying its CUDA graph
@@ -1450,15 +1452,9 @@ extern "C" int ll_forecast(ll_ctx *ctx, const ll_world_t *root, int depth, int q
 // are exact by construction and are remembered the same way.
 namespace {
 
-struct AlphaBeta {
-    ll_ctx *ctx;
-    int device_plies, quiet_extension;
-    std::unordered_map<uint32_t, uint32_t> intuition; // the "intuition bank": Patch -> credit (mind.rs:353-359)
-    uint64_t expanded = 0, handed_off = 0, remembered = 0;
-    int rc = LL_OK;
-    bool timebound = false, out_of_time = false; // mind.rs:416-420: a search that overruns its deadline is abandoned
-    std::chrono::steady_clock::time_point deadline;
-
+// the "memory bank" (mind.rs:256-267, 312-344, 367-372): least-recently-used eviction under a byte budget, like the
+// reference's LruCache sized by déjà_vu_table_size_bound
+struct Bank {
     struct Key { // the position and the plies left
         u64 w[13];
         bool operator==(const Key &o) const { return memcmp(w, o.w, sizeof w) == 0; }
@@ -1477,19 +1473,64 @@ struct AlphaBeta {
     struct Memory {
         float value;
         uint8_t kind;
+        uint32_t best; // patch_key of the commit that gave the value (0xFFFFFFFF: none -- a frontier value, a leaf)
     };
-    static constexpr size_t BANK_MAX = 1u << 22; // ~0.6 GB of host memory at most; past it nothing new is filed
-    std::unordered_map<Key, Memory, KeyHash> bank;
+    struct Entry {
+        Memory memory;
+        std::list<Key>::iterator at;
+    };
+    static constexpr size_t ENTRY_BYTES = sizeof(Key) * 2 + sizeof(Entry) + 64; // key in the map and in the list + node overheads
+    std::unordered_map<Key, Entry, KeyHash> map;
+    std::list<Key> order; // most recently used first
+    size_t capacity = 1;
+    uint64_t evicted = 0;
+    explicit Bank(double gib) {
+        const double bytes = gib * 1024.0 * 1024.0 * 1024.0;
+        capacity = bytes / ENTRY_BYTES < 1024.0 ? 1024 : (size_t)(bytes / ENTRY_BYTES);
+    }
     static Key key_of(const ll_world_t &w, int plies) {
         Key k;
         for (int j = 0; j < 12; j++) k.w[j] = w.plane[j];
         k.w[12] = (u64)w.initiative | ((u64)w.service_eligibility << 8) | ((u64)w.passing_by << 16) | ((u64)(uint32_t)plies << 32);
         return k;
     }
-    void file(const Key &k, float value, uint8_t kind) {
-        if (bank.size() < BANK_MAX) bank[k] = Memory{value, kind};
+    const Memory *find(const Key &k) {
+        auto it = map.find(k);
+        if (it == map.end()) return nullptr;
+        order.splice(order.begin(), order, it->second.at); // used: to the front
+        return &it->second.memory;
     }
+    void file(const Key &k, float value, uint8_t kind, uint32_t best) {
+        auto it = map.find(k);
+        if (it != map.end()) {
+            it->second.memory = Memory{value, kind, best};
+            order.splice(order.begin(), order, it->second.at);
+            return;
+        }
+        if (map.size() >= capacity) { // forget the least recently used
+            map.erase(order.back());
+            order.pop_back();
+            evicted++;
+        }
+        order.push_front(k);
+        map.emplace(k, Entry{Memory{value, kind, best}, order.begin()});
+    }
+};
 
+using Intuition = std::unordered_map<uint32_t, uint32_t>; // the "intuition bank": Patch -> credit (mind.rs:353-359)
+
+struct AlphaBeta {
+    ll_ctx *ctx;
+    int device_plies, quiet_extension;
+    Intuition &intuition; // lives as long as the caller wants: across the iterations of an iterative deepening (mind.rs:456-464)
+    Bank bank;
+    uint64_t expanded = 0, handed_off = 0, remembered = 0;
+    int rc = LL_OK;
+    bool timebound = false, out_of_time = false; // mind.rs:416-420: a search that overruns its deadline is abandoned
+    std::chrono::steady_clock::time_point deadline;
+    AlphaBeta(ll_ctx *c, int plies, int quiet, Intuition &i) : ctx(c), device_plies(plies), quiet_extension(quiet), intuition(i), bank(c->deja_vu_gib) {}
+
+    static constexpr uint32_t NO_PATCH = 0xFFFFFFFFu;
     static uint32_t patch_key(const ll_commit_t &c) { return (uint32_t)c.team | ((uint32_t)c.job << 1) | ((uint32_t)c.whence << 8) | ((uint32_t)c.whither << 16); }
     static float figurine_valuation(uint8_t agent) { // mind.rs:36-48
         static const float value[6] = {1.0f, 3.2f, 3.3f, 5.1f, 8.8f, 20000.0f};
@@ -1527,9 +1568,9 @@ struct AlphaBeta {
         std::vector<ll_world_t> unknown;
         std::vector<size_t> where;
         for (size_t i = 0; i < n; i++) {
-            const auto it = bank.find(key_of(nodes[i], plies));
-            if (it != bank.end()) { // frontier entries are always exact
-                values[i] = it->second.value;
+            const Bank::Memory *m = bank.find(Bank::key_of(nodes[i], plies));
+            if (m) { // frontier entries are always exact
+                values[i] = m->value;
                 remembered++;
             } else {
                 unknown.push_back(nodes[i]);
@@ -1543,7 +1584,7 @@ struct AlphaBeta {
         handed_off += unknown.size();
         for (size_t j = 0; j < unknown.size(); j++) {
             values[where[j]] = fresh[j];
-            file(key_of(unknown[j], plies), fresh[j], EXACT);
+            bank.file(Bank::key_of(unknown[j], plies), fresh[j], Bank::EXACT, NO_PATCH);
         }
         return true;
     }
@@ -1560,11 +1601,10 @@ struct AlphaBeta {
             device_values(&node, 1, depth < 0 ? 0 : depth, &v);
             return v;
         }
-        const Key key = key_of(node, depth);
-        const auto seen = bank.find(key);
-        if (seen != bank.end()) { // mind.rs:316-325, with the kinds of value told apart
-            const Memory m = seen->second;
-            if (m.kind == EXACT || (m.kind == LOWER && m.value >= beta) || (m.kind == UPPER && m.value <= alpha)) {
+        const Bank::Key key = Bank::key_of(node, depth);
+        if (const Bank::Memory *seen = bank.find(key)) { // mind.rs:316-325, with the kinds of value told apart
+            const Bank::Memory m = *seen;
+            if (m.kind == Bank::EXACT || (m.kind == Bank::LOWER && m.value >= beta) || (m.kind == Bank::UPPER && m.value <= alpha)) {
                 remembered++;
                 return m.value;
             }
@@ -1575,17 +1615,21 @@ struct AlphaBeta {
         if (premonitions.empty()) { // mind.rs:282-287 at depth > 0: the node is its own leaf
             float v = 0.0f;
             rc = ll_horizon_batch(ctx, &node, 1, 0, -1, &v);
-            if (rc == LL_OK) file(key, v, EXACT);
+            if (rc == LL_OK) bank.file(key, v, Bank::EXACT, NO_PATCH);
             return v;
         }
         order(premonitions);
         float optimum = -INFINITY;
+        uint32_t optimand = NO_PATCH;
         auto remember = [&]() { // mind.rs:340-343
-            if (rc == LL_OK) file(key, optimum, optimum <= alpha_in ? UPPER : optimum >= beta ? LOWER : EXACT);
+            if (rc == LL_OK) bank.file(key, optimum, optimum <= alpha_in ? Bank::UPPER : optimum >= beta ? Bank::LOWER : Bank::EXACT, optimand);
             return optimum;
         };
         auto consider = [&](const ll_commit_t &c, float value) { // mind.rs:346-361
-            if (value > optimum) optimum = value;
+            if (value > optimum) {
+                optimum = value;
+                optimand = patch_key(c);
+            }
             if (value > alpha) alpha = value;
             if (alpha >= beta) {
                 intuition[patch_key(c)] += 1u << (depth > 30 ? 30 : depth);
@@ -1615,14 +1659,46 @@ struct AlphaBeta {
         }
         return remember();
     }
+    // The principal variation below a root move (the `Variation` memory, mind.rs:208-224): follow the bank's exact entries
+    // through the plies the host searched -- every node of a principal variation has an exact entry naming its best commit --
+    // then ask the device for the rest of the line below the frontier node (ll_forecast's variation kernel).
+    void variation_below(ll_world_t node, int depth, ll_patch_t *line, uint32_t *len) {
+        std::vector<ll_commit_t> kids;
+        while (*len < LL_MAX_VARIATION && rc == LL_OK) {
+            if (depth <= device_plies) {
+                if (depth < 1) return;
+                std::vector<ll_forecast_t> tail(1024);
+                uint32_t n = 0;
+                if (ll_forecast(ctx, &node, depth, quiet_extension, 1, tail.data(), 1024, &n, nullptr) != LL_OK || !n) return; // (reckless children, as everywhere below the root)
+                for (uint32_t j = 0; j < tail[0].variation_len && *len < LL_MAX_VARIATION; j++) line[(*len)++] = tail[0].variation[j];
+                return;
+            }
+            const Bank::Memory *m = bank.find(Bank::key_of(node, depth));
+            if (!m || m->kind != Bank::EXACT || m->best == NO_PATCH) return;
+            const uint32_t best = m->best;
+            if (!children(node, kids)) return;
+            bool found = false;
+            for (const ll_commit_t &c : kids)
+                if (patch_key(c) == best && (!found)) { // (ascensions share a patch: the first, like the reference's flash(patch))
+                    line[(*len)++] = ll_patch_t{c.team, c.job, c.whence, c.whither};
+                    node = c.tree;
+                    found = true;
+                }
+            if (!found) return;
+            depth--;
+        }
+    }
 };
 
 } // namespace
 
-// `deadline` (nullable): give up once it has passed -> *timed_out = true, forecasts untouched
+// `deadline` (nullable): give up once it has passed -> *timed_out = true, forecasts untouched.  `intuition` (nullable): the
+// caller's intuition bank, kept across calls.  shard_world > 1: only the root moves i % shard_world == shard_rank are
+// searched (the others get -INFINITY and no variation: gather with a max, like ll_kickoff).
 static int alpha_beta_core(ll_ctx *ctx, const ll_world_t *root, int depth, int device_plies, int quiet_extension, int nihilistically,
                            ll_forecast_t *forecasts, uint32_t cap, uint32_t *n_forecasts, uint64_t *stats3,
-                           const std::chrono::steady_clock::time_point *deadline, bool *timed_out) {
+                           const std::chrono::steady_clock::time_point *deadline, bool *timed_out, Intuition *intuition = nullptr, int shard_rank = 0,
+                           int shard_world = 1, bool sorted = true) {
     if (timed_out) *timed_out = false;
     uint32_t offsets[2] = {0, 0};
     std::vector<ll_commit_t> roots(1024);
@@ -1632,13 +1708,25 @@ static int alpha_beta_core(ll_ctx *ctx, const ll_world_t *root, int depth, int d
         *n_forecasts = offsets[1];
         return fail(LL_ERR_CAPACITY, "%u forecasts do not fit the capacity of %u", offsets[1], cap);
     }
-    AlphaBeta ab{ctx, device_plies, quiet_extension};
+    Intuition local;
+    AlphaBeta ab(ctx, device_plies, quiet_extension, intuition ? *intuition : local);
     if (deadline) {
         ab.timebound = true;
         ab.deadline = *deadline;
     }
-    std::vector<float> scores(roots.size());
-    for (size_t i = 0; i < roots.size(); i++) { // every root move gets the full window (mind.rs:406-411)
+    // the root moves are searched in the order the intuition bank suggests (mind.rs:393-396); what is returned is ordered by
+    // score, ties in canonical order
+    std::vector<uint32_t> sequence(roots.size());
+    {
+        std::vector<ll_commit_t> ordered = roots;
+        ab.order(ordered);
+        for (uint32_t k = 0; k < ordered.size(); k++)
+            for (uint32_t i = 0; i < roots.size(); i++)
+                if (!memcmp(&ordered[k], &roots[i], sizeof(ll_commit_t))) sequence[k] = i;
+    }
+    std::vector<float> scores(roots.size(), -INFINITY);
+    for (uint32_t i : sequence) { // every root move gets the full window (mind.rs:406-411)
+        if ((int)(i % (uint32_t)shard_world) != shard_rank) continue;
         scores[i] = -ab.search(roots[i].tree, depth - 1, -INFINITY, INFINITY);
         if (ab.out_of_time) {
             if (timed_out) *timed_out = true;
@@ -1649,21 +1737,33 @@ static int alpha_beta_core(ll_ctx *ctx, const ll_world_t *root, int depth, int d
     *n_forecasts = offsets[1];
     std::vector<uint32_t> order(roots.size());
     for (uint32_t i = 0; i < roots.size(); i++) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return scores[x] > scores[y]; }); // mind.rs:436
+    if (sorted) std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return scores[x] > scores[y]; }); // mind.rs:436
     for (uint32_t k = 0; k < roots.size(); k++) {
         const uint32_t i = order[k];
         ll_forecast_t &f = forecasts[k];
         memset(&f, 0, sizeof f);
         f.commit = roots[i];
         f.score = scores[i];
-        f.variation[0] = ll_patch_t{roots[i].team, roots[i].job, roots[i].whence, roots[i].whither};
+        f.variation[0] = ll_patch_t{roots[i].team, roots[i].job, roots[i].whence, roots[i].whither}; // T::flash(premonition.patch), mind.rs:426
         f.variation_len = 1;
+        if ((int)(i % (uint32_t)shard_world) == shard_rank && !ab.out_of_time) {
+            ab.timebound = false; // (the line is read out of the bank; the deadline decided the search, not this)
+            ab.variation_below(roots[i].tree, depth - 1, f.variation, &f.variation_len);
+            if (ab.rc != LL_OK) return ab.rc;
+        }
     }
     if (stats3) {
         stats3[0] = ab.expanded;
         stats3[1] = ab.handed_off;
         stats3[2] = ab.remembered;
     }
+    return LL_OK;
+}
+
+extern "C" int ll_set_deja_vu_bound(ll_ctx *ctx, double gib) {
+    if (!ctx) return fail(LL_ERR_INVALID_ARG, "null context");
+    if (!(gib > 0.0) || gib > 1024.0) return fail(LL_ERR_INVALID_ARG, "memory bound %g GiB out of range", gib);
+    ctx->deja_vu_gib = gib;
     return LL_OK;
 }
 
@@ -1701,21 +1801,21 @@ extern "C" int ll_iterative_deepening_forecast(ll_ctx *ctx, const ll_world_t *ro
     // as the variation) and is abandoned in mid-search if it overruns, like the reference's time-bound search.
     LL_TRY(ll_forecast(ctx, root, 1, -1, nihilistically, forecasts, cap, n_forecasts, nullptr));
     *depth_reached = 1;
-    std::vector<ll_forecast_t> next(cap);
+    std::vector<ll_forecast_t> next(cap < 1024 ? cap : 1024);
+    Intuition intuition; // one intuition bank for all the iterations (mind.rs:456-464)
     bool full_width = true;
     for (int depth = 2; depth <= 32; depth++) {
-        const double before = elapsed();
-        if (before >= timeout_seconds) break;
+        if (elapsed() >= timeout_seconds) break;
         uint32_t n = 0;
         if (full_width && depth >= 8) full_width = false;
         if (full_width) {
-            const int rc = ll_forecast(ctx, root, depth, -1, nihilistically, next.data(), cap, &n, nullptr);
+            const int rc = ll_forecast(ctx, root, depth, -1, nihilistically, next.data(), (uint32_t)next.size(), &n, nullptr);
             if (rc == LL_ERR_OOM) full_width = false; // the full-width tree no longer fits HBM
             else LL_TRY(rc);
         }
         if (!full_width) {
             bool timed_out = false;
-            LL_TRY(alpha_beta_core(ctx, root, depth, depth >= 9 ? 5 : 4, -1, nihilistically, next.data(), cap, &n, nullptr, &deadline, &timed_out));
+            LL_TRY(alpha_beta_core(ctx, root, depth, depth >= 9 ? 5 : 4, -1, nihilistically, next.data(), (uint32_t)next.size(), &n, nullptr, &deadline, &timed_out, &intuition));
             if (timed_out) break;
         }
         if (elapsed() > timeout_seconds) break; // finished late: discarded, like the reference's `None` (mind.rs:416-420)
@@ -1723,10 +1823,8 @@ extern "C" int ll_iterative_deepening_forecast(ll_ctx *ctx, const ll_world_t *ro
         *n_forecasts = n;
         *depth_reached = (uint32_t)depth;
         if (!n) break; // nothing to play
-        const double took = elapsed() - before;
-        // a full-width ply is ~30x wider than the last; the pruned search grows ~9x per ply (and ~6x over the last full-width one)
-        const double growth = full_width && depth + 1 < 8 ? 20.0 : full_width ? 8.0 : 9.5;
-        if (elapsed() + took * growth > timeout_seconds) break; // the next iteration cannot finish in time
+        // (no guess at whether the next iteration can finish: like the reference, the budget is used -- an iteration that
+        // overruns is abandoned in mid-search, mind.rs:416-420)
     }
     return LL_OK;
     LL_ABI_END

@@ -12,7 +12,9 @@
 //
 // NCCL is loaded at run time (dlopen of libnccl.so.2 -- in a torch process that is the copy torch already mapped), so the
 // library has no link-time dependency on it and single-GPU callers never touch it.
+#include <array>
 #include <atomic>
+#include <climits>
 #include <condition_variable>
 #include <dlfcn.h>
 #include <functional>
@@ -894,6 +896,78 @@ int member_kickoff(Member &m, const ll_world_t *root, int depth, int quiet_exten
     return LL_OK;
 }
 
+// ---- the host alpha-beta driver over the group: the root moves are searched concurrently, one subset per GPU (the reference
+// runs one thread per root move, mind.rs:399-414); scores, variations and counters are gathered in ONE max-reduction (every
+// rank writes only its own root moves' slots, the others hold INT_MIN there) -------------------------------------------------
+int member_alpha_beta(Member &m, const ll_world_t *root, int depth, int device_plies, int quiet_extension, int nihilistically, ll_forecast_t *forecasts,
+                      uint32_t cap, uint32_t *n_forecasts, uint64_t *stats3) {
+    ll_ctx *ctx = m.ctx;
+    const int W = m.group->world;
+    if (W == 1) return ll_alpha_beta_forecast(ctx, root, depth, device_plies, quiet_extension, nihilistically, forecasts, cap, n_forecasts, stats3);
+    uint32_t n = 0;
+    uint64_t stats[3] = {0, 0, 0};
+    std::vector<ll_forecast_t> mine(1024);
+    int own = check_ctx(ctx);
+    if (own == LL_OK) own = alpha_beta_core(ctx, root, depth, device_plies, quiet_extension, nihilistically, mine.data(), 1024, &n, stats, nullptr, nullptr, nullptr, m.rank, W, false);
+    if (own == LL_OK && n > cap) own = fail(LL_ERR_CAPACITY, "%u forecasts do not fit the capacity of %u", n, cap);
+    u64 *d = (u64 *)m.words.ptr;
+    m.host_words[0] = own != LL_OK;
+    m.host_words[1] = 0;
+    CUDA_TRY(cudaMemcpyAsync(d, m.host_words, 2 * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    LL_TRY(exchange_words(m, 2));
+    if (m.host_words[0]) return some_rank_failed(m, own);
+    constexpr size_t PER_ROOT = 2 + LL_MAX_VARIATION; // score key, variation length, the patches
+    const size_t tail = (size_t)n * PER_ROOT, total = (tail + 6 * (size_t)W + 1) & ~(size_t)1;
+    std::vector<int> keys(total, INT_MIN);
+    for (uint32_t i = 0; i < n; i++) {
+        if ((int)(i % (uint32_t)W) != m.rank) continue;
+        int *k = keys.data() + (size_t)i * PER_ROOT;
+        const int bits = *(const int *)&mine[i].score;
+        k[0] = bits >= 0 ? bits : bits ^ 0x7FFFFFFF; // float_key
+        k[1] = (int)mine[i].variation_len;
+        for (uint32_t j = 0; j < mine[i].variation_len; j++) {
+            const ll_patch_t &p = mine[i].variation[j];
+            k[2 + j] = (int)p.team | ((int)p.job << 8) | ((int)p.whence << 16) | ((int)p.whither << 24);
+        }
+    }
+    for (int c = 0; c < 3; c++) {
+        keys[tail + 6 * (size_t)m.rank + 2 * c] = (int)(stats[c] & 0x7FFFFFFFull);
+        keys[tail + 6 * (size_t)m.rank + 2 * c + 1] = (int)((stats[c] >> 31) & 0x7FFFFFFFull);
+    }
+    LL_TRY(ensure(ctx, m.keys, (total + 2) * sizeof(int)));
+    int *dk = (int *)m.keys.ptr;
+    CUDA_TRY(cudaMemcpyAsync(dk, keys.data(), total * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    LL_TRY(allreduce_key_max(m, dk, total));
+    CUDA_TRY(cudaMemcpyAsync(keys.data(), dk, total * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    std::vector<uint32_t> order(n);
+    std::vector<float> scores(n);
+    for (uint32_t i = 0; i < n; i++) {
+        order[i] = i;
+        const int k = keys[(size_t)i * PER_ROOT], bits = k >= 0 ? k : k ^ 0x7FFFFFFF;
+        scores[i] = *(const float *)&bits;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return scores[x] > scores[y]; }); // mind.rs:436
+    for (uint32_t r = 0; r < n; r++) {
+        const uint32_t i = order[r];
+        ll_forecast_t &f = forecasts[r];
+        f = mine[i]; // the commit (every rank listed every root move)
+        f.score = scores[i];
+        const int *k = keys.data() + (size_t)i * PER_ROOT;
+        f.variation_len = (uint32_t)k[1];
+        for (uint32_t j = 0; j < f.variation_len && j < LL_MAX_VARIATION; j++)
+            f.variation[j] = ll_patch_t{(uint8_t)(k[2 + j] & 0xFF), (uint8_t)((k[2 + j] >> 8) & 0xFF), (uint8_t)((k[2 + j] >> 16) & 0xFF), (uint8_t)((k[2 + j] >> 24) & 0xFF)};
+    }
+    *n_forecasts = n;
+    if (stats3)
+        for (int c = 0; c < 3; c++) {
+            stats3[c] = 0;
+            for (int r = 0; r < W; r++)
+                stats3[c] += (uint64_t)(u32)keys[tail + 6 * (size_t)r + 2 * c] | ((uint64_t)(u32)keys[tail + 6 * (size_t)r + 2 * c + 1] << 31);
+        }
+    return LL_OK;
+}
+
 int check_group(ll_mctx *g) {
     if (!g || g->members.empty()) return fail(LL_ERR_INVALID_ARG, "null group");
     return LL_OK;
@@ -958,6 +1032,31 @@ extern "C" int ll_kickoff_multi(ll_mctx *g, const ll_world_t *root, int depth, i
     LL_TRY(run_on_all(g, job));
     *n_roots = outs[0].n_roots;
     if (leaves_scored) *leaves_scored = outs[0].leaves_scored;
+    return LL_OK;
+    LL_ABI_END
+}
+
+extern "C" int ll_alpha_beta_forecast_multi(ll_mctx *g, const ll_world_t *root, int depth, int device_plies, int quiet_extension, int nihilistically,
+                                            ll_forecast_t *forecasts, uint32_t cap, uint32_t *n_forecasts, uint64_t *stats3) {
+    LL_ABI_BEGIN
+    LL_TRY(check_group(g));
+    if (!root || !forecasts || !n_forecasts) return fail(LL_ERR_INVALID_ARG, "null argument");
+    if (depth < 1 || depth > 32) return fail(LL_ERR_INVALID_ARG, "depth %d out of range (1..32)", depth);
+    if (device_plies < 0 || device_plies > 8) return fail(LL_ERR_INVALID_ARG, "device_plies %d out of range (0..8)", device_plies);
+    if (quiet_extension > 8) return fail(LL_ERR_INVALID_ARG, "quiet extension %d out of range", quiet_extension);
+    *n_forecasts = 0;
+    std::vector<std::vector<ll_forecast_t>> spare(g->members.size());
+    std::vector<uint32_t> counts(g->members.size(), 0);
+    std::vector<std::array<uint64_t, 3>> stats(g->members.size());
+    for (size_t i = 1; i < g->members.size(); i++) spare[i].resize(cap);
+    Job job{[&](Member &m) {
+        size_t i = 0;
+        while (g->members[i] != &m) i++;
+        return member_alpha_beta(m, root, depth, device_plies, quiet_extension, nihilistically, i ? spare[i].data() : forecasts, cap, &counts[i], stats[i].data());
+    }};
+    LL_TRY(run_on_all(g, job));
+    *n_forecasts = counts[0];
+    if (stats3) memcpy(stats3, stats[0].data(), 3 * sizeof(uint64_t));
     return LL_OK;
     LL_ABI_END
 }

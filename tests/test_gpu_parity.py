@@ -569,6 +569,47 @@ def test_host_alpha_beta_memory_bank_is_sound(eng):
             assert eng.last_search_stats["values_remembered"] > 0
 
 
+def test_host_alpha_beta_variations_memory_budget_and_group(eng):
+    """mind.rs:208-224, 367-372, 399-414: the driver returns real principal variations (every line, played out, reaches a
+    position whose static value is the forecast's score), forgets under a byte budget without changing a score, and
+    searches the root moves concurrently over a group of GPUs with the same results."""
+    import leafline_b200 as ll
+
+    for fen, depth, device_plies in ((OPENING, 6, 3), (KIWIPETE, 5, 2), ("8/2p5/3p4/KP5r/1R3p1k/8/4P1P1/8 w - -", 7, 3)):
+        w = ll.reconstruct(fen)
+        full = eng.forecast(w, depth)
+        pruned, _, _ = eng.alpha_beta_forecast(w, depth, device_plies=device_plies)
+        assert pruned["score"].tobytes() == full["score"].tobytes()
+        for f in pruned[:6]:
+            n = int(f["variation_len"])
+            assert n == depth, (fen, n)  # a full line: nobody ran out of moves on these
+            cur = w
+            for p in f["variation"][:n]:  # play the line with the oracle's generator (ply 0 legal, below it reckless)
+                kids = O.lookahead(cur) if cur is w else O.reckless_lookahead(cur)
+                hit = [c for c in kids if (c["team"], c["job"], c["whence"], c["whither"]) == (p["team"], p["job"], p["whence"], p["whither"])]
+                assert hit, (fen, ll.pagan_variation(f))
+                # (an ascension's four commits share a patch: any of them may be the one; take the one that keeps the score)
+                cur = min(hit, key=lambda c: abs(float(O.score(c["tree"])) * (1 if w["initiative"] == 0 else -1) - float(f["score"])))["tree"] if len(hit) > 1 else hit[0]["tree"]
+            leaf = float(O.score(cur)) * (1.0 if int(w["initiative"]) == 0 else -1.0)
+            assert np.float32(leaf) == f["score"], (fen, ll.pagan_variation(f), leaf, float(f["score"]))
+    # a tiny memory bank forgets (least recently used first) and the scores do not move
+    w = ll.new_world()
+    full = eng.forecast(w, 6)
+    eng.set_deja_vu_bound(1e-4)  # ~300 entries
+    tight, _, _ = eng.alpha_beta_forecast(w, 6, device_plies=2)
+    eng.set_deja_vu_bound(0.25)
+    assert tight["score"].tobytes() == full["score"].tobytes()
+    # the group: root moves dealt to the members, one max-reduction gathers scores and lines
+    with ll.MultiEngine([0, 0, 0]) as g:
+        for fen, depth, device_plies in ((OPENING, 6, 3), (KIWIPETE, 5, 2)):
+            w = ll.reconstruct(fen)
+            one, _, handed_one = eng.alpha_beta_forecast(w, depth, device_plies=device_plies)
+            many, _, handed_many = g.alpha_beta_forecast(w, depth, device_plies=device_plies)
+            assert many["score"].tobytes() == one["score"].tobytes() and many["commit"].tobytes() == one["commit"].tobytes()
+            assert [int(x) for x in many["variation_len"]] == [int(x) for x in one["variation_len"]]
+            assert handed_many > 0
+
+
 def test_kickoff_family(eng):
     import leafline_b200 as ll
 
