@@ -95,6 +95,7 @@ struct ll_ctx {
     double deja_vu_gib = 0.25; // byte budget of the search drivers' memory bank (mind.rs:367-372; ll_set_deja_vu_bound)
     bool literal = false;      // this call holds a position outside domain W: the literal path answers it (ll_device.cuh: DOMAIN_LITERAL)
     bool force_synced = false; // tests: always take the level-by-level path
+    bool head_cluster = false; // the device runs a 16-CTA cluster of 512 threads: the chain's first plies go into one launch (k_expand_head)
     bool no_graph = false;     // tests: issue the perft launch chain launch by launch instead of replaying its CUDA graph
     uint64_t chain_sig = 0;    // the captured perft chain (same plan, same buffers, same stream -> replay)
     cudaGraphExec_t chain_exec = nullptr;
@@ -565,6 +566,27 @@ static int init_ctx(ll_ctx *ctx) {
     }
     CUDA_TRY(cudaMemcpyToSymbol(d_line_table, lines, sizeof lines));
     LL_TRY(ensure(ctx, ctx->scalars, SC_SLOTS * sizeof(u64)));
+    { // can the head of the perft chain run as one 16-CTA cluster here?  (non-portable cluster size: opt in, then ask)
+        // MEASURED SLOWER (perft(6) 0.357 ms against 0.343 ms with a launch per ply): off unless LEAFLINE_B200_HEAD_CLUSTER=1
+        const char *on = getenv("LEAFLINE_B200_HEAD_CLUSTER");
+        ctx->head_cluster = false;
+        if (on && *on == '1' && cudaFuncSetAttribute(k_expand_head, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof cfg);
+            cfg.gridDim = dim3(HEAD_CTAS, 1, 1);
+            cfg.blockDim = dim3(HEAD_WARPS * 32, 1, 1);
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = HEAD_CTAS;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            int clusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&clusters, k_expand_head, &cfg) == cudaSuccess && clusters >= 1) ctx->head_cluster = true;
+        }
+        cudaGetLastError();
+    }
     return LL_OK;
 }
 
@@ -967,6 +989,7 @@ static int perft_chain_launch(ll_ctx *ctx, int depth, int shard_rank, int shard_
         int kinds[CHAIN_MAX_STEPS];
         unsigned grids[CHAIN_MAX_STEPS];
         int n_steps;
+        int head_steps; // the first plies fused into one cluster launch (k_expand_head); 0: every ply its own launch
     };
     static_assert(std::is_trivially_copyable<Plan>::value, "the plan is hashed byte-wise");
     Plan plan;
@@ -1008,10 +1031,35 @@ static int perft_chain_launch(ll_ctx *ctx, int depth, int shard_rank, int shard_
         kinds[n_steps++] = small ? STEP_EMIT_SMALL : STEP_EMIT;
     }
     plan.n_steps = n_steps;
-    // (a single cooperative launch with grid-wide barriers between the plies was measured: no faster -- DESIGN.md)
+    int head_steps = 0; // leading narrow plies (0, 1, 2) that go into the cluster launch
+    while (ctx->head_cluster && head_steps < HEAD_MAX_STEPS && head_steps < n_steps && kinds[head_steps] == STEP_EMIT_SMALL && head_steps < 3) head_steps++;
+    if (head_steps < 2) head_steps = 0;
+    plan.head_steps = head_steps;
+    // (a single cooperative launch of the WHOLE chain with grid-wide barriers between the plies was measured: no faster -- DESIGN.md)
     auto issue = [&]() -> int {
         CUDA_TRY(cudaMemsetAsync(sc + SC_LEAVES, 0, (SC_SLOTS - SC_LEAVES) * sizeof(u64), ctx->stream));
-        for (int s = 0; s < n_steps; s++) {
+        if (head_steps) {
+            HeadArgs h;
+            memset(&h, 0, sizeof h);
+            for (int s = 0; s < head_steps; s++) h.step[s] = steps[s];
+            h.n_steps = head_steps;
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof cfg);
+            cfg.gridDim = dim3(HEAD_CTAS, 1, 1);
+            cfg.blockDim = dim3(HEAD_WARPS * 32, 1, 1);
+            cfg.stream = ctx->stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = HEAD_CTAS;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            Timed t(ctx, "emit_legal");
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, k_expand_head, h));
+            LL_TRY(check_launch("k_expand_head"));
+        }
+        for (int s = head_steps; s < n_steps; s++) {
             const int kind = kinds[s];
             Timed t(ctx, kind == STEP_TAIL ? "perft_tail" : "emit_legal");
             // order-free steps expand from legal RECORDS (small code: these launches are bound by instruction fetch and by one
@@ -1060,7 +1108,7 @@ static int perft_chain_launch(ll_ctx *ctx, int depth, int shard_rank, int shard_
         ctx->chain_stream = ctx->stream;
     }
     CUDA_TRY(cudaGraphLaunch(ctx->chain_exec, ctx->stream));
-    ctx->launches += (uint64_t)n_steps;
+    ctx->launches += (uint64_t)(n_steps - head_steps + (head_steps ? 1 : 0));
     *launched = true;
     return LL_OK;
 }

@@ -13,6 +13,7 @@
 // k_score is the HBM-bound streaming scorer; the rest are scans, back-ups, repacking and test utilities.
 #pragma once
 #include "ll_device.cuh"
+#include <cooperative_groups.h>
 
 namespace ll {
 
@@ -745,7 +746,7 @@ template <int T> __device__ __forceinline__ void coop_expand_parent(const Expand
             if (lane + 32 * r < total) descs[rank[r]] = moved[r];
         __syncwarp();
     }
-    const u32 root = a.root_is_index ? 0u : a.root_in[parent];
+    const u32 root = a.root_is_index ? 0u : __ldcg(a.root_in + parent); // (possibly written earlier in the same launch: k_expand_head)
     for (u32 k = lane; k < kept; k += 32) { // 32 children at a time: coalesced plane stores
         const u32 i = first + k * stride;
         Pos c;
@@ -1033,6 +1034,54 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
     if ((tid & 31) == 0 && scored && a.scored) atomicAdd((unsigned long long *)a.scored, (unsigned long long)scored);
     if (!CHAIN) break;
     __syncthreads(); // the tile and the claim slot are reused by the next round
+    }
+}
+
+// ---- EXPERIMENT, off by default (LEAFLINE_B200_HEAD_CLUSTER=1 turns it on; measured slower) ---------------------
+// the head of the perft chain: plies 0, 1 and 2 (1, ~30, ~900 parents) in ONE launch of one thread-block cluster
+// Each of those plies is a dependent chain of ~2 000 warp instructions per parent on a machine that is otherwise idle; as
+// separate launches every ply pays a launch gap and starts on cold instruction caches (~13 us a ply, of which ~4 us are
+// work).  Here sixteen CTAs of sixteen warps (256 warps: one parent each, ply 2 in two or three rounds) stay resident across
+// the three plies, the levels' sizes are read from the device between them and a cluster barrier (which also writes the L1s
+// back) stands where the kernel boundary was.  The levels are materialised exactly as by k_expand_coop -- order-free
+// placement, root ids travelling with the nodes, the shard rule of a dealt level -- so everything downstream is unchanged.
+constexpr int HEAD_WARPS = 16, HEAD_CTAS = 16, HEAD_MAX_STEPS = 3;
+struct HeadArgs {
+    ExpandArgs step[HEAD_MAX_STEPS];
+    int n_steps;
+};
+LL_HD Pos soa_load_cg(const Soa &s, size_t i) { // written earlier in this launch by another SM: not through the read-only path
+    Pos p;
+#pragma unroll
+    for (int j = 0; j < 12; j++) p.pl[j] = __ldcg(s.pl + (size_t)j * s.stride + i);
+    p.meta = __ldcg(s.meta + i);
+    return p;
+}
+__global__ void __launch_bounds__(HEAD_WARPS * 32, 1) k_expand_head(const HeadArgs h) {
+    __shared__ u32 descs[HEAD_WARPS][COOP_CAP];
+    __shared__ u32 keys[HEAD_WARPS][COOP_CAP];
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int warp = threadIdx.x >> 5;
+    const size_t first = (size_t)cluster.block_rank() * HEAD_WARPS + warp, stride = (size_t)cluster.num_blocks() * HEAD_WARPS;
+    for (int s = 0; s < h.n_steps; s++) {
+        const ExpandArgs &a = h.step[s];
+        u32 outgrown = 0;
+        size_t n = a.n;
+        if (a.n_in) {
+            outgrown = *(volatile u32 *)a.overflow;
+            n = (size_t)*(volatile const u64 *)a.n_in;
+        }
+        if (!outgrown)
+            for (size_t parent = first; parent < n; parent += stride) {
+                const Pos p = soa_load_cg(a.in, parent);
+                if (meta_stm(p.meta) == 0) coop_expand_parent<0>(a, p, parent, descs[warp], keys[warp]);
+                else coop_expand_parent<1>(a, p, parent, descs[warp], keys[warp]);
+            }
+        if (s + 1 < h.n_steps) {
+            __threadfence();
+            cluster.sync();
+        }
     }
 }
 
