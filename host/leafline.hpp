@@ -181,7 +181,9 @@ using Forecast = std::tuple<Commit, float, Variation>;      // what the kickoff 
 class Mind {
   public:
     explicit Mind(int device = 0) { check(ll_init(device, &ctx_)); }
-    ~Mind() { ll_shutdown(ctx_); }
+    ~Mind() {
+        if (owned_) ll_shutdown(ctx_);
+    }
     Mind(const Mind &) = delete;
     Mind &operator=(const Mind &) = delete;
 
@@ -238,9 +240,12 @@ class Mind {
         check(ll_fixed_depth_sequence_forecast(ctx_, &w.raw, depth_sequence.data(), (uint32_t)depth_sequence.size(), nihilistically, raw.data(), 1024, &n));
         return convert(raw, n);
     }
+    void set_deja_vu_bound(double gib) { check(ll_set_deja_vu_bound(ctx_, gib)); } // the kickoff functions' `déjà_vu_bound` (mind.rs:367-372)
 
   private:
+    friend class Minds;
     ll_ctx *ctx_ = nullptr;
+    bool owned_ = true;
     static void check(int rc) {
         if (rc != LL_OK) throw MoralPanic(std::string("leafline_b200: ") + ll_last_error());
     }
@@ -264,6 +269,51 @@ class Mind {
             out.emplace_back(Commit::from_raw(raw[i].commit), raw[i].score, line);
         }
         return out;
+    }
+};
+
+// Several GPUs sharing ONE tree (ll_mctx): the reference's fan-out inside the engine -- a thread per root move, results
+// gathered over a channel, mind.rs:399-437 -- as one call.  One process drives every device (a host thread and a stream
+// each, NCCL communicator and device-resident reduction owned by the group); for one process per GPU see
+// ll_init_multi_rank in the header.
+class Minds {
+  public:
+    explicit Minds(const std::vector<int> &devices) { check(ll_init_multi(devices.data(), (int)devices.size(), &group_)); }
+    ~Minds() { ll_shutdown_multi(group_); }
+    Minds(const Minds &) = delete;
+    Minds &operator=(const Minds &) = delete;
+    int world() const { return ll_multi_world(group_); }
+    const char *reduce_path() const { return ll_multi_reduce_path(group_) ? "peer-memory" : "nccl"; }
+
+    uint64_t perft(const WorldState &w, int depth, std::vector<uint64_t> *divide = nullptr) {
+        uint64_t leaves = 0, per_root[1024];
+        uint32_t n = 0;
+        check(ll_perft_multi(group_, &w.raw, depth, &leaves, per_root, 1024, &n));
+        if (divide) divide->assign(per_root, per_root + n);
+        return leaves;
+    }
+    // root commits with their exact scores, lookahead() order (the scores of mind::kickoff before the sort, mind.rs:436)
+    std::vector<std::pair<Commit, float>> root_scores(const WorldState &w, uint8_t depth, std::optional<uint8_t> extension, bool nihilistically) {
+        std::vector<ll_commit_t> roots(1024);
+        std::vector<float> scores(1024);
+        uint32_t n = 0;
+        check(ll_kickoff_multi(group_, &w.raw, depth, extension ? (int)*extension : -1, nihilistically, roots.data(), scores.data(), 1024, &n, nullptr));
+        std::vector<std::pair<Commit, float>> out;
+        for (uint32_t i = 0; i < n; i++) out.emplace_back(Commit::from_raw(roots[i]), scores[i]);
+        return out;
+    }
+    // mind::kickoff by the host alpha-beta driver, the root moves searched concurrently over the GPUs (mind.rs:399-414)
+    std::vector<Forecast> kickoff(const WorldState &w, uint8_t depth, uint8_t device_plies, std::optional<uint8_t> extension, bool nihilistically) {
+        std::vector<ll_forecast_t> raw(1024);
+        uint32_t n = 0;
+        check(ll_alpha_beta_forecast_multi(group_, &w.raw, depth, device_plies, extension ? (int)*extension : -1, nihilistically, raw.data(), 1024, &n, nullptr));
+        return Mind::convert(raw, n);
+    }
+
+  private:
+    ll_mctx *group_ = nullptr;
+    static void check(int rc) {
+        if (rc != LL_OK) throw MoralPanic(std::string("leafline_b200: ") + ll_last_error());
     }
 };
 

@@ -59,6 +59,7 @@ pub struct LlForecast {
 }
 
 pub enum LlCtx {}
+pub enum LlMctx {}              // ll_mctx: several GPUs sharing one tree
 
 extern "C" {
     fn ll_init(device: c_int, ctx: *mut *mut LlCtx) -> c_int;
@@ -84,6 +85,18 @@ extern "C" {
                                        forecasts: *mut LlForecast, cap: u32, n: *mut u32, depth_reached: *mut u32) -> c_int;
     fn ll_fixed_depth_sequence_forecast(ctx: *mut LlCtx, root: *const LlWorld, depths: *const u8, n_depths: u32,
                                         nihilistically: c_int, forecasts: *mut LlForecast, cap: u32, n: *mut u32) -> c_int;
+    fn ll_set_deja_vu_bound(ctx: *mut LlCtx, gib: f64) -> c_int;
+    // several GPUs, one tree (replaces the thread-per-root-move fan-out of mind.rs:399-437)
+    fn ll_init_multi(devices: *const c_int, n: c_int, group: *mut *mut LlMctx) -> c_int;
+    fn ll_shutdown_multi(group: *mut LlMctx) -> c_int;
+    fn ll_multi_world(group: *mut LlMctx) -> c_int;
+    fn ll_perft_multi(group: *mut LlMctx, root: *const LlWorld, depth: c_int, leaves: *mut u64, per_root: *mut u64,
+                      root_cap: u32, n_roots: *mut u32) -> c_int;
+    fn ll_kickoff_multi(group: *mut LlMctx, root: *const LlWorld, depth: c_int, quiet_extension: c_int, nihilistically: c_int,
+                        roots: *mut LlCommit, scores: *mut f32, root_cap: u32, n_roots: *mut u32, leaves_scored: *mut u64) -> c_int;
+    fn ll_alpha_beta_forecast_multi(group: *mut LlMctx, root: *const LlWorld, depth: c_int, device_plies: c_int,
+                                    quiet_extension: c_int, nihilistically: c_int, forecasts: *mut LlForecast, cap: u32,
+                                    n: *mut u32, stats3: *mut u64) -> c_int;
 }
 
 // ---- conversions ---------------------------------------------------------------------------------------
@@ -382,4 +395,77 @@ pub fn sharded_root_scores(world: &WorldState, depth: u8, extension: Option<u8>,
     });
     unsafe { roots.set_len(n as usize); }
     roots.into_iter().map(Commit::from).zip(scores.into_iter()).collect()
+}
+
+
+// ---- several GPUs, one tree ---------------------------------------------------------------------------------------------
+// `potentially_timebound_kickoff` spawns a thread per root move and gathers over an mpsc channel (mind.rs:399-437).  The
+// group below is that fan-out on the GPUs of one box: the library owns a context, a host thread and a stream per device, the
+// NCCL communicator between them and the reduction of the results on the devices; the caller makes ONE call.
+
+/// One process driving `devices` (ll_init_multi).  Not `Sync`: use from one thread at a time.
+pub struct Minds {
+    group: *mut LlMctx,
+}
+
+impl Minds {
+    pub fn new(devices: &[i32]) -> Minds {
+        let mut group: *mut LlMctx = ptr::null_mut();
+        check(unsafe { ll_init_multi(devices.as_ptr(), devices.len() as c_int, &mut group) });
+        Minds { group }
+    }
+
+    pub fn world(&self) -> usize {
+        unsafe { ll_multi_world(self.group) as usize }
+    }
+
+    /// leaf count of the legal-move tree, its ply-3 nodes dealt to the GPUs, counts summed on the devices -> (leaves, divide)
+    pub fn perft(&self, world: &WorldState, depth: u8) -> (u64, Vec<u64>) {
+        let raw = LlWorld::from(world);
+        let mut leaves = 0u64;
+        let mut per_root = vec![0u64; 1024];
+        let mut n = 0u32;
+        check(unsafe { ll_perft_multi(self.group, &raw, depth as c_int, &mut leaves, per_root.as_mut_ptr(), 1024, &mut n) });
+        per_root.truncate(n as usize);
+        (leaves, per_root)
+    }
+
+    /// exact root scores in `lookahead()` order: the full-width search dealt by ply-3 nodes, values folded back on the devices
+    pub fn root_scores(&self, world: &WorldState, depth: u8, extension: Option<u8>, nihilistically: bool) -> Vec<(Commit, f32)> {
+        let raw = LlWorld::from(world);
+        let mut roots: Vec<LlCommit> = Vec::with_capacity(1024);
+        let mut scores = vec![0f32; 1024];
+        let mut n = 0u32;
+        check(unsafe {
+            ll_kickoff_multi(self.group, &raw, depth as c_int, quiet_argument(extension), nihilistically as c_int, roots.as_mut_ptr(),
+                             scores.as_mut_ptr(), 1024, &mut n, ptr::null_mut())
+        });
+        unsafe { roots.set_len(n as usize); }
+        roots.into_iter().map(Commit::from).zip(scores.into_iter()).collect()
+    }
+
+    /// `kickoff::<Variation>` by the host alpha-beta driver, root move i searched on GPU i % world (mind.rs:399-414)
+    pub fn kickoff(&self, world: &WorldState, depth: u8, device_plies: u8, extension: Option<u8>, nihilistically: bool)
+                   -> Vec<(Commit, f32, Vec<Patch>)> {
+        let raw = LlWorld::from(world);
+        let mut forecasts: Vec<LlForecast> = Vec::with_capacity(1024);
+        let mut n = 0u32;
+        check(unsafe {
+            ll_alpha_beta_forecast_multi(self.group, &raw, depth as c_int, device_plies as c_int, quiet_argument(extension),
+                                         nihilistically as c_int, forecasts.as_mut_ptr(), 1024, &mut n, ptr::null_mut())
+        });
+        unsafe { forecasts.set_len(n as usize); }
+        forecasts_from(forecasts)
+    }
+}
+
+impl Drop for Minds {
+    fn drop(&mut self) {
+        unsafe { ll_shutdown_multi(self.group); }
+    }
+}
+
+/// the `déjà_vu_bound` of the reference's kickoff functions (GiB of memory bank, mind.rs:367-372) for this thread's context
+pub fn set_deja_vu_bound(gib: f32) {
+    with_context(|ctx| check(unsafe { ll_set_deja_vu_bound(ctx, gib as f64) }));
 }

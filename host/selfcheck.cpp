@@ -81,6 +81,20 @@ int main() {
            std::get<0>(pruned[0]).tree == std::get<0>(forecasts[0]).tree);
     auto [deep, depth] = mind.iterative_deepening_kickoff(opening, 0.3, false);
     EXPECT(depth >= 3 && deep.size() == 20);
+    // the variations are principal: a full line below every root move
+    auto pv = mind.alpha_beta_kickoff(opening, 5, 2, std::nullopt, false);
+    EXPECT(pv.size() == 20 && std::get<2>(pv[0]).size() == 5);
+    {   // a group of one process driving two members (sharing the device on a one-GPU box): one tree, dealt by subtree
+        Minds minds(std::vector<int>{0, 0});
+        EXPECT(minds.world() == 2);
+        std::vector<uint64_t> dealt;
+        EXPECT(minds.perft(opening, 5, &dealt) == 4865609 && dealt.size() == 20);
+        EXPECT(minds.perft(opening, 6) == 119060324 && minds.perft(opening, 6) == 119060324);
+        auto whole = mind.kickoff(opening, 4, std::nullopt, false);
+        auto many = minds.kickoff(opening, 4, 2, std::nullopt, false);
+        EXPECT(many.size() == whole.size() && std::get<1>(many[0]) == std::get<1>(whole[0]));
+        EXPECT(minds.root_scores(opening, 6, std::nullopt, false).size() == 20);
+    }
     puts("host selfcheck ok");
     return 0;
 }
