@@ -384,6 +384,26 @@ def main():
                     "note": "the reference's rules (orthodox chess counts 374190009323: SURVEY.md 8(a) quirks 1-2)"})
         result["config5"] = out
 
+    if not args.no_extras:
+        # the reference's search structure: host alpha-beta (MVV-LVA + history, full window per root move, one searcher thread per
+        # root move whose device requests are combined) over device frontier batches -- depth 8 from the opening, beyond what a
+        # full-width tree fits in HBM; on a group the root moves are searched concurrently, one subset per GPU
+        searcher = group if world > 1 else eng
+        searcher.alpha_beta_forecast(root, 6, device_plies=3)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        fc8, host_nodes, handed_off = searcher.alpha_beta_forecast(root, 8, device_plies=4)
+        seconds = time.perf_counter() - t0
+        t8 = torch.tensor([seconds], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t8, op=dist.ReduceOp.MAX)
+        result["alpha_beta_depth8"] = {"seconds": float(t8.item()), "best_score": float(fc8[0]["score"]), "principal_variation": ll.pagan_variation(fc8[0]),
+                                       "host_nodes_expanded": host_nodes, "values_remembered": searcher.last_search_stats["values_remembered"],
+                                       "frontier_nodes_handed_to_device": handed_off, "device_plies": 4,
+                                       "what": ("ll_alpha_beta_forecast" if world == 1 else f"ll_alpha_beta_forecast_multi over {world} ranks") +
+                                               ": exact root scores (alpha-beta prunes work, not values)"}
+
     if rank == 0 and world == 1 and not args.no_extras:
         peaks, peak_src = measured_peaks()
         consts, consts_problem = profile_constants()
@@ -454,13 +474,6 @@ def main():
             "what": "reckless movegen of every frontier node + static score of every child + negamax max; leaves never leave the SM",
         }
         eng.soa_free(soa)
-        # the reference's search structure: host alpha-beta (MVV-LVA + history, full window per root move) over device
-        # frontier batches -- depth 8 from the opening, beyond what a full-width tree fits in HBM
-        t0 = time.perf_counter()
-        fc8, host_nodes, handed_off = eng.alpha_beta_forecast(root, 8, device_plies=4)
-        result["alpha_beta_depth8"] = {"seconds": time.perf_counter() - t0, "best_score": float(fc8[0]["score"]), "host_nodes_expanded": host_nodes, "values_remembered": eng.last_search_stats["values_remembered"],
-                                       "frontier_nodes_handed_to_device": handed_off, "device_plies": 4,
-                                       "what": "ll_alpha_beta_forecast: exact root scores (alpha-beta prunes work, not values)"}
         # batched static scoring of 2^24 seeded playout positions (configs[2])
         n = 1 << 24
         soa = eng.playout_soa(n)

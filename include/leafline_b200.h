@@ -210,6 +210,10 @@ int ll_alpha_beta_forecast(ll_ctx *ctx, const ll_world_t *root, int depth, int d
  * one max-reduction on the devices.  stats3 are summed over the ranks. */
 int ll_alpha_beta_forecast_multi(ll_mctx *group, const ll_world_t *root, int depth, int device_plies, int quiet_extension, int nihilistically,
                                  ll_forecast_t *forecasts, uint32_t cap, uint32_t *n_forecasts, uint64_t *stats3);
+/* searcher threads of the host alpha-beta driver: the reference searches every root move on a thread of its own
+ * (src/mind.rs:399-414); so does ll_alpha_beta_forecast, up to this many threads (default 32; 1 = a single depth-first walk).
+ * The threads' device requests are combined into one batch a round, so more threads mean fewer, larger hand-offs. */
+int ll_set_search_threads(ll_ctx *ctx, int threads);
 /* the `déjà_vu_bound` argument of the reference's kickoff functions (GiB of memory bank, src/mind.rs:367-372, 441-448) for the
  * searches of this context; default 0.25 */
 int ll_set_deja_vu_bound(ll_ctx *ctx, double gib);

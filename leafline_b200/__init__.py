@@ -269,6 +269,10 @@ class Engine:
                                   "values_remembered": int(stats[2])}
         return out[: n.value].copy(), int(stats[0]), int(stats[1])
 
+    def set_search_threads(self, threads):
+        """Searcher threads of the host alpha-beta driver (one per root move up to this many, mind.rs:399-414)."""
+        _abi.check(self._lib.ll_set_search_threads(self._ctx, int(threads)))
+
     def set_deja_vu_bound(self, gib):
         """The `déjà_vu_bound` of the reference's kickoff functions: GiB of memory bank for this engine's searches."""
         _abi.check(self._lib.ll_set_deja_vu_bound(self._ctx, float(gib)))

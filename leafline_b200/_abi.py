@@ -71,6 +71,7 @@ SIGNATURES = {
     "ll_alpha_beta_forecast": ([_vp, _vp, _i, _i, _i, _i, _vp, C.c_uint32, C.POINTER(C.c_uint32), _vp], _i),
     "ll_alpha_beta_forecast_multi": ([_vp, _vp, _i, _i, _i, _i, _vp, C.c_uint32, C.POINTER(C.c_uint32), _vp], _i),
     "ll_set_deja_vu_bound": ([_vp, C.c_double], _i),
+    "ll_set_search_threads": ([_vp, _i], _i),
     "ll_fixed_depth_sequence_forecast": ([_vp, _vp, _vp, C.c_uint32, _i, _vp, C.c_uint32, C.POINTER(C.c_uint32)], _i),
     "ll_iterative_deepening_forecast": ([_vp, _vp, C.c_double, _i, _vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)], _i),
     "ll_soa_alloc": ([_vp, _sz, C.POINTER(Soa)], _i),

@@ -9,7 +9,11 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
 #include <list>
+#include <mutex>
+#include <thread>
 #include <new>
 #include <stdexcept>
 #include <string>
@@ -92,6 +96,7 @@ struct ll_ctx {
     void *pinned = nullptr; // small host staging
     size_t pinned_cap = 0;
     bool timing = false;
+    int search_threads = 32;   // searcher threads of the host alpha-beta driver (one per root move up to this many; ll_set_search_threads)
     double deja_vu_gib = 0.25; // byte budget of the search drivers' memory bank (mind.rs:367-372; ll_set_deja_vu_bound)
     bool literal = false;      // this call holds a position outside domain W: the literal path answers it (ll_device.cuh: DOMAIN_LITERAL)
     bool force_synced = false; // tests: always take the level-by-level path
@@ -1567,16 +1572,120 @@ struct Bank {
 
 using Intuition = std::unordered_map<uint32_t, uint32_t>; // the "intuition bank": Patch -> credit (mind.rs:353-359)
 
-struct AlphaBeta {
+// The searchers' single door to the context.  The reference searches every root move on a thread of its own
+// (mind.rs:399-414); so does this driver, and since an ll_ctx serves one caller at a time the threads' requests -- "the
+// commits of this node", "the exact values of these frontier nodes" -- are COMBINED: a thread that needs the device files its
+// request and sleeps; the last thread still running finds everybody else asleep and serves the whole round with one
+// ll_lookahead_batch and one ll_horizon_batch per distinct depth.  Twenty root moves mean twenty times fewer device round
+// trips than a single depth-first walk -- the host's latency, not the device's work, is what bounds the pruned search.
+struct DeviceGate {
+    struct Request {
+        int kind; // 0: reckless commits of nodes[0]; 1: values of nodes[0..n) with `plies` plies left
+        const ll_world_t *nodes;
+        size_t n;
+        int plies;
+        std::vector<ll_commit_t> *commits;
+        float *values;
+        int rc = LL_OK;
+        bool done = false;
+    };
     ll_ctx *ctx;
-    int device_plies, quiet_extension;
-    Intuition &intuition; // lives as long as the caller wants: across the iterations of an iterative deepening (mind.rs:456-464)
+    int quiet_extension;
+    std::mutex mu;
+    std::condition_variable cv;
+    int active = 0, waiting = 0;
+    std::vector<Request *> pending;
+    char err[sizeof g_error] = "";
+    uint64_t rounds = 0;
+    std::vector<ll_world_t> worlds;
+    std::vector<uint32_t> offsets;
+    std::vector<ll_commit_t> commits;
+    std::vector<float> values;
+
+    void serve_round() { // mu held; every other searcher is asleep on its request
+        rounds++;
+        std::vector<Request *> kids, vals;
+        for (Request *r : pending) (r->kind == 0 ? kids : vals).push_back(r);
+        if (!kids.empty()) {
+            worlds.resize(kids.size());
+            for (size_t i = 0; i < kids.size(); i++) worlds[i] = kids[i]->nodes[0];
+            offsets.assign(kids.size() + 1, 0);
+            if (commits.size() < kids.size() * 128) commits.resize(kids.size() * 128);
+            int rc = ll_lookahead_batch(ctx, worlds.data(), worlds.size(), 1, offsets.data(), commits.data(), commits.size()); // reckless, mind.rs:279
+            if (rc == LL_ERR_CAPACITY && offsets[kids.size()] > commits.size()) { // the counts came back: make room and ask again
+                commits.resize(offsets[kids.size()]);
+                rc = ll_lookahead_batch(ctx, worlds.data(), worlds.size(), 1, offsets.data(), commits.data(), commits.size());
+            }
+            if (rc != LL_OK) memcpy(err, g_error, sizeof err);
+            for (size_t i = 0; i < kids.size(); i++) {
+                kids[i]->rc = rc;
+                if (rc == LL_OK) kids[i]->commits->assign(commits.begin() + offsets[i], commits.begin() + offsets[i + 1]);
+            }
+        }
+        while (!vals.empty()) { // one batch per distinct depth (usually one)
+            const int plies = vals[0]->plies;
+            std::vector<Request *> now, later;
+            for (Request *r : vals) (r->plies == plies ? now : later).push_back(r);
+            size_t total = 0;
+            for (Request *r : now) total += r->n;
+            worlds.resize(total);
+            values.resize(total);
+            size_t at = 0;
+            for (Request *r : now) {
+                memcpy(worlds.data() + at, r->nodes, r->n * sizeof(ll_world_t));
+                at += r->n;
+            }
+            const int rc = ll_horizon_batch(ctx, worlds.data(), total, plies, quiet_extension, values.data());
+            if (rc != LL_OK) memcpy(err, g_error, sizeof err);
+            at = 0;
+            for (Request *r : now) {
+                r->rc = rc;
+                if (rc == LL_OK) memcpy(r->values, values.data() + at, r->n * sizeof(float));
+                at += r->n;
+            }
+            vals.swap(later);
+        }
+        for (Request *r : pending) r->done = true;
+        pending.clear();
+        waiting = 0;
+        cv.notify_all();
+    }
+    int submit(Request &r) {
+        std::unique_lock<std::mutex> lk(mu);
+        pending.push_back(&r);
+        waiting++;
+        if (waiting == active) serve_round();
+        else cv.wait(lk, [&] { return r.done; });
+        if (r.rc != LL_OK) memcpy(g_error, err, sizeof g_error);
+        return r.rc;
+    }
+    void leave() { // a searcher has no more root moves: the others may all be waiting for a round nobody would serve
+        std::lock_guard<std::mutex> lk(mu);
+        active--;
+        if (waiting && waiting == active) serve_round();
+    }
+};
+
+struct SearchShared { // what the searcher threads of one kickoff share (mind.rs:381-386: the banks behind Arc<Mutex>)
+    DeviceGate gate;
+    Intuition &intuition;
     Bank bank;
+    std::mutex banks;
+    int device_plies;
+    bool timebound = false;
+    std::chrono::steady_clock::time_point deadline;
+    std::atomic<bool> out_of_time{false};
+    SearchShared(ll_ctx *ctx, int plies, int quiet, Intuition &i) : intuition(i), bank(ctx->deja_vu_gib), device_plies(plies) {
+        gate.ctx = ctx;
+        gate.quiet_extension = quiet;
+    }
+};
+
+struct AlphaBeta { // one searcher
+    SearchShared &sh;
     uint64_t expanded = 0, handed_off = 0, remembered = 0;
     int rc = LL_OK;
-    bool timebound = false, out_of_time = false; // mind.rs:416-420: a search that overruns its deadline is abandoned
-    std::chrono::steady_clock::time_point deadline;
-    AlphaBeta(ll_ctx *c, int plies, int quiet, Intuition &i) : ctx(c), device_plies(plies), quiet_extension(quiet), intuition(i), bank(c->deja_vu_gib) {}
+    explicit AlphaBeta(SearchShared &s) : sh(s) {}
 
     static constexpr uint32_t NO_PATCH = 0xFFFFFFFFu;
     static uint32_t patch_key(const ll_commit_t &c) { return (uint32_t)c.team | ((uint32_t)c.job << 1) | ((uint32_t)c.whence << 8) | ((uint32_t)c.whither << 16); }
@@ -1590,9 +1699,12 @@ struct AlphaBeta {
     }
     void order(std::vector<ll_commit_t> &commits) { // mind.rs:155-169 (history first, then MVV-LVA; stable here)
         std::vector<std::tuple<uint32_t, float, uint32_t>> keys(commits.size());
-        for (uint32_t i = 0; i < commits.size(); i++) {
-            auto it = intuition.find(patch_key(commits[i]));
-            keys[i] = {it == intuition.end() ? 0u : it->second + 1u, mvv_lva(commits[i]), i};
+        {
+            std::lock_guard<std::mutex> lk(sh.banks);
+            for (uint32_t i = 0; i < commits.size(); i++) {
+                auto it = sh.intuition.find(patch_key(commits[i]));
+                keys[i] = {it == sh.intuition.end() ? 0u : it->second + 1u, mvv_lva(commits[i]), i};
+            }
         }
         std::stable_sort(keys.begin(), keys.end(), [](const auto &a, const auto &b) {
             if (std::get<0>(a) != std::get<0>(b)) return std::get<0>(a) > std::get<0>(b);
@@ -1602,23 +1714,31 @@ struct AlphaBeta {
         for (uint32_t i = 0; i < commits.size(); i++) sorted[i] = commits[std::get<2>(keys[i])];
         commits.swap(sorted);
     }
+    bool recall(const Bank::Key &k, Bank::Memory *out) {
+        std::lock_guard<std::mutex> lk(sh.banks);
+        const Bank::Memory *m = sh.bank.find(k);
+        if (m) *out = *m;
+        return m != nullptr;
+    }
+    void file(const Bank::Key &k, float value, uint8_t kind, uint32_t best) {
+        std::lock_guard<std::mutex> lk(sh.banks);
+        sh.bank.file(k, value, kind, best);
+    }
     bool children(const ll_world_t &node, std::vector<ll_commit_t> &out) {
-        uint32_t offsets[2] = {0, 0};
-        out.resize(1024);
-        rc = ll_lookahead_batch(ctx, &node, 1, 1, offsets, out.data(), out.size()); // reckless, mind.rs:279
+        DeviceGate::Request r{0, &node, 1, 0, &out, nullptr};
+        rc = sh.gate.submit(r);
         if (rc != LL_OK) return false;
-        out.resize(offsets[1]);
         expanded++;
         return true;
     }
-    // exact values of frontier nodes with `plies` plies left: the remembered ones from the bank, the others in ONE device batch
+    // exact values of frontier nodes with `plies` plies left: the remembered ones from the bank, the others from the device
     bool device_values(const ll_world_t *nodes, size_t n, int plies, float *values) {
         std::vector<ll_world_t> unknown;
         std::vector<size_t> where;
         for (size_t i = 0; i < n; i++) {
-            const Bank::Memory *m = bank.find(Bank::key_of(nodes[i], plies));
-            if (m) { // frontier entries are always exact
-                values[i] = m->value;
+            Bank::Memory m;
+            if (recall(Bank::key_of(nodes[i], plies), &m)) { // frontier entries are always exact
+                values[i] = m.value;
                 remembered++;
             } else {
                 unknown.push_back(nodes[i]);
@@ -1627,31 +1747,33 @@ struct AlphaBeta {
         }
         if (unknown.empty()) return true;
         std::vector<float> fresh(unknown.size());
-        rc = ll_horizon_batch(ctx, unknown.data(), unknown.size(), plies, quiet_extension, fresh.data());
+        DeviceGate::Request r{1, unknown.data(), unknown.size(), plies, nullptr, fresh.data()};
+        rc = sh.gate.submit(r);
         if (rc != LL_OK) return false;
         handed_off += unknown.size();
         for (size_t j = 0; j < unknown.size(); j++) {
             values[where[j]] = fresh[j];
-            bank.file(Bank::key_of(unknown[j], plies), fresh[j], Bank::EXACT, NO_PATCH);
+            file(Bank::key_of(unknown[j], plies), fresh[j], Bank::EXACT, NO_PATCH);
         }
         return true;
     }
     // value of `node` for its side to move with `depth` plies left, window (alpha, beta); fail-soft
     float search(const ll_world_t &node, int depth, float alpha, float beta) {
         if (rc != LL_OK) return 0.0f;
-        if (timebound && std::chrono::steady_clock::now() > deadline) {
-            out_of_time = true;
+        if (sh.out_of_time.load(std::memory_order_relaxed) || (sh.timebound && std::chrono::steady_clock::now() > sh.deadline)) {
+            sh.out_of_time.store(true);
             rc = LL_ERR_CAPACITY; // unwinds the recursion; the caller reports the time-out, not this code
             return 0.0f;
         }
+        const int device_plies = sh.device_plies;
         if (depth <= device_plies) {
             float v = 0.0f;
             device_values(&node, 1, depth < 0 ? 0 : depth, &v);
             return v;
         }
         const Bank::Key key = Bank::key_of(node, depth);
-        if (const Bank::Memory *seen = bank.find(key)) { // mind.rs:316-325, with the kinds of value told apart
-            const Bank::Memory m = *seen;
+        Bank::Memory m;
+        if (recall(key, &m)) { // mind.rs:316-325, with the kinds of value told apart
             if (m.kind == Bank::EXACT || (m.kind == Bank::LOWER && m.value >= beta) || (m.kind == Bank::UPPER && m.value <= alpha)) {
                 remembered++;
                 return m.value;
@@ -1662,15 +1784,16 @@ struct AlphaBeta {
         if (!children(node, premonitions)) return 0.0f;
         if (premonitions.empty()) { // mind.rs:282-287 at depth > 0: the node is its own leaf
             float v = 0.0f;
-            rc = ll_horizon_batch(ctx, &node, 1, 0, -1, &v);
-            if (rc == LL_OK) bank.file(key, v, Bank::EXACT, NO_PATCH);
+            DeviceGate::Request r{1, &node, 1, 0, nullptr, &v};
+            rc = sh.gate.submit(r); // (a leaf: plies 0; a quiescence extension finds nothing to stun here either)
+            if (rc == LL_OK) file(key, v, Bank::EXACT, NO_PATCH);
             return v;
         }
         order(premonitions);
         float optimum = -INFINITY;
         uint32_t optimand = NO_PATCH;
         auto remember = [&]() { // mind.rs:340-343
-            if (rc == LL_OK) bank.file(key, optimum, optimum <= alpha_in ? Bank::UPPER : optimum >= beta ? Bank::LOWER : Bank::EXACT, optimand);
+            if (rc == LL_OK) file(key, optimum, optimum <= alpha_in ? Bank::UPPER : optimum >= beta ? Bank::LOWER : Bank::EXACT, optimand);
             return optimum;
         };
         auto consider = [&](const ll_commit_t &c, float value) { // mind.rs:346-361
@@ -1680,7 +1803,8 @@ struct AlphaBeta {
             }
             if (value > alpha) alpha = value;
             if (alpha >= beta) {
-                intuition[patch_key(c)] += 1u << (depth > 30 ? 30 : depth);
+                std::lock_guard<std::mutex> lk(sh.banks);
+                sh.intuition[patch_key(c)] += 1u << (depth > 30 ? 30 : depth);
                 return true;
             }
             return false;
@@ -1709,25 +1833,29 @@ struct AlphaBeta {
     }
     // The principal variation below a root move (the `Variation` memory, mind.rs:208-224): follow the bank's exact entries
     // through the plies the host searched -- every node of a principal variation has an exact entry naming its best commit --
-    // then ask the device for the rest of the line below the frontier node (ll_forecast's variation kernel).
+    // then ask the device for the rest of the line below the frontier node (ll_forecast's variation kernel).  Called after
+    // the searchers have finished: straight calls on the context.
     void variation_below(ll_world_t node, int depth, ll_patch_t *line, uint32_t *len) {
-        std::vector<ll_commit_t> kids;
+        ll_ctx *ctx = sh.gate.ctx;
+        std::vector<ll_commit_t> kids(1024);
         while (*len < LL_MAX_VARIATION && rc == LL_OK) {
-            if (depth <= device_plies) {
+            if (depth <= sh.device_plies) {
                 if (depth < 1) return;
                 std::vector<ll_forecast_t> tail(1024);
                 uint32_t n = 0;
-                if (ll_forecast(ctx, &node, depth, quiet_extension, 1, tail.data(), 1024, &n, nullptr) != LL_OK || !n) return; // (reckless children, as everywhere below the root)
+                if (ll_forecast(ctx, &node, depth, sh.gate.quiet_extension, 1, tail.data(), 1024, &n, nullptr) != LL_OK || !n) return; // (reckless children, as everywhere below the root)
                 for (uint32_t j = 0; j < tail[0].variation_len && *len < LL_MAX_VARIATION; j++) line[(*len)++] = tail[0].variation[j];
                 return;
             }
-            const Bank::Memory *m = bank.find(Bank::key_of(node, depth));
-            if (!m || m->kind != Bank::EXACT || m->best == NO_PATCH) return;
-            const uint32_t best = m->best;
-            if (!children(node, kids)) return;
+            Bank::Memory m;
+            if (!recall(Bank::key_of(node, depth), &m) || m.kind != Bank::EXACT || m.best == NO_PATCH) return;
+            uint32_t offsets[2] = {0, 0};
+            kids.resize(1024);
+            if (ll_lookahead_batch(ctx, &node, 1, 1, offsets, kids.data(), kids.size()) != LL_OK) return;
+            kids.resize(offsets[1]);
             bool found = false;
             for (const ll_commit_t &c : kids)
-                if (patch_key(c) == best && (!found)) { // (ascensions share a patch: the first, like the reference's flash(patch))
+                if (patch_key(c) == m.best && !found) { // (ascensions share a patch: the first, like the reference's flash(patch))
                     line[(*len)++] = ll_patch_t{c.team, c.job, c.whence, c.whither};
                     node = c.tree;
                     found = true;
@@ -1757,35 +1885,63 @@ static int alpha_beta_core(ll_ctx *ctx, const ll_world_t *root, int depth, int d
         return fail(LL_ERR_CAPACITY, "%u forecasts do not fit the capacity of %u", offsets[1], cap);
     }
     Intuition local;
-    AlphaBeta ab(ctx, device_plies, quiet_extension, intuition ? *intuition : local);
+    SearchShared shared(ctx, device_plies, quiet_extension, intuition ? *intuition : local);
     if (deadline) {
-        ab.timebound = true;
-        ab.deadline = *deadline;
+        shared.timebound = true;
+        shared.deadline = *deadline;
     }
-    // the root moves are searched in the order the intuition bank suggests (mind.rs:393-396); what is returned is ordered by
-    // score, ties in canonical order
-    std::vector<uint32_t> sequence(roots.size());
+    // the root moves are taken up in the order the intuition bank suggests (mind.rs:393-396), each by a searcher thread of
+    // its own (mind.rs:399-414); what is returned is ordered by score, ties in canonical order
+    std::vector<uint32_t> sequence;
     {
+        AlphaBeta orderer(shared);
         std::vector<ll_commit_t> ordered = roots;
-        ab.order(ordered);
-        for (uint32_t k = 0; k < ordered.size(); k++)
+        orderer.order(ordered);
+        for (const ll_commit_t &c : ordered)
             for (uint32_t i = 0; i < roots.size(); i++)
-                if (!memcmp(&ordered[k], &roots[i], sizeof(ll_commit_t))) sequence[k] = i;
+                if (!memcmp(&c, &roots[i], sizeof(ll_commit_t)) && (int)(i % (uint32_t)shard_world) == shard_rank) sequence.push_back(i);
     }
     std::vector<float> scores(roots.size(), -INFINITY);
-    for (uint32_t i : sequence) { // every root move gets the full window (mind.rs:406-411)
-        if ((int)(i % (uint32_t)shard_world) != shard_rank) continue;
-        scores[i] = -ab.search(roots[i].tree, depth - 1, -INFINITY, INFINITY);
-        if (ab.out_of_time) {
-            if (timed_out) *timed_out = true;
-            return LL_OK;
+    const size_t n_threads = std::min<size_t>(sequence.size(), ctx->search_threads > 0 ? (size_t)ctx->search_threads : 1);
+    std::vector<AlphaBeta> searchers(n_threads ? n_threads : 1, AlphaBeta(shared));
+    std::atomic<size_t> next{0};
+    shared.gate.active = (int)n_threads;
+    auto work = [&](size_t t) {
+        AlphaBeta &ab = searchers[t];
+        try {
+            for (;;) {
+                const size_t k = next.fetch_add(1);
+                if (k >= sequence.size() || ab.rc != LL_OK) break;
+                const uint32_t i = sequence[k];
+                scores[i] = -ab.search(roots[i].tree, depth - 1, -INFINITY, INFINITY); // every root move gets the full window (mind.rs:406-411)
+            }
+        } catch (...) {
+            ab.rc = fail(LL_ERR_OOM, "host allocation failed in a searcher thread");
         }
-        if (ab.rc != LL_OK) return ab.rc;
+        shared.gate.leave();
+    };
+    if (n_threads <= 1) {
+        if (n_threads) work(0);
+    } else {
+        std::vector<std::thread> threads;
+        for (size_t t = 1; t < n_threads; t++) threads.emplace_back(work, t);
+        work(0);
+        for (std::thread &t : threads) t.join();
     }
+    if (shared.out_of_time.load()) {
+        if (timed_out) *timed_out = true;
+        return LL_OK;
+    }
+    for (AlphaBeta &ab : searchers)
+        if (ab.rc != LL_OK) {
+            if (shared.gate.err[0]) memcpy(g_error, shared.gate.err, sizeof g_error);
+            return ab.rc;
+        }
     *n_forecasts = offsets[1];
     std::vector<uint32_t> order(roots.size());
     for (uint32_t i = 0; i < roots.size(); i++) order[i] = i;
     if (sorted) std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return scores[x] > scores[y]; }); // mind.rs:436
+    AlphaBeta reader(shared);
     for (uint32_t k = 0; k < roots.size(); k++) {
         const uint32_t i = order[k];
         ll_forecast_t &f = forecasts[k];
@@ -1794,17 +1950,23 @@ static int alpha_beta_core(ll_ctx *ctx, const ll_world_t *root, int depth, int d
         f.score = scores[i];
         f.variation[0] = ll_patch_t{roots[i].team, roots[i].job, roots[i].whence, roots[i].whither}; // T::flash(premonition.patch), mind.rs:426
         f.variation_len = 1;
-        if ((int)(i % (uint32_t)shard_world) == shard_rank && !ab.out_of_time) {
-            ab.timebound = false; // (the line is read out of the bank; the deadline decided the search, not this)
-            ab.variation_below(roots[i].tree, depth - 1, f.variation, &f.variation_len);
-            if (ab.rc != LL_OK) return ab.rc;
-        }
+        if ((int)(i % (uint32_t)shard_world) == shard_rank) reader.variation_below(roots[i].tree, depth - 1, f.variation, &f.variation_len);
     }
     if (stats3) {
-        stats3[0] = ab.expanded;
-        stats3[1] = ab.handed_off;
-        stats3[2] = ab.remembered;
+        stats3[0] = stats3[1] = stats3[2] = 0;
+        for (AlphaBeta &ab : searchers) {
+            stats3[0] += ab.expanded;
+            stats3[1] += ab.handed_off;
+            stats3[2] += ab.remembered;
+        }
     }
+    return LL_OK;
+}
+
+extern "C" int ll_set_search_threads(ll_ctx *ctx, int threads) {
+    if (!ctx) return fail(LL_ERR_INVALID_ARG, "null context");
+    if (threads < 1 || threads > 256) return fail(LL_ERR_INVALID_ARG, "%d searcher threads out of range (1..256)", threads);
+    ctx->search_threads = threads;
     return LL_OK;
 }
 

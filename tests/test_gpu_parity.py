@@ -393,6 +393,28 @@ def test_perft_device_resident_counts(eng):
         ll.Engine(0).perft_device(ll.new_world(), 5, out.data_ptr())  # a fresh context has no level buffers yet
 
 
+def test_kiwipete_prefix_subtrees_equal_the_oracle_recounts(eng):
+    """configs[4] (perft(7) of Kiwipete, 3.7e11 leaves) is beyond the faithful oracle; SURVEY.md 8(d) prescribes the hierarchy:
+    a seeded sample of 2-ply prefixes recounted by the oracle at sub-depth 5 (tests/golden/kiwipete_prefix_perft5.json, ~1.8e8
+    leaves each, written by tests/golden/make_kiwipete_prefixes.py), the whole tree held by GPU self-consistency (bench.py config5:
+    one GPU against many, the sum of the 48 root children)."""
+    import json
+    import os
+
+    import leafline_b200 as ll
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kiwipete_prefix_perft5.json")) as f:
+        fx = json.load(f)
+    assert fx["sub_depth"] == 5 and len(fx["samples"]) >= 16 and fx["n_prefixes"] == 2038
+    root = ll.reconstruct(fx["position"])
+    _, first = eng.lookahead(root)
+    for s in fx["samples"]:
+        w = ll.reconstruct(s["runes"])
+        _, replies = eng.lookahead(first[s["root_move"]]["tree"])
+        assert replies[s["reply"]]["tree"].tobytes() == w.tobytes()  # the sample really is that 2-ply prefix
+        assert eng.perft(w, 5)[0] == s["perft5"], s
+
+
 @pytest.mark.parametrize("world_size", [2, 3, 8])
 def test_perft_shards_sum_to_the_whole(eng, world_size):
     import leafline_b200 as ll
