@@ -24,6 +24,15 @@
 
 using namespace ll;
 
+#ifndef LL_TAIL_TILE
+#define LL_TAIL_TILE 128 // parents per tile of the perft tail in the launch chain
+#endif
+#ifndef LL_NARROW_TILE_NODES
+#define LL_NARROW_TILE_NODES 0 // levels at most this wide (a rank's share of a dealt tree) are expanded with 32-parent tiles
+#endif
+#ifndef LL_SMALL_LEVEL_NODES
+#define LL_SMALL_LEVEL_NODES 0 // levels at most this wide are expanded by one warp per parent whatever their ply
+#endif
 #ifndef LL_SMALL_TILE_PLIES
 #define LL_SMALL_TILE_PLIES 4 // plies of the perft launch chain expanded with 32-parent tiles
 #endif
@@ -1013,7 +1022,7 @@ static int perft_chain_launch(ll_ctx *ctx, int depth, int shard_rank, int shard_
         a.tile_counter = tileq + q++;
         a.root_in = ply == 0 ? nullptr : (const u32 *)f.root.ptr;
         a.overflow = overflow;
-        grids[n_steps] = ply == 0 ? 1u : (unsigned)std::min<size_t>(nblocks(f.cap), resident);
+        grids[n_steps] = ply == 0 ? 1u : (unsigned)std::min<size_t>(nblocks(f.cap, ply == tail_ply ? LL_TAIL_TILE : BLOCK), resident);
         if (ply == tail_ply) {
             a.per_root = sc + SC_PER_ROOT;
             a.total = sc + SC_LEAVES;
@@ -1031,9 +1040,13 @@ static int perft_chain_launch(ll_ctx *ctx, int depth, int shard_rank, int shard_
             a.shard_world = shard_world;
         }
         // the first plies are narrow (1, ~30, ~900, ~27 000 nodes): one warp per parent reaches more SMs and finishes sooner
-        const bool small = ply < LL_SMALL_TILE_PLIES;
+        // (so are the deeper levels of a rank's share of a dealt tree: ~25 000 nodes are 200 tiles of 128, a fifth of the blocks
+        // the machine holds, each waiting on one thread's walk through the generator)
+        const bool small = ply < LL_SMALL_TILE_PLIES || f.cap <= (size_t)LL_SMALL_LEVEL_NODES;
+        const bool narrow_tiles = !small && f.cap <= (size_t)LL_NARROW_TILE_NODES; // 32-parent tiles: four times the blocks at work
         if (small && ply != 0) grids[n_steps] = (unsigned)std::min<size_t>(nblocks(f.cap, COOP_WARPS), resident);
-        kinds[n_steps++] = small ? STEP_EMIT_SMALL : STEP_EMIT;
+        if (narrow_tiles) grids[n_steps] = (unsigned)std::min<size_t>(nblocks(f.cap, 32), resident);
+        kinds[n_steps++] = small ? STEP_EMIT_SMALL : narrow_tiles ? STEP_EMIT_NARROW : STEP_EMIT;
     }
     plan.n_steps = n_steps;
     int head_steps = 0; // leading narrow plies (0, 1, 2) that go into the cluster launch
@@ -1069,8 +1082,9 @@ static int perft_chain_launch(ll_ctx *ctx, int depth, int shard_rank, int shard_
             Timed t(ctx, kind == STEP_TAIL ? "perft_tail" : "emit_legal");
             // order-free steps expand from legal RECORDS (small code: these launches are bound by instruction fetch and by one
             // thread's serial latency); narrow levels by one warp per parent
-            if (kind == STEP_TAIL) k_expand_records<MODE_PERFT><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
+            if (kind == STEP_TAIL) k_expand_records<MODE_PERFT, LL_TAIL_TILE><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
             else if (kind == STEP_EMIT_SMALL) k_expand_coop<<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
+            else if (kind == STEP_EMIT_NARROW) k_expand_records<MODE_EMIT, 32><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
             else k_expand_records<MODE_EMIT><<<grids[s], BLOCK, 0, ctx->stream>>>(steps[s]);
             LL_TRY(check_launch("perft chain step"));
         }

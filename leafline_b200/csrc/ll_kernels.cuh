@@ -291,6 +291,7 @@ struct ExpandShared {
     u32 descs[DESC_CAP];
     int acc[BLOCK]; // PERFT: leaves below each parent
     u64 claim;      // next tile / claimed output base
+    u32 n_desc;     // k_expand_records: descriptors claimed so far by the tile's records
 #ifdef LL_TAIL_STAGED_LINES
     alignas(16) u64 lines[64 * 4]; // PERFT tail: the lines through every square (StagedLines), 2 KiB, read 128 bits at a time
 #endif
@@ -433,6 +434,24 @@ struct RecordSink {
         }
     }
 };
+// The usual case needs no counting pass at all: nothing downstream depends on the ORDER of a tile's commits, so every record
+// claims its run of the descriptor list with one shared-memory atomicAdd and writes it at once -- the generator runs once per
+// parent instead of twice.  Only a tile whose commits outgrow the list (> DESC_CAP: 40 a parent on average) falls back to
+// count, scan and windows.
+struct ClaimSink {
+    u32 *buf;
+    u32 *claimed;
+    u32 slot_bits, team, count;
+    LL_HDM void put(u64 mask, u32 info) {
+#ifdef __CUDACC__
+        const u32 c = (u32)__popcll(mask);
+        u32 at = atomicAdd(claimed, c);
+        count += c;
+        if (at + c > (u32)DESC_CAP) return; // the tile has outgrown the list: the windowed passes will redo it
+        for (; mask; mask &= mask - 1) buf[at++] = rec_move_to(info, __ffsll((long long)mask) - 1, team) | slot_bits;
+#endif
+    }
+};
 template <int MODE, int P> __device__ __forceinline__ void expand_tiles_records(const ExpandArgs &a, ExpandShared &sh) {
     const int tid = threadIdx.x;
 #ifdef LL_TAIL_STAGED_LINES
@@ -458,22 +477,30 @@ template <int MODE, int P> __device__ __forceinline__ void expand_tiles_records(
             sh.tile_meta[tid] = p.meta;
         }
         if (MODE == MODE_PERFT && tid < P) sh.acc[tid] = 0;
+        if (tid == 0) sh.n_desc = 0;
+        __syncthreads();
         u32 cnt = 0, ex = 0, total = 0;
         size_t out_base = 0;
-        bool writable = true;
-        // pass 0 counts; pass 1 + w writes window w of the tile's descriptor list and consumes it
+        bool writable = true, direct = false;
+        // pass 0 writes the tile's descriptor list by atomic claims (and counts); if the list held them all, pass 1 consumes it
+        // as it stands; otherwise pass 1 + w rewrites window w in scan order and consumes it
 #pragma unroll 1
         for (u32 pass = 0;; pass++) {
             const u32 w0 = pass ? (pass - 1) * DESC_CAP : 0;
             if (pass && (w0 >= total || !writable)) break;
-            if (mine && (pass == 0 || (cnt && ex < w0 + DESC_CAP && ex + cnt > w0))) {
+            if (mine && pass == 0) {
                 const Pos p = tile_load(sh, tid);
-                RecordSink sink{sh.descs, pass ? ex : 0u, w0, w0 + DESC_CAP, (u32)tid << 20, meta_stm(p.meta), pass != 0};
+                ClaimSink sink{sh.descs, &sh.n_desc, (u32)tid << 20, meta_stm(p.meta), 0u};
                 legal_records(p, sink);
-                if (pass == 0) cnt = sink.idx;
+                cnt = sink.count;
+            } else if (mine && !direct && cnt && ex < w0 + DESC_CAP && ex + cnt > w0) {
+                const Pos p = tile_load(sh, tid);
+                RecordSink sink{sh.descs, ex, w0, w0 + DESC_CAP, (u32)tid << 20, meta_stm(p.meta), true};
+                legal_records(p, sink);
             }
             if (pass == 0) {
-                ex = block_exclusive_scan(cnt, &total);
+                ex = block_exclusive_scan(cnt, &total); // (its barriers also order the claimed writes before phase 2)
+                direct = total <= (u32)DESC_CAP;
                 if (MODE == MODE_EMIT) { // order-free: claim a contiguous range for this tile's children
                     if (tid == 0) sh.claim = atomicAdd((unsigned long long *)a.n_out, (unsigned long long)total);
                     __syncthreads();
@@ -1123,7 +1150,7 @@ __global__ void __launch_bounds__(BLOCK) k_deal_units(Soa in, const u32 *__restr
 
 // ---- the perft launch chain: one step per ply (+ the shard filter), every size resident on the device --------
 constexpr int CHAIN_MAX_STEPS = 12;
-enum { STEP_EMIT_SMALL = 0, STEP_EMIT = 1, STEP_TAIL = 2 };
+enum { STEP_EMIT_SMALL = 0, STEP_EMIT = 1, STEP_TAIL = 2, STEP_EMIT_NARROW = 3 };
 
 // ll_perft_device: gather the chain's results into the caller's device buffer (see the header for the layout)
 __global__ void __launch_bounds__(1024) k_pack_perft_result(const u64 *leaves, const u64 *n_roots, const u32 *overflow, const u64 *per_root, u64 *out) {

@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Turn ncu captures (gpurun_out/) into the committed summaries under profiles/.
 
-usage: summarise.py <round tag, e.g. r01> <launches.csv> <hot.ncu-rep>
+usage: summarise.py <round tag, e.g. r02> <launches.csv> <hot.ncu-rep> [<pipes.csv>]
 writes profiles/<tag>_launches.md, profiles/<tag>_kernels.csv, profiles/constants.json
+(<pipes.csv>: `ncu --metrics sm__inst_executed_pipe_{alu,fma,lsu,xu}.sum,... --csv` of the same workload: warp instructions per pipe)
 """
 import collections
 import csv
@@ -14,6 +15,7 @@ import subprocess
 import sys
 
 tag, launches_csv, rep = sys.argv[1:4]
+pipes_csv = sys.argv[4] if len(sys.argv) > 4 else None
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 OUT = os.path.join(ROOT, "profiles")
 csv.field_size_limit(10**9)
@@ -108,6 +110,22 @@ with open(os.path.join(OUT, f"{tag}_kernels.csv"), "w", newline="") as f:
             consts[f"{key}_alu_pipe_pct"] = float(r[hdr.index("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active")])
             consts[f"{key}_issue_active_pct"] = float(r[hdr.index("smsp__issue_active.avg.pct_of_peak_sustained_active")])
             consts[f"{key}_lanes_active_of_32"] = float(r[hdr.index("smsp__thread_inst_executed_per_inst_executed.ratio")])
+if pipes_csv:  # warp instructions per pipe, the last launch of each kind
+    with open(pipes_csv, newline="") as f:
+        lines = [l for l in f if l.startswith('"')]
+    for r in csv.DictReader(lines):
+        name = short(r["Kernel Name"])
+        key = {"k_expand_records<PERFT>": "perft6_tail", "k_horizon<0, 0>": "horizon_2p20", "k_horizon<false, false>": "horizon_2p20", "k_score": "score"}.get(name)
+        m = re.match(r"sm__inst_executed_pipe_(\w+)\.sum", r["Metric Name"])
+        if key and m:
+            consts[f"{key}_{m.group(1)}_pipe_warp_inst"] = float(r["Metric Value"].replace(",", ""))
+import hashlib
+
+h = hashlib.sha256()
+for name in ("ll_device.cuh", "ll_kernels.cuh"):
+    with open(os.path.join(ROOT, "leafline_b200", "csrc", name), "rb") as f:
+        h.update(f.read())
+consts["device_code_sha256"] = h.hexdigest()  # bench.py withholds the instruction-count rooflines when the sources no longer hash to this
 consts["source"] = f"profiles/{tag}_kernels.csv (ncu --set full of profiles/workload.py)"
 json.dump(consts, open(os.path.join(OUT, "constants.json"), "w"), indent=1)
 print(json.dumps(consts, indent=1))
