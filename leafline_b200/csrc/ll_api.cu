@@ -1649,7 +1649,26 @@ struct DeviceGate {
                 memcpy(worlds.data() + at, r->nodes, r->n * sizeof(ll_world_t));
                 at += r->n;
             }
-            const int rc = ll_horizon_batch(ctx, worlds.data(), total, plies, quiet_extension, values.data());
+            // the levels below a hand-off grow ~30-fold a ply: the combined batch goes to the device in pieces whose deepest
+            // materialised level stays within a few GB (and in halves of that if HBM is short all the same)
+            size_t piece = total;
+            {
+                double grown = 1.0;
+                for (int p = 1; p < plies; p++) grown *= 30.0;
+                const double fit = 3.2e7 / grown;
+                if (fit < (double)piece) piece = fit < 1.0 ? 1 : (size_t)fit;
+            }
+            int rc = LL_OK;
+            for (size_t first = 0; first < total && rc == LL_OK;) {
+                const size_t m = std::min(piece, total - first);
+                rc = ll_horizon_batch(ctx, worlds.data() + first, m, plies, quiet_extension, values.data() + first);
+                if (rc == LL_ERR_OOM && m > 1) {
+                    piece = m / 2;
+                    rc = LL_OK;
+                    continue;
+                }
+                first += m;
+            }
             if (rc != LL_OK) memcpy(err, g_error, sizeof err);
             at = 0;
             for (Request *r : now) {
