@@ -169,13 +169,18 @@ def reference_arm(args, rank, world):
     }))
 
 
-def timed(stream, fn, reps, torch, flush=None):
-    """median CUDA-event time (ms) of fn() on `stream` (L2 flushed before every repetition when `flush` is given)"""
+def timed(stream, fn, reps, torch, flush=None, align=None):
+    """median CUDA-event time (ms) of fn() on `stream` (L2 flushed before every repetition when `flush` is given).
+    align (a collective call is being timed): a one-element all-reduce is enqueued on the timing stream right before the start
+    event, so that every rank's timed region starts together on the devices -- what is measured is the collective call, not how
+    far apart the ranks' host loops happened to be"""
     times = []
     for _ in range(reps):
         if flush is not None:
             flush.fill_(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if align is not None:
+            align()
         a.record(stream)
         fn()
         b.record(stream)
@@ -320,13 +325,15 @@ def main():
     if world > 1:
         result["reduce_path"] = group.reduce_path
 
+    align_word = torch.zeros(1, dtype=torch.int32, device="cuda")
+
     def strong(name, fn_multi, fn_solo, reps, units, unit_name):
         """ONE tree on the whole group and, in the same run, on one GPU: ms (max over ranks), rate, efficiency t1 / (N * tN)"""
         want = fn_solo()
         got = fn_multi()
         if world > 1:
             dist.barrier()
-        ms_n = timed(stream, fn_multi, reps, torch, flush)
+        ms_n = timed(stream, fn_multi, reps, torch, flush, align=(lambda: dist.all_reduce(align_word)) if world > 1 else None)
         ms_1 = timed(stream, fn_solo, reps, torch, flush) if world > 1 else ms_n
         tt = torch.tensor([ms_n, ms_1], dtype=torch.float64, device="cuda")
         if world > 1:
