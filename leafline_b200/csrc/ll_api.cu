@@ -235,7 +235,7 @@ int pinned(ll_ctx *ctx, size_t bytes) {
 // scalars buffer layout (u64 slots): 4, 5 = first bad index and literal-path flag, 1 = scan total, 2 = leaf total, 3 = leaves scored,
 // 8.. = per-root counts
 constexpr size_t SC_BAD = 4 /* and 5: needs-the-literal-path flag, see validate_level */, SC_TOTAL = 1, SC_LEAVES = 2, SC_SCORED = 3, SC_PER_ROOT = 8, SC_SPARE = 8 + 1024,
-                 SC_N = 1040 /* 64 device-resident level sizes */, SC_TILEQ = 1104 /* 64 u32 tile queues */, SC_OVERFLOW = 1136, SC_SLOTS = 1152;
+                 SC_N = 1040 /* 64 device-resident level sizes */, SC_TILEQ = 1104 /* 64 u32 tile queues */, SC_OVERFLOW = 1136, SC_HZ_OVERFLOW = 1137, SC_SLOTS = 1152;
 
 int upload_worlds(ll_ctx *ctx, const ll_world_t *worlds, size_t n, size_t level) {
     LL_TRY(reserve_level(ctx, level, n, false, false));
@@ -427,9 +427,17 @@ int horizon_levels(ll_ctx *ctx, size_t l, int plies, int quiet_ext, uint64_t *sc
         a.values = (float *)fb.values.ptr;
         a.scored = sc + SC_SCORED;
         a.stand_pat = quiet;
+        LL_TRY(ensure(ctx, fb.tag, fb.cap * sizeof(u32))); // the list of parents whose records outgrow a tile (rarely any)
+        a.overflow_list = (u32 *)fb.tag.ptr;
+        a.overflow_count = (u32 *)(sc + SC_HZ_OVERFLOW);
+        CUDA_TRY(cudaMemsetAsync(a.overflow_count, 0, sizeof(u32), ctx->stream));
         Timed t(ctx, "horizon_last_ply");
         if (quiet) k_horizon<true><<<(unsigned)nblocks(fb.n, HP), BLOCK, 0, ctx->stream>>>(a);
         else k_horizon<false><<<(unsigned)nblocks(fb.n, HP), BLOCK, 0, ctx->stream>>>(a);
+        LL_TRY(check_launch("k_horizon"));
+        ctx->launches++;
+        if (quiet) k_horizon_overflow<true><<<(unsigned)ctx->sm_count, BLOCK, 0, ctx->stream>>>(a);
+        else k_horizon_overflow<false><<<(unsigned)ctx->sm_count, BLOCK, 0, ctx->stream>>>(a);
     }
     LL_TRY(check_launch("k_horizon"));
     for (size_t lev = bottom; lev > l; lev--) {
@@ -505,9 +513,15 @@ int horizon_chain(ll_ctx *ctx, size_t l0, int plies, bool *launched) {
         a.overflow = overflow;
         a.values = (float *)fb.values.ptr;
         a.scored = sc + SC_SCORED;
+        LL_TRY(ensure(ctx, fb.tag, fb.cap * sizeof(u32)));
+        a.overflow_list = (u32 *)fb.tag.ptr;
+        a.overflow_count = (u32 *)(sc + SC_HZ_OVERFLOW); // (zeroed by the memset at the head of the chain)
         Timed t(ctx, "horizon_last_ply");
         k_horizon<false, true><<<(unsigned)std::min<size_t>(nblocks(fb.cap, HP), resident), BLOCK, 0, ctx->stream>>>(a);
         LL_TRY(check_launch("k_horizon<CHAIN>"));
+        ctx->launches++;
+        k_horizon_overflow<false><<<(unsigned)ctx->sm_count, BLOCK, 0, ctx->stream>>>(a);
+        LL_TRY(check_launch("k_horizon_overflow"));
     }
     for (size_t lev = bottom; lev > l0; lev--) {
         Frontier &par = ctx->levels[lev - 1];
@@ -638,7 +652,7 @@ extern "C" int ll_shutdown(ll_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     auto drop = [](DevBuf &b) { drop_buf(b); };
-    drop(ctx->ext.counts); drop(ctx->ext.block_sums); drop(ctx->ext.block_base); drop(ctx->ext.values);
+    drop(ctx->ext.counts); drop(ctx->ext.block_sums); drop(ctx->ext.block_base); drop(ctx->ext.values); drop(ctx->ext.tag);
     for (Frontier &f : ctx->levels)
         if (!f.borrowed) drop_level(f);
     drop_level(ctx->unit_scratch);
@@ -1338,6 +1352,7 @@ extern "C" int ll_horizon_soa(ll_ctx *ctx, const ll_soa_t *soa, int plies, int q
     LL_TRY(ensure(ctx, ext.block_sums, (nblocks(soa->stride) + 1) * sizeof(u32)));
     LL_TRY(ensure(ctx, ext.block_base, (nblocks(soa->stride) + 1) * sizeof(u64)));
     LL_TRY(ensure(ctx, ext.values, soa->stride * sizeof(float)));
+    LL_TRY(ensure(ctx, ext.tag, soa->stride * sizeof(u32)));
     const Frontier saved = ctx->levels[0];
     Frontier view = ext;
     view.planes.ptr = soa->planes;

@@ -279,6 +279,7 @@ struct ExpandArgs {
     // k_horizon
     float *values;
     u64 *scored;
+    u32 *overflow_count, *overflow_list; // parents with more records than a tile keeps (HZ_REC_CAP), for k_horizon_overflow
 };
 
 #ifndef LL_EXPAND_MIN_BLOCKS
@@ -823,17 +824,27 @@ __global__ void __launch_bounds__(BLOCK, LL_EXPAND_MIN_BLOCKS) k_expand_coop(con
 #endif
 constexpr int HP = LL_HP; // parents per horizon tile
 constexpr u32 OWNER_CAP = 3072; // children of a tile whose parent is looked up, not searched for
+// Records a parent may keep in the tile.  A position can have up to REC_MAX = 36 (ll_device.cuh) but rarely has more than
+// sixteen, and the record arrays are most of the block's shared memory, which is what limits the resident warps of a kernel
+// bound by latency: 36 slots = 40 KB = five blocks a SM, 24 slots = 30 KB = seven: 3.24 -> 2.9 ms.  (21 slots = eight blocks
+// were measured too: 3-5 % of the playout positions have 22-24 records, and their trip through k_horizon_overflow costs more
+// than the eighth block gains.)  A parent with more records is handed, whole, to k_horizon_overflow (one thread walks the
+// canonical generator): none among 2^22 playout positions.
+#ifndef LL_HZ_REC_CAP
+#define LL_HZ_REC_CAP 24
+#endif
+constexpr int HZ_REC_CAP = LL_HZ_REC_CAP;
 #ifndef LL_HORIZON_MIN_BLOCKS
-#define LL_HORIZON_MIN_BLOCKS 5
+#define LL_HORIZON_MIN_BLOCKS 7
 #endif
 struct HorizonShared {
     u64 tile_op[6][HP]; // the OPPOSITION's planes of every parent: all that the loud children's evaluation reads of the board
     unsigned char owner[OWNER_CAP]; // quiet child k -> owner[k], loud child k -> owner[OWNER_CAP - 1 - k]
     u32 tile_meta[HP];
     u64 tile_opp[HP]; // the union of the six
-    u64 rec_mask[REC_MAX][HP]; // transposed: neighbouring parents write neighbouring words
-    u32 rec_info[REC_MAX][HP]; // kind, job, from, ascension, passing-by (16 bits) | number of the record's first QUIET commit << 16
-    unsigned char rec_loud[REC_MAX][HP]; // number of the record's first LOUD commit (<= 8 stuns a piece, <= 12 loud commits a servant: < 256)
+    u64 rec_mask[HZ_REC_CAP][HP]; // transposed: neighbouring parents write neighbouring words
+    u32 rec_info[HZ_REC_CAP][HP]; // kind, job, from, ascension, passing-by (16 bits) | number of the record's first QUIET commit << 16
+    unsigned char rec_loud[HZ_REC_CAP][HP]; // number of the record's first LOUD commit (<= 8 stuns a piece, <= 12 loud commits a servant: < 256)
     u32 exq[HP + 1], exl[HP + 1]; // exclusive prefixes of the parents' quiet / loud commit counts
     u32 n_rec[HP];
     int acc[HP];
@@ -868,8 +879,12 @@ struct SharedRecordOut {
     int slot;
     u64 opp;
     u32 n_rec = 0, n_quiet = 0, n_loud = 0;
+    bool outgrown = false; // more records than the tile keeps a parent: k_horizon_overflow takes the parent
     LL_HDM void put(u64 mask, u32 info) {
-        if (n_rec >= REC_MAX) return; // cannot happen on a well-formed position (<= 16 figurines a team); never write past the tile
+        if (n_rec >= (u32)HZ_REC_CAP) {
+            outgrown = true;
+            return;
+        }
         const u32 kind = info & 7u, asc = (info >> 12) & 7u;
         const u32 all = (u32)__popcll(mask);
         const u32 quiet = rec_splits(info) ? (u32)__popcll(mask & ~opp) : ((kind == REC_PUSH || kind == REC_DOUBLE) && asc == ASC_NONE) ? all : 0u;
@@ -913,6 +928,7 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
     const size_t i = tile * HP + tid;
     const bool mine = tid < HP && i < n;
     u32 cnt_q = 0, cnt_l = 0;
+    bool outgrown = false;
     if (mine) {
         const Pos p = soa_load(a.in, i);
         const bool blue = meta_stm(p.meta) != 0;
@@ -927,6 +943,11 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
         sh.tile_meta[tid] = p.meta;
         SharedRecordOut out{sh, tid, opp};
         reckless_records<STUNS>(p, out);
+        outgrown = out.outgrown;
+        if (outgrown) { // no commit of this parent enters the tile; the overflow kernel values it (and counts its leaves)
+            out.n_quiet = out.n_loud = out.n_rec = 0;
+            a.overflow_list[atomicAdd(a.overflow_count, 1u)] = (u32)i;
+        }
         cnt_q = out.n_quiet;
         cnt_l = out.n_loud;
         sh.n_rec[tid] = out.n_rec;
@@ -1043,7 +1064,7 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
     }
     __syncthreads();
     u32 scored = 0;
-    if (mine) {
+    if (mine && !outgrown) {
         const u32 cnt = cnt_q + cnt_l;
         float v = cnt ? key_float(sh.acc[tid]) : -INFINITY;
         if (cnt == 0 || (STUNS && a.stand_pat)) { // nothing to play: the node is itself a leaf (mind.rs:281-283, 295-299)
@@ -1061,6 +1082,64 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
     if ((tid & 31) == 0 && scored && a.scored) atomicAdd((unsigned long long *)a.scored, (unsigned long long)scored);
     if (!CHAIN) break;
     __syncthreads(); // the tile and the claim slot are reused by the next round
+    }
+}
+
+// the parents k_horizon would not keep in its tile (more than HZ_REC_CAP records: a dozen pieces AND servants stepping every
+// way): one BLOCK per parent -- a single thread would take ~0.2 ms over the generator and fifty evaluations, and the launch
+// waits for it.  Thread 0 lists the parent's records (all REC_MAX of them fit here), then the block makes and scores one child
+// per thread: the definition itself (mind.rs:279-301), score(make_child(...)).
+struct OverflowRecords {
+    u64 mask[REC_MAX];
+    u32 info[REC_MAX]; // rec_info with the record's first commit number
+    u32 n_rec, n_moves;
+    LL_HDM void put(u64 m, u32 i) {
+        if (n_rec < (u32)REC_MAX) {
+            mask[n_rec] = m;
+            info[n_rec] = i | (n_moves << 16);
+            n_rec++;
+        }
+        n_moves += (u32)popc64(m);
+    }
+};
+template <bool STUNS> __global__ void __launch_bounds__(BLOCK) k_horizon_overflow(const ExpandArgs a) {
+    __shared__ OverflowRecords rec;
+    __shared__ int best_s;
+    const u32 n = *(volatile u32 *)a.overflow_count;
+    for (u32 k = blockIdx.x; k < n; k += gridDim.x) {
+        const size_t i = a.overflow_list[k];
+        const Pos p = soa_load(a.in, i); // every thread holds the parent
+        if (threadIdx.x == 0) {
+            rec.n_rec = rec.n_moves = 0;
+            reckless_records<STUNS>(p, rec);
+            best_s = float_key(-INFINITY);
+        }
+        __syncthreads();
+        const u32 total = rec.n_moves, team = meta_stm(p.meta);
+        int best = float_key(-INFINITY);
+        for (u32 j = threadIdx.x; j < total; j += BLOCK) {
+            u32 r = 0;
+            while (r + 1 < rec.n_rec && rec_base(rec.info[r + 1]) <= j) r++;
+            const u32 m = rec_move(rec.mask[r], rec.info[r], j - rec_base(rec.info[r]), team);
+            Pos c;
+            make_child(p, m, c);
+            const float s = score(c);
+            const int key = float_key(team ? -s : s); // -(orientation(child) * score(child)), the child's initiative being the other team's
+            best = key > best ? key : best;
+        }
+        best = __reduce_max_sync(0xffffffffu, best);
+        if ((threadIdx.x & 31) == 0) atomicMax(&best_s, best);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float v = total ? key_float(best_s) : -INFINITY;
+            if (total == 0 || (STUNS && a.stand_pat)) {
+                const float s = score(p);
+                v = fmaxf(v, team ? -s : s);
+            }
+            a.values[i] = v;
+            if (a.scored) atomicAdd((unsigned long long *)a.scored, (unsigned long long)(total ? total : 1u));
+        }
+        __syncthreads();
     }
 }
 

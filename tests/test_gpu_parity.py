@@ -467,6 +467,31 @@ def test_horizon_launch_chain_equals_level_by_level(eng, playouts, reckless_worl
         eng.horizon(bad, 2)
 
 
+def test_horizon_parents_with_more_records_than_a_tile_keeps(eng, playouts):
+    """k_horizon keeps 24 (piece / servant-step, target mask) records a parent in its tile; a position can have up to 36 -- a
+    dozen pieces and servants ascending every way.  Such parents go, whole, to k_horizon_overflow; values must not notice."""
+    import leafline_b200 as ll
+
+    crowded = [  # twelve pieces, the figurehead, and two servants that between them step every way a servant can: 29 records
+        "1n1n3k/2P5/BBBB4/RRRR4/NNNN4/5p1p/6P1/4K3 w - -",
+        "4k3/6p1/5P1P/nnnn4/rrrr4/bbbb4/2p5/1N1N3K b - -",      # the same for Blue
+        "1n1n3k/2P5/QQQQ4/QQQQ4/QQQQ4/5p1p/6P1/4K3 w - -",
+        "1n1n1n2/P1P1P1P1/8/8/NNNN4/BBBB4/RRR5/4K2k w - -",    # 22 records: stays in the tile
+    ]
+    worlds = np.array([ll.reconstruct(f) for f in crowded], dtype=ll.WORLD_DTYPE)
+    assert max(len(O.reckless_lookahead(w)) for w in worlds) >= 90
+    mixed = np.concatenate([playouts[:100], worlds, playouts[100:164], worlds[::-1]])  # overflowing parents among ordinary ones
+    for plies in (1, 2):
+        got = eng.horizon(mixed, plies)
+        want = np.array([O.negamax(w, plies) for w in mixed], dtype=np.float32)
+        assert got.tobytes() == want.tobytes(), plies
+    got = eng.horizon(mixed, 1, quiet=2)
+    assert got.tobytes() == np.array([O.negamax(w, 1, quiet=2) for w in mixed], dtype=np.float32).tobytes()
+    for w in worlds[:2]:
+        _, s_got, _ = eng.kickoff(w, 2)
+        assert s_got.tobytes() == O.kickoff(w, 2, False, threads=4)[1].tobytes()
+
+
 def test_horizon_depth_3_on_a_few(eng, playouts):
     worlds = playouts[:4]
     got = eng.horizon(worlds, 3)
