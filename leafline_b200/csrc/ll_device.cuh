@@ -700,11 +700,13 @@ struct ServiceBits { // collects the secret-service destinations the exact path 
 };
 // Out: void put(u64 mask, u32 info_without_base) -- called only with mask != 0; returns nothing.  The caller keeps
 // the running move count (the record's base) itself.
-template <int T, bool STUNS, class Out> LL_HD void reckless_records_as(const Pos &p, Out &out) {
+// PART: 0 = every record; 1 = the servants', the figurehead's and the secret service's; 2 = the ponies' and the sliders'
+// (the horizon kernel generates a parent's records with two threads, one part each)
+template <int T, bool STUNS, class Out, int PART = 0> LL_HD void reckless_records_as(const Pos &p, Out &out) {
     const u64 own = occupied_by<T>(p), opp = occupied_by<1 - T>(p), occ = own | opp, empty = ~occ;
     const u64 allowed = STUNS ? opp : ~own;
     const u64 last = T == 0 ? RANK_1 << 56 : RANK_1;
-    { // life.rs:749-830, all servants at once
+    if (PART != 2) { // life.rs:749-830, all servants at once
         const u64 s = p.pl[6 * T + SERVANT];
         const u64 one = (T == 0 ? s << 8 : s >> 8) & empty;
         const u64 two = (T == 0 ? (one & (RANK_1 << 16)) << 8 : (one & (RANK_1 << 40)) >> 8) & empty;
@@ -729,40 +731,48 @@ template <int T, bool STUNS, class Out> LL_HD void reckless_records_as(const Pos
             }
         }
     }
-    for (u64 s = p.pl[6 * T + PONY]; s; s &= s - 1) { // life.rs:832-855
-        const int from = lsb64(s);
-        const u64 targets = pony_moves(from) & allowed;
-        if (targets) out.put(targets, rec_info(REC_PIECE, PONY, from, ASC_NONE, 0, 0));
+    if (PART != 1) {
+        for (u64 s = p.pl[6 * T + PONY]; s; s &= s - 1) { // life.rs:832-855
+            const int from = lsb64(s);
+            const u64 targets = pony_moves(from) & allowed;
+            if (targets) out.put(targets, rec_info(REC_PIECE, PONY, from, ASC_NONE, 0, 0));
+        }
+        for (u64 s = p.pl[6 * T + SCHOLAR]; s; s &= s - 1) { // life.rs:857-914
+            const int from = lsb64(s);
+            const u64 targets = diag_attacks(from, occ) & allowed;
+            if (targets) out.put(targets, rec_info(REC_PIECE, SCHOLAR, from, ASC_NONE, 0, 0));
+        }
+        for (u64 s = p.pl[6 * T + COP]; s; s &= s - 1) {
+            const int from = lsb64(s);
+            const u64 targets = orth_attacks(from, occ) & allowed;
+            if (targets) out.put(targets, rec_info(REC_PIECE, COP, from, ASC_NONE, 0, 0));
+        }
+        for (u64 s = p.pl[6 * T + PRINCESS]; s; s &= s - 1) { // life.rs:955-969, both ray families in one record
+            const int from = lsb64(s);
+            const u64 targets = (diag_attacks(from, occ) | orth_attacks(from, occ)) & allowed;
+            if (targets) out.put(targets, rec_info(REC_PIECE, PRINCESS, from, ASC_NONE, 0, 0));
+        }
     }
-    for (u64 s = p.pl[6 * T + SCHOLAR]; s; s &= s - 1) { // life.rs:857-914
-        const int from = lsb64(s);
-        const u64 targets = diag_attacks(from, occ) & allowed;
-        if (targets) out.put(targets, rec_info(REC_PIECE, SCHOLAR, from, ASC_NONE, 0, 0));
-    }
-    for (u64 s = p.pl[6 * T + COP]; s; s &= s - 1) {
-        const int from = lsb64(s);
-        const u64 targets = orth_attacks(from, occ) & allowed;
-        if (targets) out.put(targets, rec_info(REC_PIECE, COP, from, ASC_NONE, 0, 0));
-    }
-    for (u64 s = p.pl[6 * T + PRINCESS]; s; s &= s - 1) { // life.rs:955-969, both ray families in one record
-        const int from = lsb64(s);
-        const u64 targets = (diag_attacks(from, occ) | orth_attacks(from, occ)) & allowed;
-        if (targets) out.put(targets, rec_info(REC_PIECE, PRINCESS, from, ASC_NONE, 0, 0));
-    }
-    for (u64 s = p.pl[6 * T + FIGUREHEAD]; s; s &= s - 1) { // life.rs:973-978
-        const int from = lsb64(s);
-        const u64 targets = figurehead_moves(from) & allowed;
-        if (targets) out.put(targets, rec_info(REC_PIECE, FIGUREHEAD, from, ASC_NONE, 0, 0));
-    }
-    if (!STUNS) { // life.rs:980-1050: the exact path (leer tests), never a stun
-        ServiceBits service;
-        service_lookahead<T, true>(p, own, opp, service);
-        if (service.to_bits) out.put(service.to_bits, rec_info(REC_SERVICE, FIGUREHEAD, (T == 0 ? 0 : 56) + 4, ASC_NONE, 0, 0));
+    if (PART != 2) {
+        for (u64 s = p.pl[6 * T + FIGUREHEAD]; s; s &= s - 1) { // life.rs:973-978
+            const int from = lsb64(s);
+            const u64 targets = figurehead_moves(from) & allowed;
+            if (targets) out.put(targets, rec_info(REC_PIECE, FIGUREHEAD, from, ASC_NONE, 0, 0));
+        }
+        if (!STUNS) { // life.rs:980-1050: the exact path (leer tests), never a stun
+            ServiceBits service;
+            service_lookahead<T, true>(p, own, opp, service);
+            if (service.to_bits) out.put(service.to_bits, rec_info(REC_SERVICE, FIGUREHEAD, (T == 0 ? 0 : 56) + 4, ASC_NONE, 0, 0));
+        }
     }
 }
 template <bool STUNS, class Out> LL_HD void reckless_records(const Pos &p, Out &out) {
     if (meta_stm(p.meta) == 0) reckless_records_as<0, STUNS>(p, out);
     else reckless_records_as<1, STUNS>(p, out);
+}
+template <bool STUNS, int PART, class Out> LL_HD void reckless_records_part(const Pos &p, Out &out) {
+    if (meta_stm(p.meta) == 0) reckless_records_as<0, STUNS, Out, PART>(p, out);
+    else reckless_records_as<1, STUNS, Out, PART>(p, out);
 }
 
 // ---- legal commits as records (the order-free consumers of lookahead(): perft chain and tail) -----------------

@@ -837,16 +837,24 @@ constexpr int HZ_REC_CAP = LL_HZ_REC_CAP;
 #ifndef LL_HORIZON_MIN_BLOCKS
 #define LL_HORIZON_MIN_BLOCKS 7
 #endif
+// A parent's records are generated by TWO threads (phase 1 is a quarter of the kernel and would leave half the block idle):
+// thread slot takes the servants, the figurehead and secret service and files them in rows [0, REC_ROWS_A), thread HP + slot the
+// ponies and the sliders in rows [REC_ROWS_A, HZ_REC_CAP); each half numbers its own commits from zero and is, from the scan
+// on, a parent of its own ("virtual parent" v = half * HP + slot) -- only the maximum is shared.
+constexpr int REC_ROWS_A = HZ_REC_CAP * 14 / 24, REC_ROWS_B = HZ_REC_CAP - REC_ROWS_A; // 14 + 10: servant steps ascend four ways each
+constexpr int HV = 2 * HP;
+static_assert(HV == BLOCK, "one thread per half parent");
 struct HorizonShared {
     u64 tile_op[6][HP]; // the OPPOSITION's planes of every parent: all that the loud children's evaluation reads of the board
-    unsigned char owner[OWNER_CAP]; // quiet child k -> owner[k], loud child k -> owner[OWNER_CAP - 1 - k]
+    unsigned char owner[OWNER_CAP]; // quiet child k -> owner[k], loud child k -> owner[OWNER_CAP - 1 - k] (virtual parents)
     u32 tile_meta[HP];
     u64 tile_opp[HP]; // the union of the six
     u64 rec_mask[HZ_REC_CAP][HP]; // transposed: neighbouring parents write neighbouring words
     u32 rec_info[HZ_REC_CAP][HP]; // kind, job, from, ascension, passing-by (16 bits) | number of the record's first QUIET commit << 16
     unsigned char rec_loud[HZ_REC_CAP][HP]; // number of the record's first LOUD commit (<= 8 stuns a piece, <= 12 loud commits a servant: < 256)
-    u32 exq[HP + 1], exl[HP + 1]; // exclusive prefixes of the parents' quiet / loud commit counts
-    u32 n_rec[HP];
+    u32 exq[HV + 1], exl[HV + 1]; // exclusive prefixes of the virtual parents' quiet / loud commit counts
+    unsigned char n_rec[HV];
+    unsigned char outgrown[HP]; // a half ran out of rows: the whole parent goes to k_horizon_overflow
     int acc[HP];
     u32 feat[7][HP]; // the parents' evaluation features (ll_device.cuh: Feat), transposed like the records
     float material[HP]; // score_material(parent's features, the CHILD's initiative)
@@ -878,36 +886,38 @@ struct SharedRecordOut {
     HorizonShared &sh;
     int slot;
     u64 opp;
+    u32 row, row_end; // this half's rows
     u32 n_rec = 0, n_quiet = 0, n_loud = 0;
-    bool outgrown = false; // more records than the tile keeps a parent: k_horizon_overflow takes the parent
+    bool outgrown = false; // more records than the half's rows: k_horizon_overflow takes the parent
     LL_HDM void put(u64 mask, u32 info) {
-        if (n_rec >= (u32)HZ_REC_CAP) {
+        if (row >= row_end) {
             outgrown = true;
             return;
         }
         const u32 kind = info & 7u, asc = (info >> 12) & 7u;
         const u32 all = (u32)__popcll(mask);
         const u32 quiet = rec_splits(info) ? (u32)__popcll(mask & ~opp) : ((kind == REC_PUSH || kind == REC_DOUBLE) && asc == ASC_NONE) ? all : 0u;
-        sh.rec_mask[n_rec][slot] = mask;
-        sh.rec_info[n_rec][slot] = (info & 0xFFFFu) | (n_quiet << 16);
-        sh.rec_loud[n_rec][slot] = (unsigned char)n_loud;
+        sh.rec_mask[row][slot] = mask;
+        sh.rec_info[row][slot] = (info & 0xFFFFu) | (n_quiet << 16);
+        sh.rec_loud[row][slot] = (unsigned char)n_loud;
+        row++;
         n_rec++;
         n_quiet += quiet;
         n_loud += all - quiet;
     }
 };
-// the parent slot of child k of one kind: looked up, or -- a tile with more children than the map holds -- the last parent
+// the virtual parent of child k of one kind: looked up, or -- a tile with more children than the map holds -- the last one
 // whose prefix is <= k
 __device__ __forceinline__ u32 horizon_owner(const HorizonShared &sh, const u32 *ex, bool mapped, u32 at, u32 k) {
     if (mapped) return sh.owner[at];
-    u32 slot = 0, hi = HP;
+    u32 v = 0, hi = HV;
 #pragma unroll
-    for (int step = 0; step < 7; step++) { // HP <= 2^7
-        const u32 mid = (slot + hi) >> 1;
-        if (ex[mid] <= k) slot = mid;
+    for (int step = 0; step < 7; step++) { // HV = 2^7
+        const u32 mid = (v + hi) >> 1;
+        if (ex[mid] <= k) v = mid;
         else hi = mid;
     }
-    return slot;
+    return v;
 }
 // CHAIN: the level's size is resident on the device (a.n_in) and persistent blocks pull tiles from a.tile_counter -- the
 // launch needs no host round trip (the small-batch path of ll_horizon_batch)
@@ -925,51 +935,58 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
         tile = (size_t)sh.claim;
         if (tile * HP >= n) break;
     }
-    const size_t i = tile * HP + tid;
-    const bool mine = tid < HP && i < n;
-    u32 cnt_q = 0, cnt_l = 0;
+    const int slot_mine = tid & (HP - 1), half = tid / HP;
+    const size_t i = tile * HP + slot_mine;
+    const bool mine = i < n; // (both halves of the block hold the parent)
+    u32 cnt_q = 0, cnt_l = 0, n_rec = 0;
     bool outgrown = false;
     if (mine) {
         const Pos p = soa_load(a.in, i);
         const bool blue = meta_stm(p.meta) != 0;
         u64 opp = 0;
 #pragma unroll
-        for (int j = 0; j < 6; j++) {
-            const u64 pl = blue ? p.pl[j] : p.pl[6 + j];
-            sh.tile_op[j][tid] = pl;
-            opp |= pl;
+        for (int j = 0; j < 6; j++) opp |= blue ? p.pl[j] : p.pl[6 + j];
+        SharedRecordOut out{sh, slot_mine, opp, half ? (u32)REC_ROWS_A : 0u, half ? (u32)HZ_REC_CAP : (u32)REC_ROWS_A};
+        if (half == 0) {
+            reckless_records_part<STUNS, 1>(p, out);
+#pragma unroll
+            for (int j = 0; j < 6; j++) sh.tile_op[j][slot_mine] = blue ? p.pl[j] : p.pl[6 + j];
+            sh.tile_opp[slot_mine] = opp;
+            sh.tile_meta[slot_mine] = p.meta;
+            sh.acc[slot_mine] = float_key(-INFINITY);
+        } else {
+            reckless_records_part<STUNS, 2>(p, out);
+            const Feat f = features_of(p);
+#pragma unroll
+            for (int w = 0; w < 7; w++) sh.feat[w][slot_mine] = f.w[w];
+            sh.material[slot_mine] = score_material(f, meta_stm(p.meta) ^ 1u);
         }
-        sh.tile_opp[tid] = opp;
-        sh.tile_meta[tid] = p.meta;
-        SharedRecordOut out{sh, tid, opp};
-        reckless_records<STUNS>(p, out);
         outgrown = out.outgrown;
-        if (outgrown) { // no commit of this parent enters the tile; the overflow kernel values it (and counts its leaves)
-            out.n_quiet = out.n_loud = out.n_rec = 0;
-            a.overflow_list[atomicAdd(a.overflow_count, 1u)] = (u32)i;
-        }
         cnt_q = out.n_quiet;
         cnt_l = out.n_loud;
-        sh.n_rec[tid] = out.n_rec;
-        sh.acc[tid] = float_key(-INFINITY);
-        const Feat f = features_of(p);
-#pragma unroll
-        for (int w = 0; w < 7; w++) sh.feat[w][tid] = f.w[w];
-        sh.material[tid] = score_material(f, meta_stm(p.meta) ^ 1u);
+        n_rec = out.n_rec;
     }
+    if (half == 0) sh.outgrown[slot_mine] = 0;
+    __syncthreads();
+    if (outgrown) sh.outgrown[slot_mine] = 1;
+    __syncthreads();
+    outgrown = mine && sh.outgrown[slot_mine];
+    if (outgrown) { // no commit of this parent enters the tile; the overflow kernel values it (and counts its leaves)
+        cnt_q = cnt_l = n_rec = 0;
+        if (half == 0) a.overflow_list[atomicAdd(a.overflow_count, 1u)] = (u32)i;
+    }
+    sh.n_rec[tid] = (unsigned char)n_rec;
     u32 total;
     const u32 ex = block_exclusive_scan(cnt_q | (cnt_l << 16), &total); // both prefixes in one scan (a tile's quiet commits stay far below 2^16)
     const u32 ex_q = ex & 0xFFFFu, ex_l = ex >> 16, total_q = total & 0xFFFFu, total_l = total >> 16;
-    if (tid < HP) {
-        sh.exq[tid] = ex_q;
-        sh.exl[tid] = ex_l;
-    }
+    sh.exq[tid] = ex_q;
+    sh.exl[tid] = ex_l;
     if (tid == 0) {
-        sh.exq[HP] = total_q;
-        sh.exl[HP] = total_l;
+        sh.exq[HV] = total_q;
+        sh.exl[HV] = total_l;
     }
     const bool mapped = total_q + total_l <= OWNER_CAP; // block-uniform
-    if (mapped && mine) {
+    if (mapped) {
         for (u32 c = 0; c < cnt_q; c++) sh.owner[ex_q + c] = (unsigned char)tid;
         for (u32 c = 0; c < cnt_l; c++) sh.owner[OWNER_CAP - 1u - (ex_l + c)] = (unsigned char)tid;
     }
@@ -977,18 +994,20 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
     // (LL_HZ_ILP children per thread and pass: measured at 2, 3 and 4 -- 3.9-4.2 ms against 3.24 ms at one, the unrolled loop
     // bodies cost more in instruction fetch than the second chain hides in latency: DESIGN.md 7b)
     auto quiet_child = [&](u32 k, u32 &slot) -> int {
-        slot = horizon_owner(sh, sh.exq, mapped, k, k);
-        const u32 j = k - sh.exq[slot];
-        u32 r = 0, rhi = sh.n_rec[slot];
+        const u32 v = horizon_owner(sh, sh.exq, mapped, k, k);
+        slot = v & (HP - 1);
+        const u32 row0 = v >= (u32)HP ? (u32)REC_ROWS_A : 0u;
+        const u32 j = k - sh.exq[v];
+        u32 r = 0, rhi = sh.n_rec[v];
 #pragma unroll
-        for (int step = 0; step < 6; step++) { // REC_MAX <= 2^6: the last record whose first quiet commit is <= j (it has one: empty
-            const u32 mid = (r + rhi) >> 1;    // records share their successor's number); branch-free, a converged search re-reads r
-            const bool le = (sh.rec_info[mid][slot] >> 16) <= j;
+        for (int step = 0; step < 5; step++) { // a half has < 2^5 rows: the last record whose first quiet commit is <= j (it has one:
+            const u32 mid = (r + rhi) >> 1;    // empty records share their successor's number); branch-free, a converged search re-reads r
+            const bool le = (sh.rec_info[row0 + mid][slot] >> 16) <= j;
             r = le ? mid : r;
             rhi = le ? rhi : mid;
         }
-        const u32 info = sh.rec_info[r][slot];
-        const u64 mask = sh.rec_mask[r][slot];
+        const u32 info = sh.rec_info[row0 + r][slot];
+        const u64 mask = sh.rec_mask[row0 + r][slot];
         const u32 meta = sh.tile_meta[slot];
         const u32 team = meta_stm(meta);
         const int to = select_bit(rec_splits(info) ? mask & ~sh.tile_opp[slot] : mask, j - (info >> 16));
@@ -998,21 +1017,23 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
         return float_key(team ? -s : s); // -(orientation(child) * score(child)), the child's initiative being the other team's (mind.rs:283, 331-336)
     };
     auto loud_child = [&](u32 k, u32 &slot) -> int {
-        slot = horizon_owner(sh, sh.exl, mapped, OWNER_CAP - 1u - k, k);
-        const u32 j = k - sh.exl[slot];
-        u32 r = 0, rhi = sh.n_rec[slot];
+        const u32 v = horizon_owner(sh, sh.exl, mapped, OWNER_CAP - 1u - k, k);
+        slot = v & (HP - 1);
+        const u32 row0 = v >= (u32)HP ? (u32)REC_ROWS_A : 0u;
+        const u32 j = k - sh.exl[v];
+        u32 r = 0, rhi = sh.n_rec[v];
 #pragma unroll
-        for (int step = 0; step < 6; step++) {
+        for (int step = 0; step < 5; step++) {
             const u32 mid = (r + rhi) >> 1;
-            const bool le = sh.rec_loud[mid][slot] <= j;
+            const bool le = sh.rec_loud[row0 + mid][slot] <= j;
             r = le ? mid : r;
             rhi = le ? rhi : mid;
         }
-        const u32 info = sh.rec_info[r][slot];
-        const u64 mask = sh.rec_mask[r][slot];
+        const u32 info = sh.rec_info[row0 + r][slot];
+        const u64 mask = sh.rec_mask[row0 + r][slot];
         const u32 meta = sh.tile_meta[slot];
         const u32 team = meta_stm(meta);
-        const int to = select_bit(rec_splits(info) ? mask & sh.tile_opp[slot] : mask, j - sh.rec_loud[r][slot]);
+        const int to = select_bit(rec_splits(info) ? mask & sh.tile_opp[slot] : mask, j - sh.rec_loud[row0 + r][slot]);
         const u32 m = rec_move_to(info & 0xFFFFu, to, team);
         Feat f;
 #pragma unroll
@@ -1064,14 +1085,15 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
     }
     __syncthreads();
     u32 scored = 0;
-    if (mine && !outgrown) {
-        const u32 cnt = cnt_q + cnt_l;
-        float v = cnt ? key_float(sh.acc[tid]) : -INFINITY;
+    if (mine && half == 0 && !outgrown) {
+        const u32 other = (u32)HP + (u32)slot_mine;
+        const u32 cnt = cnt_q + cnt_l + (sh.exq[other + 1] - sh.exq[other]) + (sh.exl[other + 1] - sh.exl[other]);
+        float v = cnt ? key_float(sh.acc[slot_mine]) : -INFINITY;
         if (cnt == 0 || (STUNS && a.stand_pat)) { // nothing to play: the node is itself a leaf (mind.rs:281-283, 295-299)
             Feat f;
 #pragma unroll
-            for (int w = 0; w < 7; w++) f.w[w] = sh.feat[w][tid];
-            const u32 meta = sh.tile_meta[tid];
+            for (int w = 0; w < 7; w++) f.w[w] = sh.feat[w][slot_mine];
+            const u32 meta = sh.tile_meta[slot_mine];
             const float s = score_features(f, meta_stm(meta), meta_elig(meta));
             v = fmaxf(v, meta_stm(meta) ? -s : s);
         }
