@@ -277,13 +277,8 @@ def main():
     t_begin = time.perf_counter()
     device_ms = 0.0
     host_s = 0.0
-    align_step = torch.zeros(1, dtype=torch.int32, device="cuda")
     for _ in range(args.steps):
         flush.fill_(1)  # flush L2 between timed iterations (not timed)
-        if world > 1:
-            # ... and, like the flush, untimed: a one-element all-reduce, so that every rank's timed step starts together on the
-            # devices (the ranks' host loops drift apart by tens of microseconds between steps; a step is 0.36 ms)
-            dist.all_reduce(align_step)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         stream.synchronize()
         t0 = time.perf_counter()
@@ -317,9 +312,7 @@ def main():
                    "depth": depth, "leaves_per_step": leaves_total, "roots_per_step": world,
                    "sharding": (f"ll_perft_batch_multi: one root position per GPU ({world} ranks, one process each, library-owned group), no position "
                                 f"ever crosses NVLink; u64 sum of the {world} leaf counts on the devices by {group.reduce_path}") if world > 1 else "single GPU (ll_perft)",
-                   "l2": "flushed between timed steps (256 MiB write, untimed)",
-                   "between_steps": ("the ranks are re-aligned on the devices by a one-element all-reduce after the flush (untimed, like the flush); "
-                                     "the timed region of a step is the C-ABI call alone") if world > 1 else "L2 flush only"},
+                   "l2": "flushed between timed steps (256 MiB write, untimed)"},
         "clocks": clocks, "gpu_launches": launches,
         "expanded_nodes_per_sec": None if expanded_per_tree is None else expanded_per_tree * world / (ms_per_step * 1e-3),
         "expanded_nodes_note": ("SURVEY.md 8(d) work unit: a node whose legal children are generated (plies 0 .. depth-1; the last ply's children are "
