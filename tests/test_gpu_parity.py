@@ -639,6 +639,13 @@ def test_host_alpha_beta_variations_memory_budget_and_group(eng):
                 cur = min(hit, key=lambda c: abs(float(O.score(c["tree"])) * (1 if w["initiative"] == 0 else -1) - float(f["score"])))["tree"] if len(hit) > 1 else hit[0]["tree"]
             leaf = float(O.score(cur)) * (1.0 if int(w["initiative"]) == 0 else -1.0)
             assert np.float32(leaf) == f["score"], (fen, ll.pagan_variation(f), leaf, float(f["score"]))
+    # one searcher thread (a single depth-first walk) and thirty-two (one per root move, requests combined): the same scores
+    w = ll.reconstruct(KIWIPETE)
+    eng.set_search_threads(1)
+    alone, _, _ = eng.alpha_beta_forecast(w, 5, device_plies=2)
+    eng.set_search_threads(32)
+    together, _, _ = eng.alpha_beta_forecast(w, 5, device_plies=2)
+    assert alone["score"].tobytes() == together["score"].tobytes() and alone["commit"].tobytes() == together["commit"].tobytes()
     # a tiny memory bank forgets (least recently used first) and the scores do not move
     w = ll.new_world()
     full = eng.forecast(w, 6)
