@@ -109,7 +109,8 @@ struct ll_ctx {
     double deja_vu_gib = 0.25; // byte budget of the search drivers' memory bank (mind.rs:367-372; ll_set_deja_vu_bound)
     bool literal = false;      // this call holds a position outside domain W: the literal path answers it (ll_device.cuh: DOMAIN_LITERAL)
     bool force_synced = false; // tests: always take the level-by-level path
-    bool head_cluster = false; // the device runs a 16-CTA cluster of 512 threads: the chain's first plies go into one launch (k_expand_head)
+    bool head_cluster = false; // the chain's first plies go into one cluster launch (k_expand_head)
+    int head_ctas = HEAD_CTAS, head_max_steps = HEAD_MAX_STEPS; // (experiment knobs: LEAFLINE_B200_HEAD_CLUSTER=1, LEAFLINE_B200_HEAD=ctas,steps)
     bool no_graph = false;     // tests: issue the perft launch chain launch by launch instead of replaying its CUDA graph
     uint64_t chain_sig = 0;    // the captured perft chain (same plan, same buffers, same stream -> replay)
     cudaGraphExec_t chain_exec = nullptr;
@@ -598,14 +599,21 @@ static int init_ctx(ll_ctx *ctx) {
         // MEASURED SLOWER (perft(6) 0.357 ms against 0.343 ms with a launch per ply): off unless LEAFLINE_B200_HEAD_CLUSTER=1
         const char *on = getenv("LEAFLINE_B200_HEAD_CLUSTER");
         ctx->head_cluster = false;
+        if (const char *knobs = getenv("LEAFLINE_B200_HEAD")) {
+            int c = 0, st = 0;
+            if (sscanf(knobs, "%d,%d", &c, &st) == 2 && c >= 1 && c <= HEAD_CTAS && st >= 2 && st <= HEAD_MAX_STEPS) {
+                ctx->head_ctas = c;
+                ctx->head_max_steps = st;
+            }
+        }
         if (on && *on == '1' && cudaFuncSetAttribute(k_expand_head, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof cfg);
-            cfg.gridDim = dim3(HEAD_CTAS, 1, 1);
+            cfg.gridDim = dim3((unsigned)ctx->head_ctas, 1, 1);
             cfg.blockDim = dim3(HEAD_WARPS * 32, 1, 1);
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = HEAD_CTAS;
+            attr[0].val.clusterDim.x = (unsigned)ctx->head_ctas;
             attr[0].val.clusterDim.y = 1;
             attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
@@ -1064,7 +1072,7 @@ static int perft_chain_launch(ll_ctx *ctx, int depth, int shard_rank, int shard_
     }
     plan.n_steps = n_steps;
     int head_steps = 0; // leading narrow plies (0, 1, 2) that go into the cluster launch
-    while (ctx->head_cluster && head_steps < HEAD_MAX_STEPS && head_steps < n_steps && kinds[head_steps] == STEP_EMIT_SMALL && head_steps < 3) head_steps++;
+    while (ctx->head_cluster && head_steps < ctx->head_max_steps && head_steps < n_steps && kinds[head_steps] == STEP_EMIT_SMALL && head_steps < 3) head_steps++;
     if (head_steps < 2) head_steps = 0;
     plan.head_steps = head_steps;
     // (a single cooperative launch of the WHOLE chain with grid-wide barriers between the plies was measured: no faster -- DESIGN.md)
@@ -1077,12 +1085,12 @@ static int perft_chain_launch(ll_ctx *ctx, int depth, int shard_rank, int shard_
             h.n_steps = head_steps;
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof cfg);
-            cfg.gridDim = dim3(HEAD_CTAS, 1, 1);
+            cfg.gridDim = dim3((unsigned)ctx->head_ctas, 1, 1);
             cfg.blockDim = dim3(HEAD_WARPS * 32, 1, 1);
             cfg.stream = ctx->stream;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = HEAD_CTAS;
+            attr[0].val.clusterDim.x = (unsigned)ctx->head_ctas;
             attr[0].val.clusterDim.y = 1;
             attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
