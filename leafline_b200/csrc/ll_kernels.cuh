@@ -387,10 +387,7 @@ template <bool NIHIL, int MODE, int P, bool STUNS, bool LITERAL = false> __devic
                     }
                 } else {
                     const int v = live ? (int)count_moves<false>(c) : 0;
-                    // children of one parent are neighbours in the list: reduce per parent inside the warp first
-                    const unsigned peers = __match_any_sync(0xffffffffu, live ? slot : 0xFFFFFFFFu);
-                    const int r = __reduce_add_sync(peers, v);
-                    if (live && (tid & 31) == __ffs((int)peers) - 1) atomicAdd(&sh.acc[slot], r);
+                    if (live && v) atomicAdd(&sh.acc[slot], v); // (see expand_tiles_records)
                 }
             }
             __syncthreads();
@@ -556,10 +553,16 @@ template <int MODE, int P> __device__ __forceinline__ void expand_tiles_records(
 #else
                     const int v = live ? (int)count_moves<false>(c) : 0;
 #endif
-                    // children of one parent are neighbours in the list: reduce per parent inside the warp first
+                    // one shared-memory atomic a child.  (Round 1 reduced per parent inside the warp first -- __match_any_sync,
+                    // __reduce_add_sync, one atomic per (warp, parent): the match alone was 7 % of the tail's warp instructions and
+                    // its two hottest stall sites; -DLL_TAIL_MATCH_REDUCE builds that variant: perft(6) 0.347 against 0.316 ms.)
+#ifdef LL_TAIL_MATCH_REDUCE
                     const unsigned peers = __match_any_sync(0xffffffffu, live ? slot : 0xFFFFFFFFu);
                     const int r = __reduce_add_sync(peers, v);
                     if (live && (tid & 31) == __ffs((int)peers) - 1) atomicAdd(&sh.acc[slot], r);
+#else
+                    if (live && v) atomicAdd(&sh.acc[slot], v);
+#endif
                 }
             }
             __syncthreads();
@@ -1043,10 +1046,14 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
         const float s = score_features(f, team ^ 1u, elig);
         return float_key(team ? -s : s);
     };
-    auto fold = [&](bool live, u32 slot, int v) { // per parent: max inside the warp first, then one shared atomic per (warp, parent)
+    auto fold = [&](bool live, u32 slot, int v) { // per parent: a shared-memory atomicMax a child (see the perft tail: the warp-level
+#ifdef LL_HZ_MATCH_FOLD                           // segmented reduction in front of it cost more than the atomics it saved)
         const unsigned peers = __match_any_sync(0xffffffffu, live ? slot : 0xFFFFFFFFu);
         const int best = __reduce_max_sync(peers, v);
         if (live && (tid & 31) == __ffs((int)peers) - 1) atomicMax(&sh.acc[slot], best);
+#else
+        if (live) atomicMax(&sh.acc[slot], v);
+#endif
     };
 #ifndef LL_HZ_ILP
 #define LL_HZ_ILP 1
