@@ -1064,6 +1064,11 @@ LL_HD float score_material(const Feat &f, u32 stm) {
     }
     return v;
 }
+LL_HD float score_eligibility(float v, u32 elig) { // mind.rs:133-140, the last terms of the sum
+    if (elig & 0x3u) v = fadd(v, 0.1f);
+    if (elig & 0xCu) v = fadd(v, -0.1f);
+    return v;
+}
 LL_HD float score_positional(float v, u32 w3, u32 w4, u32 w5, u32 w6, u32 elig) {
     const int oc = (int)(w3 & 0xFFu), bc = (int)((w3 >> 8) & 0xFFu); // mind.rs:70-81
     v = fadd(v, fmul(0.1f, (float)(oc - bc)));
@@ -1083,9 +1088,7 @@ LL_HD float score_positional(float v, u32 w3, u32 w4, u32 w5, u32 w6, u32 elig) 
     v = fadd(v, fmul(0.6f, (float)((w4 >> 8) & 0xFFu)));
     v = fadd(v, -fmul(1.8f, (float)((w4 >> 16) & 0xFFu)));
     v = fadd(v, -fmul(0.6f, (float)(w4 >> 24)));
-    if (elig & 0x3u) v = fadd(v, 0.1f); // mind.rs:133-140
-    if (elig & 0xCu) v = fadd(v, -0.1f);
-    return v;
+    return score_eligibility(v, elig);
 }
 LL_HD float score_features(const Feat &f, u32 stm, u32 elig) {
     return score_positional(score_material(f, stm), f.w[3], f.w[4], f.w[5], f.w[6], elig);
@@ -1128,6 +1131,79 @@ LL_HD float quiet_child_score_rt(const int T, float material, u32 w3, u32 w4, u3
         w4 += (((u32)(rt == near_t) - (u32)(rf == near_t)) << (16 * T)) + (((u32)(rt == far_t) - (u32)(rf == far_t)) << (16 * T + 8));
     }
     return score_positional(material, w3, w4, w5, w6, elig);
+}
+// The quiet children of ONE parent differ from it in few ways: what a quiet commit can do to w3 / w4 is one of
+//   0 nothing (a scholar, a princess, the figurehead; a cop along its rank or between other ranks; a servant or pony that
+//     neither enters nor leaves the centre, nor reaches the opposition's third or second rank)
+//   1 / 2 a servant or pony enters / leaves the centre      3 / 4 a cop enters / leaves the opposition's second rank
+//   5 a servant reaches the opposition's third rank (from the centre's last rank into it or beside it: centre count unchanged)
+//   6 / 7 a servant steps from the third to the second rank, beside the centre / out of it
+// -- so the horizon kernel sums mind.rs:53-131 once per (parent, way), QUIET_WAYS times a parent instead of once a child, and
+// a quiet child adds the eligibility terms (the last of the sum) to the entry of its way: same integers, same float sequence.
+constexpr u32 QUIET_WAYS = 8;
+LL_HD u32 quiet_way_rt(const int T, u32 job, int from, int to) {
+    const u64 center = 0x00003C3C3C3C0000ull;
+    const int dc = job <= PONY ? (int)((center >> to) & 1u) - (int)((center >> from) & 1u) : 0;
+    u32 way = dc > 0 ? 1u : dc < 0 ? 2u : 0u;
+    if (job == COP) {
+        const int cop_rank = T == 0 ? 6 : 1;
+        const int dr = (int)((to >> 3) == cop_rank) - (int)((from >> 3) == cop_rank);
+        way = dr > 0 ? 3u : dr < 0 ? 4u : 0u;
+    }
+    if (job == SERVANT) { // a push: towards the far side, one rank or two
+        const int rt = to >> 3, near_t = T == 0 ? 6 : 1, far_t = T == 0 ? 5 : 2;
+        if (rt == far_t) way = 5u;
+        if (rt == near_t) way = dc < 0 ? 7u : 6u;
+    }
+    return way;
+}
+LL_HD void quiet_way_features(const int T, u32 way, u32 &w3, u32 &w4) { // the parent's w3 / w4 after a quiet commit of this way
+    const u32 dc = way == 1 ? 1u : (way == 2 || way == 7) ? ~0u : 0u, dr = way == 3 ? 1u : way == 4 ? ~0u : 0u;
+    w3 += (dc << (8 * T)) + (dr << (16 + 8 * T));
+    if (way == 5) w4 += 1u << (16 * T + 8);
+    if (way >= 6) w4 += (1u << (16 * T)) - (1u << (16 * T + 8));
+}
+LL_HD u32 quiet_eligibility_rt(const int T, u32 elig, u32 job, int from) { // life.rs:577-605
+    if (job == FIGUREHEAD) elig &= T == 0 ? ~0x3u : ~0xCu;
+    if (job == COP) {
+        const int file = from & 7;
+        if (file == 0) elig &= T == 0 ? ~0x1u : ~0x4u;
+        if (file == 7) elig &= T == 0 ? ~0x2u : ~0x8u;
+    }
+    return elig;
+}
+// mind.rs:70-131 for N ways of one parent at once (the files' terms are the same for all of them), each sum in score_positional's order
+template <int N> LL_HD void score_ways(float material, const u32 (&w3)[N], const u32 (&w4)[N], u32 w5, u32 w6, float (&v)[N]) {
+#pragma unroll
+    for (int u = 0; u < N; u++) {
+        const int oc = (int)(w3[u] & 0xFFu), bc = (int)((w3[u] >> 8) & 0xFFu);
+        v[u] = fadd(material, fmul(0.1f, (float)(oc - bc)));
+        v[u] = fadd(v[u], fmul(0.5f, (float)((w3[u] >> 16) & 0xFFu)));
+        v[u] = fadd(v[u], -fmul(0.5f, (float)(w3[u] >> 24)));
+    }
+    u32 files = (w5 | w6) & 0xEEEEEEEEu;
+    while (files) {
+        const int sh = lsb32(files) & ~3;
+        files &= ~(0xFu << sh);
+        const int o = (int)((w5 >> sh) & 0xFu), b = (int)((w6 >> sh) & 0xFu);
+        if (o > 1) {
+            const float t = -fmul(0.5f, (float)(o - 1));
+#pragma unroll
+            for (int u = 0; u < N; u++) v[u] = fadd(v[u], t);
+        }
+        if (b > 1) {
+            const float t = fmul(0.5f, (float)(b - 1));
+#pragma unroll
+            for (int u = 0; u < N; u++) v[u] = fadd(v[u], t);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < N; u++) {
+        v[u] = fadd(v[u], fmul(1.8f, (float)(w4[u] & 0xFFu)));
+        v[u] = fadd(v[u], fmul(0.6f, (float)((w4[u] >> 8) & 0xFFu)));
+        v[u] = fadd(v[u], -fmul(1.8f, (float)((w4[u] >> 16) & 0xFFu)));
+        v[u] = fadd(v[u], -fmul(0.6f, (float)(w4[u] >> 24)));
+    }
 }
 LL_HD void feat_count(Feat &f, u32 plane, u32 delta) { // head count of `plane` += delta (two's complement for -1)
     const u32 d = delta << (8 * (plane & 3u));

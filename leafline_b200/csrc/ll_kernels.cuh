@@ -826,7 +826,7 @@ __global__ void __launch_bounds__(BLOCK, LL_EXPAND_MIN_BLOCKS) k_expand_coop(con
 #define LL_HP 64
 #endif
 constexpr int HP = LL_HP; // parents per horizon tile
-constexpr u32 OWNER_CAP = 3072; // children of a tile whose parent is looked up, not searched for
+constexpr u32 OWNER_CAP = 2944; // children of a tile whose parent is looked up, not searched for
 // Records a parent may keep in the tile.  A position can have up to REC_MAX = 36 (ll_device.cuh) but rarely has more than
 // sixteen, and the record arrays are most of the block's shared memory, which is what limits the resident warps of a kernel
 // bound by latency: 36 slots = 40 KB = five blocks a SM, 24 slots = 30 KB = seven: 3.24 -> 2.9 ms.  (21 slots = eight blocks
@@ -848,8 +848,10 @@ constexpr int REC_ROWS_A = HZ_REC_CAP * 14 / 24, REC_ROWS_B = HZ_REC_CAP - REC_R
 constexpr int HV = 2 * HP;
 static_assert(HV == BLOCK, "one thread per half parent");
 struct HorizonShared {
-    u64 tile_op[6][HP]; // the OPPOSITION's planes of every parent: all that the loud children's evaluation reads of the board
-    unsigned char owner[OWNER_CAP]; // quiet child k -> owner[k], loud child k -> owner[OWNER_CAP - 1 - k] (virtual parents)
+    // quiet child k -> map[k], loud child k -> map[OWNER_CAP - 1 - k]: its virtual parent (low byte) and the row of the record it
+    // comes from (high byte) -- no search per child.  (Its number within the record packed in as well -- 7 + 4 + 5 bits --
+    // spares the child a load and a subtraction and costs the filling thread an OR a child: 2.59 ms against 2.48, measured.)
+    unsigned short map[OWNER_CAP];
     u32 tile_meta[HP];
     u64 tile_opp[HP]; // the union of the six
     u64 rec_mask[HZ_REC_CAP][HP]; // transposed: neighbouring parents write neighbouring words
@@ -861,28 +863,16 @@ struct HorizonShared {
     int acc[HP];
     u32 feat[7][HP]; // the parents' evaluation features (ll_device.cuh: Feat), transposed like the records
     float material[HP]; // score_material(parent's features, the CHILD's initiative)
+    float quiet[QUIET_WAYS][HP]; // the sum of mind.rs:53-131 for a quiet child of each way (ll_device.cuh: quiet_way_rt)
     u32 claim; // CHAIN: the tile this block pulled
 };
-template <int T> struct TilePlanes { // the planes of one parent (mover T), read where child_features asks for them
-    const HorizonShared &sh;
-    u32 slot;
-    const Soa &in; // the mover's own planes are read by a secret service only: from global memory
-    size_t at;
-    __device__ __forceinline__ u64 operator()(int j) const {
-        if (j / 6 == 1 - T) return sh.tile_op[j % 6][slot];
-        return ldg(in.pl + (size_t)j * in.stride + at);
-    }
-};
-struct TilePlanesRt { // the same, the mover a run-time value
-    const HorizonShared &sh;
-    u32 slot;
+// the planes of one parent as child_features asks for them: only LOUD commits read any (the opposition's six, to find the victim;
+// the mover's cop and figurehead planes for a secret service) -- from global memory, where the tile's parents were read a
+// moment ago (L1 / L2); the shared memory they used to occupy holds the record map
+struct TilePlanesRt {
     const Soa &in;
     size_t at;
-    int team;
-    __device__ __forceinline__ u64 operator()(int j) const {
-        if (j / 6 == 1 - team) return sh.tile_op[j % 6][slot];
-        return ldg(in.pl + (size_t)j * in.stride + at);
-    }
+    __device__ __forceinline__ u64 operator()(int j) const { return ldg(in.pl + (size_t)j * in.stride + at); }
 };
 LL_HD bool rec_splits(u32 info) { return (info & 7u) == REC_PIECE && !((info >> 15) & 1u); } // a piece's targets: quiet where empty, loud where the opposition stands
 struct SharedRecordOut {
@@ -909,18 +899,37 @@ struct SharedRecordOut {
         n_loud += all - quiet;
     }
 };
-// the virtual parent of child k of one kind: looked up, or -- a tile with more children than the map holds -- the last one
-// whose prefix is <= k
-__device__ __forceinline__ u32 horizon_owner(const HorizonShared &sh, const u32 *ex, bool mapped, u32 at, u32 k) {
-    if (mapped) return sh.owner[at];
-    u32 v = 0, hi = HV;
+// the virtual parent of child k of one kind and the row of the record it comes from: looked up, or -- a tile with more
+// children than the map holds -- searched for: the last virtual parent whose prefix is <= k, then the last record of that half
+// whose first commit of the kind is <= j (it has one: empty records share their successor's number)
+template <bool LOUD> __device__ __forceinline__ void horizon_whose(const HorizonShared &sh, bool mapped, u32 k, u32 &v, u32 &row, u32 &t) {
+    if (mapped) { // block-uniform
+        const u32 e = sh.map[LOUD ? OWNER_CAP - 1u - k : k];
+        v = e & 0xFFu;
+        row = e >> 8;
+        t = k - (LOUD ? sh.exl[v] + sh.rec_loud[row][v & (HP - 1)] : sh.exq[v] + (sh.rec_info[row][v & (HP - 1)] >> 16));
+        return;
+    }
+    const u32 *ex = LOUD ? sh.exl : sh.exq;
+    u32 hi = HV;
+    v = 0;
 #pragma unroll
     for (int step = 0; step < 7; step++) { // HV = 2^7
         const u32 mid = (v + hi) >> 1;
         if (ex[mid] <= k) v = mid;
         else hi = mid;
     }
-    return v;
+    const u32 slot = v & (HP - 1), j = k - ex[v], row0 = v >= (u32)HP ? (u32)REC_ROWS_A : 0u;
+    u32 r = 0, rhi = sh.n_rec[v];
+#pragma unroll
+    for (int step = 0; step < 5; step++) { // a half has < 2^5 rows; branch-free, a converged search re-reads r
+        const u32 mid = (r + rhi) >> 1;
+        const bool le = (LOUD ? (u32)sh.rec_loud[row0 + mid][slot] : sh.rec_info[row0 + mid][slot] >> 16) <= j;
+        r = le ? mid : r;
+        rhi = le ? rhi : mid;
+    }
+    row = row0 + r;
+    t = j - (LOUD ? (u32)sh.rec_loud[row][slot] : sh.rec_info[row][slot] >> 16);
 }
 // CHAIN: the level's size is resident on the device (a.n_in) and persistent blocks pull tiles from a.tile_counter -- the
 // launch needs no host round trip (the small-batch path of ll_horizon_batch)
@@ -952,8 +961,6 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
         SharedRecordOut out{sh, slot_mine, opp, half ? (u32)REC_ROWS_A : 0u, half ? (u32)HZ_REC_CAP : (u32)REC_ROWS_A};
         if (half == 0) {
             reckless_records_part<STUNS, 1>(p, out);
-#pragma unroll
-            for (int j = 0; j < 6; j++) sh.tile_op[j][slot_mine] = blue ? p.pl[j] : p.pl[6 + j];
             sh.tile_opp[slot_mine] = opp;
             sh.tile_meta[slot_mine] = p.meta;
             sh.acc[slot_mine] = float_key(-INFINITY);
@@ -989,60 +996,62 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
         sh.exl[HV] = total_l;
     }
     const bool mapped = total_q + total_l <= OWNER_CAP; // block-uniform
-    if (mapped) {
-        for (u32 c = 0; c < cnt_q; c++) sh.owner[ex_q + c] = (unsigned char)tid;
-        for (u32 c = 0; c < cnt_l; c++) sh.owner[OWNER_CAP - 1u - (ex_l + c)] = (unsigned char)tid;
+    if (mapped) { // every child's (virtual parent, record row), written by the half that owns it: record by record
+        const u32 row0 = half ? (u32)REC_ROWS_A : 0u;
+        for (u32 r = 0; r < n_rec; r++) {
+            const u32 row = row0 + r;
+            const u32 q0 = sh.rec_info[row][slot_mine] >> 16, q1 = r + 1 < n_rec ? sh.rec_info[row + 1][slot_mine] >> 16 : cnt_q;
+            const u32 l0 = sh.rec_loud[row][slot_mine], l1 = r + 1 < n_rec ? sh.rec_loud[row + 1][slot_mine] : cnt_l;
+            const unsigned short entry = (unsigned short)(tid | row << 8);
+            for (u32 c = q0; c < q1; c++) sh.map[ex_q + c] = entry;
+            for (u32 c = l0; c < l1; c++) sh.map[OWNER_CAP - 1u - (ex_l + c)] = entry;
+        }
+    }
+    { // what a quiet child of each way scores short of the eligibility terms: four ways a thread, both halves of a parent at it
+        const u32 team = meta_stm(sh.tile_meta[slot_mine]);
+        u32 w3[4], w4[4];
+        float sums[4];
+#pragma unroll
+        for (u32 u = 0; u < 4; u++) {
+            w3[u] = sh.feat[3][slot_mine], w4[u] = sh.feat[4][slot_mine];
+            quiet_way_features((int)team, 4u * half + u, w3[u], w4[u]);
+        }
+        score_ways<4>(sh.material[slot_mine], w3, w4, sh.feat[5][slot_mine], sh.feat[6][slot_mine], sums);
+#pragma unroll
+        for (u32 u = 0; u < 4; u++) sh.quiet[4u * half + u][slot_mine] = sums[u];
     }
     __syncthreads();
     // (LL_HZ_ILP children per thread and pass: measured at 2, 3 and 4 -- 3.9-4.2 ms against 3.24 ms at one, the unrolled loop
     // bodies cost more in instruction fetch than the second chain hides in latency: DESIGN.md 7b)
     auto quiet_child = [&](u32 k, u32 &slot) -> int {
-        const u32 v = horizon_owner(sh, sh.exq, mapped, k, k);
+        u32 v, row, t;
+        horizon_whose<false>(sh, mapped, k, v, row, t);
         slot = v & (HP - 1);
-        const u32 row0 = v >= (u32)HP ? (u32)REC_ROWS_A : 0u;
-        const u32 j = k - sh.exq[v];
-        u32 r = 0, rhi = sh.n_rec[v];
-#pragma unroll
-        for (int step = 0; step < 5; step++) { // a half has < 2^5 rows: the last record whose first quiet commit is <= j (it has one:
-            const u32 mid = (r + rhi) >> 1;    // empty records share their successor's number); branch-free, a converged search re-reads r
-            const bool le = (sh.rec_info[row0 + mid][slot] >> 16) <= j;
-            r = le ? mid : r;
-            rhi = le ? rhi : mid;
-        }
-        const u32 info = sh.rec_info[row0 + r][slot];
-        const u64 mask = sh.rec_mask[row0 + r][slot];
+        const u32 info = sh.rec_info[row][slot];
+        const u64 mask = sh.rec_mask[row][slot];
         const u32 meta = sh.tile_meta[slot];
         const u32 team = meta_stm(meta);
-        const int to = select_bit(rec_splits(info) ? mask & ~sh.tile_opp[slot] : mask, j - (info >> 16));
+        const int to = select_bit(rec_splits(info) ? mask & ~sh.tile_opp[slot] : mask, t);
         const u32 m = rec_move_to(info & 0xFFFFu, to, team);
-        const float s = quiet_child_score_rt((int)team, sh.material[slot], sh.feat[3][slot], sh.feat[4][slot], sh.feat[5][slot], sh.feat[6][slot],
-                                             meta_elig(meta), mv_job(m), mv_from(m), to);
+        const float s = score_eligibility(sh.quiet[quiet_way_rt((int)team, mv_job(m), mv_from(m), to)][slot],
+                                          quiet_eligibility_rt((int)team, meta_elig(meta), mv_job(m), mv_from(m)));
         return float_key(team ? -s : s); // -(orientation(child) * score(child)), the child's initiative being the other team's (mind.rs:283, 331-336)
     };
     auto loud_child = [&](u32 k, u32 &slot) -> int {
-        const u32 v = horizon_owner(sh, sh.exl, mapped, OWNER_CAP - 1u - k, k);
+        u32 v, row, t;
+        horizon_whose<true>(sh, mapped, k, v, row, t);
         slot = v & (HP - 1);
-        const u32 row0 = v >= (u32)HP ? (u32)REC_ROWS_A : 0u;
-        const u32 j = k - sh.exl[v];
-        u32 r = 0, rhi = sh.n_rec[v];
-#pragma unroll
-        for (int step = 0; step < 5; step++) {
-            const u32 mid = (r + rhi) >> 1;
-            const bool le = sh.rec_loud[row0 + mid][slot] <= j;
-            r = le ? mid : r;
-            rhi = le ? rhi : mid;
-        }
-        const u32 info = sh.rec_info[row0 + r][slot];
-        const u64 mask = sh.rec_mask[row0 + r][slot];
+        const u32 info = sh.rec_info[row][slot];
+        const u64 mask = sh.rec_mask[row][slot];
         const u32 meta = sh.tile_meta[slot];
         const u32 team = meta_stm(meta);
-        const int to = select_bit(rec_splits(info) ? mask & sh.tile_opp[slot] : mask, j - sh.rec_loud[row0 + r][slot]);
+        const int to = select_bit(rec_splits(info) ? mask & sh.tile_opp[slot] : mask, t);
         const u32 m = rec_move_to(info & 0xFFFFu, to, team);
         Feat f;
 #pragma unroll
         for (int w = 0; w < 7; w++) f.w[w] = sh.feat[w][slot];
         u32 elig = meta_elig(meta);
-        child_features_rt((int)team, f, elig, TilePlanesRt{sh, slot, a.in, tile * HP + slot, (int)team}, m);
+        child_features_rt((int)team, f, elig, TilePlanesRt{a.in, tile * HP + slot}, m);
         const float s = score_features(f, team ^ 1u, elig);
         return float_key(team ? -s : s);
     };

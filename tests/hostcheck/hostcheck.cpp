@@ -226,6 +226,18 @@ extern "C" int hc_feature_check(const ll_world_t *w, int *checked) {
                                     ? quiet_child_score<0>(material, f0.w[3], f0.w[4], f0.w[5], f0.w[6], meta_elig(p.meta), mv_job(m), mv_from(m), mv_to(m))
                                     : quiet_child_score<1>(material, f0.w[3], f0.w[4], f0.w[5], f0.w[6], meta_elig(p.meta), mv_job(m), mv_from(m), mv_to(m));
             if (bits_of(quiet) != bits_of(score(c))) same = false;
+            // ... and the same through the table of ways a quiet commit can change the features (k_horizon)
+            const int T = (int)meta_stm(p.meta);
+            const u32 way = quiet_way_rt(T, mv_job(m), mv_from(m), mv_to(m));
+            u32 w3[4], w4[4];
+            float sums[4];
+            for (u32 u = 0; u < 4; u++) {
+                w3[u] = f0.w[3], w4[u] = f0.w[4];
+                quiet_way_features(T, (way & 4u) + u, w3[u], w4[u]);
+            }
+            score_ways<4>(material, w3, w4, f0.w[5], f0.w[6], sums);
+            const float by_way = score_eligibility(sums[way & 3u], quiet_eligibility_rt(T, meta_elig(p.meta), mv_job(m), mv_from(m)));
+            if (way >= QUIET_WAYS || bits_of(by_way) != bits_of(score(c))) same = false;
         }
         if (!same) bad++;
     }

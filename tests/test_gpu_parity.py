@@ -492,6 +492,32 @@ def test_horizon_parents_with_more_records_than_a_tile_keeps(eng, playouts):
         assert s_got.tobytes() == O.kickoff(w, 2, False, threads=4)[1].tobytes()
 
 
+def test_horizon_tiles_with_more_children_than_the_map_holds(eng, playouts):
+    """k_horizon looks every child's (parent, record, number within the record) up in a per-tile map of 3072 entries; a tile
+    of 64 parents with more children than that finds them by search instead.  Whole tiles of rich positions (each within the
+    24 records), ordinary ones around them: values must not notice."""
+    import leafline_b200 as ll
+
+    rich = [
+        "1n1n1n2/P1P1P1P1/8/8/NNNN4/BBBB4/RRR5/4K2k w - -",   # 22 records
+        "r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq -",
+        "3k4/8/1q1q1q2/8/1q1q1q2/8/8/6K1 b - -",
+        "R6R/3Q4/1Q4Q1/4Q3/2Q4Q/Q4Q2/pp1Q4/kBNN1KB1 w - -",   # 218 commits
+    ]
+    worlds = np.array([ll.reconstruct(f) for f in rich], dtype=ll.WORLD_DTYPE)
+    counts = [len(O.reckless_lookahead(w)) for w in worlds]
+    assert min(counts) >= 48 and max(counts) >= 200, counts  # 64 of any of them overflow the map
+    batch = np.concatenate([playouts[:70], np.repeat(worlds, 96), playouts[70:100], np.tile(worlds, 40)])
+    for plies, quiet in ((1, None), (2, None), (1, 2)):
+        got = eng.horizon(batch, plies, quiet=quiet)
+        want = {}
+        for i, w in enumerate(batch):
+            key = w.tobytes()
+            if key not in want:
+                want[key] = np.float32(O.negamax(w, plies, quiet=quiet) if quiet else O.negamax(w, plies))
+            assert got[i].tobytes() == want[key].tobytes(), (i, plies, quiet)
+
+
 def test_horizon_depth_3_on_a_few(eng, playouts):
     worlds = playouts[:4]
     got = eng.horizon(worlds, 3)
