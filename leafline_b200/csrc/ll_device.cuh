@@ -1172,6 +1172,44 @@ LL_HD u32 quiet_eligibility_rt(const int T, u32 elig, u32 job, int from) { // li
     }
     return elig;
 }
+// the commits of a record that stun nobody, ascend nothing and are no secret service: a piece's targets on empty squares, the
+// servants' plain steps
+LL_HD u64 rec_quiet(u32 info, u64 mask, u64 opp) {
+    const u32 kind = info & 7u, asc = (info >> 12) & 7u;
+    if (kind == REC_PIECE) return (info >> 15) & 1u ? 0ull : mask & ~opp;
+    return (kind == REC_PUSH || kind == REC_DOUBLE) && asc == ASC_NONE ? mask : 0ull;
+}
+// The ways (bit w = way w of quiet_way_rt) that the quiet commits of ONE record take, from the set of their destinations
+// `quiet` (!= 0) -- a record is one piece's targets or one kind of step of all the servants, so the way depends on the
+// destination alone and the question "does any commit of the record go way w" is a mask test.  All quiet commits of a
+// record of one way score the same (same features, same eligibility: quiet_eligibility_rt reads the job and the origin's
+// file only, and a servant's step changes no eligibility), so the best of a record's quiet children is the best of its ways.
+LL_HD u32 quiet_ways_of_record(const int T, u32 info, u64 quiet) {
+    const u64 center = 0x00003C3C3C3C0000ull;
+    const u32 kind = info & 7u, job = (info >> 3) & 7u;
+    if (kind == REC_PIECE) {
+        const int from = (int)((info >> 6) & 63u);
+        if (job == PONY) {
+            const bool inside = (center >> from) & 1u;
+            return ((quiet & center) ? (inside ? 1u : 1u << 1) : 0u) | ((quiet & ~center) ? (inside ? 1u << 2 : 1u) : 0u);
+        }
+        if (job == COP) {
+            const int cop_rank = T == 0 ? 6 : 1;
+            const u64 there = RANK_1 << (8 * cop_rank);
+            const bool on = (from >> 3) == cop_rank;
+            return ((quiet & there) ? (on ? 1u : 1u << 3) : 0u) | ((quiet & ~there) ? (on ? 1u << 4 : 1u) : 0u);
+        }
+        return 1u; // scholar, princess, figurehead
+    }
+    // a step of one rank (REC_PUSH) or two (REC_DOUBLE) towards the far side: `origin_inside` = the destinations whose origin is in the centre
+    const int d = kind == REC_DOUBLE ? 16 : 8;
+    const u64 origin_inside = T == 0 ? center << d : center >> d;
+    const u64 enters = quiet & center & ~origin_inside, leaves = quiet & ~center & origin_inside;
+    const u64 far = RANK_1 << (8 * (T == 0 ? 5 : 2)), near = RANK_1 << (8 * (T == 0 ? 6 : 1));
+    const u64 rest = quiet & ~(far | near);
+    return ((quiet & far) ? 1u << 5 : 0u) | ((quiet & near & leaves) ? 1u << 7 : 0u) | ((quiet & near & ~leaves) ? 1u << 6 : 0u) |
+           ((rest & enters) ? 1u << 1 : 0u) | ((rest & leaves) ? 1u << 2 : 0u) | ((rest & ~(enters | leaves)) ? 1u : 0u);
+}
 // mind.rs:70-131 for N ways of one parent at once (the files' terms are the same for all of them), each sum in score_positional's order
 template <int N> LL_HD void score_ways(float material, const u32 (&w3)[N], const u32 (&w4)[N], u32 w5, u32 w6, float (&v)[N]) {
 #pragma unroll

@@ -826,7 +826,7 @@ __global__ void __launch_bounds__(BLOCK, LL_EXPAND_MIN_BLOCKS) k_expand_coop(con
 #define LL_HP 64
 #endif
 constexpr int HP = LL_HP; // parents per horizon tile
-constexpr u32 OWNER_CAP = 2944; // children of a tile whose parent is looked up, not searched for
+constexpr u32 OWNER_CAP = 1024; // LOUD children of a tile whose parent is looked up, not searched for (a tile of 64 has ~350)
 // Records a parent may keep in the tile.  A position can have up to REC_MAX = 36 (ll_device.cuh) but rarely has more than
 // sixteen, and the record arrays are most of the block's shared memory, which is what limits the resident warps of a kernel
 // bound by latency: 36 slots = 40 KB = five blocks a SM, 24 slots = 30 KB = seven: 3.24 -> 2.9 ms.  (21 slots = eight blocks
@@ -848,16 +848,17 @@ constexpr int REC_ROWS_A = HZ_REC_CAP * 14 / 24, REC_ROWS_B = HZ_REC_CAP - REC_R
 constexpr int HV = 2 * HP;
 static_assert(HV == BLOCK, "one thread per half parent");
 struct HorizonShared {
-    // quiet child k -> map[k], loud child k -> map[OWNER_CAP - 1 - k]: its virtual parent (low byte) and the row of the record it
-    // comes from (high byte) -- no search per child.  (Its number within the record packed in as well -- 7 + 4 + 5 bits --
-    // spares the child a load and a subtraction and costs the filling thread an OR a child: 2.59 ms against 2.48, measured.)
+    // loud child k -> map[k]: its virtual parent (low byte) and the row of the record it comes from (high byte) -- no search
+    // per child.  (Its number within the record packed in as well -- 7 + 4 + 5 bits -- spares the child a load and a
+    // subtraction and costs the filling thread an OR a child: 2.59 ms against 2.48, measured when the map held every child.)
     unsigned short map[OWNER_CAP];
     u32 tile_meta[HP];
     u64 tile_opp[HP]; // the union of the six
     u64 rec_mask[HZ_REC_CAP][HP]; // transposed: neighbouring parents write neighbouring words
-    u32 rec_info[HZ_REC_CAP][HP]; // kind, job, from, ascension, passing-by (16 bits) | number of the record's first QUIET commit << 16
+    u32 rec_info[HZ_REC_CAP][HP]; // kind, job, from, ascension, passing-by (16 bits)
     unsigned char rec_loud[HZ_REC_CAP][HP]; // number of the record's first LOUD commit (<= 8 stuns a piece, <= 12 loud commits a servant: < 256)
-    u32 exq[HV + 1], exl[HV + 1]; // exclusive prefixes of the virtual parents' quiet / loud commit counts
+    u32 exl[HV + 1]; // exclusive prefixes of the virtual parents' loud commit counts
+    unsigned short commits[HV]; // quiet + loud commits of each virtual parent
     unsigned char n_rec[HV];
     unsigned char outgrown[HP]; // a half ran out of rows: the whole parent goes to k_horizon_overflow
     int acc[HP];
@@ -874,7 +875,6 @@ struct TilePlanesRt {
     size_t at;
     __device__ __forceinline__ u64 operator()(int j) const { return ldg(in.pl + (size_t)j * in.stride + at); }
 };
-LL_HD bool rec_splits(u32 info) { return (info & 7u) == REC_PIECE && !((info >> 15) & 1u); } // a piece's targets: quiet where empty, loud where the opposition stands
 struct SharedRecordOut {
     HorizonShared &sh;
     int slot;
@@ -887,11 +887,10 @@ struct SharedRecordOut {
             outgrown = true;
             return;
         }
-        const u32 kind = info & 7u, asc = (info >> 12) & 7u;
         const u32 all = (u32)__popcll(mask);
-        const u32 quiet = rec_splits(info) ? (u32)__popcll(mask & ~opp) : ((kind == REC_PUSH || kind == REC_DOUBLE) && asc == ASC_NONE) ? all : 0u;
+        const u32 quiet = (u32)__popcll(rec_quiet(info, mask, opp));
         sh.rec_mask[row][slot] = mask;
-        sh.rec_info[row][slot] = (info & 0xFFFFu) | (n_quiet << 16);
+        sh.rec_info[row][slot] = info & 0xFFFFu;
         sh.rec_loud[row][slot] = (unsigned char)n_loud;
         row++;
         n_rec++;
@@ -899,37 +898,36 @@ struct SharedRecordOut {
         n_loud += all - quiet;
     }
 };
-// the virtual parent of child k of one kind and the row of the record it comes from: looked up, or -- a tile with more
-// children than the map holds -- searched for: the last virtual parent whose prefix is <= k, then the last record of that half
-// whose first commit of the kind is <= j (it has one: empty records share their successor's number)
-template <bool LOUD> __device__ __forceinline__ void horizon_whose(const HorizonShared &sh, bool mapped, u32 k, u32 &v, u32 &row, u32 &t) {
+// the virtual parent of LOUD child k, the row of the record it comes from and its number among the record's loud commits:
+// looked up, or -- a tile with more loud children than the map holds -- searched for: the last virtual parent whose prefix is
+// <= k, then the last record of that half whose first loud commit is <= j (it has one: records without share their successor's number)
+__device__ __forceinline__ void horizon_whose(const HorizonShared &sh, bool mapped, u32 k, u32 &v, u32 &row, u32 &t) {
     if (mapped) { // block-uniform
-        const u32 e = sh.map[LOUD ? OWNER_CAP - 1u - k : k];
+        const u32 e = sh.map[k];
         v = e & 0xFFu;
         row = e >> 8;
-        t = k - (LOUD ? sh.exl[v] + sh.rec_loud[row][v & (HP - 1)] : sh.exq[v] + (sh.rec_info[row][v & (HP - 1)] >> 16));
+        t = k - (sh.exl[v] + sh.rec_loud[row][v & (HP - 1)]);
         return;
     }
-    const u32 *ex = LOUD ? sh.exl : sh.exq;
     u32 hi = HV;
     v = 0;
 #pragma unroll
     for (int step = 0; step < 7; step++) { // HV = 2^7
         const u32 mid = (v + hi) >> 1;
-        if (ex[mid] <= k) v = mid;
+        if (sh.exl[mid] <= k) v = mid;
         else hi = mid;
     }
-    const u32 slot = v & (HP - 1), j = k - ex[v], row0 = v >= (u32)HP ? (u32)REC_ROWS_A : 0u;
+    const u32 slot = v & (HP - 1), j = k - sh.exl[v], row0 = v >= (u32)HP ? (u32)REC_ROWS_A : 0u;
     u32 r = 0, rhi = sh.n_rec[v];
 #pragma unroll
     for (int step = 0; step < 5; step++) { // a half has < 2^5 rows; branch-free, a converged search re-reads r
         const u32 mid = (r + rhi) >> 1;
-        const bool le = (LOUD ? (u32)sh.rec_loud[row0 + mid][slot] : sh.rec_info[row0 + mid][slot] >> 16) <= j;
+        const bool le = (u32)sh.rec_loud[row0 + mid][slot] <= j;
         r = le ? mid : r;
         rhi = le ? rhi : mid;
     }
     row = row0 + r;
-    t = j - (LOUD ? (u32)sh.rec_loud[row][slot] : sh.rec_info[row][slot] >> 16);
+    t = j - (u32)sh.rec_loud[row][slot];
 }
 // CHAIN: the level's size is resident on the device (a.n_in) and persistent blocks pull tiles from a.tile_counter -- the
 // launch needs no host round trip (the small-batch path of ll_horizon_batch)
@@ -986,25 +984,19 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
         if (half == 0) a.overflow_list[atomicAdd(a.overflow_count, 1u)] = (u32)i;
     }
     sh.n_rec[tid] = (unsigned char)n_rec;
-    u32 total;
-    const u32 ex = block_exclusive_scan(cnt_q | (cnt_l << 16), &total); // both prefixes in one scan (a tile's quiet commits stay far below 2^16)
-    const u32 ex_q = ex & 0xFFFFu, ex_l = ex >> 16, total_q = total & 0xFFFFu, total_l = total >> 16;
-    sh.exq[tid] = ex_q;
+    sh.commits[tid] = (unsigned short)(cnt_q + cnt_l);
+    u32 total_l;
+    const u32 ex_l = block_exclusive_scan(cnt_l, &total_l);
     sh.exl[tid] = ex_l;
-    if (tid == 0) {
-        sh.exq[HV] = total_q;
-        sh.exl[HV] = total_l;
-    }
-    const bool mapped = total_q + total_l <= OWNER_CAP; // block-uniform
-    if (mapped) { // every child's (virtual parent, record row), written by the half that owns it: record by record
+    if (tid == 0) sh.exl[HV] = total_l;
+    const bool mapped = total_l <= OWNER_CAP; // block-uniform
+    if (mapped) { // every loud child's (virtual parent, record row), written by the half that owns it: record by record
         const u32 row0 = half ? (u32)REC_ROWS_A : 0u;
         for (u32 r = 0; r < n_rec; r++) {
             const u32 row = row0 + r;
-            const u32 q0 = sh.rec_info[row][slot_mine] >> 16, q1 = r + 1 < n_rec ? sh.rec_info[row + 1][slot_mine] >> 16 : cnt_q;
             const u32 l0 = sh.rec_loud[row][slot_mine], l1 = r + 1 < n_rec ? sh.rec_loud[row + 1][slot_mine] : cnt_l;
             const unsigned short entry = (unsigned short)(tid | row << 8);
-            for (u32 c = q0; c < q1; c++) sh.map[ex_q + c] = entry;
-            for (u32 c = l0; c < l1; c++) sh.map[OWNER_CAP - 1u - (ex_l + c)] = entry;
+            for (u32 c = l0; c < l1; c++) sh.map[ex_l + c] = entry;
         }
     }
     { // what a quiet child of each way scores short of the eligibility terms: four ways a thread, both halves of a parent at it
@@ -1021,31 +1013,34 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
         for (u32 u = 0; u < 4; u++) sh.quiet[4u * half + u][slot_mine] = sums[u];
     }
     __syncthreads();
-    // (LL_HZ_ILP children per thread and pass: measured at 2, 3 and 4 -- 3.9-4.2 ms against 3.24 ms at one, the unrolled loop
-    // bodies cost more in instruction fetch than the second chain hides in latency: DESIGN.md 7b)
-    auto quiet_child = [&](u32 k, u32 &slot) -> int {
-        u32 v, row, t;
-        horizon_whose<false>(sh, mapped, k, v, row, t);
-        slot = v & (HP - 1);
-        const u32 info = sh.rec_info[row][slot];
-        const u64 mask = sh.rec_mask[row][slot];
-        const u32 meta = sh.tile_meta[slot];
-        const u32 team = meta_stm(meta);
-        const int to = select_bit(rec_splits(info) ? mask & ~sh.tile_opp[slot] : mask, t);
-        const u32 m = rec_move_to(info & 0xFFFFu, to, team);
-        const float s = score_eligibility(sh.quiet[quiet_way_rt((int)team, mv_job(m), mv_from(m), to)][slot],
-                                          quiet_eligibility_rt((int)team, meta_elig(meta), mv_job(m), mv_from(m)));
-        return float_key(team ? -s : s); // -(orientation(child) * score(child)), the child's initiative being the other team's (mind.rs:283, 331-336)
-    };
+    // ---- quiet commits: record by record, by the thread that made the records.  All quiet commits of a record that change
+    // the features the same way score the same, and which ways a record has is a matter of masks (quiet_ways_of_record):
+    // the best quiet child of a record is the best of its (one to three) ways -- no child is decoded.
+    if (cnt_q) {
+        const u32 meta = sh.tile_meta[slot_mine], team = meta_stm(meta), row0 = half ? (u32)REC_ROWS_A : 0u;
+        const u64 opp = sh.tile_opp[slot_mine];
+        int best = float_key(-INFINITY);
+        for (u32 r = 0; r < n_rec; r++) {
+            const u32 info = sh.rec_info[row0 + r][slot_mine];
+            const u64 quiet = rec_quiet(info, sh.rec_mask[row0 + r][slot_mine], opp);
+            if (!quiet) continue;
+            const u32 elig = quiet_eligibility_rt((int)team, meta_elig(meta), (info >> 3) & 7u, (int)((info >> 6) & 63u));
+            for (u32 ways = quiet_ways_of_record((int)team, info, quiet); ways; ways &= ways - 1) {
+                const float s = score_eligibility(sh.quiet[__ffs((int)ways) - 1][slot_mine], elig);
+                best = max(best, float_key(team ? -s : s)); // -(orientation(child) * score(child)), the child's initiative being the other team's (mind.rs:283, 331-336)
+            }
+        }
+        atomicMax(&sh.acc[slot_mine], best);
+    }
     auto loud_child = [&](u32 k, u32 &slot) -> int {
         u32 v, row, t;
-        horizon_whose<true>(sh, mapped, k, v, row, t);
+        horizon_whose(sh, mapped, k, v, row, t);
         slot = v & (HP - 1);
         const u32 info = sh.rec_info[row][slot];
         const u64 mask = sh.rec_mask[row][slot];
         const u32 meta = sh.tile_meta[slot];
         const u32 team = meta_stm(meta);
-        const int to = select_bit(rec_splits(info) ? mask & sh.tile_opp[slot] : mask, t);
+        const int to = select_bit(mask & ~rec_quiet(info, mask, sh.tile_opp[slot]), t);
         const u32 m = rec_move_to(info & 0xFFFFu, to, team);
         Feat f;
 #pragma unroll
@@ -1067,22 +1062,6 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
 #ifndef LL_HZ_ILP
 #define LL_HZ_ILP 1
 #endif
-    // ---- quiet commits
-    for (u32 k0 = 0; k0 < total_q; k0 += LL_HZ_ILP * BLOCK) {
-        u32 slot[LL_HZ_ILP];
-        int v[LL_HZ_ILP];
-        bool live[LL_HZ_ILP];
-#pragma unroll
-        for (int u = 0; u < LL_HZ_ILP; u++) {
-            const u32 k = k0 + u * BLOCK + tid;
-            live[u] = k < total_q;
-            slot[u] = 0;
-            v[u] = quiet_child(live[u] ? k : 0u, slot[u]); // (no branch around the chain: a dead lane evaluates child 0 and is masked out)
-            if (!live[u]) v[u] = float_key(-INFINITY);
-        }
-#pragma unroll
-        for (int u = 0; u < LL_HZ_ILP; u++) fold(live[u], slot[u], v[u]);
-    }
     // ---- loud commits
     for (u32 k0 = 0; k0 < total_l; k0 += LL_HZ_ILP * BLOCK) {
         u32 slot[LL_HZ_ILP];
@@ -1103,7 +1082,7 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
     u32 scored = 0;
     if (mine && half == 0 && !outgrown) {
         const u32 other = (u32)HP + (u32)slot_mine;
-        const u32 cnt = cnt_q + cnt_l + (sh.exq[other + 1] - sh.exq[other]) + (sh.exl[other + 1] - sh.exl[other]);
+        const u32 cnt = cnt_q + cnt_l + sh.commits[other];
         float v = cnt ? key_float(sh.acc[slot_mine]) : -INFINITY;
         if (cnt == 0 || (STUNS && a.stand_pat)) { // nothing to play: the node is itself a leaf (mind.rs:281-283, 295-299)
             Feat f;

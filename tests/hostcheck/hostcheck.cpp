@@ -136,6 +136,39 @@ extern "C" int hc_record_moves(const ll_world_t *w, int stuns, uint32_t *moves, 
     }
     return (int)rl.n_moves;
 }
+// k_horizon values a record's quiet commits by the set of ways they change the features (quiet_ways_of_record), not one by
+// one: that set must be exactly the ways quiet_way_rt gives commit by commit (which hc_feature_check holds against score()).
+// Returns the number of records that differ; *checked = quiet commits seen.
+extern "C" int hc_quiet_ways_check(const ll_world_t *w, int *checked) {
+    const Pos p = to_pos(w);
+    RecordList rl;
+    reckless_records<false>(p, rl);
+    if (rl.n_rec > REC_MAX) return -1;
+    const int T = (int)meta_stm(p.meta);
+    u64 opp = 0;
+    for (int j = 0; j < 6; j++) opp |= p.pl[6 * (1 - T) + j];
+    int bad = 0;
+    *checked = 0;
+    for (u32 r = 0; r < rl.n_rec; r++) {
+        const u64 quiet = rec_quiet(rl.info[r], rl.mask[r], opp);
+        u32 want = 0;
+        for (u64 q = quiet; q; q &= q - 1) {
+            const int to = lsb64(q);
+            const u32 m = rec_move_to(rl.info[r] & 0xFFFFu, to, (u32)T);
+            if (mv_asc(m) != ASC_NONE || (m & (MV_SERVICE | MV_PASSING_BY)) || ((opp >> to) & 1u)) bad++; // not quiet after all
+            want |= 1u << quiet_way_rt(T, mv_job(m), mv_from(m), to);
+            ++*checked;
+        }
+        if (quiet && quiet_ways_of_record(T, rl.info[r], quiet) != want) bad++;
+        // and every commit of the record that is NOT in `quiet` is loud: stuns, ascends, serves or passes by
+        for (u64 q = rl.mask[r] & ~quiet; q; q &= q - 1) {
+            const int to = lsb64(q);
+            const u32 m = rec_move_to(rl.info[r] & 0xFFFFu, to, (u32)T);
+            if (mv_asc(m) == ASC_NONE && !(m & (MV_SERVICE | MV_PASSING_BY)) && !((opp >> to) & 1u)) bad++;
+        }
+    }
+    return bad;
+}
 extern "C" int hc_generator_moves(const ll_world_t *w, int stuns, uint32_t *moves, int cap) {
     const Pos p = to_pos(w);
     static thread_local ListSink sink;

@@ -39,9 +39,16 @@ def hc():
     lib.hc_legal_generator_moves.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.hc_feature_check.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     lib.hc_canonical_key.argtypes = [C.c_uint32]
+    lib.hc_quiet_ways_check.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     lib.hc_canonical_key.restype = C.c_uint32
     lib.hc_init()
     return lib
+
+
+def quiet_commit(w, d):
+    """nobody hospitalized, nothing ascended, no secret service (a passing-by hospitalizes): what k_horizon's quiet path takes"""
+    service = int(d["job"]) == 5 and abs((int(d["whence"]) & 15) - (int(d["whither"]) & 15)) == 2
+    return int(d["hospitalization"]) == O.NONE and int(d["ascension"]) == O.NONE and not service
 
 
 def check(hc, worlds):
@@ -61,6 +68,10 @@ def check(hc, worlds):
         checked = C.c_int(0)
         assert hc.hc_feature_check(ptr, C.byref(checked)) == 0, O.preserve(w)
         assert checked.value == len(want)
+        # ... and by the ways a record's quiet commits change the features, set-wise
+        quiet = C.c_int(0)
+        assert hc.hc_quiet_ways_check(ptr, C.byref(quiet)) == 0, O.preserve(w)
+        assert quiet.value == sum(1 for d in want if quiet_commit(w, d)), O.preserve(w)
         # the record form of the reckless commits (horizon kernel) holds exactly the generator's commits, in another order
         a, b, nrec = np.zeros(1024, dtype=np.uint32), np.zeros(1024, dtype=np.uint32), C.c_int(0)
         for stuns in (0, 1):
