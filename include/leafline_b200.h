@@ -271,6 +271,10 @@ int ll_debug_selfcheck_soa(ll_ctx *ctx, const ll_soa_t *soa, uint64_t *result4);
 /* testing aid: the two generated movement tables as they are resident on the device (64 entries each), to be compared
  * with the output of the reference's generator (furniture/tablemaker.py:41-62; tests/golden/reference_tables.json). */
 int ll_debug_tables(ll_ctx *ctx, uint64_t *pony64, uint64_t *figurehead64);
+/* testing aid: how many parents of the LAST level-by-level horizon call (ll_horizon_batch with the chain forced off, or
+ * ll_horizon_soa) had more records with stunning / ascending commits than a tile of the horizon kernel keeps, and were
+ * valued by the overflow kernel instead -- so that tests can tell that path ran. */
+int ll_debug_horizon_overflowed(ll_ctx *ctx, uint32_t *parents);
 /* measurement utility for the integer roofline: sustained thread-level integer instructions per second
  * of a dependency-free stream; kind 0 = LOP3 only (ALU pipe), 1 = LOP3 + IMAD (ALU + FMA pipes) */
 int ll_measure_int_peak(ll_ctx *ctx, int kind, double *thread_ops_per_sec);

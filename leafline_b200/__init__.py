@@ -146,6 +146,12 @@ class Engine:
         _abi.check(self._lib.ll_debug_tables(self._ctx, _ptr(pony), _ptr(fig)))
         return pony, fig
 
+    def debug_horizon_overflowed(self):
+        """Testing aid: parents of the last level-by-level horizon call that went to the overflow kernel; see the header."""
+        out = np.zeros(1, dtype=np.uint32)
+        _abi.check(self._lib.ll_debug_horizon_overflowed(self._ctx, _ptr(out)))
+        return int(out[0])
+
     def measure_int_peak(self, kind=0):
         """Sustained thread-level integer instructions/s (0: LOP3 stream, 1: LOP3+IMAD) for the integer roofline."""
         v = C.c_double(0)

@@ -88,6 +88,7 @@ SIGNATURES = {
     "ll_debug_force_synced": ([_vp, _i], _i),
     "ll_debug_selfcheck_soa": ([_vp, C.POINTER(Soa), _vp], _i),
     "ll_debug_tables": ([_vp, _vp, _vp], _i),
+    "ll_debug_horizon_overflowed": ([_vp, _vp], _i),
     "ll_measure_int_peak": ([_vp, _i, C.POINTER(C.c_double)], _i),
 }
 

@@ -777,6 +777,14 @@ extern "C" int ll_debug_tables(ll_ctx *ctx, uint64_t *pony64, uint64_t *figurehe
     return LL_OK;
 }
 
+extern "C" int ll_debug_horizon_overflowed(ll_ctx *ctx, uint32_t *parents) {
+    LL_TRY(check_ctx(ctx));
+    if (!parents) return fail(LL_ERR_INVALID_ARG, "null argument");
+    CUDA_TRY(cudaMemcpyAsync(parents, (u64 *)ctx->scalars.ptr + SC_HZ_OVERFLOW, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return LL_OK;
+}
+
 extern "C" int ll_measure_int_peak(ll_ctx *ctx, int kind, double *thread_ops_per_sec) {
     LL_ABI_BEGIN
     LL_TRY(check_ctx(ctx));

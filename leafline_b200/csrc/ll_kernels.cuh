@@ -853,8 +853,7 @@ struct HorizonShared {
     // subtraction and costs the filling thread an OR a child: 2.59 ms against 2.48, measured when the map held every child.)
     unsigned short map[OWNER_CAP];
     u32 tile_meta[HP];
-    u64 tile_opp[HP]; // the union of the six
-    u64 rec_mask[HZ_REC_CAP][HP]; // transposed: neighbouring parents write neighbouring words
+    u64 rec_mask[HZ_REC_CAP][HP]; // the records with loud commits: those commits' destinations (transposed: neighbouring parents write neighbouring words)
     u32 rec_info[HZ_REC_CAP][HP]; // kind, job, from, ascension, passing-by (16 bits)
     unsigned char rec_loud[HZ_REC_CAP][HP]; // number of the record's first LOUD commit (<= 8 stuns a piece, <= 12 loud commits a servant: < 256)
     u32 exl[HV + 1]; // exclusive prefixes of the virtual parents' loud commit counts
@@ -875,29 +874,43 @@ struct TilePlanesRt {
     size_t at;
     __device__ __forceinline__ u64 operator()(int j) const { return ldg(in.pl + (size_t)j * in.stride + at); }
 };
+// What phase 1 keeps of a parent's records.  QUIET commits are never decoded: a record's quiet commits are folded, as it is
+// made, into `quiet_set` -- bit 8 * e + w: some quiet commit changes the features way w (quiet_ways_of_record) and the
+// eligibility way e (0 not at all; 1 / 2 a cop leaves its west / east corner file; 3 the figurehead moves: what
+// quiet_eligibility_rt does) -- and counted.  Only a record WITH loud commits takes a row of the tile: their destinations, its info.
 struct SharedRecordOut {
     HorizonShared &sh;
     int slot;
     u64 opp;
+    u32 team;
     u32 row, row_end; // this half's rows
-    u32 n_rec = 0, n_quiet = 0, n_loud = 0;
-    bool outgrown = false; // more records than the half's rows: k_horizon_overflow takes the parent
+    u32 n_rec = 0, n_quiet = 0, n_loud = 0, quiet_set = 0;
+    bool outgrown = false; // more loud records than the half's rows: k_horizon_overflow takes the parent
     LL_HDM void put(u64 mask, u32 info) {
+        const u64 quiet = rec_quiet(info, mask, opp), loud = mask & ~quiet;
+        if (quiet) {
+            const u32 job = (info >> 3) & 7u, file = (info >> 6) & 7u;
+            const u32 e = (info & 7u) != REC_PIECE ? 0u : job == FIGUREHEAD ? 3u : job == COP && file == 0 ? 1u : job == COP && file == 7 ? 2u : 0u;
+            quiet_set |= quiet_ways_of_record((int)team, info, quiet) << (8 * e);
+            n_quiet += (u32)__popcll(quiet);
+        }
+        if (!loud) return;
         if (row >= row_end) {
             outgrown = true;
             return;
         }
-        const u32 all = (u32)__popcll(mask);
-        const u32 quiet = (u32)__popcll(rec_quiet(info, mask, opp));
-        sh.rec_mask[row][slot] = mask;
+        sh.rec_mask[row][slot] = loud;
         sh.rec_info[row][slot] = info & 0xFFFFu;
         sh.rec_loud[row][slot] = (unsigned char)n_loud;
         row++;
         n_rec++;
-        n_quiet += quiet;
-        n_loud += all - quiet;
+        n_loud += (u32)__popcll(loud);
     }
 };
+LL_HD u32 quiet_set_eligibility(u32 team, u32 elig, u32 e) { // the eligibility after a quiet commit of eligibility way e (SharedRecordOut)
+    const u32 west = team == 0 ? 0x1u : 0x4u, east = team == 0 ? 0x2u : 0x8u;
+    return elig & ~(e == 1 ? west : e == 2 ? east : e == 3 ? west | east : 0u);
+}
 // the virtual parent of LOUD child k, the row of the record it comes from and its number among the record's loud commits:
 // looked up, or -- a tile with more loud children than the map holds -- searched for: the last virtual parent whose prefix is
 // <= k, then the last record of that half whose first loud commit is <= j (it has one: records without share their successor's number)
@@ -948,7 +961,7 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
     const int slot_mine = tid & (HP - 1), half = tid / HP;
     const size_t i = tile * HP + slot_mine;
     const bool mine = i < n; // (both halves of the block hold the parent)
-    u32 cnt_q = 0, cnt_l = 0, n_rec = 0;
+    u32 cnt_q = 0, cnt_l = 0, n_rec = 0, quiet_set = 0;
     bool outgrown = false;
     if (mine) {
         const Pos p = soa_load(a.in, i);
@@ -956,10 +969,9 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
         u64 opp = 0;
 #pragma unroll
         for (int j = 0; j < 6; j++) opp |= blue ? p.pl[j] : p.pl[6 + j];
-        SharedRecordOut out{sh, slot_mine, opp, half ? (u32)REC_ROWS_A : 0u, half ? (u32)HZ_REC_CAP : (u32)REC_ROWS_A};
+        SharedRecordOut out{sh, slot_mine, opp, (u32)blue, half ? (u32)REC_ROWS_A : 0u, half ? (u32)HZ_REC_CAP : (u32)REC_ROWS_A};
         if (half == 0) {
             reckless_records_part<STUNS, 1>(p, out);
-            sh.tile_opp[slot_mine] = opp;
             sh.tile_meta[slot_mine] = p.meta;
             sh.acc[slot_mine] = float_key(-INFINITY);
         } else {
@@ -973,6 +985,7 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
         cnt_q = out.n_quiet;
         cnt_l = out.n_loud;
         n_rec = out.n_rec;
+        quiet_set = out.quiet_set;
     }
     if (half == 0) sh.outgrown[slot_mine] = 0;
     __syncthreads();
@@ -980,7 +993,7 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
     __syncthreads();
     outgrown = mine && sh.outgrown[slot_mine];
     if (outgrown) { // no commit of this parent enters the tile; the overflow kernel values it (and counts its leaves)
-        cnt_q = cnt_l = n_rec = 0;
+        cnt_q = cnt_l = n_rec = quiet_set = 0;
         if (half == 0) a.overflow_list[atomicAdd(a.overflow_count, 1u)] = (u32)i;
     }
     sh.n_rec[tid] = (unsigned char)n_rec;
@@ -992,11 +1005,12 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
     const bool mapped = total_l <= OWNER_CAP; // block-uniform
     if (mapped) { // every loud child's (virtual parent, record row), written by the half that owns it: record by record
         const u32 row0 = half ? (u32)REC_ROWS_A : 0u;
+        u32 c = 0;
         for (u32 r = 0; r < n_rec; r++) {
             const u32 row = row0 + r;
-            const u32 l0 = sh.rec_loud[row][slot_mine], l1 = r + 1 < n_rec ? sh.rec_loud[row + 1][slot_mine] : cnt_l;
+            const u32 end = r + 1 < n_rec ? sh.rec_loud[row + 1][slot_mine] : cnt_l;
             const unsigned short entry = (unsigned short)(tid | row << 8);
-            for (u32 c = l0; c < l1; c++) sh.map[ex_l + c] = entry;
+            for (; c < end; c++) sh.map[ex_l + c] = entry;
         }
     }
     { // what a quiet child of each way scores short of the eligibility terms: four ways a thread, both halves of a parent at it
@@ -1013,22 +1027,16 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
         for (u32 u = 0; u < 4; u++) sh.quiet[4u * half + u][slot_mine] = sums[u];
     }
     __syncthreads();
-    // ---- quiet commits: record by record, by the thread that made the records.  All quiet commits of a record that change
-    // the features the same way score the same, and which ways a record has is a matter of masks (quiet_ways_of_record):
-    // the best quiet child of a record is the best of its (one to three) ways -- no child is decoded.
-    if (cnt_q) {
-        const u32 meta = sh.tile_meta[slot_mine], team = meta_stm(meta), row0 = half ? (u32)REC_ROWS_A : 0u;
-        const u64 opp = sh.tile_opp[slot_mine];
+    // ---- quiet commits: all quiet commits of a parent that change the features and the eligibility the same way score the
+    // same, and phase 1 noted which ways occur (SharedRecordOut::quiet_set) -- the best quiet child is the best of those
+    // (three or four a half, typically); no quiet child is decoded.
+    if (quiet_set) {
+        const u32 meta = sh.tile_meta[slot_mine], team = meta_stm(meta);
         int best = float_key(-INFINITY);
-        for (u32 r = 0; r < n_rec; r++) {
-            const u32 info = sh.rec_info[row0 + r][slot_mine];
-            const u64 quiet = rec_quiet(info, sh.rec_mask[row0 + r][slot_mine], opp);
-            if (!quiet) continue;
-            const u32 elig = quiet_eligibility_rt((int)team, meta_elig(meta), (info >> 3) & 7u, (int)((info >> 6) & 63u));
-            for (u32 ways = quiet_ways_of_record((int)team, info, quiet); ways; ways &= ways - 1) {
-                const float s = score_eligibility(sh.quiet[__ffs((int)ways) - 1][slot_mine], elig);
-                best = max(best, float_key(team ? -s : s)); // -(orientation(child) * score(child)), the child's initiative being the other team's (mind.rs:283, 331-336)
-            }
+        for (u32 q = quiet_set; q; q &= q - 1) {
+            const u32 b = (u32)__ffs((int)q) - 1u;
+            const float s = score_eligibility(sh.quiet[b & 7u][slot_mine], quiet_set_eligibility(team, meta_elig(meta), b >> 3));
+            best = max(best, float_key(team ? -s : s)); // -(orientation(child) * score(child)), the child's initiative being the other team's (mind.rs:283, 331-336)
         }
         atomicMax(&sh.acc[slot_mine], best);
     }
@@ -1040,7 +1048,7 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
         const u64 mask = sh.rec_mask[row][slot];
         const u32 meta = sh.tile_meta[slot];
         const u32 team = meta_stm(meta);
-        const int to = select_bit(mask & ~rec_quiet(info, mask, sh.tile_opp[slot]), t);
+        const int to = select_bit(mask, t);
         const u32 m = rec_move_to(info & 0xFFFFu, to, team);
         Feat f;
 #pragma unroll

@@ -468,26 +468,42 @@ def test_horizon_launch_chain_equals_level_by_level(eng, playouts, reckless_worl
 
 
 def test_horizon_parents_with_more_records_than_a_tile_keeps(eng, playouts):
-    """k_horizon keeps 24 (piece / servant-step, target mask) records a parent in its tile; a position can have up to 36 -- a
-    dozen pieces and servants ascending every way.  Such parents go, whole, to k_horizon_overflow; values must not notice."""
+    """k_horizon keeps, per parent, the (piece / servant-step, target mask) records that have stunning, ascending or serving
+    commits -- 14 of the servants' and the figurehead's, 10 of the other pieces' -- and values the quiet commits as the
+    records are made.  A parent with more goes, whole, to k_horizon_overflow; values must not notice."""
     import leafline_b200 as ll
 
-    crowded = [  # twelve pieces, the figurehead, and two servants that between them step every way a servant can: 29 records
-        "1n1n3k/2P5/BBBB4/RRRR4/NNNN4/5p1p/6P1/4K3 w - -",
-        "4k3/6p1/5P1P/nnnn4/rrrr4/bbbb4/2p5/1N1N3K b - -",      # the same for Blue
-        "1n1n3k/2P5/QQQQ4/QQQQ4/QQQQ4/5p1p/6P1/4K3 w - -",
-        "1n1n1n2/P1P1P1P1/8/8/NNNN4/BBBB4/RRR5/4K2k w - -",    # 22 records: stays in the tile
+    overflowing = [
+        "4k3/pppppppp/N1N1N1N1/QQQQQQQQ/8/8/8/4K3 w - -",      # twelve pieces, every one of them with somebody to stun
+        "4k3/8/8/8/qqqqqqqq/n1n1n1n1/PPPPPPPP/4K3 b - -",      # the same for Blue
+        "n1n1k3/1P6/8/3p1p2/4P3/8/7n/6K1 w - -",               # a servant ascending three ways (12 records), another stunning two ways, the figurehead
+        "6k1/7N/8/4p3/3P1P2/8/1p6/N1N1K3 b - -",               # the same for Blue
     ]
-    worlds = np.array([ll.reconstruct(f) for f in crowded], dtype=ll.WORLD_DTYPE)
+    crowded = [  # many records, few of them loud: these stay in the tile
+        "1n1n3k/2P5/BBBB4/RRRR4/NNNN4/5p1p/6P1/4K3 w - -",
+        "4k3/6p1/5P1P/nnnn4/rrrr4/bbbb4/2p5/1N1N3K b - -",
+        "1n1n3k/2P5/QQQQ4/QQQQ4/QQQQ4/5p1p/6P1/4K3 w - -",
+        "1n1n1n2/P1P1P1P1/8/8/NNNN4/BBBB4/RRR5/4K2k w - -",
+    ]
+    worlds = np.array([ll.reconstruct(f) for f in overflowing + crowded], dtype=ll.WORLD_DTYPE)
     assert max(len(O.reckless_lookahead(w)) for w in worlds) >= 90
     mixed = np.concatenate([playouts[:100], worlds, playouts[100:164], worlds[::-1]])  # overflowing parents among ordinary ones
+    eng.force_synced(True)  # (level by level: the overflow counter read below is that path's)
+    try:
+        got = eng.horizon(mixed, 1)
+        assert eng.debug_horizon_overflowed() == 2 * len(overflowing)
+        assert got.tobytes() == np.array([O.negamax(w, 1) for w in mixed], dtype=np.float32).tobytes()
+        got = eng.horizon(playouts[:164], 1)
+        assert eng.debug_horizon_overflowed() == 0
+    finally:
+        eng.force_synced(False)
     for plies in (1, 2):
         got = eng.horizon(mixed, plies)
         want = np.array([O.negamax(w, plies) for w in mixed], dtype=np.float32)
         assert got.tobytes() == want.tobytes(), plies
     got = eng.horizon(mixed, 1, quiet=2)
     assert got.tobytes() == np.array([O.negamax(w, 1, quiet=2) for w in mixed], dtype=np.float32).tobytes()
-    for w in worlds[:2]:
+    for w in worlds[:4]:
         _, s_got, _ = eng.kickoff(w, 2)
         assert s_got.tobytes() == O.kickoff(w, 2, False, threads=4)[1].tobytes()
 
