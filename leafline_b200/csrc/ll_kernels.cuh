@@ -859,7 +859,8 @@ struct HorizonShared {
     u32 exl[HV + 1]; // exclusive prefixes of the virtual parents' loud commit counts
     unsigned short commits[HV]; // quiet + loud commits of each virtual parent
     unsigned char n_rec[HV];
-    unsigned char outgrown[HP]; // a half ran out of rows: the whole parent goes to k_horizon_overflow
+    unsigned char outgrown[HV]; // a half ran out of rows: the whole parent goes to k_horizon_overflow
+    u32 warp_sums[BLOCK / 32];
     int acc[HP];
     u32 feat[7][HP]; // the parents' evaluation features (ll_device.cuh: Feat), transposed like the records
     float material[HP]; // score_material(parent's features, the CHILD's initiative)
@@ -987,19 +988,21 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
         n_rec = out.n_rec;
         quiet_set = out.quiet_set;
     }
-    if (half == 0) sh.outgrown[slot_mine] = 0;
-    __syncthreads();
-    if (outgrown) sh.outgrown[slot_mine] = 1;
-    __syncthreads();
-    outgrown = mine && sh.outgrown[slot_mine];
-    if (outgrown) { // no commit of this parent enters the tile; the overflow kernel values it (and counts its leaves)
-        cnt_q = cnt_l = n_rec = quiet_set = 0;
-        if (half == 0) a.overflow_list[atomicAdd(a.overflow_count, 1u)] = (u32)i;
-    }
+    // (a half that ran out of rows keeps the records it has: their commits are valued like any others, for nothing -- the
+    // parent's value is the overflow kernel's, see the end of the tile -- which spares the tile a barrier to tell the other half)
+    sh.outgrown[tid] = outgrown;
     sh.n_rec[tid] = (unsigned char)n_rec;
     sh.commits[tid] = (unsigned short)(cnt_q + cnt_l);
-    u32 total_l;
-    const u32 ex_l = block_exclusive_scan(cnt_l, &total_l);
+    u32 total_l = 0;
+    u32 ex_l = warp_inclusive_scan(cnt_l);
+    if ((tid & 31) == 31) sh.warp_sums[tid >> 5] = ex_l;
+    __syncthreads(); // phase 1 is over: the records, the features and the warps' loud counts are there
+    ex_l -= cnt_l;
+#pragma unroll
+    for (int w = 0; w < BLOCK / 32; w++) {
+        if (w < (tid >> 5)) ex_l += sh.warp_sums[w];
+        total_l += sh.warp_sums[w];
+    }
     sh.exl[tid] = ex_l;
     if (tid == 0) sh.exl[HV] = total_l;
     const bool mapped = total_l <= OWNER_CAP; // block-uniform
@@ -1088,7 +1091,9 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
     }
     __syncthreads();
     u32 scored = 0;
-    if (mine && half == 0 && !outgrown) {
+    if (mine && half == 0 && (sh.outgrown[slot_mine] | sh.outgrown[HP + slot_mine])) {
+        a.overflow_list[atomicAdd(a.overflow_count, 1u)] = (u32)i; // the overflow kernel values it (and counts its leaves)
+    } else if (mine && half == 0) {
         const u32 other = (u32)HP + (u32)slot_mine;
         const u32 cnt = cnt_q + cnt_l + sh.commits[other];
         float v = cnt ? key_float(sh.acc[slot_mine]) : -INFINITY;
