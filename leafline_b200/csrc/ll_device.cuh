@@ -1307,19 +1307,15 @@ template <int T, class Planes> LL_HD u32 child_features(Feat &f, u32 &elig, cons
     return hosp;
 }
 
-// the same with the mover as a run-time value (see quiet_child_score_rt)
+// the same with the mover as a run-time value (see quiet_child_score_rt).  Planes: besides operator() (the mover's cop and
+// figurehead planes, for a secret service), u32 opposition_job_at(int square) -- the job of the opposition's figurine there, or JOB_NONE
 template <class Planes> LL_HD u32 child_features_rt(const int T, Feat &f, u32 &elig, const Planes &planes, u32 m) {
     const int E = 1 - T;
     const int from = mv_from(m), to = mv_to(m);
     const u32 job = mv_job(m), asc = mv_asc(m);
     const u64 center = 0x00003C3C3C3C0000ull;
-    const u64 tb = 1ull << to;
-    const u64 victim = (m & MV_PASSING_BY) ? (T == 0 ? tb >> 8 : tb << 8) : tb;
     const int vs = (m & MV_PASSING_BY) ? (T == 0 ? to - 8 : to + 8) : to;
-    u32 hosp = JOB_NONE;
-#pragma unroll
-    for (int j = 5; j >= 0; j--)
-        if (planes(6 * E + j) & victim) hosp = (u32)j; // first in dramatis_personae order wins (life.rs:550-557)
+    const u32 hosp = planes.opposition_job_at(vs); // whom the commit stuns, if anybody (life.rs:550-557)
     // ---- eligibility (life.rs:577-605)
     if (job == FIGUREHEAD) elig &= T == 0 ? ~0x3u : ~0xCu;
     if (job == COP) {

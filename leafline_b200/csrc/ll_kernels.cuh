@@ -853,6 +853,7 @@ struct HorizonShared {
     // subtraction and costs the filling thread an OR a child: 2.59 ms against 2.48, measured when the map held every child.)
     unsigned short map[OWNER_CAP];
     u32 tile_meta[HP];
+    u64 opp_job[3][HP]; // bit k of (job + 1) of the opposition's figurine on each square (0 = nobody): whom a loud commit stuns
     u64 rec_mask[HZ_REC_CAP][HP]; // the records with loud commits: those commits' destinations (transposed: neighbouring parents write neighbouring words)
     u32 rec_info[HZ_REC_CAP][HP]; // kind, job, from, ascension, passing-by (16 bits)
     unsigned char rec_loud[HZ_REC_CAP][HP]; // number of the record's first LOUD commit (<= 8 stuns a piece, <= 12 loud commits a servant: < 256)
@@ -867,13 +868,19 @@ struct HorizonShared {
     float quiet[QUIET_WAYS][HP]; // the sum of mind.rs:53-131 for a quiet child of each way (ll_device.cuh: quiet_way_rt)
     u32 claim; // CHAIN: the tile this block pulled
 };
-// the planes of one parent as child_features asks for them: only LOUD commits read any (the opposition's six, to find the victim;
-// the mover's cop and figurehead planes for a secret service) -- from global memory, where the tile's parents were read a
-// moment ago (L1 / L2); the shared memory they used to occupy holds the record map
+// What child_features_rt reads of a parent's planes.  Whom a commit stuns: the opposition's six planes, folded in phase 1 into
+// three (bit k of job + 1, per square) in shared memory -- three shifts instead of six loads and compares a loud child.
+// A secret service also reads the mover's cop and figurehead planes: from global memory (rare).
 struct TilePlanesRt {
+    const HorizonShared &sh;
+    u32 slot;
     const Soa &in;
     size_t at;
     __device__ __forceinline__ u64 operator()(int j) const { return ldg(in.pl + (size_t)j * in.stride + at); }
+    __device__ __forceinline__ u32 opposition_job_at(int sq) const {
+        const u32 code = ((u32)(sh.opp_job[0][slot] >> sq) & 1u) | (((u32)(sh.opp_job[1][slot] >> sq) & 1u) << 1) | (((u32)(sh.opp_job[2][slot] >> sq) & 1u) << 2);
+        return code ? code - 1u : (u32)JOB_NONE;
+    }
 };
 // What phase 1 keeps of a parent's records.  QUIET commits are never decoded: a record's quiet commits are folded, as it is
 // made, into `quiet_set` -- bit 8 * e + w: some quiet commit changes the features way w (quiet_ways_of_record) and the
@@ -973,6 +980,12 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
         SharedRecordOut out{sh, slot_mine, opp, (u32)blue, half ? (u32)REC_ROWS_A : 0u, half ? (u32)HZ_REC_CAP : (u32)REC_ROWS_A};
         if (half == 0) {
             reckless_records_part<STUNS, 1>(p, out);
+            u64 o[6]; // job + 1: servant 1, pony 2, scholar 3, cop 4, princess 5, figurehead 6
+#pragma unroll
+            for (int j = 0; j < 6; j++) o[j] = blue ? p.pl[j] : p.pl[6 + j];
+            sh.opp_job[0][slot_mine] = o[SERVANT] | o[SCHOLAR] | o[PRINCESS];
+            sh.opp_job[1][slot_mine] = o[PONY] | o[SCHOLAR] | o[FIGUREHEAD];
+            sh.opp_job[2][slot_mine] = o[COP] | o[PRINCESS] | o[FIGUREHEAD];
             sh.tile_meta[slot_mine] = p.meta;
             sh.acc[slot_mine] = float_key(-INFINITY);
         } else {
@@ -1057,7 +1070,7 @@ template <bool STUNS, bool CHAIN = false> __global__ void __launch_bounds__(BLOC
 #pragma unroll
         for (int w = 0; w < 7; w++) f.w[w] = sh.feat[w][slot];
         u32 elig = meta_elig(meta);
-        child_features_rt((int)team, f, elig, TilePlanesRt{a.in, tile * HP + slot}, m);
+        child_features_rt((int)team, f, elig, TilePlanesRt{sh, slot, a.in, tile * HP + slot}, m);
         const float s = score_features(f, team ^ 1u, elig);
         return float_key(team ? -s : s);
     };
