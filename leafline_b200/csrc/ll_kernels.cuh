@@ -807,32 +807,31 @@ __global__ void __launch_bounds__(BLOCK, LL_EXPAND_MIN_BLOCKS) k_expand_coop(con
     }
 }
 
-// ---- horizon by records (mind.rs:279-301): children decoded from (piece, target mask) records ---------------
-// Phase 1 costs per PIECE, not per move: a parent thread writes at most REC_MAX records (ll_device.cuh) into shared
-// memory, together with its evaluation features, the union of the opposition's planes and the material half of the
-// evaluation as all its QUIET children will share it (score_material: their head counts are the parent's).
-// Phase 2 runs one CHILD per thread, in two passes over the tile so that the lanes of a warp run the same code:
-//   quiet commits (nobody stunned, nothing ascended, no secret service, no passing by: ~85 % of all) -- decode, update
-//     three feature words by the move alone, run the positional half of the evaluation from the parent's material value
-//     (quiet_child_score);
-//   loud commits -- the opposition's planes searched for the victim, the features updated by its loss / the ascension / the
-//     conjured cop, the whole evaluation (child_features + score_features).
-// A record's targets split into the two kinds by the opposition's squares; each kind numbers its commits by its own prefix
-// sums (per parent and per record), each has its own owner map (child -> parent slot; binary search over the prefix sums
-// only when a tile has more children than the map holds).  The child's planes are never built; both evaluations are
-// bit-identical to score(make_child(...)) (tests/hostcheck).  Per parent: max over its children, shared-memory atomicMax
-// after a warp-level segmented max.
+// ---- horizon by records (mind.rs:279-301): the best child of every frontier node, no child ever built ------------
+// Phase 1 costs per PIECE, not per move: the commits of a parent come as (piece / kind of servant step, target mask)
+// records (ll_device.cuh, at most REC_MAX), made by two threads a parent together with its evaluation features.
+// QUIET commits (nobody stunned, nothing ascended, no secret service, no passing by: ~85 % of all) are never decoded.
+//   score() reads a position through a few small integers; a quiet commit changes them in one of QUIET_WAYS = 8 ways
+//   (quiet_way_rt) and the eligibility in one of four, all quiet commits of one (way, eligibility way) score the same, and
+//   which ways a record's quiet commits take is a matter of masks on its target set (quiet_ways_of_record).  So a record's
+//   quiet commits are folded, as it is made, into a 32-bit set and counted (SharedRecordOut); the sum of mind.rs:53-131 is
+//   computed once per (parent, way) (score_ways, four ways a thread), and the best quiet child of a half parent is the best
+//   of the handful of set bits: eligibility terms added, one atomicMax.  Same integers, same float sequence as
+//   score(make_child(...)) for every one of those children: tests/hostcheck holds way by way against commit by commit.
+// LOUD commits are valued one CHILD per thread: only records that have any take a row of the tile (their loud targets);
+//   a block scan numbers them, a map gives child -> (half parent, row) (searched for only when a tile has more loud
+//   children than the map holds), the victim's job comes from three folded planes of the opposition, the features are
+//   updated by its loss / the ascension / the conjured cop, and the whole evaluation runs (child_features_rt +
+//   score_features).  Per parent: max over its children, a shared-memory atomicMax a child.
 #ifndef LL_HP
 #define LL_HP 64
 #endif
 constexpr int HP = LL_HP; // parents per horizon tile
 constexpr u32 OWNER_CAP = 1024; // LOUD children of a tile whose parent is looked up, not searched for (a tile of 64 has ~350)
-// Records a parent may keep in the tile.  A position can have up to REC_MAX = 36 (ll_device.cuh) but rarely has more than
-// sixteen, and the record arrays are most of the block's shared memory, which is what limits the resident warps of a kernel
-// bound by latency: 36 slots = 40 KB = five blocks a SM, 24 slots = 30 KB = seven: 3.24 -> 2.9 ms.  (21 slots = eight blocks
-// were measured too: 3-5 % of the playout positions have 22-24 records, and their trip through k_horizon_overflow costs more
-// than the eighth block gains.)  A parent with more records is handed, whole, to k_horizon_overflow (one thread walks the
-// canonical generator): none among 2^22 playout positions.
+// Records WITH LOUD COMMITS a parent may keep in the tile.  The record arrays are most of the block's shared memory, which
+// limits the resident warps: 36 rows (every record a position can have) = five blocks a SM, 24 rows = seven (3.24 -> 2.9 ms
+// when the tile still kept every record).  A parent with more loud records in either half is handed, whole, to
+// k_horizon_overflow (a block per parent): none among 2^22 playout positions.
 #ifndef LL_HZ_REC_CAP
 #define LL_HZ_REC_CAP 24
 #endif
@@ -840,7 +839,7 @@ constexpr int HZ_REC_CAP = LL_HZ_REC_CAP;
 #ifndef LL_HORIZON_MIN_BLOCKS
 #define LL_HORIZON_MIN_BLOCKS 7
 #endif
-// A parent's records are generated by TWO threads (phase 1 is a quarter of the kernel and would leave half the block idle):
+// A parent's records are generated by TWO threads (phase 1 would otherwise leave half the block idle):
 // thread slot takes the servants, the figurehead and secret service and files them in rows [0, REC_ROWS_A), thread HP + slot the
 // ponies and the sliders in rows [REC_ROWS_A, HZ_REC_CAP); each half numbers its own commits from zero and is, from the scan
 // on, a parent of its own ("virtual parent" v = half * HP + slot) -- only the maximum is shared.
