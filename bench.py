@@ -397,15 +397,17 @@ def main():
         # full-width tree fits in HBM; on a group the root moves are searched concurrently, one subset per GPU
         searcher = group if world > 1 else eng
         searcher.alpha_beta_forecast(root, 6, device_plies=3)
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        fc8, host_nodes, handed_off = searcher.alpha_beta_forecast(root, 8, device_plies=4)
-        seconds = time.perf_counter() - t0
-        t8 = torch.tensor([seconds], dtype=torch.float64, device="cuda")
+        times = []
+        for _ in range(3):  # the first search grows the level buffers (reported apart); a search keeps nothing of the one before
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            fc8, host_nodes, handed_off = searcher.alpha_beta_forecast(root, 8, device_plies=4)
+            times.append(time.perf_counter() - t0)
+        t8 = torch.tensor([min(times[1:]), times[0]], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t8, op=dist.ReduceOp.MAX)
-        result["alpha_beta_depth8"] = {"seconds": float(t8.item()), "best_score": float(fc8[0]["score"]), "principal_variation": ll.pagan_variation(fc8[0]),
+        result["alpha_beta_depth8"] = {"seconds": float(t8[0].item()), "first_search_seconds": float(t8[1].item()), "best_score": float(fc8[0]["score"]), "principal_variation": ll.pagan_variation(fc8[0]),
                                        "host_nodes_expanded": host_nodes, "values_remembered": searcher.last_search_stats["values_remembered"],
                                        "frontier_nodes_handed_to_device": handed_off, "device_plies": 4,
                                        "what": ("ll_alpha_beta_forecast" if world == 1 else f"ll_alpha_beta_forecast_multi over {world} ranks") +
